@@ -1,0 +1,92 @@
+"""ctypes binding of libgnc.so (include/gnc.h).  No fallback: if the CUDA library is
+missing or fails, this raises - the product path never computes on the CPU."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnc.so")
+
+GNC_OK, GNC_EINVAL, GNC_ECUDA, GNC_EWORKSPACE = 0, 1, 2, 3
+
+
+class GncSeg(Structure):
+    """struct gnc_seg (include/gnc.h)."""
+    _fields_ = [("base", c_void_p), ("idx", c_void_p), ("ld", c_int64), ("width", c_int32), ("_pad", c_int32)]
+
+
+class GncError(RuntimeError):
+    pass
+
+
+_P = c_void_p
+# name -> (restype, argtypes); mirrors include/gnc.h one to one (tests/test_abi.py checks it)
+SIGNATURES = {
+    "gnc_version": (c_int, []),
+    "gnc_last_error": (c_char_p, []),
+    "gnc_launch_count": (c_uint64, []),
+    "gnc_reset_launch_count": (None, []),
+    "gnc_grid_num_edges": (c_int64, [c_int, c_int, c_int]),
+    "gnc_build_pixel_graph_u8": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnc_build_patch_graph_u8": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnc_superpixel_workspace": (c_int64, [c_int, c_int]),
+    "gnc_build_superpixel_graph": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int64,
+                                           _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnc_csr_workspace": (c_int64, [c_int64]),
+    "gnc_csr_build": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "gnc_agg_csr_sum_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, c_int64, c_int, _P]),
+    "gnc_gather_rows_f32": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int, _P]),
+    "gnc_edge_geometry_f32": (c_int, [_P, c_int, _P, _P, c_int64, _P, _P]),
+    "gnc_linear_fwd_f32": (c_int, [POINTER(GncSeg), c_int, c_int64, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "gnc_linear_dgrad_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P]),
+    "gnc_linear_wgrad_workspace": (c_int64, [c_int64, c_int, c_int]),
+    "gnc_linear_wgrad_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(GncSeg), c_int, _P, c_int64, c_int,
+                                     _P, c_int64, _P]),
+    "gnc_colsum_workspace": (c_int64, [c_int64, c_int]),
+    "gnc_relu_bwd_colsum_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, _P, c_int64, _P, c_int,
+                                        _P, c_int64, _P]),
+    "gnc_layernorm_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_float, _P, c_int64, _P, c_int64,
+                                      _P, _P, _P]),
+    "gnc_layernorm_bwd_workspace": (c_int64, [c_int64, c_int]),
+    "gnc_layernorm_bwd_f32": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, _P, c_int64,
+                                      _P, _P, c_int, _P, c_int64, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Loads libgnc.so; raises GncError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise GncError(
+            f"{_LIB_PATH} not found: build it with `python -m graphnet_classifier_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback for this path.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != GNC_OK:
+        msg = load().gnc_last_error()
+        raise GncError(f"libgnc {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().gnc_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().gnc_reset_launch_count()

@@ -1,0 +1,268 @@
+// Aggregation / gather kernels (sm_100a), HBM-bound.
+//
+//   agg_csr_sum : out[v] = sum_{k in row v, ascending} src[eid[k]]   (scatter_sum, models/GNN.py:3-21, :99;
+//                 also the backward of the x[row] / x[col] gathers with the source-/destination-side CSR)
+//   gather_rows : out[m] = src[idx[m]]                               (x[row], x[col]; backward of scatter_sum)
+//   edge_geometry: [pos[dst]-pos[src], L1]                           (models/GNN.py:299-302)
+//
+// Rows are summed SEQUENTIALLY in ascending edge id - the order the CPU reference's
+// index_add_ uses - so the result is bit-identical to the reference whatever the
+// in-degree.  Parallelism comes from rows x feature lanes: a group of LPR lanes owns
+// one row and each lane owns 4*VPL consecutive features (128-bit accesses).  Up to
+// 4 neighbour rows are in flight per lane before the ordered adds retire them.
+#include "common.cuh"
+
+namespace gnc {
+
+template <int LPR, int VPL, bool ACC>
+__global__ void __launch_bounds__(256) agg_csr_sum_vec_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid, const float* __restrict__ src,
+    int64_t ld_src, int64_t N, int D4 /* D/4 */, float* __restrict__ out, int64_t ld_out) {
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v0 = warp_global * ROWS_PER_WARP; v0 < N; v0 += warps_total * ROWS_PER_WARP) {
+    const int64_t v = v0 + sub;
+    if (v >= N) continue;
+    const int32_t beg = __ldg(rowptr + v), end = __ldg(rowptr + v + 1);
+    float4 acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int32_t k = beg;
+    for (; k + 4 <= end; k += 4) {
+      int32_t e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = __ldg(eid + k + u);
+      float4 t[4][VPL];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int c4 = sl + q * LPR;
+          t[u][q] = (c4 < D4) ? ldg_stream(reinterpret_cast<const float4*>(src + (int64_t)e[u] * ld_src) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          acc[q].x += t[u][q].x; acc[q].y += t[u][q].y; acc[q].z += t[u][q].z; acc[q].w += t[u][q].w;
+        }
+    }
+    {  // tail of up to 3 rows, still loaded together
+      const int rem = end - k;
+      int32_t e[3];
+      float4 t[3][VPL];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) e[u] = (u < rem) ? __ldg(eid + k + u) : 0;
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int c4 = sl + q * LPR;
+          t[u][q] = (u < rem && c4 < D4)
+                        ? ldg_stream(reinterpret_cast<const float4*>(src + (int64_t)e[u] * ld_src) + c4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (u < rem) {
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) {
+            acc[q].x += t[u][q].x; acc[q].y += t[u][q].y; acc[q].z += t[u][q].z; acc[q].w += t[u][q].w;
+          }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int c4 = sl + q * LPR;
+      if (c4 < D4) {
+        float4* o = reinterpret_cast<float4*>(out + v * ld_out) + c4;
+        if (ACC) {
+          const float4 p = *o;
+          acc[q].x += p.x; acc[q].y += p.y; acc[q].z += p.z; acc[q].w += p.w;
+        }
+        stg_stream(o, acc[q]);
+      }
+    }
+  }
+}
+
+// Any D / alignment: one thread per (row, feature).
+template <bool ACC>
+__global__ void agg_csr_sum_scalar_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid,
+                                          const float* __restrict__ src, int64_t ld_src, int64_t N, int D,
+                                          float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = N * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t v = i / D;
+    const int c = (int)(i - v * D);
+    float acc = 0.f;
+    for (int32_t k = rowptr[v]; k < rowptr[v + 1]; ++k) acc += src[(int64_t)eid[k] * ld_src + c];
+    if (ACC) acc += out[v * ld_out + c];
+    out[v * ld_out + c] = acc;
+  }
+}
+
+template <int LPR, int VPL, bool ACC>
+__global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                              const int32_t* __restrict__ idx, int64_t M, int D4,
+                                                              float* __restrict__ out, int64_t ld_out) {
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m0 = warp_global * ROWS_PER_WARP; m0 < M; m0 += warps_total * ROWS_PER_WARP) {
+    const int64_t m = m0 + sub;
+    if (m >= M) continue;
+    const int64_t r = __ldg(idx + m);
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int c4 = sl + q * LPR;
+      if (c4 < D4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(src + r * ld_src) + c4);
+        float4* o = reinterpret_cast<float4*>(out + m * ld_out) + c4;
+        if (ACC) {
+          const float4 p = *o;
+          t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+        }
+        stg_stream(o, t);
+      }
+    }
+  }
+}
+
+template <bool ACC>
+__global__ void gather_rows_scalar_kernel(const float* __restrict__ src, int64_t ld_src,
+                                          const int32_t* __restrict__ idx, int64_t M, int D,
+                                          float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = M * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / D;
+    const int c = (int)(i - m * D);
+    float t = src[(int64_t)idx[m] * ld_src + c];
+    if (ACC) t += out[m * ld_out + c];
+    out[m * ld_out + c] = t;
+  }
+}
+
+__global__ void edge_geometry_kernel(const float* __restrict__ pos, int P, const int32_t* __restrict__ src,
+                                     const int32_t* __restrict__ dst, int64_t E, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const float* ps = pos + (int64_t)src[e] * P;
+    const float* pd = pos + (int64_t)dst[e] * P;
+    float l1 = 0.f;
+    float* o = out + e * (P + 1);
+    for (int d = 0; d < P; ++d) {       // torch.sum over dim 1 of |diff|: left-to-right for P <= 8
+      const float r = pd[d] - ps[d];
+      o[d] = r;
+      l1 += fabsf(r);
+    }
+    o[P] = l1;
+  }
+}
+
+static inline unsigned row_grid(int64_t rows, int rows_per_block) {
+  int64_t blocks = ceil_div<int64_t>(rows, rows_per_block);
+  const int64_t cap = (int64_t)kNumSMs * 8;     // 8 resident 256-thread CTAs per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+template <bool ACC>
+static int launch_agg(const int32_t* rowptr, const int32_t* eid, const float* src, int64_t ld_src, int64_t N, int D,
+                      float* out, int64_t ld_out, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(src) && aligned16(out) &&
+                   D <= 512;
+  if (!vec) {
+    int64_t blocks = ceil_div<int64_t>(N * D, 256);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    agg_csr_sum_scalar_kernel<ACC><<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(rowptr, eid, src, ld_src,
+                                                                                        N, D, out, ld_out);
+    return check_launch("agg_csr_sum_scalar_kernel");
+  }
+  const int D4 = D / 4;
+#define GNC_AGG(LPR, VPL)                                                                                  \
+  agg_csr_sum_vec_kernel<LPR, VPL, ACC><<<row_grid(N, 8 * (32 / LPR)), 256, 0, st>>>(rowptr, eid, src, ld_src, N, \
+                                                                                     D4, out, ld_out)
+  if (D4 <= 4) GNC_AGG(4, 1);
+  else if (D4 <= 8) GNC_AGG(8, 1);
+  else if (D4 <= 16) GNC_AGG(16, 1);
+  else if (D4 <= 32) GNC_AGG(32, 1);
+  else if (D4 <= 64) GNC_AGG(32, 2);
+  else GNC_AGG(32, 4);
+#undef GNC_AGG
+  return check_launch("agg_csr_sum_vec_kernel");
+}
+
+template <bool ACC>
+static int launch_gather(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D, float* out,
+                         int64_t ld_out, cudaStream_t st) {
+  const bool vec = (D % 4 == 0) && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(src) && aligned16(out) &&
+                   D <= 512;
+  if (!vec) {
+    int64_t blocks = ceil_div<int64_t>(M * D, 256);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    gather_rows_scalar_kernel<ACC><<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(src, ld_src, idx, M, D, out,
+                                                                                        ld_out);
+    return check_launch("gather_rows_scalar_kernel");
+  }
+  const int D4 = D / 4;
+#define GNC_GATHER(LPR, VPL)                                                                                 \
+  gather_rows_vec_kernel<LPR, VPL, ACC><<<row_grid(M, 8 * (32 / LPR)), 256, 0, st>>>(src, ld_src, idx, M, D4, out, \
+                                                                                     ld_out)
+  if (D4 <= 4) GNC_GATHER(4, 1);
+  else if (D4 <= 8) GNC_GATHER(8, 1);
+  else if (D4 <= 16) GNC_GATHER(16, 1);
+  else if (D4 <= 32) GNC_GATHER(32, 1);
+  else if (D4 <= 64) GNC_GATHER(32, 2);
+  else GNC_GATHER(32, 4);
+#undef GNC_GATHER
+  return check_launch("gather_rows_vec_kernel");
+}
+
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" {
+
+int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid, const float* src, int64_t ld_src, int64_t N,
+                        int D, float* out, int64_t ld_out, int accumulate, gnc_stream_t stream) {
+  GNC_REQUIRE(N >= 0 && D > 0 && ld_src >= D && ld_out >= D, "agg_csr_sum: bad sizes");
+  if (N == 0) return GNC_OK;
+  GNC_REQUIRE(rowptr && out, "agg_csr_sum: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  return accumulate ? launch_agg<true>(rowptr, eid, src, ld_src, N, D, out, ld_out, st)
+                    : launch_agg<false>(rowptr, eid, src, ld_src, N, D, out, ld_out, st);
+}
+
+int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D, float* out,
+                        int64_t ld_out, int accumulate, gnc_stream_t stream) {
+  GNC_REQUIRE(M >= 0 && D > 0 && ld_src >= D && ld_out >= D, "gather_rows: bad sizes");
+  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(src && idx && out, "gather_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  return accumulate ? launch_gather<true>(src, ld_src, idx, M, D, out, ld_out, st)
+                    : launch_gather<false>(src, ld_src, idx, M, D, out, ld_out, st);
+}
+
+int gnc_edge_geometry_f32(const float* pos, int P, const int32_t* src, const int32_t* dst, int64_t E, float* out,
+                          gnc_stream_t stream) {
+  GNC_REQUIRE(P >= 1 && P <= 8 && E >= 0, "edge_geometry: need 1 <= P <= 8");
+  if (E == 0) return GNC_OK;
+  GNC_REQUIRE(pos && src && dst && out, "edge_geometry: null pointer");
+  int64_t blocks = ceil_div<int64_t>(E, 256);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  edge_geometry_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pos, P, src, dst, E, out);
+  return check_launch("edge_geometry_kernel");
+}
+
+}  // extern "C"

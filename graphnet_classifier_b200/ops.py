@@ -1,0 +1,387 @@
+"""Torch-facing operators over the C ABI (include/gnc.h).
+
+torch is used for device memory, streams and autograd bookkeeping only; every
+arithmetic step is a libgnc kernel.  Tensors must live on a CUDA device - there is
+no CPU path (``_require_cuda`` raises).
+
+Operators (each with its backward wired through ``torch.autograd.Function``):
+  GraphIndex           int32 endpoints + stable CSR by destination and by source
+  linear               act(concat(gathered segments) @ W.T + b)       models/MLP.py:24-27
+  layer_norm           LayerNorm (+ residual)                          models/MLP.py:34-35, GNN.py:62,102
+  aggregate            scatter_sum(edge_attr, col)                     models/GNN.py:99
+  gather_rows          x[row] / x[col]                                 PyG MetaLayer, models/GNN.py:146
+  edge_geometry        [pos[col]-pos[row], L1]                         models/GNN.py:299-302
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import GncSeg, check
+
+
+def _require_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "graphnet_classifier_b200 operators run on CUDA tensors only (sm_100a kernels, "
+                "no CPU fallback); got a tensor on " + str(t.device))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: Tensor) -> Tensor:
+    """2-D fp32 view whose rows are unit-stride (the layout every kernel expects)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        t = t.reshape(t.shape[0], -1) if t.dim() > 0 else t.reshape(1, 1)
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    if t.shape[1] == 1 and t.shape[0] > 1 and t.stride(0) < 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device, n_elems: int, dtype=torch.float32) -> Tensor:
+    """Per-(device, stream, dtype) scratch buffer, grown on demand.  Kernels using it
+    are ordered on the stream, so one buffer per stream is enough."""
+    key = (device, _stream(), dtype)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < n_elems:
+        buf = torch.empty(max(int(n_elems), 1024), dtype=dtype, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------
+# graph index
+# ----------------------------------------------------------------------------
+class GraphIndex:
+    """Topology of a (batched) graph as the kernels consume it: int32 endpoints and
+    the stable CSR of edge ids by destination (in-edges, ascending edge id - the CPU
+    reference's summation order) and by source."""
+
+    __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid")
+
+    def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
+        self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
+        self.src, self.dst = src, dst
+        self.dst_rowptr, self.dst_eid = dst_rowptr, dst_eid
+        self.src_rowptr, self.src_eid = src_rowptr, src_eid
+
+    @staticmethod
+    def from_edge_index(edge_index: Tensor, num_nodes: int, validate: bool = True) -> "GraphIndex":
+        """Stable counting-sort CSR of an arbitrary int64 ``[2, E]`` edge_index (any
+        strides - the reference hands over a transposed view)."""
+        _require_cuda(edge_index)
+        if edge_index.dtype != torch.int64:
+            edge_index = edge_index.long()
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
+        E = int(edge_index.shape[1])
+        N = int(num_nodes)
+        dev = edge_index.device
+        lib = _lib.load()
+        i32 = dict(dtype=torch.int32, device=dev)
+        out = []
+        bad = torch.zeros(1, **i32)
+        work = _workspace(dev, int(lib.gnc_csr_workspace(N)), torch.int32)
+        for k in (0, 1):
+            rowptr = torch.empty(N + 1, **i32)
+            eid = torch.empty(max(E, 1), **i32)[:E]
+            key32 = torch.empty(max(E, 1), **i32)[:E]
+            row = edge_index[k]
+            stride = row.stride(0) if E > 1 else 1
+            check(lib.gnc_csr_build(row.data_ptr(), stride, E, N, rowptr.data_ptr(), eid.data_ptr(),
+                                    key32.data_ptr(), work.data_ptr(), bad.data_ptr(), _stream()), "csr_build")
+            out.append((key32, rowptr, eid))
+        if validate and int(bad.item()) != 0:
+            raise IndexError(f"edge_index has node ids outside [0, {N})")
+        (src, srp, seid), (dst, drp, deid) = out
+        return GraphIndex(N, E, src, dst, drp, deid, srp, seid)
+
+
+def attach_graph(edge_index: Tensor, graph: GraphIndex) -> Tensor:
+    """Remember the prebuilt CSR on the edge_index tensor object so that a model
+    called with the reference signature ``forward(x, pos, edge_index)`` finds it."""
+    edge_index._gnc_graph = graph
+    return edge_index
+
+
+def graph_of(edge_index: Tensor, num_nodes: int) -> GraphIndex:
+    g = getattr(edge_index, "_gnc_graph", None)
+    if g is not None and g.num_nodes == num_nodes and g.num_edges == edge_index.shape[1]:
+        return g
+    return GraphIndex.from_edge_index(edge_index, num_nodes)
+
+
+# ----------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# ----------------------------------------------------------------------------
+def _agg_raw(rowptr: Tensor, eid: Tensor, src: Tensor, n_rows: int, out: Optional[Tensor] = None,
+             accumulate: bool = False) -> Tensor:
+    src = _rows(src)
+    D = src.shape[1]
+    if out is None:
+        out = torch.empty(n_rows, D, dtype=torch.float32, device=src.device)
+        accumulate = False
+    check(_lib.load().gnc_agg_csr_sum_f32(rowptr.data_ptr(), _p(eid), src.data_ptr(), _ld(src), n_rows, D,
+                                          out.data_ptr(), _ld(out), int(accumulate), _stream()), "agg_csr_sum")
+    return out
+
+
+def _gather_raw(src: Tensor, idx: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    src = _rows(src)
+    M, D = int(idx.shape[0]), src.shape[1]
+    if out is None:
+        out = torch.empty(M, D, dtype=torch.float32, device=src.device)
+        accumulate = False
+    check(_lib.load().gnc_gather_rows_f32(src.data_ptr(), _ld(src), idx.data_ptr(), M, D, out.data_ptr(), _ld(out),
+                                          int(accumulate), _stream()), "gather_rows")
+    return out
+
+
+def _make_segs(srcs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]]):
+    arr = (GncSeg * len(srcs))()
+    for i, (s, ix) in enumerate(zip(srcs, idxs)):
+        arr[i].base = s.data_ptr()
+        arr[i].idx = None if ix is None else ix.data_ptr()
+        arr[i].ld = _ld(s)
+        arr[i].width = s.shape[1]
+    return arr
+
+
+def _linear_fwd_raw(srcs, idxs, M, W, b, relu) -> Tensor:
+    N = W.shape[0]
+    Y = torch.empty(M, N, dtype=torch.float32, device=W.device)
+    segs = _make_segs(srcs, idxs)
+    check(_lib.load().gnc_linear_fwd_f32(segs, len(srcs), M, W.data_ptr(), W.stride(0), _p(b), N, int(relu),
+                                         Y.data_ptr(), _ld(Y), _stream()), "linear_fwd")
+    return Y
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = act(concat_s(src_s[idx_s]) @ W.T + b).  ``meta`` = per segment
+    (idx int32 | None, (rowptr, eid) of the CSR grouping rows by idx | None, n_src_rows)."""
+
+    @staticmethod
+    def forward(ctx, W, b, relu, meta, *srcs):
+        srcs = tuple(_rows(s) for s in srcs)
+        idxs = [m[0] for m in meta]
+        M = int(idxs[0].shape[0]) if idxs[0] is not None else srcs[0].shape[0]
+        Wc = W if W.stride(1) == 1 else W.contiguous()
+        Y = _linear_fwd_raw(srcs, idxs, M, Wc, b, relu)
+        ctx.relu, ctx.meta, ctx.M = bool(relu), meta, M
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(Wc, Y if relu else None, *srcs)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        Wc, Y, *srcs = ctx.saved_tensors
+        lib = _lib.load()
+        dev = dY.device
+        M, N, K = ctx.M, Wc.shape[0], Wc.shape[1]
+        dY = _rows(dY)
+        need_W, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_bias
+        # bias + ReLU backward: dZ = dY * (Y > 0), db = column sums
+        dZ, db = dY, None
+        if ctx.relu or need_b:
+            if ctx.relu:
+                dZ = torch.empty(M, N, dtype=torch.float32, device=dev)
+            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+            ws_n = int(lib.gnc_colsum_workspace(M, N))
+            ws = _workspace(dev, ws_n)
+            check(lib.gnc_relu_bwd_colsum_f32(dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None,
+                                              _ld(Y) if ctx.relu else 0, M, N,
+                                              dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0,
+                                              ws.data_ptr(), ws_n, _stream()), "relu_bwd_colsum")
+        dW = None
+        if need_W:
+            dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+            segs = _make_segs(srcs, [m[0] for m in ctx.meta])
+            ws_n = int(lib.gnc_linear_wgrad_workspace(M, N, K))
+            ws = _workspace(dev, ws_n)
+            check(lib.gnc_linear_wgrad_f32(dZ.data_ptr(), _ld(dZ), M, N, segs, len(srcs), dW.data_ptr(), K, 0,
+                                           ws.data_ptr(), ws_n, _stream()), "linear_wgrad")
+        dsrcs = []
+        k0 = 0
+        for i, s in enumerate(srcs):
+            w = s.shape[1]
+            g = None
+            if ctx.needs_input_grad[4 + i]:
+                dX = torch.empty(M, w, dtype=torch.float32, device=dev)
+                Wv = Wc[:, k0:k0 + w]
+                check(lib.gnc_linear_dgrad_f32(dZ.data_ptr(), _ld(dZ), M, N, Wv.data_ptr(), Wc.stride(0), w,
+                                               dX.data_ptr(), w, 0, _stream()), "linear_dgrad")
+                idx, csr, n_src = ctx.meta[i]
+                if idx is None:
+                    g = dX
+                else:
+                    # backward of the row gather = ordered segmented sum over the CSR of idx
+                    g = _agg_raw(csr[0], csr[1], dX, n_src)
+            dsrcs.append(g)
+            k0 += w
+        return (dW, db, None, None, *dsrcs)
+
+
+def linear(srcs: Sequence[Tensor], W: Tensor, b: Optional[Tensor], relu: bool = False,
+           gathers: Optional[Sequence] = None) -> Tensor:
+    """``gathers[i]`` is None (rows used as is) or (idx32, (rowptr, eid), n_src_rows)."""
+    _require_cuda(W, *srcs)
+    if gathers is None:
+        gathers = [None] * len(srcs)
+    meta = tuple((None, None, 0) if g is None else g for g in gathers)
+    return _LinearFn.apply(W, b, relu, meta, *srcs)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, gamma, beta, eps, res):
+        z = _rows(z)
+        M, D = z.shape
+        dev = z.device
+        y = torch.empty(M, D, dtype=torch.float32, device=dev)
+        mean = torch.empty(M, dtype=torch.float32, device=dev)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        r = _rows(res) if res is not None else None
+        check(_lib.load().gnc_layernorm_fwd_f32(z.data_ptr(), _ld(z), M, D, gamma.data_ptr(), beta.data_ptr(),
+                                                float(eps), _p(r), _ld(r) if r is not None else 0, y.data_ptr(),
+                                                _ld(y), mean.data_ptr(), rstd.data_ptr(), _stream()), "layernorm_fwd")
+        ctx.save_for_backward(z, mean, rstd, gamma)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma = ctx.saved_tensors
+        lib = _lib.load()
+        M, D = z.shape
+        dev = z.device
+        dy = _rows(dy)
+        dz = torch.empty(M, D, dtype=torch.float32, device=dev)
+        need_g, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dg = torch.empty(D, dtype=torch.float32, device=dev) if need_g else None
+        db = torch.empty(D, dtype=torch.float32, device=dev) if need_b else None
+        ws_n = int(lib.gnc_layernorm_bwd_workspace(M, D))
+        ws = _workspace(dev, ws_n)
+        check(lib.gnc_layernorm_bwd_f32(dy.data_ptr(), _ld(dy), z.data_ptr(), _ld(z), mean.data_ptr(),
+                                        rstd.data_ptr(), gamma.data_ptr(), M, D, dz.data_ptr(), _ld(dz),
+                                        _p(dg), _p(db), 0, ws.data_ptr(), ws_n, _stream()), "layernorm_bwd")
+        return dz, dg, db, None, (dy if ctx.has_res else None)
+
+
+def layer_norm(z: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, res: Optional[Tensor] = None) -> Tensor:
+    _require_cuda(z, gamma, beta, res)
+    return _LayerNormFn.apply(z, gamma, beta, eps, res)
+
+
+class _AggregateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e, rowptr, eid, idx, n_rows):
+        ctx.save_for_backward(idx)
+        return _agg_raw(rowptr, eid, e, n_rows)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        return _gather_raw(dout, idx), None, None, None, None
+
+
+def aggregate(edge_attr: Tensor, graph: GraphIndex) -> Tensor:
+    """scatter_sum(edge_attr, col, dim=0, dim_size=N): ordered CSR segmented sum."""
+    _require_cuda(edge_attr)
+    return _AggregateFn.apply(edge_attr, graph.dst_rowptr, graph.dst_eid, graph.dst, graph.num_nodes)
+
+
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, rowptr, eid):
+        ctx.save_for_backward(rowptr, eid)
+        ctx.n = x.shape[0]
+        return _gather_raw(x, idx)
+
+    @staticmethod
+    def backward(ctx, dout):
+        rowptr, eid = ctx.saved_tensors
+        return _agg_raw(rowptr, eid, dout, ctx.n), None, None, None
+
+
+def gather_rows(x: Tensor, idx: Tensor, rowptr: Tensor, eid: Tensor) -> Tensor:
+    """x[idx]; (rowptr, eid) is the CSR grouping positions by idx (for the backward)."""
+    _require_cuda(x, idx)
+    return _GatherFn.apply(x, idx, rowptr, eid)
+
+
+def edge_geometry(pos: Tensor, graph: GraphIndex) -> Tensor:
+    _require_cuda(pos)
+    if pos.requires_grad:
+        raise NotImplementedError("gradients with respect to node positions are not part of this path")
+    pos = _rows(pos).contiguous()
+    P = pos.shape[1]
+    out = torch.empty(graph.num_edges, P + 1, dtype=torch.float32, device=pos.device)
+    check(_lib.load().gnc_edge_geometry_f32(pos.data_ptr(), P, graph.src.data_ptr(), graph.dst.data_ptr(),
+                                            graph.num_edges, out.data_ptr(), _stream()), "edge_geometry")
+    return out
+
+
+class _ScatterSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, rowptr, eid, idx32, n_rows):
+        ctx.save_for_backward(idx32)
+        return _agg_raw(rowptr, eid, src, n_rows)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx32,) = ctx.saved_tensors
+        return _gather_raw(dout, idx32), None, None, None, None
+
+
+def scatter_sum(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = None) -> Tensor:
+    """Drop-in for the reference's module-level ``scatter_sum`` (models/GNN.py:3-21):
+    rows of ``src`` summed into ``out[index]`` in ascending row order; new tensor;
+    ``dim_size`` defaults to ``index.max() + 1`` (a host sync, as in the reference)."""
+    if dim != 0:
+        raise NotImplementedError("scatter_sum supports dim=0 only")
+    _require_cuda(src, index)
+    if src.dim() == 1:
+        src = src.unsqueeze(-1)
+    E = int(index.shape[0])
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if E > 0 else 0
+    N = int(dim_size)
+    dev = src.device
+    if N == 0:
+        return src.new_zeros((0, src.shape[1]))
+    lib = _lib.load()
+    key = index if index.dtype == torch.int64 else index.long()
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
+    key32 = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = _workspace(dev, int(lib.gnc_csr_workspace(N)), torch.int32)
+    check(lib.gnc_csr_build(key.data_ptr(), key.stride(0) if E > 1 else 1, E, N, rowptr.data_ptr(), eid.data_ptr(),
+                            key32.data_ptr(), work.data_ptr(), bad.data_ptr(), _stream()), "csr_build")
+    if int(bad.item()) != 0:
+        raise IndexError(f"scatter_sum: index out of range for dim_size {N}")
+    return _ScatterSumFn.apply(src, rowptr, eid, key32, N)

@@ -1,0 +1,100 @@
+"""Batched image -> logits pipeline: the public call for the hot path end to end.
+
+    pipe = GraphClassifierPipeline(model, resize_value=128)
+    logits = pipe.infer(images_u8)                      # [B, classes]
+    loss = pipe.train_step(images_u8, labels, optimizer)
+
+``images_u8`` is ``uint8 [B, r, r, 3]`` on the host (pinned or not) or on the device.
+Per call: one host->device copy of the pixels (if needed), the fused graph-build
+kernel, the GraphNet kernels over block-diagonal micro-batches, and - for training -
+gradient accumulation across micro-batches followed by the optional cross-rank
+all-reduce (utils/distributed.GradBucket) and the optimizer step.
+
+Micro-batching bounds activation memory: one ``[E, 128]`` fp32 edge
+tensor is 16.6 MB per resize-128 graph and the backward keeps ~4 of them per block.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .utils.image_to_graph.batched import build_patch_graphs, build_pixel_graphs
+
+
+class GraphClassifierPipeline:
+    def __init__(self, model: torch.nn.Module, resize_value: int, diagonals: bool = False, method: str = "pixel",
+                 patch_size: int = 8, micro_batch: Optional[int] = None, train_micro_batch: Optional[int] = None,
+                 device=None):
+        self.model = model
+        self.resize_value = int(resize_value)
+        self.diagonals = bool(diagonals)
+        self.method = method
+        self.patch_size = int(patch_size)
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("GraphClassifierPipeline needs the model on a CUDA device (no CPU fallback)")
+        n = self.resize_value * self.resize_value if method == "pixel" else (self.resize_value // self.patch_size) ** 2
+        # ~70 KB of live activations per node in inference, ~500 KB per node kept for the backward
+        self.micro_batch = micro_batch or max(1, min(512, (24 << 30) // (n * 70_000)))
+        self.train_micro_batch = train_micro_batch or max(1, min(256, (48 << 30) // (n * 100_000)))
+
+    # -- staging ----------------------------------------------------------------
+    def _to_device(self, images) -> Tensor:
+        t = images if isinstance(images, Tensor) else torch.as_tensor(images)
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        return t
+
+    def _build(self, images_dev: Tensor):
+        if self.method == "pixel":
+            return build_pixel_graphs(images_dev, diagonals=self.diagonals)
+        if self.method == "patch":
+            return build_patch_graphs(images_dev, patch_size=self.patch_size)
+        raise ValueError(f"Unknown method: {self.method}")
+
+    # -- inference ----------------------------------------------------------------
+    @torch.no_grad()
+    def infer(self, images) -> Tensor:
+        img = self._to_device(images)
+        B = img.shape[0]
+        outs = []
+        for lo in range(0, B, self.micro_batch):
+            gb = self._build(img[lo:lo + self.micro_batch])
+            out = self.model(gb.as_tuple())
+            outs.append(out.reshape(1, -1) if out.dim() == 1 else out)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    # -- training -----------------------------------------------------------------
+    def forward_backward(self, images, labels) -> Tensor:
+        """Accumulates d(mean CE over this call's graphs)/d(params) into ``.grad``;
+        returns the mean loss as a 0-d device tensor (no host sync)."""
+        img = self._to_device(images)
+        lab = labels if isinstance(labels, Tensor) else torch.as_tensor(labels)
+        lab = lab.to(self.device, non_blocking=True).long()
+        B = img.shape[0]
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        for lo in range(0, B, self.train_micro_batch):
+            gb = self._build(img[lo:lo + self.train_micro_batch])
+            logits = self.model(gb.as_tuple())
+            if logits.dim() == 1:
+                logits = logits.reshape(1, -1)
+            loss = F.cross_entropy(logits, lab[lo:lo + self.train_micro_batch], reduction="sum") / B
+            loss.backward()
+            total += loss.detach()
+        return total
+
+    def train_step(self, images, labels, optimizer, grad_bucket=None) -> Tensor:
+        if grad_bucket is not None:
+            grad_bucket.zero()
+        else:
+            optimizer.zero_grad(set_to_none=False)
+        loss = self.forward_backward(images, labels)
+        if grad_bucket is not None:
+            grad_bucket.all_reduce(average=True)
+        optimizer.step()
+        return loss

@@ -1,0 +1,79 @@
+"""Data parallelism over independent graphs: one process per GPU, one flat fp32
+gradient bucket, one all-reduce per step.
+
+Every image graph is independent, so ranks take disjoint slices of the batch and
+exchange nothing on the data path; the only collective is the gradient sum.  All
+parameter gradients are views into ONE contiguous buffer, so the all-reduce needs no
+packing copies and is a single NCCL launch over NVLink (4.3 / 10.6 / 35.8 MB at
+resize 64 / 128 / 256 - latency-bound, far below the step's compute time).
+
+Backend-agnostic on purpose: the same code runs under ``gloo`` on CPU tensors, which
+is how tests/test_distributed.py covers it with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of ``n_items`` graphs owned by ``rank``; sizes differ
+    by at most one and cover the batch exactly."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class GradBucket:
+    """Flat gradient storage for ``params``: ``p.grad`` of every parameter is a view
+    into ``self.flat``.  ``all_reduce()`` sums the bucket across ranks and scales by
+    ``1 / world_size`` (mean over ranks = mean over the global batch when every rank
+    averages over its own equal-sized shard)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket needs at least one trainable parameter")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def rebind(self) -> None:
+        """Re-attach views after something replaced ``p.grad`` (e.g. ``zero_grad(set_to_none=True)``)."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            off += n
+
+    def all_reduce(self, average: bool = True) -> None:
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        self.rebind()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        if average:
+            self.flat.mul_(1.0 / dist.get_world_size())
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """Make every rank start from rank ``src``'s weights."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)

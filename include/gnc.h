@@ -1,0 +1,196 @@
+/*
+ * gnc.h - C ABI of libgnc.so, the B200 (sm_100a) implementation of the
+ * GraphNet_Classifier hot path: image -> graph construction and the GraphNet
+ * forward / backward operators.
+ *
+ * Conventions (every entry point):
+ *   - extern "C", plain pointers and sizes, no framework types;
+ *   - unless a parameter is documented as HOST, every pointer is a DEVICE pointer
+ *     owned by the caller; nothing is allocated, freed or retained by the library;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued on it and the call returns without synchronising;
+ *   - return value: GNC_OK (0) or a GNC_E* code; gnc_last_error() gives the text of
+ *     the most recent failure on the calling thread;
+ *   - fp32 data, row-major, leading dimensions (`ld*`) counted in elements;
+ *     node / edge ids are int32 inside the library, int64 only at the
+ *     edge_index boundary (the reference's torch.long tensors);
+ *   - stateless and re-entrant (the launch counter below is the only global).
+ *
+ * The reference (alexisvannson/GraphNet_Classifier) is pure Python with no FFI of
+ * its own; each entry point cites the reference lines whose work it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ */
+#ifndef GNC_H_
+#define GNC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNC_OK 0
+#define GNC_EINVAL 1   /* bad argument (shape, alignment, null pointer) */
+#define GNC_ECUDA 2    /* a CUDA runtime call or kernel launch failed */
+#define GNC_EWORKSPACE 3 /* caller-provided workspace too small */
+
+typedef void* gnc_stream_t;
+
+/* A gathered, column-concatenated matrix operand: logical row m is
+ *   concat_s( base_s[(idx_s ? idx_s[m] : m) * ld_s + 0 .. width_s) ).
+ * This is how cat([x[row], x[col], edge_attr]) (models/GNN.py:58-60, with the
+ * gathers PyG's MetaLayer does at models/GNN.py:146/215) and cat([x, agg])
+ * (models/GNN.py:100) are consumed without being materialised. */
+typedef struct gnc_seg {
+  const float* base;
+  const int32_t* idx; /* NULL = identity */
+  int64_t ld;
+  int32_t width;
+  int32_t _pad;
+} gnc_seg_t;
+
+/* ---- library state --------------------------------------------------------- */
+int gnc_version(void);
+const char* gnc_last_error(void);
+/* number of kernels this library has launched since load / last reset */
+uint64_t gnc_launch_count(void);
+void gnc_reset_launch_count(void);
+
+/* ---- graph construction ---------------------------------------------------- */
+
+/* Edge count of the directed H x W grid (image_to_graph_optimized.py:22-37). */
+int64_t gnc_grid_num_edges(int H, int W, int diagonals);
+
+/* Batched pixel-graph builder: replaces image_to_graph_pixel_optimized lines
+ * 71-87 + the casts at utils/dataloader.py:49-51 for B already-resized images.
+ *   img        uint8  [B, H, W, 3]
+ *   x          float  [B*H*W, 3]     pixel values 0..255 (un-normalised)
+ *   pos        float  [B*H*W, 2]     (row, col); may be NULL (positions depend on the
+ *                                    shape only, callers cache them)
+ *   edge_index int64  [2, B*E]       contiguous rows (src; dst), graph b offset by
+ *                                    b*H*W, edge order of create_grid_edges_optimized
+ *                                    (image_to_graph_optimized.py:7-39); may be NULL
+ * CSR outputs (all int32, any may be NULL as a group - pass all six or none):
+ *   src32,dst32 [B*E]; dst_rowptr [B*N+1], dst_eid [B*E] (in-edges of each node,
+ *   ascending edge id = the CPU summation order of models/GNN.py:99);
+ *   src_rowptr, src_eid likewise for out-edges. */
+int gnc_build_pixel_graph_u8(const uint8_t* img, int B, int H, int W, int diagonals,
+                             float* x, float* pos, int64_t* edge_index,
+                             int32_t* src32, int32_t* dst32,
+                             int32_t* dst_rowptr, int32_t* dst_eid,
+                             int32_t* src_rowptr, int32_t* src_eid,
+                             gnc_stream_t stream);
+
+/* Batched patch-graph builder (image_to_graph_patch.py:25-54): one node per
+ * p x p tile, x = tile mean RGB (0..255), pos = tile centre, grid edges over the
+ * (H/p) x (W/p) tiles.  Output shapes as above with N = (H/p)*(W/p). */
+int gnc_build_patch_graph_u8(const uint8_t* img, int B, int H, int W, int patch,
+                             float* x, float* pos, int64_t* edge_index,
+                             int32_t* src32, int32_t* dst32,
+                             int32_t* dst_rowptr, int32_t* dst_eid,
+                             int32_t* src_rowptr, int32_t* src_eid,
+                             gnc_stream_t stream);
+
+/* Label map -> superpixel graph (image_to_graph_superpixel.py:34-71), one image
+ * per call slot b; labels need not be contiguous, node id = rank among the
+ * labels present.  `max_label` bounds label values (0 <= label <= max_label).
+ *   img      uint8 [B, H, W, 3];  labels int32 [B, H, W]
+ *   n_nodes  int32 [B]            S_b
+ *   x        float [B, S_max, 3]  mean of img/255 per segment
+ *   pos      float [B, S_max, 2]  centroid (row, col)
+ *   adj      uint8 [B, S_max, S_max] 4-connected adjacency (symmetric, zero diag)
+ *   n_edges  int32 [B]            2 * (#adjacent pairs)
+ *   edges    int64 [B, 2, E_max]  (i,j),(j,i) for i<j lexicographic, local ids
+ *   work     int32 [B * gnc_superpixel_workspace(S_max, max_label)] scratch
+ * Entries beyond S_b / n_edges[b] are left zero. */
+int64_t gnc_superpixel_workspace(int S_max, int max_label);
+int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B, int H, int W,
+                               int max_label, int S_max, int64_t E_max,
+                               int32_t* n_nodes, float* x, float* pos, uint8_t* adj,
+                               int32_t* n_edges, int64_t* edges, int32_t* work,
+                               gnc_stream_t stream);
+
+/* Stable CSR of edge ids grouped by key (= edge_index row 0 or row 1): the order
+ * index_add_ visits edges in (models/GNN.py:20).  key is read with an element
+ * stride so that non-contiguous edge_index is accepted.
+ *   key int64 [E] (strided); rowptr int32 [N+1]; eid int32 [E];
+ *   key32 int32 [E] or NULL (narrowed copy of key);
+ *   work  int32 [gnc_csr_workspace(N)] scratch.
+ * Returns GNC_EINVAL via the device flag if a key is outside [0, N) - checked
+ * lazily: `bad` (int32 [1], device, may be NULL) is set non-zero. */
+int64_t gnc_csr_workspace(int64_t N);
+int gnc_csr_build(const int64_t* key, int64_t key_stride, int64_t E, int64_t N,
+                  int32_t* rowptr, int32_t* eid, int32_t* key32, int32_t* work, int32_t* bad,
+                  gnc_stream_t stream);
+
+/* ---- aggregation / gathers -------------------------------------------------- */
+
+/* out[v, :] (+)= sum over k in [rowptr[v], rowptr[v+1]) of src[eid[k], :], summed
+ * sequentially in ascending k.  Replaces scatter_sum(edge_attr, col, dim=0)
+ * (models/GNN.py:3-21, call site :99) and, with the source-side CSR, the
+ * index_put_(accumulate) backward of the x[row] / x[col] gathers. */
+int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid,
+                        const float* src, int64_t ld_src, int64_t N, int D,
+                        float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);
+
+/* out[m, :] (+)= src[idx[m], :]   (x[row], x[col]; backward of the aggregation) */
+int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D,
+                        float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);
+
+/* edge_attr[e] = [pos[dst[e]] - pos[src[e]], sum |.|]  (models/GNN.py:299-302).
+ * pos float [N, P]; out float [E, P+1]; 1 <= P <= 8. */
+int gnc_edge_geometry_f32(const float* pos, int P, const int32_t* src, const int32_t* dst, int64_t E,
+                          float* out, gnc_stream_t stream);
+
+/* ---- dense operators (nn.Linear / ReLU / LayerNorm of models/MLP.py:24-37) -- */
+
+/* Y[M, N] = act( concat(segs)[M, K] * W[N, K]^T + bias ),  K = sum of widths.
+ * relu != 0 applies max(.,0).  bias may be NULL. */
+int gnc_linear_fwd_f32(const gnc_seg_t* segs /*HOST*/, int nseg, int64_t M,
+                       const float* W, int64_t ldw, const float* bias, int N, int relu,
+                       float* Y, int64_t ldy, gnc_stream_t stream);
+
+/* dX[M, K] (+)= dZ[M, N] * W[N, K]   (W may point at a column slice, ldw = full K) */
+int gnc_linear_dgrad_f32(const float* dZ, int64_t lddz, int64_t M, int N,
+                         const float* W, int64_t ldw, int K,
+                         float* dX, int64_t lddx, int accumulate, gnc_stream_t stream);
+
+/* dW[N, K] (+)= dZ[M, N]^T * concat(segs)[M, K]; deterministic split reduction.
+ * work: float [gnc_linear_wgrad_workspace(M, N, K)]. */
+int64_t gnc_linear_wgrad_workspace(int64_t M, int N, int K);
+int gnc_linear_wgrad_f32(const float* dZ, int64_t lddz, int64_t M, int N,
+                         const gnc_seg_t* segs /*HOST*/, int nseg,
+                         float* dW, int64_t lddw, int accumulate,
+                         float* work, int64_t work_elems, gnc_stream_t stream);
+
+/* dZ = dY * (Y > 0) (if Y != NULL, else dZ = dY; dZ may be NULL to skip the
+ * store), db[N] (+)= column sums of dZ.  Backward of bias + ReLU.
+ * work: float [gnc_colsum_workspace(M, N)]. */
+int64_t gnc_colsum_workspace(int64_t M, int N);
+int gnc_relu_bwd_colsum_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                            int64_t M, int N, float* dZ, int64_t lddz,
+                            float* db, int accumulate, float* work, int64_t work_elems,
+                            gnc_stream_t stream);
+
+/* y = LayerNorm(z; gamma, beta, eps) (+ res).  mean / rstd float [M] are saved
+ * for the backward (may be NULL).  models/MLP.py:34-35, residuals
+ * models/GNN.py:62, 102. */
+int gnc_layernorm_fwd_f32(const float* z, int64_t ldz, int64_t M, int D,
+                          const float* gamma, const float* beta, float eps,
+                          const float* res, int64_t ldres,
+                          float* y, int64_t ldy, float* mean, float* rstd, gnc_stream_t stream);
+
+/* dz = LN backward; dgamma/dbeta (+)= column reductions.
+ * work: float [gnc_layernorm_bwd_workspace(M, D)]. */
+int64_t gnc_layernorm_bwd_workspace(int64_t M, int D);
+int gnc_layernorm_bwd_f32(const float* dy, int64_t lddy, const float* z, int64_t ldz,
+                          const float* mean, const float* rstd, const float* gamma,
+                          int64_t M, int D, float* dz, int64_t lddz,
+                          float* dgamma, float* dbeta, int accumulate,
+                          float* work, int64_t work_elems, gnc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNC_H_ */

@@ -1,0 +1,118 @@
+"""CPU: the oracle restatement reproduces the committed golden vectors, which were
+produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+from oracle import graph_build as ogb
+from oracle.weights import fill_deterministic
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def test_grid_edges_bit_exact(golden):
+    g = golden["grid_edges"]
+    n = 0
+    for k, ref in g.items():
+        if k.startswith("grid_"):
+            hw, d = k[len("grid_"):].split("_d")
+            H, W = map(int, hw.split("x"))
+            out = ogb.grid_edges(H, W, bool(int(d)))
+            assert out.dtype == np.int64 and np.array_equal(out, ref), k
+            n += 1
+        elif k.startswith("gridsha_"):
+            r, d = k[len("gridsha_"):].split("_d")
+            assert np.array_equal(_sha(ogb.grid_edges(int(r), int(r), bool(int(d)))), ref), k
+            n += 1
+    assert n >= 20
+
+
+def test_pixel_patch_superpixel_builders(golden):
+    b = golden["builders"]
+    for k in [k for k in b if k.startswith("pixel_") and k.endswith("_img")]:
+        tag = k[:-4]
+        diag = tag.endswith("d1")
+        x, pos, ei = ogb.pixel_graph(b[k], diag)
+        assert np.array_equal(x, b[tag + "_x"]) and x.dtype == np.uint8
+        assert np.array_equal(pos, b[tag + "_pos"]) and np.array_equal(ei, b[tag + "_ei"])
+    for k in [k for k in b if k.startswith("patch_") and k.endswith("_img")]:
+        tag = k[:-4]
+        p = int(tag.split("_")[-1])
+        x, pos, ei = ogb.patch_graph(b[k], p)
+        assert np.array_equal(x, b[tag + "_x"]) and np.array_equal(pos, b[tag + "_pos"])
+        assert np.array_equal(ei, b[tag + "_ei"])
+    for k in [k for k in b if k.startswith("superpixel_") and k.endswith("_img")]:
+        tag = k[:-4]
+        x, pos, ei = ogb.superpixel_graph_from_labels(b[k], b[tag + "_labels"])
+        assert np.array_equal(x, b[tag + "_x"]) and np.array_equal(pos, b[tag + "_pos"])
+        assert np.array_equal(ei, b[tag + "_ei"]) and ei.dtype == np.int64
+    for k in [k for k in b if k.startswith("jpeg_") and k.endswith("_img")]:
+        x, _, _ = ogb.pixel_graph(b[k])
+        assert np.array_equal(_sha(x), b[k[:-4] + "_xsha"])
+
+
+def test_superpixel_no_edges_is_float_empty():
+    img = np.zeros((4, 4, 3), np.uint8)
+    _, _, ei = ogb.superpixel_graph_from_labels(img, np.zeros((4, 4), np.int64))
+    assert ei.shape == (2, 0) and ei.dtype == np.float64     # reference superpixel.py:70-71
+
+
+def test_state_dict_contract(golden):
+    m = golden["model"]
+    om = ognn.build_reference_config_model(8, seed=0)
+    assert list(om.state_dict().keys()) == list(m["state_dict_keys"])
+    assert [str(tuple(v.shape)) for v in om.state_dict().values()] == list(m["state_dict_shapes_r8"])
+    om32 = ognn.build_reference_config_model(32, seed=0)
+    assert list(om32.state_dict().keys()) == list(m["checkpoint_keys"])
+    assert [str(tuple(v.shape)) for v in om32.state_dict().values()] == list(m["checkpoint_shapes"])
+    assert len(m["checkpoint_keys"]) == 76
+
+
+@pytest.mark.parametrize("r,diag", [(8, False), (8, True), (12, False)])
+def test_model_logits_loss_grads(golden, r, diag):
+    m = golden["model"]
+    tag = f"model_r{r}_d{int(diag)}"
+    om = ognn.build_reference_config_model(r, seed=None)
+    fill_deterministic(om, seed=7)
+    imgs = m[tag + "_imgs"]
+    for b in range(imgs.shape[0]):
+        inp = ogb.to_model_inputs(*ogb.pixel_graph(imgs[b], diag))
+        with torch.no_grad():
+            out = om(inp)
+        np.testing.assert_allclose(out.numpy(), m[tag + "_logits"][b], rtol=2e-6, atol=1e-7)
+    inp = ogb.to_model_inputs(*ogb.pixel_graph(imgs[0], diag))
+    loss = torch.nn.functional.cross_entropy(om(inp), torch.tensor(int(m[tag + "_label"])))
+    assert abs(loss.item() - float(m[tag + "_loss"])) < 2e-6
+    loss.backward()
+    for name, p in om.named_parameters():
+        samp = m[f"{tag}_grad_{name}_samp"]
+        f = p.grad.flatten()
+        stride = max(1, -(-f.numel() // 512))
+        got = f[::stride].numpy()
+        scale = float(m[f"{tag}_grad_{name}_sn"][1]) / np.sqrt(f.numel()) + 1e-30
+        assert np.max(np.abs(got - samp)) <= 1e-5 * max(scale, np.max(np.abs(samp))), name
+
+
+def test_scatter_sum_golden(golden):
+    m = golden["model"]
+    out = ognn.scatter_sum(torch.from_numpy(m["scatter_src"]), torch.from_numpy(m["scatter_idx"]))
+    assert np.array_equal(out.numpy(), m["scatter_out"])
+    with pytest.raises(NotImplementedError):
+        ognn.scatter_sum(torch.zeros(3, 2), torch.zeros(3, dtype=torch.long), dim=1)
+
+
+def test_batched_equals_per_sample(golden):
+    m = golden["model"]
+    om = ognn.build_reference_config_model(8, seed=None)
+    fill_deterministic(om, seed=7)
+    imgs = m["model_r8_d0_imgs"]
+    gs = [ogb.pixel_graph(im) for im in imgs]
+    bx, bp, be = ogb.batch_graphs([g[0] for g in gs], [g[1] for g in gs], [g[2] for g in gs])
+    with torch.no_grad():
+        out = om(ogb.to_model_inputs(bx, bp, be))
+    np.testing.assert_allclose(out.numpy(), m["model_r8_d0_logits"], rtol=2e-6, atol=1e-7)
