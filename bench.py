@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the GraphNet_Classifier hot path on B200 (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W              # our arm
+    python bench.py --impl reference --gpus N --steps K ...    # reference CPU arm
+
+Workload (BASELINE.json configs[1]): GNN inference, resize 128 pixel-grid graphs,
+batch 512 synthetic RGB images per GPU (weak scaling).  One "step" = graph build +
+GraphNet forward + classifier head for one batch.  ``value`` is graphs/s with the
+uint8 images already resident in HBM; ``e2e`` is the same through the public
+pipeline call with pinned HOST images (H2D + D2H inside the timed region).
+The JSON line also carries a training measurement (fwd + bwd + gradient all-reduce +
+Adam, BASELINE configs[2] per-GPU shape), the roofline of the dominant kernel, the
+aggregation kernel's HBM roofline and the CPU baseline (the oracle = a validated
+port of the reference, timed on this box's host cores).
+
+Only the cpu_baseline leg and ``--impl reference`` import ``oracle/``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "graphs_per_sec_inference_resize128_batch512_per_gpu"
+UNIT = "graphs/s"
+FWD_FLOP_PER_NODE = 525_568          # fwd FLOPs per graph = 525568*N + 557824*E
+FWD_FLOP_PER_EDGE = 557_824
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--resize", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=512, help="graphs per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=512, help="graphs per GPU per training step")
+    ap.add_argument("--train-steps", type=int, default=2)
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-graphs", type=int, default=48, help="graphs in the bounded CPU sample")
+    ap.add_argument("--ref-graphs-per-step", type=int, default=4)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # the median over samples taken while the GPU was busy (the top half of the samples)
+        busy = sm[len(sm) // 2:] if sm else []
+        med = busy[len(busy) // 2] if busy else None
+        return dict(sm_mhz=med, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (validated port of the reference) on host cores
+# ------------------------------------------------------------------------------
+def cpu_reference_run(resize: int, n_graphs: int, warm: int, state_dict=None, seed: int = 0):
+    """One graph per step exactly like the reference loop (utils/train_model.py:35-45 minus
+    the backward): builder (numpy) + loader casts + CombinedModel forward under no_grad."""
+    import numpy as np
+    import torch
+    from oracle import gnn as ognn
+    from oracle import graph_build as ogb
+
+    model = ognn.build_reference_config_model(resize, seed=0)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    model.eval()
+    imgs = np.random.default_rng(seed).integers(0, 256, (n_graphs + warm, resize, resize, 3), dtype=np.uint8)
+    outs = []
+    with torch.no_grad():
+        for i in range(warm):
+            model(ogb.to_model_inputs(*ogb.pixel_graph(imgs[i])))
+        t0 = time.perf_counter()
+        for i in range(warm, warm + n_graphs):
+            outs.append(model(ogb.to_model_inputs(*ogb.pixel_graph(imgs[i]))))
+        dt = time.perf_counter() - t0
+    return n_graphs / dt, dt, torch.get_num_threads(), torch.stack(outs), imgs[warm:]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    g = args.ref_graphs_per_step
+    # warm-up steps then exactly K timed steps of g graphs each
+    import numpy as np
+    from oracle import gnn as ognn
+    from oracle import graph_build as ogb
+    model = ognn.build_reference_config_model(args.resize, seed=0).eval()
+    total = (args.warmup + args.steps) * g
+    imgs = np.random.default_rng(0).integers(0, 256, (total, args.resize, args.resize, 3), dtype=np.uint8)
+    with torch.no_grad():
+        k = 0
+        for _ in range(args.warmup):
+            for _ in range(g):
+                model(ogb.to_model_inputs(*ogb.pixel_graph(imgs[k]))); k += 1
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for _ in range(g):
+                model(ogb.to_model_inputs(*ogb.pixel_graph(imgs[k]))); k += 1
+        dt = time.perf_counter() - t0
+    v = args.steps * g / dt
+    cores = torch.get_num_threads()
+    sample = f"{g} graphs per step, one graph per forward (reference loop), resize {args.resize}, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GNN inference, resize {args.resize} pixel-grid graphs (BASELINE configs[1]); "
+                               f"reference CPU path = oracle port, bounded sample", "resize": args.resize,
+                   "graphs_per_step": g},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    from graphnet_classifier_b200 import _lib, build, ops
+    build.build()
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.pipeline import GraphClassifierPipeline
+    from graphnet_classifier_b200.utils.distributed import GradBucket, broadcast_parameters
+
+    r, B = args.resize, args.batch
+    N, E = r * r, 2 * r * (r - 1)
+    torch.manual_seed(0)
+    model = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=N,
+                          classes=2).to(dev)
+    broadcast_parameters(model)
+    pipe = GraphClassifierPipeline(model, resize_value=r)
+    rng = np.random.default_rng(rank)
+    imgs_host = torch.from_numpy(rng.integers(0, 256, (B, r, r, 3), dtype=np.uint8)).pin_memory()
+    labels_host = torch.from_numpy(rng.integers(0, 2, B)).pin_memory()
+    imgs_dev = imgs_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, steps, warmup):
+        """W untimed steps, then exactly K steps, each bracketed by CUDA events on the
+        launching stream, L2 flushed between steps (outside the event pairs)."""
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        evs = []
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step_fn()
+            e.record()
+            evs.append((s, e))
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        return max_over_ranks(ms), wall
+
+    # ---- inference, inputs resident in HBM (value) -------------------------------
+    def infer_step():
+        return pipe.infer(imgs_dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    for _ in range(args.warmup):
+        infer_step()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() // max(args.warmup, 1)
+    ms_total, wall = timed(infer_step, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_gpus * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host images in, logits back on the host -----------------
+    def e2e_step():
+        return pipe.infer(imgs_host).cpu()
+
+    e2e_ms, _ = timed(e2e_step, args.steps, 1)
+    e2e_value = n_gpus * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- per-kernel attribution of one inference step (events around every launch) ---
+    ops.PROFILE = ops.KernelProfile()
+    infer_step()
+    prof = ops.PROFILE.summary()
+    ops.PROFILE = None
+    prof_ms = sum(d["ms"] for d in prof.values())
+    pk = peaks()
+    lin = prof.get("linear_fwd", dict(ms=0.0, flops=0.0, calls=0))
+    gemm_tflops = lin["flops"] / (lin["ms"] / 1e3) / 1e12 if lin["ms"] > 0 else 0.0
+    fp32_fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    roofline = {
+        "kernel": "sgemm_128x128_kernel (linear_fwd, fp32 FMA)", "bound": "tensor",
+        "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tflops / pk["bf16_sustained"], "traffic": None,
+        "peak_source": pk["source"] + ": dense bf16 cuBLAS, sustained (kernel timed inside a long step)",
+        "note": "fp32 CUDA-core GEMM (1e-5 parity rules out single-pass TF32/BF16); "
+                f"fraction of the nominal fp32 FMA peak ({fp32_fma_peak:.1f} TFLOP/s) = {gemm_tflops / fp32_fma_peak:.3f}",
+        "launches_per_step": lin["calls"], "share_of_step": lin["ms"] / prof_ms if prof_ms else None,
+        "algorithmic_flops_per_step": lin["flops"],
+    }
+    kernel_shares = {k: {"ms": round(d["ms"], 3), "calls": d["calls"], "share": round(d["ms"] / prof_ms, 4)}
+                     for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- aggregation kernel alone at the step's shape (HBM roofline, BASELINE metric) ---
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    mb = min(B, pipe.micro_batch)
+    gb = build_pixel_graphs(imgs_dev[:mb])
+    e_lat = torch.randn(gb.graph.num_edges, 128, device=dev)
+    for _ in range(3):
+        ops.aggregate(e_lat, gb.graph)
+    torch.cuda.synchronize()
+    agg_ms = []
+    for _ in range(10):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); ops.aggregate(e_lat, gb.graph); e.record()
+        torch.cuda.synchronize()
+        agg_ms.append(s.elapsed_time(e))
+    agg_ms = sum(agg_ms) / len(agg_ms)
+    En, Nn = gb.graph.num_edges, gb.graph.num_nodes
+    agg_bytes = 4.0 * (En * 128 + En + (Nn + 1) + Nn * 128)
+    agg_gbs = agg_bytes / (agg_ms / 1e3) / 1e9
+    roofline_agg = {"kernel": "agg_csr_sum_vec_kernel<32,1>", "bound": "hbm", "achieved": agg_gbs, "peak": pk["hbm"],
+                    "unit": "GB/s", "frac": agg_gbs / pk["hbm"], "traffic": None, "edges": En, "nodes": Nn, "D": 128,
+                    "algorithmic_bytes_per_launch": agg_bytes, "ms_per_launch": agg_ms, "peak_source": pk["source"]}
+    del e_lat, gb
+
+    # ---- training: fwd + bwd + gradient all-reduce + Adam (BASELINE configs[2] per-GPU shape) ---
+    train = None
+    if not args.no_train:
+        Bt = args.train_batch
+        timg = imgs_dev[:Bt] if Bt <= B else torch.from_numpy(rng.integers(0, 256, (Bt, r, r, 3), dtype=np.uint8)).to(dev)
+        tlab = torch.from_numpy(rng.integers(0, 2, Bt)).to(dev)
+        bucket = GradBucket(model.parameters())
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def train_step():
+            return pipe.train_step(timg, tlab, opt, grad_bucket=bucket)
+
+        _lib.reset_launch_count()
+        train_step()
+        torch.cuda.synchronize()
+        t_launches = _lib.launch_count()
+        t_ms, _ = timed(train_step, args.train_steps, 0)
+        train = {"value": n_gpus * Bt * args.train_steps / (t_ms / 1e3), "unit": UNIT, "steps": args.train_steps,
+                 "ms_per_step": t_ms / args.train_steps, "graphs_per_gpu_per_step": Bt,
+                 "micro_batch": pipe.train_micro_batch, "gpu_launches_per_step": t_launches,
+                 "what": "graph build + forward + CE + backward + flat-bucket all-reduce (NCCL) + Adam"}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on this box's host cores -----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        v, dt, cores, ref_logits, ref_imgs = cpu_reference_run(r, args.cpu_graphs, 1, state_dict=sd, seed=1234)
+        # parity gate on the very graphs the CPU just classified
+        got = pipe.infer(torch.from_numpy(ref_imgs)).cpu()
+        err = float((got - ref_logits).abs().max() / ref_logits.abs().max())
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_graphs} graphs of the same workload (resize {r}), one graph per forward as the "
+                         f"reference loop does, builder included, {dt:.1f} s",
+               "host_cpu_count": os.cpu_count(), "max_rel_logit_diff_vs_gpu": err}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"GNN inference, resize {r} pixel-grid graphs, batch {B} per GPU "
+                                   f"(BASELINE configs[1]); graph build + GraphNet(3 blocks, width 128) + head",
+                       "resize": r, "graphs_per_gpu": B, "nodes_per_graph": N, "edges_per_graph": E,
+                       "micro_batch": pipe.micro_batch, "parallelism": f"dp{n_gpus} (independent graphs, no data-path collective)",
+                       "l2": "256 MiB buffer zeroed between timed steps (outside the event pairs); "
+                             "per-step working set (8.5 GB edge tensors) >> 126 MB L2",
+                       "algorithmic_fwd_tflop_per_step": B * (FWD_FLOP_PER_NODE * N + FWD_FLOP_PER_EDGE * E) / 1e12},
+            "wall_s_timed_region": wall,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(imgs_host.numel()),
+                    "d2h_bytes_per_step": int(B * 2 * 4), "ms_per_step": e2e_ms / args.steps,
+                    "api": "GraphClassifierPipeline.infer(pinned uint8 host images) -> logits.cpu()"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_aggregation": roofline_agg,
+            "kernel_shares": kernel_shares,
+            "train": train,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

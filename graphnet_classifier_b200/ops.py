@@ -59,6 +59,41 @@ def _ld(t: Tensor) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
 
 
+class KernelProfile:
+    """Optional per-launch timing (CUDA events on the launching stream) used by bench.py
+    to attribute step time to kernels and to compute achieved FLOP/s / GB/s live.
+    Enable with ``ops.PROFILE = KernelProfile()``; ``summary()`` synchronises."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, nbytes, s, e in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILE: Optional[KernelProfile] = None
+
+
+def _call(name: str, flops: float, nbytes: float, fn, *args) -> int:
+    prof = PROFILE
+    if prof is None:
+        return fn(*args)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    prof.records.append((name, flops, nbytes, s, e))
+    return rc
+
+
 _workspaces: dict = {}
 
 
@@ -145,8 +180,11 @@ def _agg_raw(rowptr: Tensor, eid: Tensor, src: Tensor, n_rows: int, out: Optiona
     if out is None:
         out = torch.empty(n_rows, D, dtype=torch.float32, device=src.device)
         accumulate = False
-    check(_lib.load().gnc_agg_csr_sum_f32(rowptr.data_ptr(), _p(eid), src.data_ptr(), _ld(src), n_rows, D,
-                                          out.data_ptr(), _ld(out), int(accumulate), _stream()), "agg_csr_sum")
+    E = int(eid.shape[0])
+    nbytes = 4.0 * (E * D + E + (n_rows + 1) + n_rows * D)          # messages + eid + rowptr + out
+    check(_call("agg_csr_sum", 0.0, nbytes, _lib.load().gnc_agg_csr_sum_f32, rowptr.data_ptr(), _p(eid),
+                src.data_ptr(), _ld(src), n_rows, D, out.data_ptr(), _ld(out), int(accumulate), _stream()),
+          "agg_csr_sum")
     return out
 
 
@@ -156,8 +194,9 @@ def _gather_raw(src: Tensor, idx: Tensor, out: Optional[Tensor] = None, accumula
     if out is None:
         out = torch.empty(M, D, dtype=torch.float32, device=src.device)
         accumulate = False
-    check(_lib.load().gnc_gather_rows_f32(src.data_ptr(), _ld(src), idx.data_ptr(), M, D, out.data_ptr(), _ld(out),
-                                          int(accumulate), _stream()), "gather_rows")
+    nbytes = 4.0 * (src.shape[0] * D + M + M * D)
+    check(_call("gather_rows", 0.0, nbytes, _lib.load().gnc_gather_rows_f32, src.data_ptr(), _ld(src),
+                idx.data_ptr(), M, D, out.data_ptr(), _ld(out), int(accumulate), _stream()), "gather_rows")
     return out
 
 
@@ -175,8 +214,10 @@ def _linear_fwd_raw(srcs, idxs, M, W, b, relu) -> Tensor:
     N = W.shape[0]
     Y = torch.empty(M, N, dtype=torch.float32, device=W.device)
     segs = _make_segs(srcs, idxs)
-    check(_lib.load().gnc_linear_fwd_f32(segs, len(srcs), M, W.data_ptr(), W.stride(0), _p(b), N, int(relu),
-                                         Y.data_ptr(), _ld(Y), _stream()), "linear_fwd")
+    K = W.shape[1]
+    check(_call("linear_fwd", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), _lib.load().gnc_linear_fwd_f32,
+                segs, len(srcs), M, W.data_ptr(), W.stride(0), _p(b), N, int(relu), Y.data_ptr(), _ld(Y), _stream()),
+          "linear_fwd")
     return Y
 
 
@@ -212,18 +253,19 @@ class _LinearFn(torch.autograd.Function):
             db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
             ws_n = int(lib.gnc_colsum_workspace(M, N))
             ws = _workspace(dev, ws_n)
-            check(lib.gnc_relu_bwd_colsum_f32(dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None,
-                                              _ld(Y) if ctx.relu else 0, M, N,
-                                              dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0,
-                                              ws.data_ptr(), ws_n, _stream()), "relu_bwd_colsum")
+            check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N * (3 if ctx.relu else 1), lib.gnc_relu_bwd_colsum_f32,
+                        dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None, _ld(Y) if ctx.relu else 0, M, N,
+                        dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0, ws.data_ptr(), ws_n, _stream()),
+                  "relu_bwd_colsum")
         dW = None
         if need_W:
             dW = torch.empty(N, K, dtype=torch.float32, device=dev)
             segs = _make_segs(srcs, [m[0] for m in ctx.meta])
             ws_n = int(lib.gnc_linear_wgrad_workspace(M, N, K))
             ws = _workspace(dev, ws_n)
-            check(lib.gnc_linear_wgrad_f32(dZ.data_ptr(), _ld(dZ), M, N, segs, len(srcs), dW.data_ptr(), K, 0,
-                                           ws.data_ptr(), ws_n, _stream()), "linear_wgrad")
+            check(_call("linear_wgrad", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K), lib.gnc_linear_wgrad_f32,
+                        dZ.data_ptr(), _ld(dZ), M, N, segs, len(srcs), dW.data_ptr(), K, 0, ws.data_ptr(), ws_n,
+                        _stream()), "linear_wgrad")
         dsrcs = []
         k0 = 0
         for i, s in enumerate(srcs):
@@ -232,8 +274,9 @@ class _LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[4 + i]:
                 dX = torch.empty(M, w, dtype=torch.float32, device=dev)
                 Wv = Wc[:, k0:k0 + w]
-                check(lib.gnc_linear_dgrad_f32(dZ.data_ptr(), _ld(dZ), M, N, Wv.data_ptr(), Wc.stride(0), w,
-                                               dX.data_ptr(), w, 0, _stream()), "linear_dgrad")
+                check(_call("linear_dgrad", 2.0 * M * N * w, 4.0 * (M * N + N * w + M * w), lib.gnc_linear_dgrad_f32,
+                            dZ.data_ptr(), _ld(dZ), M, N, Wv.data_ptr(), Wc.stride(0), w, dX.data_ptr(), w, 0,
+                            _stream()), "linear_dgrad")
                 idx, csr, n_src = ctx.meta[i]
                 if idx is None:
                     g = dX
@@ -265,9 +308,10 @@ class _LayerNormFn(torch.autograd.Function):
         mean = torch.empty(M, dtype=torch.float32, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
         r = _rows(res) if res is not None else None
-        check(_lib.load().gnc_layernorm_fwd_f32(z.data_ptr(), _ld(z), M, D, gamma.data_ptr(), beta.data_ptr(),
-                                                float(eps), _p(r), _ld(r) if r is not None else 0, y.data_ptr(),
-                                                _ld(y), mean.data_ptr(), rstd.data_ptr(), _stream()), "layernorm_fwd")
+        check(_call("layernorm_fwd", 0.0, 4.0 * M * D * (3 if r is not None else 2), _lib.load().gnc_layernorm_fwd_f32,
+                    z.data_ptr(), _ld(z), M, D, gamma.data_ptr(), beta.data_ptr(), float(eps), _p(r),
+                    _ld(r) if r is not None else 0, y.data_ptr(), _ld(y), mean.data_ptr(), rstd.data_ptr(), _stream()),
+              "layernorm_fwd")
         ctx.save_for_backward(z, mean, rstd, gamma)
         ctx.has_res = res is not None
         return y
@@ -285,9 +329,9 @@ class _LayerNormFn(torch.autograd.Function):
         db = torch.empty(D, dtype=torch.float32, device=dev) if need_b else None
         ws_n = int(lib.gnc_layernorm_bwd_workspace(M, D))
         ws = _workspace(dev, ws_n)
-        check(lib.gnc_layernorm_bwd_f32(dy.data_ptr(), _ld(dy), z.data_ptr(), _ld(z), mean.data_ptr(),
-                                        rstd.data_ptr(), gamma.data_ptr(), M, D, dz.data_ptr(), _ld(dz),
-                                        _p(dg), _p(db), 0, ws.data_ptr(), ws_n, _stream()), "layernorm_bwd")
+        check(_call("layernorm_bwd", 0.0, 4.0 * M * D * 3, lib.gnc_layernorm_bwd_f32, dy.data_ptr(), _ld(dy),
+                    z.data_ptr(), _ld(z), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), M, D, dz.data_ptr(),
+                    _ld(dz), _p(dg), _p(db), 0, ws.data_ptr(), ws_n, _stream()), "layernorm_bwd")
         return dz, dg, db, None, (dy if ctx.has_res else None)
 
 
@@ -340,8 +384,9 @@ def edge_geometry(pos: Tensor, graph: GraphIndex) -> Tensor:
     pos = _rows(pos).contiguous()
     P = pos.shape[1]
     out = torch.empty(graph.num_edges, P + 1, dtype=torch.float32, device=pos.device)
-    check(_lib.load().gnc_edge_geometry_f32(pos.data_ptr(), P, graph.src.data_ptr(), graph.dst.data_ptr(),
-                                            graph.num_edges, out.data_ptr(), _stream()), "edge_geometry")
+    check(_call("edge_geometry", 0.0, 4.0 * graph.num_edges * (2 + 2 * P + P + 1), _lib.load().gnc_edge_geometry_f32,
+                pos.data_ptr(), P, graph.src.data_ptr(), graph.dst.data_ptr(), graph.num_edges, out.data_ptr(),
+                _stream()), "edge_geometry")
     return out
 
 

@@ -37,9 +37,10 @@ class GraphClassifierPipeline:
         if self.device.type != "cuda":
             raise RuntimeError("GraphClassifierPipeline needs the model on a CUDA device (no CPU fallback)")
         n = self.resize_value * self.resize_value if method == "pixel" else (self.resize_value // self.patch_size) ** 2
-        # ~70 KB of live activations per node in inference, ~500 KB per node kept for the backward
-        self.micro_batch = micro_batch or max(1, min(512, (24 << 30) // (n * 70_000)))
-        self.train_micro_batch = train_micro_batch or max(1, min(256, (48 << 30) // (n * 100_000)))
+        # live fp32 activations: ~8 KB per node in inference (5 edge tensors + node tensors of
+        # width 128, E ~ 2N), ~40 KB per node kept for the backward over 3 blocks; budget 64 GB
+        self.micro_batch = micro_batch or max(1, min(512, (64 << 30) // (n * 8192)))
+        self.train_micro_batch = train_micro_batch or max(1, min(256, (64 << 30) // (n * 40_000)))
 
     # -- staging ----------------------------------------------------------------
     def _to_device(self, images) -> Tensor:
@@ -57,14 +58,22 @@ class GraphClassifierPipeline:
             return build_patch_graphs(images_dev, patch_size=self.patch_size)
         raise ValueError(f"Unknown method: {self.method}")
 
+    @staticmethod
+    def _even_chunk(total: int, limit: int) -> int:
+        """Largest chunk <= limit that splits ``total`` into equal-sized pieces (up to rounding),
+        so the topology cache sees at most two distinct batch shapes."""
+        n_chunks = -(-total // max(1, limit))
+        return -(-total // n_chunks)
+
     # -- inference ----------------------------------------------------------------
     @torch.no_grad()
     def infer(self, images) -> Tensor:
         img = self._to_device(images)
         B = img.shape[0]
         outs = []
-        for lo in range(0, B, self.micro_batch):
-            gb = self._build(img[lo:lo + self.micro_batch])
+        mb = self._even_chunk(B, self.micro_batch)
+        for lo in range(0, B, mb):
+            gb = self._build(img[lo:lo + mb])
             out = self.model(gb.as_tuple())
             outs.append(out.reshape(1, -1) if out.dim() == 1 else out)
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
@@ -78,12 +87,13 @@ class GraphClassifierPipeline:
         lab = lab.to(self.device, non_blocking=True).long()
         B = img.shape[0]
         total = torch.zeros((), dtype=torch.float32, device=self.device)
-        for lo in range(0, B, self.train_micro_batch):
-            gb = self._build(img[lo:lo + self.train_micro_batch])
+        mb = self._even_chunk(B, self.train_micro_batch)
+        for lo in range(0, B, mb):
+            gb = self._build(img[lo:lo + mb])
             logits = self.model(gb.as_tuple())
             if logits.dim() == 1:
                 logits = logits.reshape(1, -1)
-            loss = F.cross_entropy(logits, lab[lo:lo + self.train_micro_batch], reduction="sum") / B
+            loss = F.cross_entropy(logits, lab[lo:lo + mb], reduction="sum") / B
             loss.backward()
             total += loss.detach()
         return total

@@ -1,0 +1,179 @@
+"""GPU: graph construction through the C ABI vs the golden vectors (reference output)
+and the oracle.  Integer / index outputs are compared bit-exactly."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_build as ogb
+from oracle.weights import synthetic_images, voronoi_labels
+
+pytestmark = pytest.mark.gpu
+
+
+def _sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def _build(imgs, **kw):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    return build_pixel_graphs(torch.from_numpy(np.ascontiguousarray(imgs)), use_cache=False, **kw)
+
+
+def test_pixel_builder_vs_golden(golden, libgnc):
+    b = golden["builders"]
+    for k in [k for k in b if k.startswith("pixel_") and k.endswith("_img")]:
+        tag = k[:-4]
+        diag = tag.endswith("d1")
+        gb = _build(b[k], diagonals=diag)
+        assert gb.x.dtype == torch.float32 and gb.pos.dtype == torch.float32 and gb.edge_index.dtype == torch.int64
+        assert np.array_equal(gb.x.cpu().numpy(), b[tag + "_x"].astype(np.float32))
+        assert np.array_equal(gb.pos.cpu().numpy(), b[tag + "_pos"].astype(np.float32))
+        assert np.array_equal(gb.edge_index.cpu().numpy(), b[tag + "_ei"])
+    for k in [k for k in b if k.startswith("jpeg_") and k.endswith("_img")]:
+        gb = _build(b[k])
+        assert np.array_equal(_sha(gb.x.cpu().numpy().astype(np.uint8)), b[k[:-4] + "_xsha"])
+
+
+@pytest.mark.parametrize("H,W,diag,B", [(1, 1, 0, 1), (1, 4, 1, 2), (5, 1, 1, 3), (3, 5, 0, 2), (7, 16, 1, 3),
+                                        (32, 32, 0, 5), (33, 17, 1, 2)])
+def test_grid_edges_and_csr_vs_oracle(libgnc, H, W, diag, B):
+    imgs = np.random.default_rng(H * 100 + W).integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    gb = _build(imgs, diagonals=bool(diag))
+    ref = ogb.grid_edges(H, W, bool(diag))
+    N, E = H * W, ref.shape[1]
+    exp = np.concatenate([ref + b * N for b in range(B)], axis=1)
+    got = gb.edge_index.cpu().numpy()
+    assert got.shape == exp.shape and np.array_equal(got, exp)
+    g = gb.graph
+    assert g.num_nodes == B * N and g.num_edges == B * E
+    assert np.array_equal(g.src.cpu().numpy(), exp[0].astype(np.int32))
+    assert np.array_equal(g.dst.cpu().numpy(), exp[1].astype(np.int32))
+    for key, rp, eid in ((exp[1], g.dst_rowptr, g.dst_eid), (exp[0], g.src_rowptr, g.src_eid)):
+        orp, oeid = ogb.csr_by_key(key, B * N)
+        assert np.array_equal(rp.cpu().numpy(), orp)
+        assert np.array_equal(eid.cpu().numpy(), oeid)
+    # x / pos of every image
+    x = gb.x.cpu().numpy().reshape(B, N, 3)
+    assert np.array_equal(x, imgs.reshape(B, N, 3).astype(np.float32))
+    v = np.arange(N)
+    pos = gb.pos.cpu().numpy().reshape(B, N, 2)
+    assert np.array_equal(pos[0], np.stack([v // W, v % W], 1).astype(np.float32)) and np.array_equal(pos[0], pos[-1])
+
+
+def test_full_size_grids_checksum(golden, libgnc):
+    # BASELINE resize shapes: compare with the sha256 of the reference's own edge_index
+    g = golden["grid_edges"]
+    for r in (64, 128, 256):
+        for diag in (0, 1):
+            gb = _build(np.zeros((1, r, r, 3), np.uint8), diagonals=bool(diag))
+            assert np.array_equal(_sha(gb.edge_index.cpu().numpy()), g[f"gridsha_{r}_d{diag}"]), (r, diag)
+
+
+def test_generic_csr_build_matches_closed_form_and_oracle(libgnc):
+    from graphnet_classifier_b200.ops import GraphIndex
+    gb = _build(np.zeros((3, 9, 14, 3), np.uint8), diagonals=True)
+    g2 = GraphIndex.from_edge_index(gb.edge_index, gb.graph.num_nodes)
+    for a in ("src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid"):
+        assert torch.equal(getattr(g2, a), getattr(gb.graph, a)), a
+    # random multigraph with heavy rows (exercises the heapsort path) and isolated nodes,
+    # given as the reference does: the transposed view of an [E, 2] array (strides (1, 2))
+    rng = np.random.default_rng(5)
+    N, E = 500, 20000
+    dst = np.where(rng.random(E) < 0.3, 7, rng.integers(0, N - 50, E))
+    src = rng.integers(0, N, E)
+    ei = torch.from_numpy(np.stack([src, dst], axis=1)).cuda().t()
+    assert not ei.is_contiguous()
+    g3 = GraphIndex.from_edge_index(ei, N)
+    for key, rp, eid in ((dst, g3.dst_rowptr, g3.dst_eid), (src, g3.src_rowptr, g3.src_eid)):
+        orp, oeid = ogb.csr_by_key(key, N)
+        assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(eid.cpu().numpy(), oeid)
+    # empty edge set, and out-of-range ids
+    g4 = GraphIndex.from_edge_index(torch.zeros(2, 0, dtype=torch.long, device="cuda"), 5)
+    assert g4.num_edges == 0 and g4.dst_rowptr.cpu().tolist() == [0] * 6
+    with pytest.raises(IndexError):
+        GraphIndex.from_edge_index(torch.tensor([[0, 1], [1, 9]], device="cuda"), 5)
+
+
+def test_large_csr_scan_multilevel(libgnc):
+    # N large enough for three scan levels (> 2048^2 = 4.2M rows)
+    from graphnet_classifier_b200.ops import GraphIndex
+    N, E = 5_000_000, 6_000_000
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    dst = torch.randint(0, N, (E,), device="cuda", generator=gen)
+    src = torch.randint(0, N, (E,), device="cuda", generator=gen)
+    g = GraphIndex.from_edge_index(torch.stack([src, dst]), N)
+    counts = torch.bincount(dst, minlength=N)
+    exp = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+    exp[1:] = torch.cumsum(counts, 0)
+    assert torch.equal(g.dst_rowptr.long(), exp)
+    eid = g.dst_eid.long()
+    assert torch.equal(torch.sort(eid).values, torch.arange(E, device="cuda"))
+    keyed = dst[eid]
+    assert bool((keyed[1:] >= keyed[:-1]).all())
+    same = keyed[1:] == keyed[:-1]
+    assert bool((eid[1:][same] > eid[:-1][same]).all())
+
+
+def test_patch_builder_vs_golden(golden, libgnc):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_patch_graphs
+    b = golden["builders"]
+    for k in [k for k in b if k.startswith("patch_") and k.endswith("_img")]:
+        tag = k[:-4]
+        p = int(tag.split("_")[-1])
+        gb = build_patch_graphs(torch.from_numpy(b[k]), patch_size=p, use_cache=False)
+        assert np.array_equal(gb.x.cpu().numpy(), b[tag + "_x"].astype(np.float32)), tag
+        assert np.array_equal(gb.pos.cpu().numpy(), b[tag + "_pos"].astype(np.float32))
+        assert np.array_equal(gb.edge_index.cpu().numpy(), b[tag + "_ei"])
+
+
+def test_superpixel_builder_vs_golden(golden, libgnc):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_superpixel_graphs
+    b = golden["builders"]
+    for k in [k for k in b if k.startswith("superpixel_") and k.endswith("_img")]:
+        tag = k[:-4]
+        n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(torch.from_numpy(b[k]), torch.from_numpy(b[tag + "_labels"]))
+        S, E = int(n_nodes[0]), int(n_edges[0])
+        assert S == b[tag + "_x"].shape[0]
+        # indices: bit-exact; features/centroids: equal after the loader's float32 cast
+        assert np.array_equal(edges[0, :, :E].cpu().numpy(), b[tag + "_ei"]), tag
+        np.testing.assert_allclose(x[0, :S].cpu().numpy(), b[tag + "_x"].astype(np.float32), rtol=1e-6, atol=0)
+        np.testing.assert_allclose(pos[0, :S].cpu().numpy(), b[tag + "_pos"].astype(np.float32), rtol=1e-6, atol=0)
+
+
+def test_superpixel_batch_and_edge_cases(libgnc):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_superpixel_graphs
+    B, r = 4, 40
+    imgs = synthetic_images(B, r, seed=11)
+    labs = np.stack([voronoi_labels(r, r, 9 + 3 * b, seed=b) for b in range(B)])
+    labs[3] = 0                                            # one-segment image: no edges
+    n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(torch.from_numpy(imgs), torch.from_numpy(labs))
+    for b in range(B):
+        ox, opos, oei = ogb.superpixel_graph_from_labels(imgs[b], labs[b])
+        S, E = int(n_nodes[b]), int(n_edges[b])
+        assert S == len(ox) and E == oei.shape[1]
+        if E:
+            assert np.array_equal(edges[b, :, :E].cpu().numpy(), oei)
+        np.testing.assert_allclose(x[b, :S].cpu().numpy(), ox.astype(np.float32), rtol=1e-6)
+        np.testing.assert_allclose(pos[b, :S].cpu().numpy(), opos.astype(np.float32), rtol=1e-6)
+
+
+def test_reference_named_builders(golden, libgnc):
+    from PIL import Image
+    from graphnet_classifier_b200.utils.image_to_graph import (
+        create_grid_edges_optimized, get_cached_edge_index, image_to_graph_patch, image_to_graph_pixel_optimized,
+        image_to_graph_superpixel)
+    b = golden["builders"]
+    assert np.array_equal(create_grid_edges_optimized(3, 5, True), golden["grid_edges"]["grid_3x5_d1"])
+    assert get_cached_edge_index(8, False) is get_cached_edge_index(8, False)       # lru_cache aliasing (Q9)
+    img = b["pixel_8_d0_img"]
+    x, pos, ei = image_to_graph_pixel_optimized(Image.fromarray(img), 8)
+    assert x.dtype == np.uint8 and pos.dtype == np.int64 and ei.dtype == np.int64
+    assert np.array_equal(x, b["pixel_8_d0_x"]) and np.array_equal(pos, b["pixel_8_d0_pos"])
+    assert np.array_equal(ei, b["pixel_8_d0_ei"])
+    x, pos, ei = image_to_graph_patch(Image.fromarray(b["patch_32_8_img"]), 32, 8)
+    assert np.array_equal(x, b["patch_32_8_x"].astype(np.float32)) and np.array_equal(ei, b["patch_32_8_ei"])
+    x, pos, ei = image_to_graph_superpixel(Image.fromarray(b["superpixel_32_img"]), 32,
+                                           segments=b["superpixel_32_labels"])
+    assert np.array_equal(ei, b["superpixel_32_ei"])

@@ -1,0 +1,186 @@
+"""GPU: GraphNet / CombinedModel end to end through the reference-shaped API vs the
+golden vectors (reference output) and the oracle: logits, loss and every parameter
+gradient within 1e-5 relative; batching; checkpoint exchange; the train loop."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+from oracle import graph_build as ogb
+from oracle.weights import fill_deterministic, synthetic_images
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _models(r, n_blocks=3, seed=7, **gn_kw):
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    kw = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=n_blocks)
+    kw.update(gn_kw)
+    om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**kw), num_nodes=r * r, classes=2)
+    fill_deterministic(om, seed=seed)
+    gm = CombinedModel(GraphNet(**kw), num_nodes=r * r, classes=2)
+    gm.load_state_dict(om.state_dict())
+    return om, gm.cuda()
+
+
+def _inputs(img, diag):
+    return ogb.to_model_inputs(*ogb.pixel_graph(img, diag))
+
+
+@pytest.mark.parametrize("r,diag", [(8, False), (8, True), (12, False)])
+def test_logits_loss_grads_vs_golden_reference(golden, libgnc, r, diag):
+    m = golden["model"]
+    tag = f"model_r{r}_d{int(diag)}"
+    om, gm = _models(r)
+    imgs = m[tag + "_imgs"]
+    for b in range(imgs.shape[0]):
+        x, pos, ei = _inputs(imgs[b], diag)
+        # the reference hands over a non-contiguous edge_index (transposed view): keep that
+        out = gm((x.cuda(), pos.cuda(), ei.cuda()))
+        assert out.shape == (2,)                                        # 1-D logits (Q11)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), m[tag + "_logits"][b], rtol=RTOL, atol=1e-7)
+    x, pos, ei = _inputs(imgs[0], diag)
+    label = torch.tensor(int(m[tag + "_label"]))
+    loss = torch.nn.functional.cross_entropy(gm((x.cuda(), pos.cuda(), ei.cuda())), label.cuda())
+    assert abs(loss.item() - float(m[tag + "_loss"])) < 1e-5 * max(1.0, float(m[tag + "_loss"]))
+    loss.backward()
+    torch.nn.functional.cross_entropy(om((x, pos, ei)), label).backward()
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        assert _rel(p.grad, po.grad) < RTOL, name                      # full tensor vs oracle
+        samp = m[f"{tag}_grad_{name}_samp"]                             # sampled entries vs reference golden
+        f = p.grad.flatten().cpu()
+        stride = max(1, -(-f.numel() // 512))
+        scale = float(m[f"{tag}_grad_{name}_sn"][1]) / np.sqrt(f.numel()) + 1e-30
+        assert np.max(np.abs(f[::stride].numpy() - samp)) <= 10 * RTOL * max(scale, np.max(np.abs(samp))), name
+
+
+def test_batched_equals_per_sample_and_builder_path(golden, libgnc):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    m = golden["model"]
+    om, gm = _models(8)
+    imgs = m["model_r8_d0_imgs"]
+    gb = build_pixel_graphs(torch.from_numpy(imgs))
+    out = gm(gb.as_tuple())                                            # [B, classes]
+    assert out.shape == (3, 2)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), m["model_r8_d0_logits"], rtol=RTOL, atol=1e-7)
+    out2 = gm(gb.x, gb.pos, gb.edge_index)                             # positional form
+    assert torch.equal(out, out2)
+    # edge_index without the attached CSR (generic csr_build path) gives the same bits
+    out3 = gm(gb.x, gb.pos, gb.edge_index.clone())
+    assert torch.equal(out, out3)
+
+
+def test_resize32_seed0_matches_survey_probe_and_checkpoint_roundtrip(golden, libgnc, tmp_path):
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    torch.manual_seed(0)
+    gm = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=1024,
+                       classes=2)
+    om = ognn.build_reference_config_model(32, seed=0)
+    for k, v in om.state_dict().items():
+        assert torch.equal(v, gm.state_dict()[k]), k
+    gm = gm.cuda()
+    img = np.random.default_rng(0).integers(0, 256, (32, 32, 3), dtype=np.uint8)
+    x, pos, ei = _inputs(img, False)
+    out = gm((x.cuda(), pos.cuda(), ei.cuda()))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), golden["model"]["seed0_r32_logits_img0"], rtol=RTOL)
+    # checkpoint written by us loads into the reference-shaped oracle tree and vice versa
+    path = os.path.join(tmp_path, "ck.pth")
+    torch.save(gm.state_dict(), path)
+    sd = torch.load(path, map_location="cpu")
+    assert list(sd.keys()) == list(golden["model"]["checkpoint_keys"])
+    om2 = ognn.build_reference_config_model(32, seed=1)
+    om2.load_state_dict(sd)
+    with torch.no_grad():
+        np.testing.assert_allclose(om2((x, pos, ei)).numpy(), out.detach().cpu().numpy(), rtol=RTOL)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_blocks=2, out_dim_node=64, out_dim_edge=32, hidden_dim_processor_edge=96),
+    dict(n_blocks=1, activation="Tanh", hidden_layers_processor_node=3),
+    dict(n_blocks=1, norm_type=None, out_channels=2),
+])
+def test_non_default_configurations(libgnc, kw):
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    base = dict(num_local_features=3, space_dim=2, out_channels=1)
+    base.update(kw)
+    r = 6
+    ogn = ognn.OracleGraphNet(**base)
+    om = ognn.OracleCombinedModel(ogn, num_nodes=r * r, classes=3)
+    fill_deterministic(om, seed=3)
+    gm = CombinedModel(GraphNet(**base), num_nodes=r * r, classes=3)
+    gm.load_state_dict(om.state_dict())
+    gm = gm.cuda()
+    x, pos, ei = _inputs(synthetic_images(1, r, 5)[0], True)
+    label = torch.tensor(2)
+    lo = torch.nn.functional.cross_entropy(om((x, pos, ei)), label)
+    lg = torch.nn.functional.cross_entropy(gm((x.cuda(), pos.cuda(), ei.cuda())), label.cuda())
+    assert abs(lo.item() - lg.item()) < RTOL * max(1.0, abs(lo.item()))
+    lo.backward(), lg.backward()
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        assert _rel(p.grad, po.grad) < 5 * RTOL, name
+
+
+def test_pipeline_infer_and_train_step_match_oracle(libgnc):
+    from graphnet_classifier_b200.pipeline import GraphClassifierPipeline
+    r, B = 10, 7
+    om, gm = _models(r, n_blocks=2)
+    imgs = synthetic_images(B, r, seed=21)
+    labels = np.random.default_rng(1).integers(0, 2, B)
+    pipe = GraphClassifierPipeline(gm, resize_value=r, micro_batch=3, train_micro_batch=2)
+    got = pipe.infer(torch.from_numpy(imgs))                           # 3 micro-batches: 3 + 3 + 1
+    with torch.no_grad():
+        exp = torch.stack([om(_inputs(im, False)) for im in imgs])
+    np.testing.assert_allclose(got.cpu().numpy(), exp.numpy(), rtol=RTOL, atol=1e-7)
+    # one training step: mean CE over the batch, gradient accumulation over micro-batches, Adam
+    opt_g = torch.optim.Adam(gm.parameters(), lr=1e-3)
+    opt_o = torch.optim.Adam(om.parameters(), lr=1e-3)
+    loss_g = pipe.train_step(torch.from_numpy(imgs), torch.from_numpy(labels), opt_g)
+    opt_o.zero_grad()
+    loss_o = sum(torch.nn.functional.cross_entropy(om(_inputs(im, False)), torch.tensor(int(l))) for im, l in
+                 zip(imgs, labels)) / B
+    loss_o.backward()
+    assert abs(loss_g.item() - loss_o.item()) < RTOL * max(1.0, loss_o.item())
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        assert _rel(p.grad, po.grad) < RTOL, name
+    opt_o.step()
+    # Adam's first step is lr*sign(g)-like, so parameters are compared with an absolute bar
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        assert float((p.detach().cpu() - po.detach()).abs().max()) < 2e-3 * 1.01, name
+
+
+def test_reference_train_loop_one_graph_per_step(libgnc, tmp_path):
+    # utils/train_model.train with a batch_size=1 style iterable, like main.py:60
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    from graphnet_classifier_b200.utils.train_model import train
+    r = 8
+    om, gm = _models(r, n_blocks=1)
+    imgs = synthetic_images(4, r, seed=9)
+    labels = [0, 1, 1, 0]
+    data = [(build_pixel_graphs(torch.from_numpy(im), use_cache=True).as_tuple(), torch.tensor(l)) for im, l in
+            zip(imgs, labels)]
+    best = train(gm, data, epochs=2, patience=5, output_path=str(tmp_path))
+    # same loop on the oracle model (reference semantics: Adam 1e-3, CE, one step per item)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(2):
+        tot = 0.0
+        for im, l in zip(imgs, labels):
+            loss = torch.nn.functional.cross_entropy(om(_inputs(im, False)), torch.tensor(l))
+            opt.zero_grad(), loss.backward(), opt.step()
+            tot += loss.item()
+        losses.append(tot / 4)
+    assert abs(best - min(losses)) < 5e-3
+    files = sorted(os.listdir(tmp_path))
+    assert "final_model.pth" in files and "best_model_epoch1.pth" in files
+    log = [f for f in files if f.startswith("training_logs_")]
+    assert len(log) == 1
+    text = open(os.path.join(tmp_path, log[0])).read()
+    assert "Epochs: 2, Patience: 5" in text and "Epoch 2/2, avg_loss=" in text and "Best loss achieved:" in text

@@ -1,0 +1,215 @@
+"""GPU: operator-level parity through the C ABI.
+
+* aggregation / gathers / edge geometry: BIT-EXACT against the CPU reference order
+  (index_add_ on the CPU, advanced indexing) - including in-degree > 2;
+* linear / LayerNorm forward and backward: <= 1e-5 relative (north_star tolerance)
+  against an fp64 torch evaluation of the same op.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+from oracle import graph_build as ogb
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5        # BASELINE.json north_star: logits/gradients within 1e-5 relative in fp32
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _graph(H, W, diag, B=1):
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    return build_pixel_graphs(torch.zeros(B, H, W, 3, dtype=torch.uint8), diagonals=diag, use_cache=False)
+
+
+@pytest.mark.parametrize("D", [1, 3, 32, 64, 128, 130, 256, 512])
+@pytest.mark.parametrize("diag", [False, True])
+def test_aggregate_bit_exact_vs_index_add(libgnc, D, diag):
+    from graphnet_classifier_b200 import ops
+    gb = _graph(13, 11, diag, B=3)
+    g = gb.graph
+    e = torch.randn(g.num_edges, D, generator=torch.Generator().manual_seed(D))
+    exp = ognn.scatter_sum(e, gb.edge_index[1].cpu(), dim_size=g.num_nodes)     # CPU, sequential in edge order
+    got = ops.aggregate(e.cuda(), g)
+    assert torch.equal(got.cpu(), exp)
+
+
+def test_aggregate_random_multigraph_bit_exact_and_scatter_sum_api(libgnc, golden):
+    from graphnet_classifier_b200 import ops
+    from graphnet_classifier_b200.models.GNN import scatter_sum
+    gen = torch.Generator().manual_seed(1)
+    N, E, D = 300, 12000, 128
+    idx = torch.where(torch.rand(E, generator=gen) < 0.25, torch.tensor(5), torch.randint(0, N, (E,), generator=gen))
+    src = torch.randn(E, D, generator=gen)
+    exp = ognn.scatter_sum(src, idx)                       # dim_size = idx.max()+1
+    got = scatter_sum(src.cuda(), idx.cuda())
+    assert got.shape == exp.shape and torch.equal(got.cpu(), exp)
+    got2 = scatter_sum(src.cuda(), idx.cuda().int(), dim=0, dim_size=N + 7)
+    assert got2.shape[0] == N + 7 and torch.equal(got2[:exp.shape[0]].cpu(), exp) and float(got2[exp.shape[0]:].abs().sum()) == 0
+    m = golden["model"]
+    g3 = scatter_sum(torch.from_numpy(m["scatter_src"]).cuda(), torch.from_numpy(m["scatter_idx"]).cuda())
+    assert np.array_equal(g3.cpu().numpy(), m["scatter_out"])
+    with pytest.raises(NotImplementedError):
+        scatter_sum(src.cuda(), idx.cuda(), dim=1)
+    one_d = scatter_sum(src[:, 0].cuda(), idx.cuda())      # 1-D src -> [N, 1] (Q2)
+    assert one_d.shape == (exp.shape[0], 1)
+    # empty index
+    assert scatter_sum(torch.zeros(0, 4).cuda(), torch.zeros(0, dtype=torch.long).cuda()).shape == (0, 4)
+
+
+def test_aggregate_backward_is_gather_and_gather_backward_is_ordered_sum(libgnc):
+    from graphnet_classifier_b200 import ops
+    gb = _graph(6, 9, True, B=2)
+    g = gb.graph
+    gen = torch.Generator().manual_seed(2)
+    e = torch.randn(g.num_edges, 64, generator=gen)
+    w = torch.randn(g.num_nodes, 64, generator=gen)
+    ec = e.cuda().requires_grad_(True)
+    (ops.aggregate(ec, g) * w.cuda()).sum().backward()
+    assert torch.equal(ec.grad.cpu(), w[gb.edge_index[1].cpu()])
+    h = torch.randn(g.num_nodes, 64, generator=gen)
+    u = torch.randn(g.num_edges, 64, generator=gen)
+    hc = h.cuda().requires_grad_(True)
+    out = ops.gather_rows(hc, g.src, g.src_rowptr, g.src_eid)
+    assert torch.equal(out.detach().cpu(), h[gb.edge_index[0].cpu()])
+    (out * u.cuda()).sum().backward()
+    exp = torch.zeros_like(h).index_add_(0, gb.edge_index[0].cpu(), u)    # CPU index_put_(accumulate) order
+    assert torch.equal(hc.grad.cpu(), exp)
+
+
+def test_aggregate_linearity_at_full_size(libgnc):
+    # size-independent property at a BASELINE shape (r=128, batch 8): agg(a*x + y) == a*agg(x) + agg(y)
+    # holds exactly for in-degree <= 2 when a is a power of two
+    from graphnet_classifier_b200 import ops
+    gb = _graph(128, 128, False, B=8)
+    g = gb.graph
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(g.num_edges, 128, device="cuda", generator=gen)
+    y = torch.randn(g.num_edges, 128, device="cuda", generator=gen)
+    lhs = ops.aggregate(4.0 * x + y, g)
+    ax, ay = ops.aggregate(x, g), ops.aggregate(y, g)
+    assert _rel(lhs, 4.0 * ax + ay) < 1e-6
+    # total mass is conserved: column sums of the output equal column sums of the input
+    assert _rel(ax.double().sum(0), x.double().sum(0)) < 1e-6
+    # nodes without in-edges (pixel 0 of every image) are exactly zero
+    assert float(ax[:: 128 * 128].abs().max()) == 0.0
+
+
+def test_edge_geometry_bit_exact(libgnc):
+    from graphnet_classifier_b200 import ops
+    gb = _graph(7, 5, True, B=2)
+    got = ops.edge_geometry(gb.pos, gb.graph).cpu()
+    exp = ognn.OracleGraphNet.edge_geometry(gb.pos.cpu(), gb.edge_index.cpu())
+    assert torch.equal(got, exp)
+    vals = {tuple(r) for r in got.tolist()}
+    assert vals == {(0.0, 1.0, 1.0), (1.0, 0.0, 1.0), (1.0, 1.0, 2.0), (1.0, -1.0, 2.0)}
+    pos = torch.randn(gb.graph.num_nodes, 3)               # arbitrary positions, space_dim 3
+    got = ops.edge_geometry(pos.cuda(), gb.graph).cpu()
+    exp = ognn.OracleGraphNet.edge_geometry(pos, gb.edge_index.cpu())
+    assert torch.equal(got, exp)
+
+
+def _ref_linear(segs, idxs, W, b, relu):
+    X = torch.cat([s.double()[ix.long()] if ix is not None else s.double() for s, ix in zip(segs, idxs)], dim=1)
+    y = X @ W.double().t()
+    if b is not None:
+        y = y + b.double()
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("M,K,N,relu,bias", [
+    (1000, 128, 128, True, True), (257, 3, 128, True, True), (129, 128, 1, False, True),
+    (5, 64, 2, False, True), (300, 16384 // 8, 128, True, True), (77, 130, 96, False, False),
+    (513, 32, 32, True, True), (1, 128, 128, True, True)])
+def test_linear_forward_backward(libgnc, M, K, N, relu, bias):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen)
+    W = torch.randn(N, K, generator=gen) / np.sqrt(K)
+    b = torch.randn(N, generator=gen) if bias else None
+    dy = torch.randn(M, N, generator=gen)
+    xc, Wc = x.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    bc = b.cuda().requires_grad_(True) if bias else None
+    y = ops.linear([xc], Wc, bc, relu=relu)
+    xr, Wr = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    br = b.double().requires_grad_(True) if bias else None
+    yr = _ref_linear([xr], [None], Wr, br, relu)
+    assert _rel(y, yr) < RTOL
+    y.backward(dy.cuda())
+    yr.backward(dy.double())
+    assert _rel(xc.grad, xr.grad) < RTOL and _rel(Wc.grad, Wr.grad) < RTOL
+    if bias:
+        assert _rel(bc.grad, br.grad) < RTOL
+
+
+@pytest.mark.parametrize("Dn,De", [(128, 128), (64, 32), (20, 12)])
+def test_linear_gathered_segments_edge_block(libgnc, Dn, De):
+    # cat([h[row], h[col], e]) @ W0.T with the gathers inside the GEMM operand loads
+    from graphnet_classifier_b200 import ops
+    gb = _graph(10, 12, True, B=2)
+    g = gb.graph
+    gen = torch.Generator().manual_seed(Dn)
+    h = torch.randn(g.num_nodes, Dn, generator=gen)
+    e = torch.randn(g.num_edges, De, generator=gen)
+    W = torch.randn(128, 2 * Dn + De, generator=gen) / 10
+    b = torch.randn(128, generator=gen)
+    dy = torch.randn(g.num_edges, 128, generator=gen)
+    hc, ec, Wc, bc = (t.cuda().requires_grad_(True) for t in (h, e, W, b))
+    gathers = [(g.src, (g.src_rowptr, g.src_eid), g.num_nodes), (g.dst, (g.dst_rowptr, g.dst_eid), g.num_nodes), None]
+    y = ops.linear([hc, hc, ec], Wc, bc, relu=True, gathers=gathers)
+    hr, er, Wr, br = (t.double().requires_grad_(True) for t in (h, e, W, b))
+    ei = gb.edge_index.cpu()
+    yr = _ref_linear([hr, hr, er], [ei[0], ei[1], None], Wr, br, True)
+    assert _rel(y, yr) < RTOL
+    y.backward(dy.cuda())
+    yr.backward(dy.double())
+    for a, r in ((hc, hr), (ec, er), (Wc, Wr), (bc, br)):
+        assert _rel(a.grad, r.grad) < RTOL
+
+
+@pytest.mark.parametrize("M,D,res", [(1000, 128, True), (33, 128, False), (50, 64, True), (40, 100, True),
+                                     (17, 30, False), (9, 512, True)])
+def test_layernorm_forward_backward(libgnc, M, D, res):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + D)
+    z = torch.randn(M, D, generator=gen) * 3 + 1
+    gamma = 1 + 0.1 * torch.randn(D, generator=gen)
+    beta = 0.1 * torch.randn(D, generator=gen)
+    r = torch.randn(M, D, generator=gen) if res else None
+    dy = torch.randn(M, D, generator=gen)
+    zc, gc, bc = (t.cuda().requires_grad_(True) for t in (z, gamma, beta))
+    rc = r.cuda().requires_grad_(True) if res else None
+    y = ops.layer_norm(zc, gc, bc, 1e-5, rc)
+    zr, gr, br = (t.double().requires_grad_(True) for t in (z, gamma, beta))
+    rr = r.double().requires_grad_(True) if res else None
+    yr = torch.nn.functional.layer_norm(zr, (D,), gr, br, 1e-5)
+    if res:
+        yr = yr + rr
+    assert _rel(y, yr) < RTOL
+    y.backward(dy.cuda())
+    yr.backward(dy.double())
+    assert _rel(zc.grad, zr.grad) < RTOL and _rel(gc.grad, gr.grad) < RTOL and _rel(bc.grad, br.grad) < RTOL
+    if res:
+        assert torch.equal(rc.grad.cpu(), dy)
+
+
+def test_mlp_module_matches_torch_module(libgnc):
+    # the kernel walk over nn.Sequential == the Sequential itself (incl. a non-default config)
+    from graphnet_classifier_b200.models.MLP import MLP
+    torch.manual_seed(0)
+    for kw in (dict(in_dim=3, out_dim=128), dict(in_dim=128, out_dim=1, norm_type=None),
+               dict(in_dim=40, out_dim=24, hidden_dim=48, hidden_layers=3, activation="Tanh"),
+               dict(in_dim=16, out_dim=8, hidden_dim=32, hidden_layers=1, initializer="xavier_uniform_")):
+        m = MLP(**kw).cuda()
+        x = torch.randn(200, kw["in_dim"], device="cuda")
+        got = m(x)
+        exp = m.model.double()(x.double())
+        m.model.float()
+        assert _rel(got, exp) < RTOL, kw
+    with pytest.raises(AssertionError):
+        MLP(3, 4, norm_type="GroupNorm")
