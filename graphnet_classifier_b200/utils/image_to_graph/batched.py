@@ -52,13 +52,16 @@ def _as_device_u8(images, device) -> Tensor:
 
 def _alloc_topology(B, N, E, device, want_edge_index=True):
     i32 = dict(dtype=torch.int32, device=device)
-    ei = torch.empty(2, E * B, dtype=torch.int64, device=device) if want_edge_index else None
-    src = torch.empty(B * E, **i32)
-    dst = torch.empty(B * E, **i32)
+    BE = B * E
+    # zero-edge grids (1 x 1): torch reports a null data_ptr for empty tensors, so the
+    # buffers are allocated with at least one element and sliced after the launch
+    ei = torch.empty(2, max(BE, 1), dtype=torch.int64, device=device) if want_edge_index else None
+    src = torch.empty(max(BE, 1), **i32)
+    dst = torch.empty(max(BE, 1), **i32)
     drp = torch.empty(B * N + 1, **i32)
-    deid = torch.empty(B * E, **i32)
+    deid = torch.empty(max(BE, 1), **i32)
     srp = torch.empty(B * N + 1, **i32)
-    seid = torch.empty(B * E, **i32)
+    seid = torch.empty(max(BE, 1), **i32)
     return ei, src, dst, drp, deid, srp, seid
 
 
@@ -104,7 +107,10 @@ def _build_grid(images, patch: int, diagonals: bool, device, use_cache: bool) ->
         check(fn(img.data_ptr(), B, H, W, fifth, x.data_ptr(), pos.data_ptr(), ei.data_ptr(),
                  src.data_ptr(), dst.data_ptr(), drp.data_ptr(), deid.data_ptr(), srp.data_ptr(), seid.data_ptr(),
                  _stream()), "build_graph")
-        graph = GraphIndex(B * N, B * E, src, dst, drp, deid, srp, seid)
+        BE = B * E
+        if BE == 0:
+            ei, src, dst, deid, seid = ei[:, :0], src[:0], dst[:0], deid[:0], seid[:0]
+        graph = GraphIndex(B * N, BE, src, dst, drp, deid, srp, seid)
         attach_graph(ei, graph)
         if use_cache:
             _topology_cache.put(key, (pos, ei, graph))
