@@ -16,6 +16,18 @@ class GncSeg(Structure):
     _fields_ = [("base", c_void_p), ("idx", c_void_p), ("ld", c_int64), ("width", c_int32), ("_pad", c_int32)]
 
 
+class GncTcEpilogue(Structure):
+    """struct gnc_tc_epilogue (include/gnc.h)."""
+    _fields_ = [("bias", c_void_p),
+                ("addend", c_void_p), ("ld_addend", c_int64),
+                ("gather0", c_void_p), ("gather0_idx", c_void_p), ("ld_gather0", c_int64),
+                ("gather1", c_void_p), ("gather1_idx", c_void_p), ("ld_gather1", c_int64),
+                ("relu", c_int32), ("_pad0", c_int32),
+                ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
+                ("residual", c_void_p), ("ld_residual", c_int64),
+                ("dot_w", c_void_p), ("dot_b", c_void_p)]
+
+
 class GncError(RuntimeError):
     pass
 
@@ -51,6 +63,8 @@ SIGNATURES = {
     "gnc_layernorm_bwd_workspace": (c_int64, [c_int64, c_int]),
     "gnc_layernorm_bwd_f32": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, _P, c_int64,
                                       _P, _P, c_int, _P, c_int64, _P]),
+    "gnc_tc_linear_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, POINTER(GncTcEpilogue),
+                                  _P, c_int64, _P]),
 }
 
 _lib = None

@@ -1,0 +1,469 @@
+// tcgen05 (5th-gen tensor core) 3xTF32 linear layer for the width-128 GraphNet MLPs.
+//
+//   Y[M,128] = epilogue( A[M,128] * B^T ),  B = W[128,128]  (or W^T for the data gradient)
+//
+// fp32 parity (1e-5 on logits/gradients) rules out a single TF32 pass, so
+// every operand is split a = hi + lo with hi = tf32(a), lo = tf32(a - hi) and each product
+// is three kind::tf32 MMAs (lo*hi, hi*lo, hi*hi) accumulated in fp32 in TMEM: error ~2^-22.
+//
+// One persistent CTA per SM, 9 warps, three roles connected by mbarriers:
+//   warps 0-3  loader   : coalesced 128-bit global loads of A rows (two K-blocks prefetched
+//                         in registers), hi/lo split, store into the UMMA K-major SWIZZLE_128B
+//                         smem image (2 stages x {hi,lo} x 16 KB)
+//   warp  4    MMA      : one elected thread issues tcgen05.mma (M=128,N=128,K=8), A and B
+//                         from smem descriptors; B (the weights, hi+lo = 128 KB) is built
+//                         once per CTA and stays resident; accumulators double-buffered in
+//                         TMEM (2 x 128 columns) so the epilogue of tile i overlaps tile i+1
+//   warps 5-8  epilogue : tcgen05.ld (thread = row), row-domain math (bias, LayerNorm, dot),
+//                         warp-local transpose through smem, then coalesced 128-bit global
+//                         traffic for addends / residual / output.
+//
+// Reference semantics covered (models/MLP.py:24-37, models/GNN.py:57-64, 95-104, 289-295):
+//   MODE_ELEMENTWISE: y = act(acc + bias + addend[m] + g0[i0[m]] + g1[i1[m]]) + residual[m]
+//   MODE_LAYERNORM  : y = LayerNorm(acc + bias) * gamma + beta + residual[m]
+//   MODE_RELU_DOT   : y[m] = relu(acc + bias) . w + b          (decoder tail, out_channels = 1)
+#include "common.cuh"
+
+namespace gnc {
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kD = 128;
+constexpr int kKB = 32;                 // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int kNumKB = kD / kKB;        // 4
+constexpr int kStages = 2;
+constexpr int kBlockBytes = kTileM * kKB * 4;   // 16 KB: one operand K-block image
+constexpr int kLoaderWarps = 4, kEpiWarps = 4;
+constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;   // 288
+constexpr int kStagePitch = 36;         // floats per staged row (16-byte aligned, conflict-free)
+constexpr int kTmemCols = 256;          // two fp32 accumulators of 128 columns
+
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int kOffWhi = 0;
+constexpr int kOffWlo = kOffWhi + kNumKB * kBlockBytes;                 //  65536
+constexpr int kOffA = kOffWlo + kNumKB * kBlockBytes;                   // 131072: [stage][hi|lo][16 KB]
+constexpr int kOffStage = kOffA + kStages * 2 * kBlockBytes;            // 196608
+constexpr int kOffConst = kOffStage + kEpiWarps * 32 * kStagePitch * 4; // 215040: bias,gamma,beta,dotw
+constexpr int kOffBar = kOffConst + 4 * kD * 4;                         // 217088
+constexpr int kSmemBytes = kOffBar + 128 + 1024;                        // + alignment slack
+
+enum { MODE_ELEMENTWISE = 0, MODE_LAYERNORM = 1, MODE_RELU_DOT = 2 };
+
+struct Params {
+  const float* A; long long lda; long long M;
+  const float* W; long long ldw; int transpose_w;
+  const float* bias;
+  const float* addend; long long ld_addend;
+  const float* g0; const int32_t* i0; long long ld_g0;
+  const float* g1; const int32_t* i1; long long ld_g1;
+  int relu;
+  const float* gamma; const float* beta; float eps;
+  const float* residual; long long ld_res;
+  const float* dot_w; const float* dot_b;
+  float* Y; long long ldy;
+  long long num_tiles;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), swizzle applied by the hardware.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);         // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                          // descriptor version
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offset of (row, 16-byte chunk) inside one 16 KB K-block image
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- the kernel -------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_const = reinterpret_cast<float*>(sm + kOffConst);
+  const uint32_t bar0 = base + kOffBar;
+  // barrier slots (8 bytes each): a_full[2] a_empty[2] d_full[2] d_empty[2]; then the TMEM base pointer
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 16u + 8u * s; };
+  auto d_full = [&](int d) { return bar0 + 32u + 8u * d; };
+  auto d_empty = [&](int d) { return bar0 + 48u + 8u * d; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 64);
+
+  // ---- one-time setup ----------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(a_full(s), kLoaderWarps * 32); mbar_init(a_empty(s), 1); }
+    for (int d = 0; d < 2; ++d) { mbar_init(d_full(d), 1); mbar_init(d_empty(d), kEpiWarps * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kLoaderWarps) {   // the MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident B operand: hi/lo images of W (row n = output feature, K-major), or of W^T
+  for (int item = threadIdx.x; item < kD * kNumKB * 8; item += kThreads) {
+    const int c = item & 7, n = (item >> 3) & (kD - 1), kb = item >> 10;
+    const int k0 = kb * kKB + c * 4;
+    float4 v;
+    if (!p.transpose_w) {
+      v = __ldg(reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + k0));
+    } else {
+      v.x = __ldg(p.W + (long long)(k0 + 0) * p.ldw + n);
+      v.y = __ldg(p.W + (long long)(k0 + 1) * p.ldw + n);
+      v.z = __ldg(p.W + (long long)(k0 + 2) * p.ldw + n);
+      v.w = __ldg(p.W + (long long)(k0 + 3) * p.ldw + n);
+    }
+    float4 hi, lo;
+    split4(v, hi, lo);
+    const uint32_t off = (uint32_t)kb * kBlockBytes + swz_off(n, c);
+    sts128(base + kOffWhi + off, hi);
+    sts128(base + kOffWlo + off, lo);
+  }
+  for (int i = threadIdx.x; i < kD; i += kThreads) {
+    s_const[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    s_const[kD + i] = p.gamma ? __ldg(p.gamma + i) : 1.f;
+    s_const[2 * kD + i] = p.beta ? __ldg(p.beta + i) : 0.f;
+    s_const[3 * kD + i] = p.dot_w ? __ldg(p.dot_w + i) : 0.f;
+  }
+  fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long first = blockIdx.x, step = gridDim.x;
+
+  if (warp < kLoaderWarps) {
+    // ======================= loader =======================
+    const int rsub = warp * 4 + (lane >> 3), c = lane & 7;
+    long long n_my = (p.num_tiles > first) ? (p.num_tiles - first + step - 1) / step : 0;
+    const long long total = n_my * kNumKB;
+    float4 buf[2][8];
+    auto issue = [&](long long it, float4* v) {
+      const long long tile = first + (it >> 2) * step;
+      const int kb = (int)(it & 3);
+      const long long row0 = tile * kTileM;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = row0 + i * 16 + rsub;
+        v[i] = (row < p.M) ? ldg_stream(reinterpret_cast<const float4*>(p.A + row * p.lda + kb * kKB + c * 4))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store = [&](long long it, const float4* v) {
+      const int s = (int)(it & 1);
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      mbar_wait(a_empty(s), ph ^ 1u);
+      const uint32_t hi_base = base + kOffA + (uint32_t)s * 2 * kBlockBytes;
+      const uint32_t lo_base = hi_base + kBlockBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 hi, lo;
+        split4(v[i], hi, lo);
+        const uint32_t off = swz_off(i * 16 + rsub, c);
+        sts128(hi_base + off, hi);
+        sts128(lo_base + off, lo);
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full(s));
+    };
+    if (total > 0) issue(0, buf[0]);
+    if (total > 1) issue(1, buf[1]);
+    for (long long it = 0; it < total; it += 2) {
+      store(it, buf[0]);
+      if (it + 2 < total) issue(it + 2, buf[0]);
+      if (it + 1 < total) {
+        store(it + 1, buf[1]);
+        if (it + 3 < total) issue(it + 3, buf[1]);
+      }
+    }
+  } else if (warp == kLoaderWarps) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      long long it = 0, tcount = 0;
+      for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
+        const int d = (int)(tcount & 1);
+        const uint32_t dph = (uint32_t)((tcount >> 1) & 1);
+        mbar_wait(d_empty(d), dph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)d * kD;
+        for (int kb = 0; kb < kNumKB; ++kb, ++it) {
+          const int s = (int)(it & 1);
+          const uint32_t ph = (uint32_t)((it >> 1) & 1);
+          mbar_wait(a_full(s), ph);
+          tc_fence_after();
+          const uint32_t a_hi = base + kOffA + (uint32_t)s * 2 * kBlockBytes;
+          const uint32_t a_lo = a_hi + kBlockBytes;
+          const uint32_t b_hi = base + kOffWhi + (uint32_t)kb * kBlockBytes;
+          const uint32_t b_lo = base + kOffWlo + (uint32_t)kb * kBlockBytes;
+#pragma unroll
+          for (int k = 0; k < kKB / 8; ++k) {
+            const uint32_t ko = (uint32_t)k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
+            const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
+            const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
+            umma_tf32(d_tmem, dal, dbh, kInstrDesc, (kb | k) != 0);
+            umma_tf32(d_tmem, dah, dbl, kInstrDesc, 1);
+            umma_tf32(d_tmem, dah, dbh, kInstrDesc, 1);
+          }
+          umma_commit(a_empty(s));      // smem stage reusable once these MMAs have read it
+        }
+        umma_commit(d_full(d));         // accumulator complete
+      }
+    }
+  } else {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(sm + kOffStage) + (warp - kLoaderWarps - 1) * 32 * kStagePitch;
+    const float* s_bias = s_const;
+    const float* s_gamma = s_const + kD;
+    const float* s_beta = s_const + 2 * kD;
+    const float* s_dotw = s_const + 3 * kD;
+    long long tcount = 0;
+    for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
+      const int d = (int)(tcount & 1);
+      const uint32_t dph = (uint32_t)((tcount >> 1) & 1);
+      mbar_wait(d_full(d), dph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)d * kD + ((uint32_t)(q * 32) << 16);
+      const long long wrow0 = tile * kTileM + q * 32;     // first global row of this warp
+
+      if constexpr (MODE == MODE_ELEMENTWISE) {
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(d)); }   // accumulator drained
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const int c4 = lane & 7;
+          const int col = ch * 32 + c4 * 4;
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int lrow = j * 4 + (lane >> 3);
+            const long long grow = wrow0 + lrow;
+            if (grow < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(stg + lrow * kStagePitch + 4 * c4);
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              if (p.addend) {
+                const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow * p.ld_addend + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
+              if (p.g0) {
+                const long long gi = __ldg(p.i0 + grow);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.g0 + gi * p.ld_g0 + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
+              if (p.g1) {
+                const long long gi = __ldg(p.i1 + grow);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.g1 + gi * p.ld_g1 + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
+              if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (p.residual) {
+                const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + col));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
+              stg_stream(reinterpret_cast<float4*>(p.Y + grow * p.ldy + col), v);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // row-domain modes: the whole 128-wide row lives in this thread's registers
+        float r[kD];
+        tmem_ld32(taddr + 0, r);
+        tmem_ld32(taddr + 32, r + 32);
+        tmem_ld32(taddr + 64, r + 64);
+        tmem_ld32(taddr + 96, r + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(d_empty(d));
+        if constexpr (MODE == MODE_RELU_DOT) {
+          float acc = 0.f;
+#pragma unroll
+          for (int cidx = 0; cidx < kD; ++cidx) acc = fmaf(fmaxf(r[cidx] + s_bias[cidx], 0.f), s_dotw[cidx], acc);
+          const long long grow = wrow0 + lane;
+          if (grow < p.M) p.Y[grow * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
+        } else {
+          float s = 0.f;
+#pragma unroll
+          for (int cidx = 0; cidx < kD; ++cidx) { r[cidx] += s_bias[cidx]; s += r[cidx]; }
+          const float mu = s * (1.0f / kD);
+          float ss = 0.f;
+#pragma unroll
+          for (int cidx = 0; cidx < kD; ++cidx) { const float dlt = r[cidx] - mu; ss = fmaf(dlt, dlt, ss); }
+          const float rs = 1.0f / sqrtf(ss * (1.0f / kD) + p.eps);
+#pragma unroll
+          for (int cidx = 0; cidx < kD; ++cidx) r[cidx] = (r[cidx] - mu) * rs * s_gamma[cidx] + s_beta[cidx];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) =
+                  make_float4(r[ch * 32 + 4 * j], r[ch * 32 + 4 * j + 1], r[ch * 32 + 4 * j + 2], r[ch * 32 + 4 * j + 3]);
+            __syncwarp();
+            const int c4 = lane & 7;
+            const int col = ch * 32 + c4 * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int lrow = j * 4 + (lane >> 3);
+              const long long grow = wrow0 + lrow;
+              if (grow < p.M) {
+                float4 v = *reinterpret_cast<const float4*>(stg + lrow * kStagePitch + 4 * c4);
+                if (p.residual) {
+                  const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + col));
+                  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                }
+                stg_stream(reinterpret_cast<float4*>(p.Y + grow * p.ldy + col), v);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kLoaderWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  tc_linear_kernel<MODE><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(p);
+  return check_launch("tc_linear_kernel");
+}
+
+}  // namespace tc
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, const float* W, int64_t ldw, int N,
+                                 int transpose_w, const gnc_tc_epilogue_t* epi, float* Y, int64_t ldy,
+                                 gnc_stream_t stream) {
+  GNC_REQUIRE(K == tc::kD && N == tc::kD, "tc_linear: this engine is specialised for 128 x 128 weight tiles");
+  GNC_REQUIRE(A && W && Y && epi && M >= 0 && lda >= K && ldw >= tc::kD, "tc_linear: bad arguments");
+  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W) && ldw % 4 == 0, "tc_linear: A / W rows must be 16-byte aligned");
+  tc::Params p;
+  p.A = A; p.lda = lda; p.M = M; p.W = W; p.ldw = ldw; p.transpose_w = transpose_w;
+  p.bias = epi->bias;
+  p.addend = epi->addend; p.ld_addend = epi->ld_addend;
+  p.g0 = epi->gather0; p.i0 = epi->gather0_idx; p.ld_g0 = epi->ld_gather0;
+  p.g1 = epi->gather1; p.i1 = epi->gather1_idx; p.ld_g1 = epi->ld_gather1;
+  p.relu = epi->relu;
+  p.gamma = epi->gamma; p.beta = epi->beta; p.eps = epi->eps;
+  p.residual = epi->residual; p.ld_res = epi->ld_residual;
+  p.dot_w = epi->dot_w; p.dot_b = epi->dot_b;
+  p.Y = Y; p.ldy = ldy;
+  p.num_tiles = (M + tc::kTileM - 1) / tc::kTileM;
+  GNC_REQUIRE(!p.g0 || p.i0, "tc_linear: gather0 needs gather0_idx");
+  GNC_REQUIRE(!p.g1 || p.i1, "tc_linear: gather1 needs gather1_idx");
+  auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0); };
+  GNC_REQUIRE(ok4(p.addend, p.ld_addend) && ok4(p.g0, p.ld_g0) && ok4(p.g1, p.ld_g1) && ok4(p.residual, p.ld_res),
+              "tc_linear: addend / gather / residual rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (epi->dot_w) {
+    GNC_REQUIRE(!epi->gamma && !p.addend && !p.g0 && !p.g1 && !p.residual && epi->relu && ldy >= 1,
+                "tc_linear: dot epilogue = relu(acc + bias) . w only");
+    return tc::launch<tc::MODE_RELU_DOT>(p, st);
+  }
+  GNC_REQUIRE(ldy >= tc::kD && ldy % 4 == 0 && aligned16(Y), "tc_linear: Y rows must be 16-byte aligned");
+  if (epi->gamma) {
+    GNC_REQUIRE(epi->beta && !p.addend && !p.g0 && !p.g1 && !epi->relu, "tc_linear: LayerNorm epilogue takes bias + residual only");
+    return tc::launch<tc::MODE_LAYERNORM>(p, st);
+  }
+  return tc::launch<tc::MODE_ELEMENTWISE>(p, st);
+}

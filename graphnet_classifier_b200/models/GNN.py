@@ -164,8 +164,85 @@ class GraphNet(nn.Module):
         self.node_decoder = MLP(c["out_dim_node"], self.out_dim, c["hidden_dim_decoder"],
                                 c["hidden_layers_decoder"], norm_type=None)
 
+    # -- tensor-core inference path ------------------------------------------------
+    def _tc_eligible(self) -> bool:
+        """tcgen05 engine: every MLP is Linear(.,128)-ReLU-Linear(128,128)-ReLU-Linear(128,128|1)
+        with LayerNorm (none on the decoder), i.e. the configuration main.py builds."""
+        if ops.ENGINE != "tc":
+            return False
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return False
+        cached = getattr(self, "_tc_ok", None)
+        if cached is not None:
+            return cached
+
+        def mlp_ok(mlp, in_dim, out_dim, norm):
+            m = list(mlp.model)
+            if len(m) != (6 if norm else 5) or not all(isinstance(m[i], nn.Linear) for i in (0, 2, 4)):
+                return False
+            if not all(isinstance(m[i], nn.ReLU) for i in (1, 3)):
+                return False
+            if [tuple(m[i].weight.shape) for i in (0, 2, 4)] != [(128, in_dim), (128, 128), (out_dim, 128)]:
+                return False
+            if any(m[i].bias is None for i in (0, 2, 4)):
+                return False
+            if norm:
+                ln = m[5]
+                return isinstance(ln, nn.LayerNorm) and ln.elementwise_affine and ln.bias is not None
+            return True
+
+        ok = self.out_dim == 1 and mlp_ok(self.node_decoder, 128, 1, False)
+        ok = ok and mlp_ok(self.node_encoder, self.node_encoder.model[0].in_features, 128, True)
+        ok = ok and mlp_ok(self.edge_encoder, self.edge_encoder.model[0].in_features, 128, True)
+        for blk in self.graph_processor.blocks:
+            ok = ok and isinstance(blk.edge_model, EdgeProcessor) and isinstance(blk.node_model, NodeProcessor)
+            ok = ok and mlp_ok(blk.edge_model.edge_processor, 384, 128, True)
+            ok = ok and mlp_ok(blk.node_model.node_processor, 256, 128, True)
+        self._tc_ok = bool(ok)
+        return self._tc_ok
+
+    def _forward_tc(self, x, pos, graph: GraphIndex):
+        """Same function as ``forward`` on the 3xTF32 tensor-core engine.  The first Linear of
+        the edge processor is evaluated as ``e @ Wc.T + (h @ Wa.T)[row] + (h @ Wb.T)[col] + b``
+        - algebraically ``cat([h[row], h[col], e]) @ W0.T + b`` with the two node-side products
+        done once per node instead of once per edge - and the node processor's as
+        ``agg @ Vb.T + h @ Va.T + c``; every contraction is then a [rows,128] x [128,128] tile."""
+        tcl = ops.tc_linear
+
+        def tail(a1, mlp, residual=None):
+            m = mlp.model
+            a2 = tcl(a1, m[2].weight, bias=m[2].bias, relu=True)
+            return tcl(a2, m[4].weight, bias=m[4].bias, gamma=m[5].weight, beta=m[5].bias, eps=m[5].eps,
+                       residual=residual)
+
+        ne, ee = self.node_encoder.model, self.edge_encoder.model
+        h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder)
+        e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+        for blk in self.graph_processor.blocks:
+            em = blk.edge_model.edge_processor
+            W0, b0 = em.model[0].weight, em.model[0].bias
+            P = tcl(h, W0[:, 0:128])
+            Q = tcl(h, W0[:, 128:256])
+            a1 = tcl(e, W0[:, 256:384], bias=b0, gather0=(P, graph.src), gather1=(Q, graph.dst), relu=True)
+            del P, Q
+            e = tail(a1, em, residual=e)
+            del a1
+            nm = blk.node_model.node_processor
+            V0, c0 = nm.model[0].weight, nm.model[0].bias
+            agg = ops.aggregate(e, graph)
+            T = tcl(h, V0[:, 0:128])
+            n1 = tcl(agg, V0[:, 128:256], bias=c0, addend=T, relu=True)
+            del agg, T
+            h = tail(n1, nm, residual=h)
+            del n1
+        dec = self.node_decoder.model
+        d1 = tcl(h, dec[0].weight, bias=dec[0].bias, relu=True)
+        return tcl(d1, dec[2].weight, bias=dec[2].bias, relu=True, dot_w=dec[4].weight, dot_b=dec[4].bias)
+
     def forward(self, x, pos, edge_index):
         graph = edge_index if isinstance(edge_index, GraphIndex) else ops.graph_of(edge_index, x.size(0))
+        if x.is_cuda and self._tc_eligible():
+            return self._forward_tc(x, pos, graph)
         edge_attr = ops.edge_geometry(pos, graph)          # [pos[col]-pos[row], L1]  (reference :299-302)
         out = self.node_encoder(x)
         edge_attr = self.edge_encoder(edge_attr)

@@ -20,8 +20,15 @@ from typing import Optional, Sequence
 import torch
 from torch import Tensor
 
+import os
+
 from . import _lib
-from ._lib import GncSeg, check
+from ._lib import GncSeg, GncTcEpilogue, check
+
+# Dense engine for width-128 layers: "tc" = tcgen05 3xTF32 kernels (csrc/tc_linear.cu),
+# "fp32" = CUDA-core GEMM (csrc/dense.cu).  Both meet the 1e-5 parity bar; "fp32" is the
+# implementation the tensor-core path is tested against.
+ENGINE = os.environ.get("GNC_ENGINE", "tc")
 
 
 def _require_cuda(*ts: Tensor) -> None:
@@ -430,3 +437,64 @@ def scatter_sum(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int
     if int(bad.item()) != 0:
         raise IndexError(f"scatter_sum: index out of range for dim_size {N}")
     return _ScatterSumFn.apply(src, rowptr, eid, key32, N)
+
+
+# ----------------------------------------------------------------------------
+# tensor-core engine (no autograd: used by the inference path)
+# ----------------------------------------------------------------------------
+def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional[Tensor] = None,
+              addend: Optional[Tensor] = None, gather0=None, gather1=None, relu: bool = False,
+              gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
+              residual: Optional[Tensor] = None, dot_w: Optional[Tensor] = None,
+              dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """``epilogue(A @ W.T)`` on the tcgen05 3xTF32 engine (``A @ W`` with transpose_w).
+    ``gather0`` / ``gather1`` are ``(rows [R, 128], idx int32 [M])`` pairs added row-wise as
+    ``rows[idx[m]]``.  See include/gnc.h ``gnc_tc_epilogue_t`` for the epilogue algebra."""
+    _require_cuda(A, W)
+    A = _rows(A)
+    M, K = A.shape
+    N = W.shape[1] if transpose_w else W.shape[0]
+    if W.stride(1) != 1:
+        W = W.contiguous()
+    epi = GncTcEpilogue()
+    keep = []
+
+    def rows(t):
+        t = _rows(t)
+        keep.append(t)
+        return t
+
+    if bias is not None:
+        epi.bias = bias.data_ptr()
+    if addend is not None:
+        t = rows(addend)
+        epi.addend, epi.ld_addend = t.data_ptr(), _ld(t)
+    if gather0 is not None:
+        t = rows(gather0[0])
+        epi.gather0, epi.gather0_idx, epi.ld_gather0 = t.data_ptr(), gather0[1].data_ptr(), _ld(t)
+    if gather1 is not None:
+        t = rows(gather1[0])
+        epi.gather1, epi.gather1_idx, epi.ld_gather1 = t.data_ptr(), gather1[1].data_ptr(), _ld(t)
+    epi.relu = int(bool(relu))
+    if gamma is not None:
+        epi.gamma, epi.beta, epi.eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
+    if residual is not None:
+        t = rows(residual)
+        epi.residual, epi.ld_residual = t.data_ptr(), _ld(t)
+    if dot_w is not None:
+        dw = dot_w.reshape(-1)
+        if dw.stride(0) != 1:
+            dw = dw.contiguous()
+        keep.append(dw)
+        epi.dot_w = dw.data_ptr()
+        epi.dot_b = None if dot_b is None else dot_b.data_ptr()
+    n_out = 1 if dot_w is not None else N
+    if out is None:
+        out = torch.empty(M, n_out, dtype=torch.float32, device=A.device)
+    nbytes = 4.0 * (M * K + M * n_out + N * K
+                    + M * 128 * ((addend is not None) + (gather0 is not None) + (gather1 is not None)
+                                 + (residual is not None)))
+    check(_call("tc_linear", 2.0 * M * N * K, nbytes, _lib.load().gnc_tc_linear_f32, A.data_ptr(), _ld(A), M, K,
+                W.data_ptr(), W.stride(0), N, int(transpose_w), ctypes.byref(epi), out.data_ptr(), _ld(out),
+                _stream()), "tc_linear")
+    return out

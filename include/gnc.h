@@ -190,6 +190,32 @@ int gnc_layernorm_bwd_f32(const float* dy, int64_t lddy, const float* z, int64_t
                           float* dgamma, float* dbeta, int accumulate,
                           float* work, int64_t work_elems, gnc_stream_t stream);
 
+/* ---- tensor-core engine (tcgen05, 3xTF32) for width-128 layers ----------------- */
+
+/* Epilogue of gnc_tc_linear_f32.  With acc = A * B^T (fp32-accurate, see csrc/tc_linear.cu):
+ *   dot_w != NULL : Y[m, 0] = relu(acc + bias) . dot_w + *dot_b         (decoder tail, models/GNN.py:289-295)
+ *   gamma != NULL : Y = LayerNorm(acc + bias; gamma, beta, eps) + residual[m]   (models/MLP.py:34-35, GNN.py:62,102)
+ *   otherwise     : Y = act(acc + bias + addend[m] + gather0[gather0_idx[m]] + gather1[gather1_idx[m]])
+ *                       + residual[m],  act = relu if relu != 0
+ * Every pointer may be NULL (term absent).  Rows of addend / gather / residual are 128 wide. */
+typedef struct gnc_tc_epilogue {
+  const float* bias;
+  const float* addend;  int64_t ld_addend;
+  const float* gather0; const int32_t* gather0_idx; int64_t ld_gather0;
+  const float* gather1; const int32_t* gather1_idx; int64_t ld_gather1;
+  int32_t relu; int32_t _pad0;
+  const float* gamma; const float* beta; float eps; int32_t _pad1;
+  const float* residual; int64_t ld_residual;
+  const float* dot_w; const float* dot_b;
+} gnc_tc_epilogue_t;
+
+/* Y[M, N] = epilogue( A[M, K] * B^T ), B = W[N, K] (transpose_w = 0) or B = W^T with W[K, N]
+ * (transpose_w = 1: the data gradient dX = dZ * W).  K = N = 128 only (GNC_EINVAL otherwise:
+ * callers fall back to gnc_linear_*_f32).  epi is a HOST pointer. */
+int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K,
+                      const float* W, int64_t ldw, int N, int transpose_w,
+                      const gnc_tc_epilogue_t* epi /*HOST*/, float* Y, int64_t ldy, gnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""GPU: the tcgen05 3xTF32 engine (csrc/tc_linear.cu) against fp64 and against the fp32
+CUDA-core engine, per epilogue mode and end to end, at the north_star tolerance (1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn as ognn
+from oracle import graph_build as ogb
+from oracle.weights import fill_deterministic, synthetic_images
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _maxrel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("M", [1, 100, 128, 129, 1000, 128 * 148 + 77, 128 * 148 * 3 + 5])
+def test_plain_and_bias_relu(libgnc, M):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    A = torch.randn(M, 128, generator=gen) * 3
+    W = torch.randn(128, 128, generator=gen) / 11
+    b = torch.randn(128, generator=gen)
+    Ac, Wc, bc = A.cuda(), W.cuda(), b.cuda()
+    ref = A.double() @ W.double().t()
+    got = ops.tc_linear(Ac, Wc)
+    assert _rel(got, ref) < 2e-6 and _maxrel(got, ref) < RTOL
+    got = ops.tc_linear(Ac, Wc, bias=bc, relu=True)
+    assert _maxrel(got, torch.relu(ref + b.double())) < RTOL
+    # data-gradient form: A @ W (W used transposed)
+    got = ops.tc_linear(Ac, Wc, transpose_w=True)
+    assert _maxrel(got, A.double() @ W.double()) < RTOL
+
+
+def test_weight_slice_gathered_addends_and_residual(libgnc):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    M, R = 3000, 700
+    A = torch.randn(M, 128, generator=gen)
+    W = torch.randn(128, 384, generator=gen) / 20        # column slice of a wider weight (ldw = 384)
+    b = torch.randn(128, generator=gen)
+    P, Q = torch.randn(R, 128, generator=gen), torch.randn(R, 128, generator=gen)
+    i0, i1 = torch.randint(0, R, (M,), generator=gen), torch.randint(0, R, (M,), generator=gen)
+    T, res = torch.randn(M, 128, generator=gen), torch.randn(M, 128, generator=gen)
+    Wc = W.cuda()
+    got = ops.tc_linear(A.cuda(), Wc[:, 256:384], bias=b.cuda(), addend=T.cuda(),
+                        gather0=(P.cuda(), i0.int().cuda()), gather1=(Q.cuda(), i1.int().cuda()), relu=True,
+                        residual=res.cuda())
+    ref = torch.relu(A.double() @ W[:, 256:384].double().t() + b.double() + T.double() + P.double()[i0] + Q.double()[i1]) + res.double()
+    assert _maxrel(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("M,res", [(5, False), (777, True), (128 * 300, True)])
+def test_layernorm_epilogue(libgnc, M, res):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    A = torch.randn(M, 128, generator=gen)
+    W = torch.randn(128, 128, generator=gen) / 8
+    b = torch.randn(128, generator=gen)
+    g, be = 1 + 0.1 * torch.randn(128, generator=gen), 0.1 * torch.randn(128, generator=gen)
+    r = torch.randn(M, 128, generator=gen) if res else None
+    got = ops.tc_linear(A.cuda(), W.cuda(), bias=b.cuda(), gamma=g.cuda(), beta=be.cuda(), eps=1e-5,
+                        residual=r.cuda() if res else None)
+    ref = torch.nn.functional.layer_norm(A.double() @ W.double().t() + b.double(), (128,), g.double(), be.double(), 1e-5)
+    if res:
+        ref = ref + r.double()
+    assert _maxrel(got, ref) < RTOL
+
+
+def test_relu_dot_epilogue(libgnc):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    M = 20000
+    A = torch.randn(M, 128, generator=gen)
+    W = torch.randn(128, 128, generator=gen) / 8
+    b, w2, b2 = torch.randn(128, generator=gen), torch.randn(1, 128, generator=gen), torch.randn(1, generator=gen)
+    got = ops.tc_linear(A.cuda(), W.cuda(), bias=b.cuda(), relu=True, dot_w=w2.cuda(), dot_b=b2.cuda())
+    ref = torch.relu(A.double() @ W.double().t() + b.double()) @ w2.double().t() + b2.double()
+    assert got.shape == (M, 1) and _maxrel(got, ref) < RTOL
+
+
+def test_error_is_fp32_class_not_tf32_class(libgnc):
+    # 3xTF32 must sit with the fp32 engine (~1e-7), far from single-pass TF32 (~1e-3 on these inputs)
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    A, W = torch.randn(4096, 128, generator=gen), torch.randn(128, 128, generator=gen)
+    ref = A.double() @ W.double().t()
+    e_tc = _rel(ops.tc_linear(A.cuda(), W.cuda()), ref)
+    e_fp32 = _rel(ops.linear([A.cuda()], W.cuda(), None), ref)
+    print("rel err tc", e_tc, "fp32", e_fp32)
+    assert e_tc < 1e-6 and e_tc < 20 * max(e_fp32, 5e-8), (e_tc, e_fp32)
+
+
+@pytest.mark.parametrize("r,diag,B", [(8, False, 3), (12, True, 2), (32, False, 5)])
+def test_model_tc_engine_vs_oracle_and_fp32_engine(libgnc, monkeypatch, r, diag, B):
+    from graphnet_classifier_b200 import ops
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
+    om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=r * r, classes=2)
+    fill_deterministic(om, seed=5)
+    gm = CombinedModel(GraphNet(**cfg), num_nodes=r * r, classes=2)
+    gm.load_state_dict(om.state_dict())
+    gm = gm.cuda().eval()
+    imgs = synthetic_images(B, r, seed=r)
+    gb = build_pixel_graphs(torch.from_numpy(imgs), diagonals=diag)
+    with torch.no_grad():
+        monkeypatch.setattr(ops, "ENGINE", "tc")
+        assert gm.graph_net._tc_eligible()
+        out_tc = gm(gb.as_tuple())
+        y_tc = gm.graph_net(*gb.as_tuple())
+        monkeypatch.setattr(ops, "ENGINE", "fp32")
+        assert not gm.graph_net._tc_eligible()
+        out_fp = gm(gb.as_tuple())
+        exp = torch.stack([om(ogb.to_model_inputs(*ogb.pixel_graph(im, diag))) for im in imgs])
+        y_or = torch.cat([om.graph_net(*ogb.to_model_inputs(*ogb.pixel_graph(im, diag))) for im in imgs])
+    np.testing.assert_allclose(out_tc.cpu().numpy(), exp.numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(out_fp.cpu().numpy(), exp.numpy(), rtol=RTOL, atol=1e-7)
+    assert _maxrel(y_tc, y_or) < RTOL          # node-level decoder outputs, not only the 2 logits
