@@ -6,17 +6,21 @@
 // every operand is split a = hi + lo with hi = tf32(a), lo = tf32(a - hi) and each product
 // is three kind::tf32 MMAs (lo*hi, hi*lo, hi*hi) accumulated in fp32 in TMEM: error ~2^-22.
 //
-// One persistent CTA per SM, 9 warps, three roles connected by mbarriers:
-//   warps 0-3  loader   : coalesced 128-bit global loads of A rows (two K-blocks prefetched
-//                         in registers), hi/lo split, store into the UMMA K-major SWIZZLE_128B
-//                         smem image (2 stages x {hi,lo} x 16 KB)
-//   warp  4    MMA      : one elected thread issues tcgen05.mma (M=128,N=128,K=8), A and B
-//                         from smem descriptors; B (the weights, hi+lo = 128 KB) is built
-//                         once per CTA and stays resident; accumulators double-buffered in
-//                         TMEM (2 x 128 columns) so the epilogue of tile i overlaps tile i+1
-//   warps 5-8  epilogue : tcgen05.ld (thread = row), row-domain math (bias, LayerNorm, dot),
-//                         warp-local transpose through smem, then coalesced 128-bit global
-//                         traffic for addends / residual / output.
+// One persistent CTA per SM, 20 warps in 5 warpgroups, three roles connected by mbarriers
+// (register budget rebalanced with setmaxnreg: loaders 64, MMA group 40, epilogue 232):
+//   warps 0-11  loaders  : three groups of four warps; group g owns K-block stages
+//                          it = g (mod 3), so three independent batches of coalesced 128-bit
+//                          global loads (48 KB per SM) are in flight while only two smem
+//                          stages exist; each batch is split hi/lo in registers and stored
+//                          into the UMMA K-major SWIZZLE_128B image (2 stages x {hi,lo} x 16 KB)
+//   warp  12    MMA      : one thread issues tcgen05.mma (M=128,N=128,K=8), A and B from smem
+//                          descriptors; B (the weights, hi+lo = 128 KB) is built once per CTA
+//                          and stays resident; accumulators double-buffered in TMEM
+//                          (2 x 128 columns) so the epilogue of tile i overlaps tile i+1
+//   warps 16-19 epilogue : tcgen05.ld (thread = row), row-domain math (bias, LayerNorm, dot),
+//                          warp-local transpose through smem, then coalesced 128-bit global
+//                          traffic for addends / residual / output, with the global loads of a
+//                          chunk issued as one batch and prefetched one chunk ahead.
 //
 // Reference semantics covered (models/MLP.py:24-37, models/GNN.py:57-64, 95-104, 289-295):
 //   MODE_ELEMENTWISE: y = act(acc + bias + addend[m] + g0[i0[m]] + g1[i1[m]]) + residual[m]
@@ -33,8 +37,13 @@ constexpr int kKB = 32;                 // fp32 elements per K-block = one 128-b
 constexpr int kNumKB = kD / kKB;        // 4
 constexpr int kStages = 2;
 constexpr int kBlockBytes = kTileM * kKB * 4;   // 16 KB: one operand K-block image
-constexpr int kLoaderWarps = 4, kEpiWarps = 4;
-constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;   // 288
+constexpr int kLoaderGroups = 3;                    // independent load batches in flight
+constexpr int kLoaderWarps = 4 * kLoaderGroups;     // warps 0..11
+constexpr int kMmaWarp = kLoaderWarps;              // warp 12 (warps 13-15 idle: warpgroup padding)
+constexpr int kEpiWarp0 = kLoaderWarps + 4;         // warps 16..19
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (kLoaderWarps + 4 + kEpiWarps) * 32;   // 640
+constexpr int kRegsLoader = 64, kRegsMma = 40, kRegsEpi = 232;
 constexpr int kStagePitch = 36;         // floats per staged row (16-byte aligned, conflict-free)
 constexpr int kTmemCols = 256;          // two fp32 accumulators of 128 columns
 
@@ -147,6 +156,13 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
 }
 
 // ---- the kernel -------------------------------------------------------------------
+template <int REGS>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -166,11 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
 
   // ---- one-time setup ----------------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(a_full(s), kLoaderWarps * 32); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
     for (int d = 0; d < 2; ++d) { mbar_init(d_full(d), 1); mbar_init(d_empty(d), kEpiWarps * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kLoaderWarps) {   // the MMA warp owns the TMEM allocation
+  if (warp == kMmaWarp) {   // the MMA warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -207,28 +223,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   const uint32_t tmem_base = *tmem_slot;
 
   const long long first = blockIdx.x, step = gridDim.x;
+  const long long n_my = (p.num_tiles > first) ? (p.num_tiles - first + step - 1) / step : 0;
 
   if (warp < kLoaderWarps) {
-    // ======================= loader =======================
-    const int rsub = warp * 4 + (lane >> 3), c = lane & 7;
-    long long n_my = (p.num_tiles > first) ? (p.num_tiles - first + step - 1) / step : 0;
+    // ======================= loaders =======================
+    reg_dec<kRegsLoader>();
+    const int group = warp >> 2, w4 = warp & 3;
+    const int rsub = w4 * 4 + (lane >> 3), c = lane & 7;
     const long long total = n_my * kNumKB;
-    float4 buf[2][8];
-    auto issue = [&](long long it, float4* v) {
+    for (long long it = group; it < total; it += kLoaderGroups) {
       const long long tile = first + (it >> 2) * step;
       const int kb = (int)(it & 3);
       const long long row0 = tile * kTileM;
+      float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long row = row0 + i * 16 + rsub;
         v[i] = (row < p.M) ? ldg_stream(reinterpret_cast<const float4*>(p.A + row * p.lda + kb * kKB + c * 4))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    };
-    auto store = [&](long long it, const float4* v) {
       const int s = (int)(it & 1);
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      // Parity waits are only unambiguous when the waiter is at most one phase ahead of the
+      // barrier, but a loader group may run several K-blocks ahead.  The groups therefore
+      // take turns: group(it) may look at a_empty only after group(it-1) has passed its own
+      // wait (named barriers 1..3: 128 arriving + 128 waiting threads).  Loads are already in
+      // flight at this point, so the turn-taking costs no memory-level parallelism.
+      if (it > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)(it % kLoaderGroups)) : "memory");
       mbar_wait(a_empty(s), ph ^ 1u);
+      if (it + 1 < total) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (int)((it + 1) % kLoaderGroups)) : "memory");
       const uint32_t hi_base = base + kOffA + (uint32_t)s * 2 * kBlockBytes;
       const uint32_t lo_base = hi_base + kBlockBytes;
 #pragma unroll
@@ -241,20 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
       }
       fence_proxy_async();
       mbar_arrive(a_full(s));
-    };
-    if (total > 0) issue(0, buf[0]);
-    if (total > 1) issue(1, buf[1]);
-    for (long long it = 0; it < total; it += 2) {
-      store(it, buf[0]);
-      if (it + 2 < total) issue(it + 2, buf[0]);
-      if (it + 1 < total) {
-        store(it + 1, buf[1]);
-        if (it + 3 < total) issue(it + 3, buf[1]);
-      }
     }
-  } else if (warp == kLoaderWarps) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+  } else if (warp < kEpiWarp0) {
+    // ======================= MMA issuer (warp 12; warps 13-15 pad the warpgroup) =======================
+    reg_dec<kRegsMma>();
+    if (warp == kMmaWarp && lane == 0) {
       long long it = 0, tcount = 0;
       for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
         const int d = (int)(tcount & 1);
@@ -285,24 +299,69 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
         umma_commit(d_full(d));         // accumulator complete
       }
     }
+    __syncwarp();
   } else {
     // ======================= epilogue =======================
+    reg_inc<kRegsEpi>();
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(sm + kOffStage) + (warp - kLoaderWarps - 1) * 32 * kStagePitch;
+    float* stg = reinterpret_cast<float*>(sm + kOffStage) + (warp - kEpiWarp0) * 32 * kStagePitch;
     const float* s_bias = s_const;
     const float* s_gamma = s_const + kD;
     const float* s_beta = s_const + 2 * kD;
     const float* s_dotw = s_const + 3 * kD;
+    const int c4 = lane & 7, rl = lane >> 3;        // coalesced domain: 8 lanes per row, 4 rows per pass
     long long tcount = 0;
     for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
       const int d = (int)(tcount & 1);
       const uint32_t dph = (uint32_t)((tcount >> 1) & 1);
-      mbar_wait(d_full(d), dph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)d * kD + ((uint32_t)(q * 32) << 16);
       const long long wrow0 = tile * kTileM + q * 32;     // first global row of this warp
+      // rows this lane touches in the coalesced domain (clamped: loads stay in bounds, stores are guarded)
+      long long grow[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long g = wrow0 + j * 4 + rl;
+        grow[j] = g < p.M ? g : p.M - 1;
+      }
 
       if constexpr (MODE == MODE_ELEMENTWISE) {
+        // gather indices of this lane's rows: loaded once per tile, before the accumulator is ready
+        long long gi0[8], gi1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gi0[j] = p.g0 ? (long long)__ldg(p.i0 + grow[j]) : 0;
+          gi1[j] = p.g1 ? (long long)__ldg(p.i1 + grow[j]) : 0;
+        }
+        // ext[j] = sum of the addend terms of (row j, this lane's 4 columns) for one chunk
+        auto load_ext = [&](int ch, float4* ext) {
+          const int col = ch * 32 + c4 * 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.addend) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow[j] * p.ld_addend + col));
+          }
+          if (p.g0) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(p.g0 + gi0[j] * p.ld_g0 + col));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) add4(ext[j], t[j]);
+          }
+          if (p.g1) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(p.g1 + gi1[j] * p.ld_g1 + col));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) add4(ext[j], t[j]);
+          }
+        };
+        const bool has_ext = p.addend || p.g0 || p.g1;
+        float4 ext[8];
+        if (has_ext) load_ext(0, ext);                 // overlaps the wait for the accumulator
+        mbar_wait(d_full(d), dph);
+        tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           float r[32];
@@ -313,42 +372,56 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
-          const int c4 = lane & 7;
           const int col = ch * 32 + c4 * 4;
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col);
+          float4 res[8];
+          if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col));
+          }
+          float4 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int lrow = j * 4 + (lane >> 3);
-            const long long grow = wrow0 + lrow;
-            if (grow < p.M) {
-              float4 v = *reinterpret_cast<const float4*>(stg + lrow * kStagePitch + 4 * c4);
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              if (p.addend) {
-                const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow * p.ld_addend + col));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-              }
-              if (p.g0) {
-                const long long gi = __ldg(p.i0 + grow);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.g0 + gi * p.ld_g0 + col));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-              }
-              if (p.g1) {
-                const long long gi = __ldg(p.i1 + grow);
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.g1 + gi * p.ld_g1 + col));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-              }
-              if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              if (p.residual) {
-                const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + col));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-              }
-              stg_stream(reinterpret_cast<float4*>(p.Y + grow * p.ldy + col), v);
-            }
+            v[j] = *reinterpret_cast<const float4*>(stg + (j * 4 + rl) * kStagePitch + 4 * c4);
+            add4(v[j], b4);
+            if (has_ext) add4(v[j], ext[j]);
           }
-          __syncwarp();
+          __syncwarp();                                // staging tile free for the next chunk
+          if (has_ext && ch < 3) load_ext(ch + 1, ext); // next chunk's addends fly during this chunk's stores
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (p.relu) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
+            if (p.residual) add4(v[j], res[j]);
+            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
+          }
         }
+      } else if constexpr (MODE == MODE_RELU_DOT) {
+        mbar_wait(d_full(d), dph);
+        tc_fence_after();
+        float acc = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(d)); }
+#pragma unroll
+          for (int cidx = 0; cidx < 32; ++cidx)
+            acc = fmaf(fmaxf(r[cidx] + s_bias[ch * 32 + cidx], 0.f), s_dotw[ch * 32 + cidx], acc);
+        }
+        const long long g = wrow0 + lane;
+        if (g < p.M) p.Y[g * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
       } else {
-        // row-domain modes: the whole 128-wide row lives in this thread's registers
+        // LayerNorm: the whole 128-wide row lives in this thread's registers
+        float4 res[8];
+        if (p.residual) {                               // chunk 0 of the residual, ahead of the accumulator
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + c4 * 4));
+        }
+        mbar_wait(d_full(d), dph);
+        tc_fence_after();
         float r[kD];
         tmem_ld32(taddr + 0, r);
         tmem_ld32(taddr + 32, r + 32);
@@ -357,47 +430,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(d_empty(d));
-        if constexpr (MODE == MODE_RELU_DOT) {
-          float acc = 0.f;
+        float s = 0.f;
 #pragma unroll
-          for (int cidx = 0; cidx < kD; ++cidx) acc = fmaf(fmaxf(r[cidx] + s_bias[cidx], 0.f), s_dotw[cidx], acc);
-          const long long grow = wrow0 + lane;
-          if (grow < p.M) p.Y[grow * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
-        } else {
-          float s = 0.f;
+        for (int cidx = 0; cidx < kD; ++cidx) { r[cidx] += s_bias[cidx]; s += r[cidx]; }
+        const float mu = s * (1.0f / kD);
+        float ss = 0.f;
 #pragma unroll
-          for (int cidx = 0; cidx < kD; ++cidx) { r[cidx] += s_bias[cidx]; s += r[cidx]; }
-          const float mu = s * (1.0f / kD);
-          float ss = 0.f;
+        for (int cidx = 0; cidx < kD; ++cidx) { const float dlt = r[cidx] - mu; ss = fmaf(dlt, dlt, ss); }
+        const float rs = 1.0f / sqrtf(ss * (1.0f / kD) + p.eps);
 #pragma unroll
-          for (int cidx = 0; cidx < kD; ++cidx) { const float dlt = r[cidx] - mu; ss = fmaf(dlt, dlt, ss); }
-          const float rs = 1.0f / sqrtf(ss * (1.0f / kD) + p.eps);
+        for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
-          for (int cidx = 0; cidx < kD; ++cidx) r[cidx] = (r[cidx] - mu) * rs * s_gamma[cidx] + s_beta[cidx];
+          for (int j = 0; j < 8; ++j) {
+            const int cb = ch * 32 + 4 * j;
+            float4 o;
+            o.x = (r[cb + 0] - mu) * rs * s_gamma[cb + 0] + s_beta[cb + 0];
+            o.y = (r[cb + 1] - mu) * rs * s_gamma[cb + 1] + s_beta[cb + 1];
+            o.z = (r[cb + 2] - mu) * rs * s_gamma[cb + 2] + s_beta[cb + 2];
+            o.w = (r[cb + 3] - mu) * rs * s_gamma[cb + 3] + s_beta[cb + 3];
+            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = o;
+          }
+          __syncwarp();
+          const int col = ch * 32 + c4 * 4;
+          float4 v[8];
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int j = 0; j < 8; ++j) {
+            v[j] = *reinterpret_cast<const float4*>(stg + (j * 4 + rl) * kStagePitch + 4 * c4);
+            if (p.residual) add4(v[j], res[j]);
+          }
+          __syncwarp();
+          if (p.residual && ch < 3) {                   // next chunk's residual flies during these stores
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) =
-                  make_float4(r[ch * 32 + 4 * j], r[ch * 32 + 4 * j + 1], r[ch * 32 + 4 * j + 2], r[ch * 32 + 4 * j + 3]);
-            __syncwarp();
-            const int c4 = lane & 7;
-            const int col = ch * 32 + c4 * 4;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int lrow = j * 4 + (lane >> 3);
-              const long long grow = wrow0 + lrow;
-              if (grow < p.M) {
-                float4 v = *reinterpret_cast<const float4*>(stg + lrow * kStagePitch + 4 * c4);
-                if (p.residual) {
-                  const float4 t = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow * p.ld_res + col));
-                  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                }
-                stg_stream(reinterpret_cast<float4*>(p.Y + grow * p.ldy + col), v);
-              }
-            }
-            __syncwarp();
+              res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col + 32));
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
         }
       }
     }
@@ -406,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   // ---- teardown ---------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == kLoaderWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
   }
