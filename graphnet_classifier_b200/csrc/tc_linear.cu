@@ -6,21 +6,25 @@
 // every operand is split a = hi + lo with hi = tf32(a), lo = tf32(a - hi) and each product
 // is three kind::tf32 MMAs (lo*hi, hi*lo, hi*hi) accumulated in fp32 in TMEM: error ~2^-22.
 //
-// One persistent CTA per SM, 20 warps in 5 warpgroups, three roles connected by mbarriers
-// (register budget rebalanced with setmaxnreg: loaders 64, MMA group 40, epilogue 232):
-//   warps 0-11  loaders  : three groups of four warps; group g owns K-block stages
-//                          it = g (mod 3), so three independent batches of coalesced 128-bit
-//                          global loads (48 KB per SM) are in flight while only two smem
-//                          stages exist; each batch is split hi/lo in registers and stored
-//                          into the UMMA K-major SWIZZLE_128B image (2 stages x {hi,lo} x 16 KB)
-//   warp  12    MMA      : one thread issues tcgen05.mma (M=128,N=128,K=8), A and B from smem
-//                          descriptors; B (the weights, hi+lo = 128 KB) is built once per CTA
-//                          and stays resident; accumulators double-buffered in TMEM
-//                          (2 x 128 columns) so the epilogue of tile i overlaps tile i+1
-//   warps 16-19 epilogue : tcgen05.ld (thread = row), row-domain math (bias, LayerNorm, dot),
-//                          warp-local transpose through smem, then coalesced 128-bit global
-//                          traffic for addends / residual / output, with the global loads of a
-//                          chunk issued as one batch and prefetched one chunk ahead.
+// One persistent CTA per SM, 16 warps in 4 warpgroups, three roles connected by mbarriers
+// (register budget rebalanced with setmaxnreg: loaders 64, MMA group 40, epilogue 192):
+//   warps 0-3   loaders  : warp q owns rows 32q..32q+31 of every tile (= its TMEM lane quarter).
+//                          K-blocks (32 rows x 128 B) are copied global -> smem with cp.async
+//                          (no registers, no scoreboard coupling) into a ring of 3 private
+//                          transpose tiles, so 48 KB per SM is always in flight; the warp then
+//                          reads its tile with thread = row, splits hi/lo and writes the A operand
+//                          straight into TMEM with tcgen05.st (4 stages x {hi,lo} x 32 columns).
+//   warp  4     MMA      : one thread issues tcgen05.mma (M=128,N=128,K=8) with A from TMEM and B
+//                          from smem descriptors; B (the weights, hi+lo = 128 KB, K-major
+//                          SWIZZLE_128B) is built once per CTA and stays resident, so the only
+//                          shared-memory traffic of the MMAs is the weight reads.  Accumulators are
+//                          double-buffered in TMEM (2 x 128 columns).
+//   warps 8-15  epilogue : two groups, group e drains accumulator buffer e (alternate tiles), so a
+//                          tile's epilogue may take two MMA periods.  tcgen05.ld (thread = row),
+//                          row-domain math (bias, LayerNorm statistics, dot), warp-local transpose
+//                          through smem, then coalesced 128-bit global traffic for addends /
+//                          residual / output; the global loads of a chunk are issued as one batch,
+//                          one chunk ahead.
 //
 // Reference semantics covered (models/MLP.py:24-37, models/GNN.py:57-64, 95-104, 289-295):
 //   MODE_ELEMENTWISE: y = act(acc + bias + addend[m] + g0[i0[m]] + g1[i1[m]]) + residual[m]
@@ -35,26 +39,33 @@ constexpr int kTileM = 128;
 constexpr int kD = 128;
 constexpr int kKB = 32;                 // fp32 elements per K-block = one 128-byte swizzle row
 constexpr int kNumKB = kD / kKB;        // 4
-constexpr int kStages = 2;
-constexpr int kBlockBytes = kTileM * kKB * 4;   // 16 KB: one operand K-block image
-constexpr int kLoaderGroups = 3;                    // independent load batches in flight
-constexpr int kLoaderWarps = 4 * kLoaderGroups;     // warps 0..11
-constexpr int kMmaWarp = kLoaderWarps;              // warp 12 (warps 13-15 idle: warpgroup padding)
-constexpr int kEpiWarp0 = kLoaderWarps + 4;         // warps 16..19
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = (kLoaderWarps + 4 + kEpiWarps) * 32;   // 640
-constexpr int kRegsLoader = 64, kRegsMma = 40, kRegsEpi = 232;
+constexpr int kAStages = 4;             // TMEM A-operand stages
+constexpr int kBlockBytes = kTileM * kKB * 4;   // 16 KB: one weight K-block image
+constexpr int kLoaderWarps = 4;                     // warps 0..3: one per TMEM lane quarter
+constexpr int kLoadBufs = 3;                        // cp.async transpose tiles in flight per loader warp
+constexpr int kMmaWarp = kLoaderWarps;              // warp 4 (warps 5-7 pad the warpgroup)
+constexpr int kEpiWarp0 = kLoaderWarps + 4;         // warps 8..15
+constexpr int kEpiGroups = 2;
+constexpr int kEpiWarps = 4 * kEpiGroups;
+constexpr int kThreads = (kLoaderWarps + 4 + kEpiWarps) * 32;   // 512
+constexpr int kRegsLaunch = 128;        // 65536 / 512 threads
+constexpr int kRegsLoader = 64, kRegsMma = 40, kRegsEpi = 192;
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x launch
+// registers), not the whole SM file: an inc that does not fit blocks forever.
+static_assert(32 * (kLoaderWarps * kRegsLoader + 4 * kRegsMma + kEpiWarps * kRegsEpi) <= kThreads * kRegsLaunch,
+              "setmaxnreg budget exceeds the CTA's register pool");
 constexpr int kStagePitch = 36;         // floats per staged row (16-byte aligned, conflict-free)
-constexpr int kTmemCols = 256;          // two fp32 accumulators of 128 columns
+constexpr int kTmemCols = 512;          // [0,256): two fp32 accumulators; [256,512): 4 A stages x (hi 32 | lo 32)
+constexpr int kTmemA = 256;
 
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int kOffWhi = 0;
-constexpr int kOffWlo = kOffWhi + kNumKB * kBlockBytes;                 //  65536
-constexpr int kOffA = kOffWlo + kNumKB * kBlockBytes;                   // 131072: [stage][hi|lo][16 KB]
-constexpr int kOffStage = kOffA + kStages * 2 * kBlockBytes;            // 196608
-constexpr int kOffConst = kOffStage + kEpiWarps * 32 * kStagePitch * 4; // 215040: bias,gamma,beta,dotw
-constexpr int kOffBar = kOffConst + 4 * kD * 4;                         // 217088
-constexpr int kSmemBytes = kOffBar + 128 + 1024;                        // + alignment slack
+constexpr int kOffWlo = kOffWhi + kNumKB * kBlockBytes;                   //  65536
+constexpr int kOffXpose = kOffWlo + kNumKB * kBlockBytes;                 // 131072: loader transpose tiles
+constexpr int kOffStage = kOffXpose + kLoaderWarps * kLoadBufs * 32 * kStagePitch * 4; // 186368: epilogue transpose tiles
+constexpr int kOffConst = kOffStage + kEpiWarps * 32 * kStagePitch * 4;   // 223232: bias,gamma,beta,dotw
+constexpr int kOffBar = kOffConst + 4 * kD * 4;                           // 225280
+constexpr int kSmemBytes = kOffBar + 128 + 1024;                          // + alignment slack = 226432
 
 enum { MODE_ELEMENTWISE = 0, MODE_LAYERNORM = 1, MODE_RELU_DOT = 2 };
 
@@ -106,6 +117,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from smem
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* r) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(r);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,20 +203,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_const = reinterpret_cast<float*>(sm + kOffConst);
   const uint32_t bar0 = base + kOffBar;
-  // barrier slots (8 bytes each): a_full[2] a_empty[2] d_full[2] d_empty[2]; then the TMEM base pointer
+  // barrier slots (8 bytes each): a_full[4] a_empty[4] d_full[2] d_empty[2]; then the TMEM base pointer
   auto a_full = [&](int s) { return bar0 + 8u * s; };
-  auto a_empty = [&](int s) { return bar0 + 16u + 8u * s; };
-  auto d_full = [&](int d) { return bar0 + 32u + 8u * d; };
-  auto d_empty = [&](int d) { return bar0 + 48u + 8u * d; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 64);
+  auto a_empty = [&](int s) { return bar0 + 32u + 8u * s; };
+  auto d_full = [&](int d) { return bar0 + 64u + 8u * d; };
+  auto d_empty = [&](int d) { return bar0 + 80u + 8u * d; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 96);
 
   // ---- one-time setup ----------------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
-    for (int d = 0; d < 2; ++d) { mbar_init(d_full(d), 1); mbar_init(d_empty(d), kEpiWarps * 32); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(a_full(s), kLoaderWarps * 32); mbar_init(a_empty(s), 1); }
+    for (int d = 0; d < 2; ++d) { mbar_init(d_full(d), 1); mbar_init(d_empty(d), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {   // the MMA warp owns the TMEM allocation
+  if (warp == kMmaWarp) {   // the MMA warp owns the TMEM allocation (all 512 columns: one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -228,73 +258,97 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   if (warp < kLoaderWarps) {
     // ======================= loaders =======================
     reg_dec<kRegsLoader>();
-    const int group = warp >> 2, w4 = warp & 3;
-    const int rsub = w4 * 4 + (lane >> 3), c = lane & 7;
+    const int q = warp;                             // TMEM lane quarter = 32-row slice of the tile
+    float* xp0 = reinterpret_cast<float*>(sm + kOffXpose) + warp * kLoadBufs * 32 * kStagePitch;
+    const int rl = lane >> 3, c = lane & 7;
     const long long total = n_my * kNumKB;
-    for (long long it = group; it < total; it += kLoaderGroups) {
-      const long long tile = first + (it >> 2) * step;
-      const int kb = (int)(it & 3);
-      const long long row0 = tile * kTileM;
-      float4 v[8];
+    // copy K-block `it` (32 rows x 128 B) into transpose tile `b`; rows past M are zero-filled
+    auto issue = [&](long long it, int b) {
+      if (it < total) {
+        const long long tile = first + (it >> 2) * step;
+        const int kb = (int)(it & 3);
+        const long long row0 = tile * kTileM + q * 32;
+        const uint32_t dst0 = smem_u32(xp0 + b * 32 * kStagePitch) + (uint32_t)(rl * kStagePitch + c * 4) * 4u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const long long row = row0 + i * 16 + rsub;
-        v[i] = (row < p.M) ? ldg_stream(reinterpret_cast<const float4*>(p.A + row * p.lda + kb * kKB + c * 4))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const long long row = row0 + i * 4 + rl;
+          const long long rc = row < p.M ? row : p.M - 1;
+          const uint32_t nbytes = row < p.M ? 16u : 0u;
+          const float* src = p.A + rc * p.lda + kb * kKB + c * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(i * 4 * kStagePitch * 4)),
+                       "l"(src), "r"(nbytes) : "memory");
+        }
       }
-      const int s = (int)(it & 1);
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      // Parity waits are only unambiguous when the waiter is at most one phase ahead of the
-      // barrier, but a loader group may run several K-blocks ahead.  The groups therefore
-      // take turns: group(it) may look at a_empty only after group(it-1) has passed its own
-      // wait (named barriers 1..3: 128 arriving + 128 waiting threads).  Loads are already in
-      // flight at this point, so the turn-taking costs no memory-level parallelism.
-      if (it > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + (int)(it % kLoaderGroups)) : "memory");
-      mbar_wait(a_empty(s), ph ^ 1u);
-      if (it + 1 < total) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (int)((it + 1) % kLoaderGroups)) : "memory");
-      const uint32_t hi_base = base + kOffA + (uint32_t)s * 2 * kBlockBytes;
-      const uint32_t lo_base = hi_base + kBlockBytes;
+      asm volatile("cp.async.commit_group;" ::: "memory");     // always commit: uniform group counting
+    };
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 hi, lo;
-        split4(v[i], hi, lo);
-        const uint32_t off = swz_off(i * 16 + rsub, c);
-        sts128(hi_base + off, hi);
-        sts128(lo_base + off, lo);
+    for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+    int b = 0;
+    for (long long it = 0; it < total; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");   // K-block `it` has landed
+      __syncwarp();
+      const float* xp = xp0 + b * 32 * kStagePitch;
+      const int s = (int)(it & 3);
+      const uint32_t ph = (uint32_t)((it >> 2) & 1);
+      mbar_wait(a_empty(s), ph ^ 1u);               // in-order single producer: at most one phase ahead
+      tc_fence_after();
+      const uint32_t ta = tmem_base + kTmemA + (uint32_t)s * 64 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(xp + lane * kStagePitch + half * 16 + 4 * j);
+          float4 h4, l4;
+          split4(x, h4, l4);
+          hi[4 * j] = h4.x; hi[4 * j + 1] = h4.y; hi[4 * j + 2] = h4.z; hi[4 * j + 3] = h4.w;
+          lo[4 * j] = l4.x; lo[4 * j + 1] = l4.y; lo[4 * j + 2] = l4.z; lo[4 * j + 3] = l4.w;
+        }
+        tmem_st16(ta + half * 16, hi);
+        tmem_st16(ta + 32 + half * 16, lo);
       }
-      fence_proxy_async();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(a_full(s));
+      __syncwarp();                                 // every lane has read the tile: refill it
+      issue(it + kLoadBufs, b);
+      b = (b + 1 == kLoadBufs) ? 0 : b + 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < kEpiWarp0) {
-    // ======================= MMA issuer (warp 12; warps 13-15 pad the warpgroup) =======================
+    // ======================= MMA issuer (warp 4; warps 5-7 pad the warpgroup) =======================
     reg_dec<kRegsMma>();
     if (warp == kMmaWarp && lane == 0) {
+      // descriptors differ only in the 14-bit start-address field: derive them from one base
+      // (keeps the issuing thread's live state tiny - it runs with a 40-register budget)
+      const uint64_t desc_b0 = make_desc(base + kOffWhi);
+      constexpr uint64_t kLoDelta = (uint64_t)((kOffWlo - kOffWhi) >> 4);
       long long it = 0, tcount = 0;
+#pragma unroll 1
       for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
         const int d = (int)(tcount & 1);
         const uint32_t dph = (uint32_t)((tcount >> 1) & 1);
         mbar_wait(d_empty(d), dph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)d * kD;
+#pragma unroll 1
         for (int kb = 0; kb < kNumKB; ++kb, ++it) {
-          const int s = (int)(it & 1);
-          const uint32_t ph = (uint32_t)((it >> 1) & 1);
+          const int s = (int)(it & 3);
+          const uint32_t ph = (uint32_t)((it >> 2) & 1);
           mbar_wait(a_full(s), ph);
           tc_fence_after();
-          const uint32_t a_hi = base + kOffA + (uint32_t)s * 2 * kBlockBytes;
-          const uint32_t a_lo = a_hi + kBlockBytes;
-          const uint32_t b_hi = base + kOffWhi + (uint32_t)kb * kBlockBytes;
-          const uint32_t b_lo = base + kOffWlo + (uint32_t)kb * kBlockBytes;
+          const uint32_t a_hi = tmem_base + kTmemA + (uint32_t)s * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint64_t dkb = desc_b0 + (uint64_t)((kb * kBlockBytes) >> 4);
 #pragma unroll
           for (int k = 0; k < kKB / 8; ++k) {
-            const uint32_t ko = (uint32_t)k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
-            const uint64_t dah = make_desc(a_hi + ko), dal = make_desc(a_lo + ko);
-            const uint64_t dbh = make_desc(b_hi + ko), dbl = make_desc(b_lo + ko);
-            umma_tf32(d_tmem, dal, dbh, kInstrDesc, (kb | k) != 0);
-            umma_tf32(d_tmem, dah, dbl, kInstrDesc, 1);
-            umma_tf32(d_tmem, dah, dbh, kInstrDesc, 1);
+            const uint64_t dbh = dkb + (uint64_t)(k * 2);   // 8 tf32 = 32 bytes along K inside the swizzle row
+            const uint64_t dbl = dbh + kLoDelta;
+            umma_tf32_ts(d_tmem, a_lo + 8 * k, dbh, kInstrDesc, (kb | k) != 0);
+            umma_tf32_ts(d_tmem, a_hi + 8 * k, dbl, kInstrDesc, 1);
+            umma_tf32_ts(d_tmem, a_hi + 8 * k, dbh, kInstrDesc, 1);
           }
-          umma_commit(a_empty(s));      // smem stage reusable once these MMAs have read it
+          umma_commit(a_empty(s));      // TMEM A stage reusable once these MMAs have read it
         }
         umma_commit(d_full(d));         // accumulator complete
       }
@@ -303,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   } else {
     // ======================= epilogue =======================
     reg_inc<kRegsEpi>();
+    const int eg = (warp - kEpiWarp0) >> 2;         // epilogue group = accumulator buffer it drains
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     float* stg = reinterpret_cast<float*>(sm + kOffStage) + (warp - kEpiWarp0) * 32 * kStagePitch;
     const float* s_bias = s_const;
@@ -310,11 +365,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
     const float* s_beta = s_const + 2 * kD;
     const float* s_dotw = s_const + 3 * kD;
     const int c4 = lane & 7, rl = lane >> 3;        // coalesced domain: 8 lanes per row, 4 rows per pass
-    long long tcount = 0;
-    for (long long tile = first; tile < p.num_tiles; tile += step, ++tcount) {
-      const int d = (int)(tcount & 1);
-      const uint32_t dph = (uint32_t)((tcount >> 1) & 1);
-      const uint32_t taddr = tmem_base + (uint32_t)d * kD + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = tmem_base + (uint32_t)eg * kD + ((uint32_t)(q * 32) << 16);
+    long long k_tile = 0;                           // tiles drained by this group so far
+    for (long long tcount = eg; tcount < n_my; tcount += kEpiGroups, ++k_tile) {
+      const long long tile = first + tcount * step;
+      const uint32_t dph = (uint32_t)(k_tile & 1);
       const long long wrow0 = tile * kTileM + q * 32;     // first global row of this warp
       // rows this lane touches in the coalesced domain (clamped: loads stay in bounds, stores are guarded)
       long long grow[8];
@@ -325,61 +380,59 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
       }
 
       if constexpr (MODE == MODE_ELEMENTWISE) {
-        // gather indices of this lane's rows: loaded once per tile, before the accumulator is ready
-        long long gi0[8], gi1[8];
+        int gi0[8], gi1[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          gi0[j] = p.g0 ? (long long)__ldg(p.i0 + grow[j]) : 0;
-          gi1[j] = p.g1 ? (long long)__ldg(p.i1 + grow[j]) : 0;
+          gi0[j] = p.g0 ? __ldg(p.i0 + grow[j]) : 0;
+          gi1[j] = p.g1 ? __ldg(p.i1 + grow[j]) : 0;
         }
-        // ext[j] = sum of the addend terms of (row j, this lane's 4 columns) for one chunk
+        const bool has_ext = p.addend || p.g0 || p.g1;
+        // ext[j] = sum of the pre-activation addends of (row j, this lane's 4 columns) for one chunk
         auto load_ext = [&](int ch, float4* ext) {
           const int col = ch * 32 + c4 * 4;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.addend) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow[j] * p.ld_addend + col));
-          }
           if (p.g0) {
-            float4 t[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(p.g0 + gi0[j] * p.ld_g0 + col));
+            for (int j = 0; j < 8; ++j) ext[j] = __ldg(reinterpret_cast<const float4*>(p.g0 + (long long)gi0[j] * p.ld_g0 + col));
+          } else if (p.addend) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) add4(ext[j], t[j]);
+            for (int j = 0; j < 8; ++j) ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow[j] * p.ld_addend + col));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ext[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (p.g1) {
             float4 t[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(p.g1 + gi1[j] * p.ld_g1 + col));
+            for (int j = 0; j < 8; ++j) t[j] = __ldg(reinterpret_cast<const float4*>(p.g1 + (long long)gi1[j] * p.ld_g1 + col));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) add4(ext[j], t[j]);
+          }
+          if (p.g0 && p.addend) {
+            float4 t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = ldg_stream(reinterpret_cast<const float4*>(p.addend + grow[j] * p.ld_addend + col));
 #pragma unroll
             for (int j = 0; j < 8; ++j) add4(ext[j], t[j]);
           }
         };
-        const bool has_ext = p.addend || p.g0 || p.g1;
         float4 ext[8];
         if (has_ext) load_ext(0, ext);                 // overlaps the wait for the accumulator
-        mbar_wait(d_full(d), dph);
+        mbar_wait(d_full(eg), dph);
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
-          float r[32];
-          tmem_ld32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(d)); }   // accumulator drained
+          {
+            float r[32];
+            tmem_ld32(taddr + ch * 32, r);
+            tmem_ld_wait();
+            if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(eg)); }   // accumulator drained
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
           __syncwarp();
           const int col = ch * 32 + c4 * 4;
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col);
-          float4 res[8];
-          if (p.residual) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col));
-          }
           float4 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -388,16 +441,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
             if (has_ext) add4(v[j], ext[j]);
           }
           __syncwarp();                                // staging tile free for the next chunk
-          if (has_ext && ch < 3) load_ext(ch + 1, ext); // next chunk's addends fly during this chunk's stores
+          if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col));
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (p.relu) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
-            if (p.residual) add4(v[j], res[j]);
+            if (p.residual) add4(v[j], ext[j]);
             if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
           }
+          if (has_ext && ch < 3) load_ext(ch + 1, ext); // next chunk's addends fly during the next TMEM read
         }
       } else if constexpr (MODE == MODE_RELU_DOT) {
-        mbar_wait(d_full(d), dph);
+        mbar_wait(d_full(eg), dph);
         tc_fence_after();
         float acc = 0.f;
 #pragma unroll 1
@@ -405,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
           float r[32];
           tmem_ld32(taddr + ch * 32, r);
           tmem_ld_wait();
-          if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(d)); }
+          if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(eg)); }
 #pragma unroll
           for (int cidx = 0; cidx < 32; ++cidx)
             acc = fmaf(fmaxf(r[cidx] + s_bias[ch * 32 + cidx], 0.f), s_dotw[ch * 32 + cidx], acc);
@@ -413,42 +470,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
         const long long g = wrow0 + lane;
         if (g < p.M) p.Y[g * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
       } else {
-        // LayerNorm: the whole 128-wide row lives in this thread's registers
+        // LayerNorm.  Pass 1 over the accumulator: shifted one-pass statistics (shift = first
+        // element of the row, so the cancellation in E[d^2] - E[d]^2 is of order std^2);
+        // pass 2 re-reads TMEM, normalises and stores.  No 128-register row buffer.
         float4 res[8];
         if (p.residual) {                               // chunk 0 of the residual, ahead of the accumulator
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + c4 * 4));
         }
-        mbar_wait(d_full(d), dph);
+        mbar_wait(d_full(eg), dph);
         tc_fence_after();
-        float r[kD];
-        tmem_ld32(taddr + 0, r);
-        tmem_ld32(taddr + 32, r + 32);
-        tmem_ld32(taddr + 64, r + 64);
-        tmem_ld32(taddr + 96, r + 96);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(d_empty(d));
-        float s = 0.f;
-#pragma unroll
-        for (int cidx = 0; cidx < kD; ++cidx) { r[cidx] += s_bias[cidx]; s += r[cidx]; }
-        const float mu = s * (1.0f / kD);
-        float ss = 0.f;
-#pragma unroll
-        for (int cidx = 0; cidx < kD; ++cidx) { const float dlt = r[cidx] - mu; ss = fmaf(dlt, dlt, ss); }
-        const float rs = 1.0f / sqrtf(ss * (1.0f / kD) + p.eps);
-#pragma unroll
+        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
+          float r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (ch == 0) shift = r[0] + s_bias[0];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int cb = ch * 32 + 4 * j;
-            float4 o;
-            o.x = (r[cb + 0] - mu) * rs * s_gamma[cb + 0] + s_beta[cb + 0];
-            o.y = (r[cb + 1] - mu) * rs * s_gamma[cb + 1] + s_beta[cb + 1];
-            o.z = (r[cb + 2] - mu) * rs * s_gamma[cb + 2] + s_beta[cb + 2];
-            o.w = (r[cb + 3] - mu) * rs * s_gamma[cb + 3] + s_beta[cb + 3];
-            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = o;
+          for (int cidx = 0; cidx < 32; ++cidx) {
+            const float dlt = (r[cidx] + s_bias[ch * 32 + cidx]) - shift;
+            s1 += dlt;
+            s2 = fmaf(dlt, dlt, s2);
+          }
+        }
+        const float m1 = s1 * (1.0f / kD);
+        const float mu = shift + m1;
+        const float var = fmaxf(s2 * (1.0f / kD) - m1 * m1, 0.f);
+        const float rs = 1.0f / sqrtf(var + p.eps);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          {
+            float r[32];
+            tmem_ld32(taddr + ch * 32, r);
+            tmem_ld_wait();
+            if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(eg)); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int cb = ch * 32 + 4 * j;
+              float4 o;
+              o.x = ((r[4 * j + 0] + s_bias[cb + 0]) - mu) * rs * s_gamma[cb + 0] + s_beta[cb + 0];
+              o.y = ((r[4 * j + 1] + s_bias[cb + 1]) - mu) * rs * s_gamma[cb + 1] + s_beta[cb + 1];
+              o.z = ((r[4 * j + 2] + s_bias[cb + 2]) - mu) * rs * s_gamma[cb + 2] + s_beta[cb + 2];
+              o.w = ((r[4 * j + 3] + s_bias[cb + 3]) - mu) * rs * s_gamma[cb + 3] + s_beta[cb + 3];
+              *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = o;
+            }
           }
           __syncwarp();
           const int col = ch * 32 + c4 * 4;
