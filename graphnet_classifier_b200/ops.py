@@ -491,9 +491,11 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     n_out = 1 if dot_w is not None else N
     if out is None:
         out = torch.empty(M, n_out, dtype=torch.float32, device=A.device)
-    nbytes = 4.0 * (M * K + M * n_out + N * K
-                    + M * 128 * ((addend is not None) + (gather0 is not None) + (gather1 is not None)
-                                 + (residual is not None)))
+    # algorithmic HBM bytes: every operand row once (gathered tables count their own rows, not
+    # one row per reference - re-references are expected to hit L2)
+    nbytes = 4.0 * (M * K + M * n_out + N * K + M * 128 * ((addend is not None) + (residual is not None))
+                    + (gather0[0].shape[0] * 128 + M if gather0 is not None else 0)
+                    + (gather1[0].shape[0] * 128 + M if gather1 is not None else 0))
     check(_call("tc_linear", 2.0 * M * N * K, nbytes, _lib.load().gnc_tc_linear_f32, A.data_ptr(), _ld(A), M, K,
                 W.data_ptr(), W.stride(0), N, int(transpose_w), ctypes.byref(epi), out.data_ptr(), _ld(out),
                 _stream()), "tc_linear")
