@@ -170,8 +170,6 @@ class GraphNet(nn.Module):
         with LayerNorm (none on the decoder), i.e. the configuration main.py builds."""
         if ops.ENGINE != "tc":
             return False
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return False
         cached = getattr(self, "_tc_ok", None)
         if cached is not None:
             return cached
@@ -239,9 +237,44 @@ class GraphNet(nn.Module):
         d1 = tcl(h, dec[0].weight, bias=dec[0].bias, relu=True)
         return tcl(d1, dec[2].weight, bias=dec[2].bias, relu=True, dot_w=dec[4].weight, dot_b=dec[4].bias)
 
+    def _forward_tc_train(self, x, pos, graph: GraphIndex):
+        """Differentiable form of ``_forward_tc``: the same restructured contractions through
+        ``ops.tc_linear_autograd`` (tensor-core forward and data gradients), LayerNorm and the
+        K=3 / N=1 end layers through the fp32 operators, which save what their backward needs."""
+        tcl = ops.tc_linear_autograd
+
+        def tail(a1, mlp, residual=None):
+            m = mlp.model
+            a2 = tcl(a1, m[2].weight, m[2].bias, relu=True)
+            z3 = tcl(a2, m[4].weight, m[4].bias)
+            return ops.layer_norm(z3, m[5].weight, m[5].bias, m[5].eps, residual)
+
+        ne, ee = self.node_encoder.model, self.edge_encoder.model
+        h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder)
+        e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+        for blk in self.graph_processor.blocks:
+            em = blk.edge_model.edge_processor
+            W0, b0 = em.model[0].weight, em.model[0].bias
+            P = tcl(h, W0[:, 0:128])
+            Q = tcl(h, W0[:, 128:256])
+            a1 = tcl(e, W0[:, 256:384], b0, relu=True, P=P, Q=Q, graph=graph)
+            e = tail(a1, em, residual=e)
+            nm = blk.node_model.node_processor
+            V0, c0 = nm.model[0].weight, nm.model[0].bias
+            agg = ops.aggregate(e, graph)
+            T = tcl(h, V0[:, 0:128])
+            n1 = tcl(agg, V0[:, 128:256], c0, relu=True, addend=T)
+            h = tail(n1, nm, residual=h)
+        dec = self.node_decoder.model
+        d1 = tcl(h, dec[0].weight, dec[0].bias, relu=True)
+        d2 = tcl(d1, dec[2].weight, dec[2].bias, relu=True)
+        return ops.linear([d2], dec[4].weight, dec[4].bias, relu=False)
+
     def forward(self, x, pos, edge_index):
         graph = edge_index if isinstance(edge_index, GraphIndex) else ops.graph_of(edge_index, x.size(0))
         if x.is_cuda and self._tc_eligible():
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                return self._forward_tc_train(x, pos, graph)
             return self._forward_tc(x, pos, graph)
         edge_attr = ops.edge_geometry(pos, graph)          # [pos[col]-pos[row], L1]  (reference :299-302)
         out = self.node_encoder(x)

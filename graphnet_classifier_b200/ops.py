@@ -500,3 +500,73 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
                 W.data_ptr(), W.stride(0), N, int(transpose_w), ctypes.byref(epi), out.data_ptr(), _ld(out),
                 _stream()), "tc_linear")
     return out
+
+
+class _TcLinearFn(torch.autograd.Function):
+    """``act(A @ W.T + b + addend + P[src] + Q[dst])`` on the tensor-core engine, with its
+    backward: ReLU mask + bias column sums (gnc_relu_bwd_colsum_f32), data gradient on the
+    tensor-core engine (B = W^T), weight gradient (gnc_linear_wgrad_f32, deterministic split
+    reduction), and the gathered addends' gradients as ordered CSR segmented sums."""
+
+    @staticmethod
+    def forward(ctx, A, W, b, relu, addend, P, Q, gmeta):
+        A = _rows(A)
+        Wc = W if W.stride(1) == 1 else W.contiguous()
+        g0 = (P, gmeta[0]) if P is not None else None
+        g1 = (Q, gmeta[2]) if Q is not None else None
+        Y = tc_linear(A, Wc, bias=b, relu=relu, addend=addend, gather0=g0, gather1=g1)
+        ctx.relu, ctx.gmeta, ctx.has_bias = bool(relu), gmeta, b is not None
+        ctx.save_for_backward(A, Wc, Y if relu else None)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        A, Wc, Y = ctx.saved_tensors
+        lib = _lib.load()
+        dev = dY.device
+        M, N, K = A.shape[0], Wc.shape[0], Wc.shape[1]
+        dY = _rows(dY)
+        need = ctx.needs_input_grad          # (A, W, b, relu, addend, P, Q, gmeta)
+        need_b = need[2] and ctx.has_bias
+        dZ, db = dY, None
+        if ctx.relu or need_b:
+            if ctx.relu:
+                dZ = torch.empty(M, N, dtype=torch.float32, device=dev)
+            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+            ws_n = int(lib.gnc_colsum_workspace(M, N))
+            ws = _workspace(dev, ws_n)
+            check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N * (3 if ctx.relu else 1), lib.gnc_relu_bwd_colsum_f32,
+                        dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None, _ld(Y) if ctx.relu else 0, M, N,
+                        dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0, ws.data_ptr(), ws_n, _stream()),
+                  "relu_bwd_colsum")
+        dW = None
+        if need[1]:
+            dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+            segs = _make_segs([A], [None])
+            ws_n = int(lib.gnc_linear_wgrad_workspace(M, N, K))
+            ws = _workspace(dev, ws_n)
+            check(_call("linear_wgrad", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K), lib.gnc_linear_wgrad_f32,
+                        dZ.data_ptr(), _ld(dZ), M, N, segs, 1, dW.data_ptr(), K, 0, ws.data_ptr(), ws_n, _stream()),
+                  "linear_wgrad")
+        dA = tc_linear(dZ, Wc, transpose_w=True) if need[0] else None
+        daddend = dZ if need[4] else None
+        dP = dQ = None
+        if need[5]:
+            _, src_csr, _, _, n_nodes = ctx.gmeta
+            dP = _agg_raw(src_csr[0], src_csr[1], dZ, n_nodes)
+        if need[6]:
+            _, _, _, dst_csr, n_nodes = ctx.gmeta
+            dQ = _agg_raw(dst_csr[0], dst_csr[1], dZ, n_nodes)
+        return dA, dW, db, None, daddend, dP, dQ, None
+
+
+def tc_linear_autograd(A: Tensor, W: Tensor, b: Optional[Tensor] = None, relu: bool = False,
+                       addend: Optional[Tensor] = None, P: Optional[Tensor] = None, Q: Optional[Tensor] = None,
+                       graph: Optional[GraphIndex] = None) -> Tensor:
+    """Differentiable tensor-core linear layer (width 128).  ``P`` / ``Q`` are node tables added
+    as ``P[graph.src]`` / ``Q[graph.dst]`` (the edge processor's first layer, see GraphNet)."""
+    gmeta = None
+    if P is not None or Q is not None:
+        gmeta = (graph.src, (graph.src_rowptr, graph.src_eid), graph.dst, (graph.dst_rowptr, graph.dst_eid),
+                 graph.num_nodes)
+    return _TcLinearFn.apply(A, W, b, relu, addend, P, Q, gmeta)

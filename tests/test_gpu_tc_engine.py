@@ -125,3 +125,36 @@ def test_model_tc_engine_vs_oracle_and_fp32_engine(libgnc, monkeypatch, r, diag,
     np.testing.assert_allclose(out_tc.cpu().numpy(), exp.numpy(), rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(out_fp.cpu().numpy(), exp.numpy(), rtol=RTOL, atol=1e-7)
     assert _maxrel(y_tc, y_or) < RTOL          # node-level decoder outputs, not only the 2 logits
+
+
+@pytest.mark.parametrize("engine", ["tc", "fp32"])
+@pytest.mark.parametrize("r,diag,B", [(8, True, 2), (16, False, 3)])
+def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B):
+    """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine."""
+    from graphnet_classifier_b200 import ops
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    monkeypatch.setattr(ops, "ENGINE", engine)
+    cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
+    om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=r * r, classes=2)
+    fill_deterministic(om, seed=11)
+    gm = CombinedModel(GraphNet(**cfg), num_nodes=r * r, classes=2)
+    gm.load_state_dict(om.state_dict())
+    gm = gm.cuda()
+    imgs = synthetic_images(B, r, seed=3 * r)
+    labels = torch.tensor([i % 2 for i in range(B)])
+    gb = build_pixel_graphs(torch.from_numpy(imgs), diagonals=diag)
+    logits = gm(gb.as_tuple())
+    assert gm.graph_net._tc_eligible() == (engine == "tc")
+    loss = torch.nn.functional.cross_entropy(logits, labels.cuda())
+    loss.backward()
+    lo = sum(torch.nn.functional.cross_entropy(om(ogb.to_model_inputs(*ogb.pixel_graph(im, diag))), l) for im, l in
+             zip(imgs, labels)) / B
+    lo.backward()
+    assert abs(loss.item() - lo.item()) < RTOL * max(1.0, lo.item())
+    worst = 0.0
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        rel = _rel(p.grad, po.grad)
+        worst = max(worst, rel)
+        assert rel < RTOL, (engine, name, rel)
+    print(f"engine={engine} r={r}: worst per-tensor gradient rel-L2 error {worst:.2e}")
