@@ -325,14 +325,16 @@ __global__ void __launch_bounds__(256) superpixel_graph_kernel(
     const uint8_t* __restrict__ img, const int32_t* __restrict__ labels, int H, int W, int max_label,
     int S_max, int64_t E_max, int32_t* __restrict__ n_nodes, float* __restrict__ x, float* __restrict__ pos,
     uint8_t* __restrict__ adj, int32_t* __restrict__ n_edges, int64_t* __restrict__ edges,
-    int32_t* __restrict__ work, int64_t work_per_image, int32_t* __restrict__ bad) {
+    int32_t* __restrict__ work, int64_t work_per_image, int use_smem, int32_t* __restrict__ bad) {
+  extern __shared__ int32_t sp_smem[];
   const int b = blockIdx.x;
   const int64_t HW = (int64_t)H * W;
   const uint8_t* im = img + (int64_t)b * HW * 3;
   const int32_t* lab = labels + (int64_t)b * HW;
-  // workspace layout: rank[max_label+1] | cnt,s_r,s_g,s_b,s_row,s_col [6][S_max] (uint32; 64-bit hi parts
-  // are not needed: 255 * 2^24 pixels < 2^32 and row/col sums < 2^12 * 2^24) | rowoff[S_max+1]
-  int32_t* rank = work + (int64_t)b * work_per_image;
+  // scratch layout: rank[max_label+1] | cnt,s_r,s_g,s_b,s_row,s_col [6][S_max] (uint32; 64-bit hi parts
+  // are not needed: 255 * 2^24 pixels < 2^32 and row/col sums < 2^12 * 2^24) | rowoff[S_max+1].
+  // It lives in shared memory when it fits (the usual ~100 superpixels), else in the global workspace.
+  int32_t* rank = use_smem ? sp_smem : work + (int64_t)b * work_per_image;
   uint32_t* stat = reinterpret_cast<uint32_t*>(rank + (max_label + 1));
   int32_t* rowoff = reinterpret_cast<int32_t*>(stat + 6 * (int64_t)S_max);
   uint8_t* A = adj + (int64_t)b * S_max * S_max;
@@ -478,8 +480,10 @@ int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B,
   if (e == cudaSuccess) e = cudaMemsetAsync(pos, 0, (size_t)B * S_max * 2 * sizeof(float), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(edges, 0, (size_t)B * 2 * E_max * sizeof(int64_t), st);
   if (e != cudaSuccess) return fail(GNC_ECUDA, "superpixel memset: %s", cudaGetErrorString(e));
-  superpixel_graph_kernel<<<B, 256, 0, st>>>(img, labels, H, W, max_label, S_max, E_max, n_nodes, x, pos, adj,
-                                             n_edges, edges, work, wpi, nullptr);
+  const size_t smem = (size_t)wpi * sizeof(int32_t);
+  const int use_smem = smem <= 40 * 1024 ? 1 : 0;
+  superpixel_graph_kernel<<<B, 256, use_smem ? smem : 0, st>>>(img, labels, H, W, max_label, S_max, E_max, n_nodes, x,
+                                                               pos, adj, n_edges, edges, work, wpi, use_smem, nullptr);
   return check_launch("superpixel_graph_kernel");
 }
 

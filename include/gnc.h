@@ -111,6 +111,16 @@ int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B,
                                int32_t* n_edges, int64_t* edges, int32_t* work,
                                gnc_stream_t stream);
 
+/* SLIC superpixel labels for B images (the stage the reference delegates to scikit-image,
+ * image_to_graph_superpixel.py:31; parity unpinned - see csrc/slic.cu): RGB -> Lab, regular-grid
+ * centres, `iters` assignment/update iterations, deterministic.
+ *   img uint8 [B, H, W, 3]; labels int32 [B, H, W] in [0, gnc_slic_num_centers(H, W, n_segments));
+ *   work: gnc_slic_workspace_bytes(...) bytes of scratch. */
+int gnc_slic_num_centers(int H, int W, int n_segments);
+int64_t gnc_slic_workspace_bytes(int B, int H, int W, int n_segments);
+int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, float compactness, int iters,
+                       int32_t* labels, void* work, gnc_stream_t stream);
+
 /* Stable CSR of edge ids grouped by key (= edge_index row 0 or row 1): the order
  * index_add_ visits edges in (models/GNN.py:20).  key is read with an element
  * stride so that non-contiguous edge_index is accepted.

@@ -177,3 +177,41 @@ def test_reference_named_builders(golden, libgnc):
     x, pos, ei = image_to_graph_superpixel(Image.fromarray(b["superpixel_32_img"]), 32,
                                            segments=b["superpixel_32_labels"])
     assert np.array_equal(ei, b["superpixel_32_ei"])
+
+
+def test_device_slic_properties_and_superpixel_pipeline(libgnc):
+    """SLIC label parity is unpinned (scikit-image absent); check the algorithm's invariants and
+    that labels -> graph matches the oracle's label-map stage on the very labels SLIC produced."""
+    from graphnet_classifier_b200.utils.image_to_graph.slic import slic_labels
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_superpixel_graphs
+    from graphnet_classifier_b200.utils.image_to_graph import image_to_graph_superpixel
+    from PIL import Image
+    r, B = 64, 3
+    rng = np.random.default_rng(0)
+    # piecewise-constant images (4 x 4 coloured blocks + noise): superpixels should follow the blocks
+    blocks = rng.integers(0, 256, (B, 4, 4, 3), dtype=np.uint8)
+    imgs = np.repeat(np.repeat(blocks, 16, axis=1), 16, axis=2)
+    imgs = np.clip(imgs.astype(np.int16) + rng.integers(-3, 4, imgs.shape), 0, 255).astype(np.uint8)
+    labs = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0)
+    assert labs.shape == (B, r, r) and labs.dtype == torch.int32
+    K = libgnc.gnc_slic_num_centers(r, r, 16)
+    assert K == 16 and int(labs.min()) >= 0 and int(labs.max()) < K
+    labs2 = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0)
+    assert torch.equal(labs, labs2)                                   # deterministic
+    ln = labs.cpu().numpy()
+    for b in range(B):
+        # colour-coherent: almost every pixel of a 16 x 16 block carries the block's majority label
+        agree = 0
+        for i in range(4):
+            for j in range(4):
+                blk = ln[b, 16 * i:16 * i + 16, 16 * j:16 * j + 16]
+                agree += np.bincount(blk.ravel()).max()
+        assert agree / (r * r) > 0.9
+        ox, opos, oei = ogb.superpixel_graph_from_labels(imgs[b], ln[b].astype(np.int64))
+        n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(torch.from_numpy(imgs[b:b + 1]), labs[b:b + 1])
+        S, E = int(n_nodes[0]), int(n_edges[0])
+        assert S == len(ox) and E == oei.shape[1] and np.array_equal(edges[0, :, :E].cpu().numpy(), oei)
+    # the reference-named entry point end to end (SLIC + graph) on a PIL image
+    x, pos, ei = image_to_graph_superpixel(Image.fromarray(imgs[0]), r, n_segments=16)
+    assert x.shape[1] == 3 and pos.shape[1] == 2 and ei.shape[0] == 2 and x.shape[0] <= 16
+    assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
