@@ -541,13 +541,7 @@ class _TcLinearFn(torch.autograd.Function):
                   "relu_bwd_colsum")
         dW = None
         if need[1]:
-            dW = torch.empty(N, K, dtype=torch.float32, device=dev)
-            segs = _make_segs([A], [None])
-            ws_n = int(lib.gnc_linear_wgrad_workspace(M, N, K))
-            ws = _workspace(dev, ws_n)
-            check(_call("linear_wgrad", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K), lib.gnc_linear_wgrad_f32,
-                        dZ.data_ptr(), _ld(dZ), M, N, segs, 1, dW.data_ptr(), K, 0, ws.data_ptr(), ws_n, _stream()),
-                  "linear_wgrad")
+            dW = tc_wgrad(dZ, A)
         dA = tc_linear(dZ, Wc, transpose_w=True) if need[0] else None
         daddend = dZ if need[4] else None
         dP = dQ = None
@@ -570,3 +564,22 @@ def tc_linear_autograd(A: Tensor, W: Tensor, b: Optional[Tensor] = None, relu: b
         gmeta = (graph.src, (graph.src_rowptr, graph.src_eid), graph.dst, (graph.dst_rowptr, graph.dst_eid),
                  graph.num_nodes)
     return _TcLinearFn.apply(A, W, b, relu, addend, P, Q, gmeta)
+
+
+def tc_wgrad(dZ: Tensor, X: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
+             _lbo: int = 0, _sbo: int = 0) -> Tensor:
+    """``dZ.T @ X`` for ``[M, 128]`` operands on the tensor-core engine (weight gradient)."""
+    _require_cuda(dZ, X)
+    dZ, X = _rows(dZ), _rows(X)
+    M = dZ.shape[0]
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(dZ.shape[1], X.shape[1], dtype=torch.float32, device=dZ.device)
+        accumulate = False
+    ws_n = int(lib.gnc_tc_wgrad_workspace(M))
+    ws = _workspace(dZ.device, ws_n)
+    check(_call("tc_wgrad", 2.0 * M * dZ.shape[1] * X.shape[1], 4.0 * M * (dZ.shape[1] + X.shape[1]),
+                lib.gnc_tc_wgrad_f32, dZ.data_ptr(), _ld(dZ), X.data_ptr(), _ld(X), M, dZ.shape[1], X.shape[1],
+                out.data_ptr(), _ld(out), int(accumulate), ws.data_ptr(), ws_n, int(_lbo), int(_sbo), _stream()),
+          "tc_wgrad")
+    return out

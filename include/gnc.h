@@ -226,6 +226,14 @@ int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K,
                       const float* W, int64_t ldw, int N, int transpose_w,
                       const gnc_tc_epilogue_t* epi /*HOST*/, float* Y, int64_t ldy, gnc_stream_t stream);
 
+/* dW[N, K] (+)= dZ[M, N]^T * X[M, K] on the tensor-core engine (N = K = 128 only); both operands
+ * stream once, the result accumulates in TMEM per CTA and is reduced deterministically.
+ * work: float [gnc_tc_wgrad_workspace(M)].  lbo_units / sbo_units: reserved, pass 0. */
+int64_t gnc_tc_wgrad_workspace(int64_t M);
+int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M, int N, int K,
+                     float* dW, int64_t lddw, int accumulate, float* work, int64_t work_elems,
+                     int lbo_units, int sbo_units, gnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

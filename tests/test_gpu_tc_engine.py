@@ -171,3 +171,17 @@ def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B
         worst = max(worst, rel)
         assert rel < max(RTOL, 3 * noise), (engine, name, rel, noise)
     print(f"engine={engine} r={r}: worst per-tensor gradient rel-L2 error {worst:.2e}")
+
+
+@pytest.mark.parametrize("M", [1, 31, 32, 100, 4096, 32 * 148 * 2 + 5, 200000])
+def test_tc_wgrad(libgnc, M):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    dZ = torch.randn(M, 128, generator=gen)
+    X = torch.randn(M, 128, generator=gen) * 2 + 0.3
+    ref = dZ.double().t() @ X.double()
+    got = ops.tc_wgrad(dZ.cuda(), X.cuda())
+    assert _rel(got, ref) < 2e-6 and _maxrel(got, ref) < RTOL, (_rel(got, ref), _maxrel(got, ref))
+    acc = torch.ones(128, 128, device="cuda")
+    ops.tc_wgrad(dZ.cuda(), X.cuda(), out=acc, accumulate=True)
+    assert _maxrel(acc, ref + 1.0) < RTOL
