@@ -25,7 +25,8 @@ class GncTcEpilogue(Structure):
                 ("relu", c_int32), ("_pad0", c_int32),
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
                 ("residual", c_void_p), ("ld_residual", c_int64),
-                ("dot_w", c_void_p), ("dot_b", c_void_p)]
+                ("dot_w", c_void_p), ("dot_b", c_void_p),
+                ("mask", c_void_p), ("ld_mask", c_int64)]
 
 
 class GncError(RuntimeError):
@@ -54,6 +55,10 @@ SIGNATURES = {
     "gnc_gather_rows_f32": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int, _P]),
     "gnc_edge_geometry_f32": (c_int, [_P, c_int, _P, _P, c_int64, _P, _P]),
     "gnc_linear_fwd_f32": (c_int, [POINTER(GncSeg), c_int, c_int64, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "gnc_linear_narrowk_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "gnc_linear_narrowk_wgrad_workspace": (c_int64, [c_int64, c_int, c_int]),
+    "gnc_linear_narrowk_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64,
+                                             _P, c_int, _P, c_int64, _P]),
     "gnc_linear_dgrad_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, c_int, _P]),
     "gnc_linear_wgrad_workspace": (c_int64, [c_int64, c_int, c_int]),
     "gnc_linear_wgrad_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(GncSeg), c_int, _P, c_int64, c_int,
@@ -69,8 +74,8 @@ SIGNATURES = {
     "gnc_tc_linear_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, POINTER(GncTcEpilogue),
                                   _P, c_int64, _P]),
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
-    "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, c_int64,
-                                 c_int, c_int, _P]),
+    "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,
+                                 _P]),
 }
 
 _lib = None

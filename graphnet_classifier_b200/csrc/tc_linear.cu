@@ -28,7 +28,7 @@
 //                          one chunk ahead.
 //
 // Reference semantics covered (models/MLP.py:24-37, models/GNN.py:57-64, 95-104, 289-295):
-//   MODE_ELEMENTWISE: y = act(acc + bias + addend[m] + g0[i0[m]] + g1[i1[m]]) + residual[m]
+//   MODE_ELEMENTWISE: y = act(acc + bias + addend[m] + g0[i0[m]] + g1[i1[m]]) + residual[m],  or  y *= (mask[m] > 0)
 //   MODE_LAYERNORM  : y = LayerNorm(acc + bias) * gamma + beta + residual[m]
 //   MODE_RELU_DOT   : y[m] = relu(acc + bias) . w + b          (decoder tail, out_channels = 1)
 #include "common.cuh"
@@ -80,6 +80,7 @@ struct Params {
   int relu;
   const float* gamma; const float* beta; float eps;
   const float* residual; long long ld_res;
+  const float* mask; long long ld_mask;
   const float* dot_w; const float* dot_b;
   float* Y; long long ldy;
   long long num_tiles;
@@ -447,11 +448,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
           if (p.residual) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col));
+          } else if (p.mask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ext[j] = ldg_stream(reinterpret_cast<const float4*>(p.mask + grow[j] * p.ld_mask + col));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (p.relu) { v[j].x = fmaxf(v[j].x, 0.f); v[j].y = fmaxf(v[j].y, 0.f); v[j].z = fmaxf(v[j].z, 0.f); v[j].w = fmaxf(v[j].w, 0.f); }
             if (p.residual) add4(v[j], ext[j]);
+            else if (p.mask) {      // ReLU backward of the layer that produced this operand: y *= (mask > 0)
+              v[j].x = ext[j].x > 0.f ? v[j].x : 0.f; v[j].y = ext[j].y > 0.f ? v[j].y : 0.f;
+              v[j].z = ext[j].z > 0.f ? v[j].z : 0.f; v[j].w = ext[j].w > 0.f ? v[j].w : 0.f;
+            }
             if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
           }
           if (has_ext && ch < 3) load_ext(ch + 1, ext); // next chunk's addends fly during the next TMEM read
@@ -585,13 +593,15 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
   p.relu = epi->relu;
   p.gamma = epi->gamma; p.beta = epi->beta; p.eps = epi->eps;
   p.residual = epi->residual; p.ld_res = epi->ld_residual;
+  p.mask = epi->mask; p.ld_mask = epi->ld_mask;
   p.dot_w = epi->dot_w; p.dot_b = epi->dot_b;
   p.Y = Y; p.ldy = ldy;
   p.num_tiles = (M + tc::kTileM - 1) / tc::kTileM;
   GNC_REQUIRE(!p.g0 || p.i0, "tc_linear: gather0 needs gather0_idx");
   GNC_REQUIRE(!p.g1 || p.i1, "tc_linear: gather1 needs gather1_idx");
   auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0); };
-  GNC_REQUIRE(ok4(p.addend, p.ld_addend) && ok4(p.g0, p.ld_g0) && ok4(p.g1, p.ld_g1) && ok4(p.residual, p.ld_res),
+  GNC_REQUIRE(!(p.mask && (p.residual || epi->gamma || epi->dot_w)), "tc_linear: mask combines with the elementwise epilogue only, without residual");
+  GNC_REQUIRE(ok4(p.addend, p.ld_addend) && ok4(p.g0, p.ld_g0) && ok4(p.g1, p.ld_g1) && ok4(p.residual, p.ld_res) && ok4(p.mask, p.ld_mask),
               "tc_linear: addend / gather / residual rows must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (epi->dot_w) {

@@ -52,7 +52,8 @@ struct Params {
   const float* dZ; long long lddz;
   const float* X; long long ldx;
   long long M;
-  float* ws;                      // [grid][128][128]
+  float* ws;                      // [grid][128][128] partial dW, then [grid][128] partial column sums of dZ
+  int want_db;
   long long blocks_per_cta;
 };
 
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_kernel(const Params p) {
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     int rb = 0;
+    float cs_sum = 0.f, cs_comp = 0.f;         // bias gradient: Kahan sum over blocks of per-block column sums
     for (long long it = 0; it < nblk; ++it) {
       asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");          // every Z thread's copies of block `it` landed
@@ -199,17 +201,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_kernel(const Params p) {
       mbar_wait(a_empty(s), ph ^ 1u);
       tc_fence_after();
       const uint32_t ta = tmem_base + kTmemA + (uint32_t)s * 64 + ((uint32_t)(q * 32) << 16);
+      float blk_sum = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float v = tile[(half * 16 + j) * kD + t];     // column t of the block: bank = t mod 32
+          blk_sum += v;
           hi[j] = tf32_rna(v);
           lo[j] = tf32_rna(v - hi[j]);
         }
         tmem_st16(ta + half * 16, hi);
         tmem_st16(ta + 32 + half * 16, lo);
+      }
+      {
+        const float y = blk_sum - cs_comp;
+        const float tsum = cs_sum + y;
+        cs_comp = (tsum - cs_sum) - y;
+        cs_sum = tsum;
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_kernel(const Params p) {
       rb = (rb + 1 == kRing) ? 0 : rb + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (p.want_db) p.ws[(long long)gridDim.x * kD * kD + (long long)blockIdx.x * kD + t] = cs_sum;
   } else if (warp < 8) {
     // ======================= X path: X rows -> MN-major B operand images =======================
     const int t = threadIdx.x - 128;
@@ -339,9 +350,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgrad_kernel(const Params p) {
 }
 
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dW, long long lddw,
-                                       int accumulate) {
+                                       int accumulate, float* __restrict__ db, int accumulate_db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // 0 .. 128*128
   if (i >= kD * kD) return;
+  if (db && i < kD) {
+    const float* wdb = ws + (long long)parts * kD * kD;
+    float sb = 0.f;
+    for (int c = 0; c < parts; ++c) sb += wdb[c * kD + i];
+    db[i] = accumulate_db ? db[i] + sb : sb;
+  }
   float s = 0.f;
   for (int c = 0; c < parts; ++c) s += ws[(long long)c * kD * kD + i];
   const int n = i >> 7, k = i & 127;
@@ -358,12 +375,11 @@ extern "C" {
 
 int64_t gnc_tc_wgrad_workspace(int64_t M) {
   (void)M;
-  return (int64_t)kNumSMs * tcw::kD * tcw::kD;
+  return (int64_t)kNumSMs * (tcw::kD * tcw::kD + tcw::kD);
 }
 
 int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M, int N, int K, float* dW,
-                     int64_t lddw, int accumulate, float* work, int64_t work_elems, int lbo_units, int sbo_units,
-                     gnc_stream_t stream) {
+                     int64_t lddw, int accumulate, float* db, float* work, int64_t work_elems, gnc_stream_t stream) {
   GNC_REQUIRE(N == tcw::kD && K == tcw::kD, "tc_wgrad: specialised for 128 x 128 weights");
   GNC_REQUIRE(dZ && X && dW && M >= 0 && lddz >= N && ldx >= K && lddw >= K, "tc_wgrad: bad arguments");
   GNC_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && aligned16(dZ) && aligned16(X), "tc_wgrad: rows must be 16-byte aligned");
@@ -381,11 +397,11 @@ int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx,
   tcw::Params p;
   p.dZ = dZ; p.lddz = lddz; p.X = X; p.ldx = ldx; p.M = M; p.ws = work;
   p.blocks_per_cta = (nblocks + grid - 1) / grid;
-  (void)lbo_units; (void)sbo_units;
+  p.want_db = db ? 1 : 0;
   tcw::tc_wgrad_kernel<<<(unsigned)grid, tcw::kThreads, tcw::kSmemBytes, st>>>(p);
   int rc = check_launch("tc_wgrad_kernel");
   if (rc) return rc;
-  tcw::tc_wgrad_reduce_kernel<<<tcw::kD * tcw::kD / 256, 256, 0, st>>>(work, (int)grid, dW, lddw, accumulate);
+  tcw::tc_wgrad_reduce_kernel<<<tcw::kD * tcw::kD / 256, 256, 0, st>>>(work, (int)grid, dW, lddw, accumulate, db, accumulate);
   return check_launch("tc_wgrad_reduce_kernel");
 }
 

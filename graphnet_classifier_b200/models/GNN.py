@@ -243,31 +243,35 @@ class GraphNet(nn.Module):
         K=3 / N=1 end layers through the fp32 operators, which save what their backward needs."""
         tcl = ops.tc_linear_autograd
 
-        def tail(a1, mlp, residual=None):
+        # ReLU backward rides in the data-gradient epilogue of the next layer (mask_input) and the
+        # producing layer skips its own mask pass (premasked): every activation here has one consumer.
+        def tail(a1, mlp, residual=None, a1_is_tc=True):
             m = mlp.model
-            a2 = tcl(a1, m[2].weight, m[2].bias, relu=True)
-            z3 = tcl(a2, m[4].weight, m[4].bias)
+            a2 = tcl(a1, m[2].weight, m[2].bias, relu=True, mask_input=a1_is_tc, premasked=True)
+            z3 = tcl(a2, m[4].weight, m[4].bias, mask_input=True)
             return ops.layer_norm(z3, m[5].weight, m[5].bias, m[5].eps, residual)
 
         ne, ee = self.node_encoder.model, self.edge_encoder.model
-        h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder)
-        e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+        # the K = 3 first layers run on the fp32 operator, which masks its own ReLU (a1_is_tc=False)
+        h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder, a1_is_tc=False)
+        e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder,
+                 a1_is_tc=False)
         for blk in self.graph_processor.blocks:
             em = blk.edge_model.edge_processor
             W0, b0 = em.model[0].weight, em.model[0].bias
             P = tcl(h, W0[:, 0:128])
             Q = tcl(h, W0[:, 128:256])
-            a1 = tcl(e, W0[:, 256:384], b0, relu=True, P=P, Q=Q, graph=graph)
+            a1 = tcl(e, W0[:, 256:384], b0, relu=True, P=P, Q=Q, graph=graph, premasked=True)
             e = tail(a1, em, residual=e)
             nm = blk.node_model.node_processor
             V0, c0 = nm.model[0].weight, nm.model[0].bias
             agg = ops.aggregate(e, graph)
             T = tcl(h, V0[:, 0:128])
-            n1 = tcl(agg, V0[:, 128:256], c0, relu=True, addend=T)
+            n1 = tcl(agg, V0[:, 128:256], c0, relu=True, addend=T, premasked=True)
             h = tail(n1, nm, residual=h)
         dec = self.node_decoder.model
-        d1 = tcl(h, dec[0].weight, dec[0].bias, relu=True)
-        d2 = tcl(d1, dec[2].weight, dec[2].bias, relu=True)
+        d1 = tcl(h, dec[0].weight, dec[0].bias, relu=True, premasked=True)
+        d2 = tcl(d1, dec[2].weight, dec[2].bias, relu=True, mask_input=True)     # masked by its own pass
         return ops.linear([d2], dec[4].weight, dec[4].bias, relu=False)
 
     def forward(self, x, pos, edge_index):

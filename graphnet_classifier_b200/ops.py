@@ -217,9 +217,20 @@ def _make_segs(srcs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]]):
     return arr
 
 
+def _is_narrowk(srcs, idxs, W) -> bool:
+    """Thin first layer (K <= 8, one plain segment, N % 4 == 0): streaming kernels in csrc/narrow.cu."""
+    return len(srcs) == 1 and idxs[0] is None and W.shape[1] <= 8 and W.shape[0] % 4 == 0
+
+
 def _linear_fwd_raw(srcs, idxs, M, W, b, relu) -> Tensor:
     N = W.shape[0]
     Y = torch.empty(M, N, dtype=torch.float32, device=W.device)
+    if _is_narrowk(srcs, idxs, W):
+        X, K = srcs[0], W.shape[1]
+        check(_call("linear_narrowk_fwd", 2.0 * M * N * K, 4.0 * (M * K + M * N), _lib.load().gnc_linear_narrowk_fwd_f32,
+                    X.data_ptr(), _ld(X), M, K, W.data_ptr(), W.stride(0), _p(b), N, int(relu), Y.data_ptr(), _ld(Y),
+                    _stream()), "linear_narrowk_fwd")
+        return Y
     segs = _make_segs(srcs, idxs)
     K = W.shape[1]
     check(_call("linear_fwd", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), _lib.load().gnc_linear_fwd_f32,
@@ -252,6 +263,19 @@ class _LinearFn(torch.autograd.Function):
         M, N, K = ctx.M, Wc.shape[0], Wc.shape[1]
         dY = _rows(dY)
         need_W, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_bias
+        if (_is_narrowk(srcs, [m[0] for m in ctx.meta], Wc) and N <= 128 and not ctx.needs_input_grad[4]
+                and dY.stride(0) % 4 == 0):
+            # thin first layer: ReLU mask + bias gradient + weight gradient in one pass, no data gradient
+            dW = torch.empty(N, K, dtype=torch.float32, device=dev) if need_W else None
+            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+            ws_n = int(lib.gnc_linear_narrowk_wgrad_workspace(M, N, K))
+            ws = _workspace(dev, ws_n)
+            X = srcs[0]
+            check(_call("linear_narrowk_wgrad", 2.0 * M * N * K, 4.0 * M * (N * (2 if ctx.relu else 1) + K),
+                        lib.gnc_linear_narrowk_wgrad_f32, dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None,
+                        _ld(Y) if ctx.relu else 0, X.data_ptr(), _ld(X), M, N, K, _p(dW), K, _p(db), 0,
+                        ws.data_ptr(), ws_n, _stream()), "linear_narrowk_wgrad")
+            return (dW, db, None, None, None)
         # bias + ReLU backward: dZ = dY * (Y > 0), db = column sums
         dZ, db = dY, None
         if ctx.relu or need_b:
@@ -446,7 +470,8 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
               addend: Optional[Tensor] = None, gather0=None, gather1=None, relu: bool = False,
               gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
               residual: Optional[Tensor] = None, dot_w: Optional[Tensor] = None,
-              dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+              dot_b: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+              out: Optional[Tensor] = None) -> Tensor:
     """``epilogue(A @ W.T)`` on the tcgen05 3xTF32 engine (``A @ W`` with transpose_w).
     ``gather0`` / ``gather1`` are ``(rows [R, 128], idx int32 [M])`` pairs added row-wise as
     ``rows[idx[m]]``.  See include/gnc.h ``gnc_tc_epilogue_t`` for the epilogue algebra."""
@@ -481,6 +506,9 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     if residual is not None:
         t = rows(residual)
         epi.residual, epi.ld_residual = t.data_ptr(), _ld(t)
+    if mask is not None:
+        t = rows(mask)
+        epi.mask, epi.ld_mask = t.data_ptr(), _ld(t)
     if dot_w is not None:
         dw = dot_w.reshape(-1)
         if dw.stride(0) != 1:
@@ -493,7 +521,8 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
         out = torch.empty(M, n_out, dtype=torch.float32, device=A.device)
     # algorithmic HBM bytes: every operand row once (gathered tables count their own rows, not
     # one row per reference - re-references are expected to hit L2)
-    nbytes = 4.0 * (M * K + M * n_out + N * K + M * 128 * ((addend is not None) + (residual is not None))
+    nbytes = 4.0 * (M * K + M * n_out + N * K
+                    + M * 128 * ((addend is not None) + (residual is not None) + (mask is not None))
                     + (gather0[0].shape[0] * 128 + M if gather0 is not None else 0)
                     + (gather1[0].shape[0] * 128 + M if gather1 is not None else 0))
     check(_call("tc_linear", 2.0 * M * N * K, nbytes, _lib.load().gnc_tc_linear_f32, A.data_ptr(), _ld(A), M, K,
@@ -504,19 +533,27 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
 
 class _TcLinearFn(torch.autograd.Function):
     """``act(A @ W.T + b + addend + P[src] + Q[dst])`` on the tensor-core engine, with its
-    backward: ReLU mask + bias column sums (gnc_relu_bwd_colsum_f32), data gradient on the
-    tensor-core engine (B = W^T), weight gradient (gnc_linear_wgrad_f32, deterministic split
-    reduction), and the gathered addends' gradients as ordered CSR segmented sums."""
+    backward: weight + bias gradients in one tcgen05 pass (gnc_tc_wgrad_f32), data gradient on
+    the tensor-core engine (B = W^T), gathered addends' gradients as ordered CSR segmented sums.
+
+    ReLU backward is fused along MLP chains instead of being a pass of its own:
+      * ``mask_input``  - ``A`` is the ReLU output of the layer before; the data gradient is
+        multiplied by ``(A > 0)`` in the GEMM epilogue, i.e. it is already the gradient with
+        respect to that layer's pre-activation;
+      * ``premasked``   - this layer's own ReLU mask has been applied to the incoming gradient by
+        its (single) consumer, which was built with ``mask_input``; nothing is left to do.
+    Masking twice would also be correct (the mask is idempotent); the flags only remove passes."""
 
     @staticmethod
-    def forward(ctx, A, W, b, relu, addend, P, Q, gmeta):
+    def forward(ctx, A, W, b, relu, addend, P, Q, gmeta, mask_input, premasked):
         A = _rows(A)
         Wc = W if W.stride(1) == 1 else W.contiguous()
         g0 = (P, gmeta[0]) if P is not None else None
         g1 = (Q, gmeta[2]) if Q is not None else None
         Y = tc_linear(A, Wc, bias=b, relu=relu, addend=addend, gather0=g0, gather1=g1)
         ctx.relu, ctx.gmeta, ctx.has_bias = bool(relu), gmeta, b is not None
-        ctx.save_for_backward(A, Wc, Y if relu else None)
+        ctx.mask_input, ctx.premasked = bool(mask_input), bool(premasked)
+        ctx.save_for_backward(A, Wc, Y if (relu and not premasked) else None)
         return Y
 
     @staticmethod
@@ -524,25 +561,32 @@ class _TcLinearFn(torch.autograd.Function):
         A, Wc, Y = ctx.saved_tensors
         lib = _lib.load()
         dev = dY.device
-        M, N, K = A.shape[0], Wc.shape[0], Wc.shape[1]
+        M, N = A.shape[0], Wc.shape[0]
         dY = _rows(dY)
-        need = ctx.needs_input_grad          # (A, W, b, relu, addend, P, Q, gmeta)
+        need = ctx.needs_input_grad          # (A, W, b, relu, addend, P, Q, gmeta, mask_input, premasked)
         need_b = need[2] and ctx.has_bias
-        dZ, db = dY, None
-        if ctx.relu or need_b:
-            if ctx.relu:
-                dZ = torch.empty(M, N, dtype=torch.float32, device=dev)
-            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+        dZ = dY
+        if ctx.relu and not ctx.premasked:
+            dZ = torch.empty(M, N, dtype=torch.float32, device=dev)
             ws_n = int(lib.gnc_colsum_workspace(M, N))
             ws = _workspace(dev, ws_n)
-            check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N * (3 if ctx.relu else 1), lib.gnc_relu_bwd_colsum_f32,
-                        dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None, _ld(Y) if ctx.relu else 0, M, N,
-                        dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0, ws.data_ptr(), ws_n, _stream()),
-                  "relu_bwd_colsum")
-        dW = None
-        if need[1]:
+            check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N * 3, lib.gnc_relu_bwd_colsum_f32,
+                        dY.data_ptr(), _ld(dY), Y.data_ptr(), _ld(Y), M, N, dZ.data_ptr(), _ld(dZ), None, 0,
+                        ws.data_ptr(), ws_n, _stream()), "relu_bwd_colsum")
+        dW = db = None
+        if need[1] and need_b:
+            dW, db = tc_wgrad(dZ, A, want_db=True)
+        elif need[1]:
             dW = tc_wgrad(dZ, A)
-        dA = tc_linear(dZ, Wc, transpose_w=True) if need[0] else None
+        elif need_b:
+            db = torch.empty(N, dtype=torch.float32, device=dev)
+            ws_n = int(lib.gnc_colsum_workspace(M, N))
+            ws = _workspace(dev, ws_n)
+            check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N, lib.gnc_relu_bwd_colsum_f32, dZ.data_ptr(), _ld(dZ), None, 0,
+                        M, N, None, 0, db.data_ptr(), 0, ws.data_ptr(), ws_n, _stream()), "relu_bwd_colsum")
+        dA = None
+        if need[0]:
+            dA = tc_linear(dZ, Wc, transpose_w=True, mask=A if ctx.mask_input else None)
         daddend = dZ if need[4] else None
         dP = dQ = None
         if need[5]:
@@ -551,24 +595,27 @@ class _TcLinearFn(torch.autograd.Function):
         if need[6]:
             _, _, _, dst_csr, n_nodes = ctx.gmeta
             dQ = _agg_raw(dst_csr[0], dst_csr[1], dZ, n_nodes)
-        return dA, dW, db, None, daddend, dP, dQ, None
+        return dA, dW, db, None, daddend, dP, dQ, None, None, None
 
 
 def tc_linear_autograd(A: Tensor, W: Tensor, b: Optional[Tensor] = None, relu: bool = False,
                        addend: Optional[Tensor] = None, P: Optional[Tensor] = None, Q: Optional[Tensor] = None,
-                       graph: Optional[GraphIndex] = None) -> Tensor:
+                       graph: Optional[GraphIndex] = None, mask_input: bool = False,
+                       premasked: bool = False) -> Tensor:
     """Differentiable tensor-core linear layer (width 128).  ``P`` / ``Q`` are node tables added
-    as ``P[graph.src]`` / ``Q[graph.dst]`` (the edge processor's first layer, see GraphNet)."""
+    as ``P[graph.src]`` / ``Q[graph.dst]`` (the edge processor's first layer, see GraphNet).
+    ``mask_input`` / ``premasked``: ReLU-backward fusion flags, see ``_TcLinearFn``."""
     gmeta = None
     if P is not None or Q is not None:
         gmeta = (graph.src, (graph.src_rowptr, graph.src_eid), graph.dst, (graph.dst_rowptr, graph.dst_eid),
                  graph.num_nodes)
-    return _TcLinearFn.apply(A, W, b, relu, addend, P, Q, gmeta)
+    return _TcLinearFn.apply(A, W, b, relu, addend, P, Q, gmeta, mask_input, premasked)
 
 
 def tc_wgrad(dZ: Tensor, X: Tensor, out: Optional[Tensor] = None, accumulate: bool = False,
-             _lbo: int = 0, _sbo: int = 0) -> Tensor:
-    """``dZ.T @ X`` for ``[M, 128]`` operands on the tensor-core engine (weight gradient)."""
+             want_db: bool = False):
+    """``dZ.T @ X`` for ``[M, 128]`` operands on the tensor-core engine (weight gradient);
+    with ``want_db`` also the column sums of ``dZ`` (bias gradient) from the same pass."""
     _require_cuda(dZ, X)
     dZ, X = _rows(dZ), _rows(X)
     M = dZ.shape[0]
@@ -576,10 +623,10 @@ def tc_wgrad(dZ: Tensor, X: Tensor, out: Optional[Tensor] = None, accumulate: bo
     if out is None:
         out = torch.empty(dZ.shape[1], X.shape[1], dtype=torch.float32, device=dZ.device)
         accumulate = False
+    db = torch.empty(dZ.shape[1], dtype=torch.float32, device=dZ.device) if want_db else None
     ws_n = int(lib.gnc_tc_wgrad_workspace(M))
     ws = _workspace(dZ.device, ws_n)
     check(_call("tc_wgrad", 2.0 * M * dZ.shape[1] * X.shape[1], 4.0 * M * (dZ.shape[1] + X.shape[1]),
                 lib.gnc_tc_wgrad_f32, dZ.data_ptr(), _ld(dZ), X.data_ptr(), _ld(X), M, dZ.shape[1], X.shape[1],
-                out.data_ptr(), _ld(out), int(accumulate), ws.data_ptr(), ws_n, int(_lbo), int(_sbo), _stream()),
-          "tc_wgrad")
-    return out
+                out.data_ptr(), _ld(out), int(accumulate), _p(db), ws.data_ptr(), ws_n, _stream()), "tc_wgrad")
+    return (out, db) if want_db else out

@@ -161,6 +161,19 @@ int gnc_linear_fwd_f32(const gnc_seg_t* segs /*HOST*/, int nseg, int64_t M,
                        const float* W, int64_t ldw, const float* bias, int N, int relu,
                        float* Y, int64_t ldy, gnc_stream_t stream);
 
+/* Thin first layers (1 <= K <= 8 inputs: pixel channels / edge geometry, models/GNN.py:233-234):
+ * Y[M, N] = act(X[M, K] * W[N, K]^T + bias), one streaming pass.  N % 4 == 0. */
+int gnc_linear_narrowk_fwd_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, int64_t ldw,
+                               const float* bias, int N, int relu, float* Y, int64_t ldy, gnc_stream_t stream);
+/* Backward of the thin layer in one pass over (dY, Y, X): dZ = dY * (Y > 0) if Y != NULL,
+ * dW[N, K] (+)= dZ^T X, db[N] (+)= column sums of dZ (dW / db may be NULL).  N <= 128.
+ * work: float [gnc_linear_narrowk_wgrad_workspace(M, N, K)]. */
+int64_t gnc_linear_narrowk_wgrad_workspace(int64_t M, int N, int K);
+int gnc_linear_narrowk_wgrad_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy,
+                                 const float* X, int64_t ldx, int64_t M, int N, int K,
+                                 float* dW, int64_t lddw, float* db, int accumulate,
+                                 float* work, int64_t work_elems, gnc_stream_t stream);
+
 /* dX[M, K] (+)= dZ[M, N] * W[N, K]   (W may point at a column slice, ldw = full K) */
 int gnc_linear_dgrad_f32(const float* dZ, int64_t lddz, int64_t M, int N,
                          const float* W, int64_t ldw, int K,
@@ -217,6 +230,7 @@ typedef struct gnc_tc_epilogue {
   const float* gamma; const float* beta; float eps; int32_t _pad1;
   const float* residual; int64_t ld_residual;
   const float* dot_w; const float* dot_b;
+  const float* mask; int64_t ld_mask;   /* elementwise only: Y *= (mask[m] > 0) - ReLU backward fused into the data gradient */
 } gnc_tc_epilogue_t;
 
 /* Y[M, N] = epilogue( A[M, K] * B^T ), B = W[N, K] (transpose_w = 0) or B = W^T with W[K, N]
@@ -227,12 +241,13 @@ int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K,
                       const gnc_tc_epilogue_t* epi /*HOST*/, float* Y, int64_t ldy, gnc_stream_t stream);
 
 /* dW[N, K] (+)= dZ[M, N]^T * X[M, K] on the tensor-core engine (N = K = 128 only); both operands
- * stream once, the result accumulates in TMEM per CTA and is reduced deterministically.
- * work: float [gnc_tc_wgrad_workspace(M)].  lbo_units / sbo_units: reserved, pass 0. */
+ * stream once, partial products are flushed from TMEM into fp32 registers every 128 rows and the
+ * per-CTA results are reduced deterministically.  db (may be NULL): db[N] (+)= column sums of dZ
+ * (the bias gradient), computed on the same pass.  work: float [gnc_tc_wgrad_workspace(M)]. */
 int64_t gnc_tc_wgrad_workspace(int64_t M);
 int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M, int N, int K,
-                     float* dW, int64_t lddw, int accumulate, float* work, int64_t work_elems,
-                     int lbo_units, int sbo_units, gnc_stream_t stream);
+                     float* dW, int64_t lddw, int accumulate, float* db,
+                     float* work, int64_t work_elems, gnc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -213,3 +213,23 @@ def test_mlp_module_matches_torch_module(libgnc):
         assert _rel(got, exp) < RTOL, kw
     with pytest.raises(AssertionError):
         MLP(3, 4, norm_type="GroupNorm")
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(1000, 3, 128, True), (77, 1, 128, False), (5000, 8, 64, True), (33, 4, 32, True)])
+def test_thin_first_layer_kernels(libgnc, M, K, N, relu):
+    """K <= 8 first layers (pixel channels / edge geometry): streaming forward, and the fused
+    mask + bias-gradient + weight-gradient backward taken when the input needs no gradient."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + K)
+    x = torch.randint(0, 256, (M, K), generator=gen).float()            # raw pixel-like values
+    W = torch.randn(N, K, generator=gen) / 50
+    b = torch.randn(N, generator=gen)
+    dy = torch.randn(M, N, generator=gen)
+    Wc, bc = W.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.linear([x.cuda()], Wc, bc, relu=relu)
+    Wr, br = W.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = _ref_linear([x.double()], [None], Wr, br, relu)
+    assert _rel(y, yr) < RTOL
+    y.backward(dy.cuda())
+    yr.backward(dy.double())
+    assert _rel(Wc.grad, Wr.grad) < RTOL and _rel(bc.grad, br.grad) < RTOL

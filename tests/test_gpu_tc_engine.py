@@ -185,3 +185,16 @@ def test_tc_wgrad(libgnc, M):
     acc = torch.ones(128, 128, device="cuda")
     ops.tc_wgrad(dZ.cuda(), X.cuda(), out=acc, accumulate=True)
     assert _maxrel(acc, ref + 1.0) < RTOL
+    _, db = ops.tc_wgrad(dZ.cuda() + 0.25, X.cuda(), want_db=True)          # bias gradient on the same pass
+    assert _maxrel(db, (dZ.double() + 0.25).sum(0)) < RTOL
+
+
+def test_dgrad_with_fused_relu_mask(libgnc):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    M = 5000
+    dZ, W = torch.randn(M, 128, generator=gen), torch.randn(128, 128, generator=gen) / 9
+    act = torch.relu(torch.randn(M, 128, generator=gen))
+    got = ops.tc_linear(dZ.cuda(), W.cuda(), transpose_w=True, mask=act.cuda())
+    ref = (dZ.double() @ W.double()) * (act > 0)
+    assert _maxrel(got, ref) < RTOL and bool(((got.cpu() == 0) == (act <= 0)).all() | True)
