@@ -55,3 +55,21 @@ def test_train_gnn_entry_point(libgnc, image_folder, tmp_path):
     assert "final_model.pth" in names and "best_model_epoch1.pth" in names
     sd = torch.load(os.path.join(out, "final_model.pth"), map_location="cpu")
     assert len(sd) == 76 and tuple(sd["classifier.fc1.weight"].shape) == (128, 64)
+
+
+def test_gnn_inference_helper(libgnc, tmp_path):
+    """reference utils/inference.py:32-71: checkpoint -> single-image logits / probabilities."""
+    from graphnet_classifier_b200.utils.inference import gnn_inference
+    from oracle import gnn as ognn
+    r = 16
+    om = ognn.build_reference_config_model(r, seed=3)
+    ck = str(tmp_path / "ck.pth")
+    torch.save(om.state_dict(), ck)                       # a checkpoint in the reference's format
+    img = np.random.default_rng(5).integers(0, 256, (r, r, 3), dtype=np.uint8)
+    path = str(tmp_path / "img.png")
+    Image.fromarray(img).save(path)
+    logits, probs = gnn_inference(path, ck, resize_value=r)
+    assert logits.shape == (1, 2) and probs.shape == (1, 2) and abs(float(probs.sum()) - 1.0) < 1e-6
+    with torch.no_grad():
+        exp = om(ogb.to_model_inputs(*ogb.pixel_graph(img)))
+    np.testing.assert_allclose(logits[0].cpu().numpy(), exp.numpy(), rtol=1e-5, atol=1e-7)
