@@ -26,7 +26,8 @@ class GncTcEpilogue(Structure):
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
                 ("residual", c_void_p), ("ld_residual", c_int64),
                 ("dot_w", c_void_p), ("dot_b", c_void_p),
-                ("mask", c_void_p), ("ld_mask", c_int64)]
+                ("mask", c_void_p), ("ld_mask", c_int64),
+                ("residual_idx", c_void_p)]
 
 
 class GncError(RuntimeError):
@@ -53,6 +54,9 @@ SIGNATURES = {
     "gnc_csr_build": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "gnc_agg_csr_sum_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, c_int64, c_int, _P]),
     "gnc_gather_rows_f32": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int, _P]),
+    "gnc_gather_add_rows_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, _P, c_int, c_int64,
+                                        c_int, _P, c_int64, _P]),
+    "gnc_grid_edge_class": (c_int, [c_int, c_int, c_int, c_int, _P, _P]),
     "gnc_edge_geometry_f32": (c_int, [_P, c_int, _P, _P, c_int64, _P, _P]),
     "gnc_linear_fwd_f32": (c_int, [POINTER(GncSeg), c_int, c_int64, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "gnc_linear_narrowk_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),

@@ -168,6 +168,58 @@ __global__ void edge_geometry_kernel(const float* __restrict__ pos, int P, const
   }
 }
 
+// out[m, :] = act( sum_s T_s[idx_s[m], :] + bias )  for up to 3 gathered tables; D = 4 * D4 <= 128 * 4.
+// Used when an operand of a linear layer is a lookup into a small table (edge classes of grid
+// graphs): the product with the weights is taken once per table row, and the layer becomes this
+// streaming gather-add (see GraphNet._forward_tc).
+struct GatherAddArgs {
+  const float* tab[3];
+  const int32_t* idx[3];
+  long long ld[3];
+  int nsrc;
+  const float* bias;
+  int relu;
+  float* out;
+  long long ld_out;
+  long long M;
+  int D4;
+};
+
+__global__ void __launch_bounds__(256) gather_add_rows_kernel(const GatherAddArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (int c4 = lane; c4 < a.D4; c4 += 32) {
+    const float4 b = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long m0 = warp_global * 4; m0 < a.M; m0 += warps_total * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = b;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (s < a.nsrc) {
+          float4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long long m = m0 + u < a.M ? m0 + u : a.M - 1;
+            const long long r = a.idx[s] ? (long long)__ldg(a.idx[s] + m) : m;
+            t[u] = __ldg(reinterpret_cast<const float4*>(a.tab[s] + r * a.ld[s]) + c4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { v[u].x += t[u].x; v[u].y += t[u].y; v[u].z += t[u].z; v[u].w += t[u].w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (m0 + u < a.M) {
+          if (a.relu) { v[u].x = fmaxf(v[u].x, 0.f); v[u].y = fmaxf(v[u].y, 0.f); v[u].z = fmaxf(v[u].z, 0.f); v[u].w = fmaxf(v[u].w, 0.f); }
+          stg_stream(reinterpret_cast<float4*>(a.out + (m0 + u) * a.ld_out) + c4, v[u]);
+        }
+      }
+    }
+  }
+}
+
 static inline unsigned row_grid(int64_t rows, int rows_per_block) {
   int64_t blocks = ceil_div<int64_t>(rows, rows_per_block);
   const int64_t cap = (int64_t)kNumSMs * 8;     // 8 resident 256-thread CTAs per SM
@@ -252,6 +304,25 @@ int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, in
   cudaStream_t st = (cudaStream_t)stream;
   return accumulate ? launch_gather<true>(src, ld_src, idx, M, D, out, ld_out, st)
                     : launch_gather<false>(src, ld_src, idx, M, D, out, ld_out, st);
+}
+
+int gnc_gather_add_rows_f32(const float* const* tables, const int32_t* const* idx, const int64_t* ld, int nsrc,
+                            const float* bias, int relu, int64_t M, int D, float* out, int64_t ld_out,
+                            gnc_stream_t stream) {
+  GNC_REQUIRE(nsrc >= 1 && nsrc <= 3 && tables && idx && ld && out && M >= 0 && D > 0 && D % 4 == 0 && ld_out >= D,
+              "gather_add_rows: need 1..3 sources, D % 4 == 0");
+  if (M == 0) return GNC_OK;
+  GatherAddArgs a;
+  for (int s = 0; s < 3; ++s) {
+    a.tab[s] = s < nsrc ? tables[s] : nullptr;
+    a.idx[s] = s < nsrc ? idx[s] : nullptr;
+    a.ld[s] = s < nsrc ? ld[s] : 0;
+    if (s < nsrc) GNC_REQUIRE(a.tab[s] && aligned16(a.tab[s]) && a.ld[s] % 4 == 0, "gather_add_rows: tables must be 16-byte aligned rows");
+  }
+  GNC_REQUIRE(aligned16(out) && ld_out % 4 == 0 && (!bias || aligned16(bias)), "gather_add_rows: out / bias alignment");
+  a.nsrc = nsrc; a.bias = bias; a.relu = relu; a.out = out; a.ld_out = ld_out; a.M = M; a.D4 = D / 4;
+  gather_add_rows_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("gather_add_rows_kernel");
 }
 
 int gnc_edge_geometry_f32(const float* pos, int P, const int32_t* src, const int32_t* dst, int64_t E, float* out,

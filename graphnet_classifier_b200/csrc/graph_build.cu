@@ -140,6 +140,16 @@ __global__ void __launch_bounds__(256) build_grid_graph_kernel(const GridBuildAr
   }
 }
 
+// family of every edge of a batched grid graph: 0 horizontal, 1 vertical, 2 / 3 the diagonals.
+// All edges of a family share one geometry row [d_row, d_col, L1].
+__global__ void grid_edge_class_kernel(GridDims g, int64_t BE, int32_t* __restrict__ cls) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ge = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ge < BE; ge += stride) {
+    const int64_t e = ge % g.E;
+    cls[ge] = e < g.Eh ? 0 : (e < g.Eh + g.Ev ? 1 : (e < g.Eh + g.Ev + g.Ed ? 2 : 3));
+  }
+}
+
 static int launch_grid_build(const uint8_t* img, int B, int imgH, int imgW, int patch, int diagonals,
                              float* x, float* pos, int64_t* ei, int32_t* src32, int32_t* dst32,
                              int32_t* drp, int32_t* deid, int32_t* srp, int32_t* seid, cudaStream_t st) {
@@ -461,6 +471,17 @@ int gnc_build_patch_graph_u8(const uint8_t* img, int B, int H, int W, int patch,
   GNC_REQUIRE(patch > 0, "patch graph: patch must be positive");
   return launch_grid_build(img, B, H, W, patch, 0, x, pos, edge_index, src32, dst32, dst_rowptr, dst_eid,
                            src_rowptr, src_eid, (cudaStream_t)stream);
+}
+
+int gnc_grid_edge_class(int B, int H, int W, int diagonals, int32_t* cls, gnc_stream_t stream) {
+  GNC_REQUIRE(B > 0 && H > 0 && W > 0 && cls, "grid_edge_class: bad arguments");
+  const GridDims g = make_grid(H, W, diagonals ? 1 : 0);
+  const int64_t BE = (int64_t)B * g.E;
+  if (BE == 0) return GNC_OK;
+  int64_t blocks = ceil_div<int64_t>(BE, 256);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  grid_edge_class_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, BE, cls);
+  return check_launch("grid_edge_class_kernel");
 }
 
 int64_t gnc_superpixel_workspace(int S_max, int max_label) {

@@ -79,7 +79,7 @@ struct Params {
   const float* g1; const int32_t* i1; long long ld_g1;
   int relu;
   const float* gamma; const float* beta; float eps;
-  const float* residual; long long ld_res;
+  const float* residual; long long ld_res; const int32_t* res_idx;
   const float* mask; long long ld_mask;
   const float* dot_w; const float* dot_b;
   float* Y; long long ldy;
@@ -485,10 +485,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
         // element of the row, so the cancellation in E[d^2] - E[d]^2 is of order std^2);
         // pass 2 re-reads TMEM, normalises and stores.  No 128-register row buffer.
         float4 res[8];
+        long long rrow[8];                              // residual rows: identity, or a table lookup
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rrow[j] = (p.residual && p.res_idx) ? (long long)__ldg(p.res_idx + grow[j]) : grow[j];
         if (p.residual) {                               // chunk 0 of the residual, ahead of the accumulator
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + c4 * 4));
+            res[j] = __ldg(reinterpret_cast<const float4*>(p.residual + rrow[j] * p.ld_res + c4 * 4));
         }
         mbar_wait(d_full(eg), dph);
         tc_fence_after();
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
           if (p.residual && ch < 3) {                   // next chunk's residual flies during these stores
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              res[j] = ldg_stream(reinterpret_cast<const float4*>(p.residual + grow[j] * p.ld_res + col + 32));
+              res[j] = __ldg(reinterpret_cast<const float4*>(p.residual + rrow[j] * p.ld_res + col + 32));
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -592,7 +595,7 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
   p.g1 = epi->gather1; p.i1 = epi->gather1_idx; p.ld_g1 = epi->ld_gather1;
   p.relu = epi->relu;
   p.gamma = epi->gamma; p.beta = epi->beta; p.eps = epi->eps;
-  p.residual = epi->residual; p.ld_res = epi->ld_residual;
+  p.residual = epi->residual; p.ld_res = epi->ld_residual; p.res_idx = epi->residual_idx;
   p.mask = epi->mask; p.ld_mask = epi->ld_mask;
   p.dot_w = epi->dot_w; p.dot_b = epi->dot_b;
   p.Y = Y; p.ldy = ldy;
@@ -610,6 +613,7 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
     return tc::launch<tc::MODE_RELU_DOT>(p, st);
   }
   GNC_REQUIRE(ldy >= tc::kD && ldy % 4 == 0 && aligned16(Y), "tc_linear: Y rows must be 16-byte aligned");
+  GNC_REQUIRE(!epi->residual_idx || (epi->gamma && epi->residual), "tc_linear: residual_idx is supported by the LayerNorm epilogue only");
   if (epi->gamma) {
     GNC_REQUIRE(epi->beta && !p.addend && !p.g0 && !p.g1 && !epi->relu, "tc_linear: LayerNorm epilogue takes bias + residual only");
     return tc::launch<tc::MODE_LAYERNORM>(p, st);

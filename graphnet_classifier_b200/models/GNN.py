@@ -215,15 +215,31 @@ class GraphNet(nn.Module):
 
         ne, ee = self.node_encoder.model, self.edge_encoder.model
         h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder)
-        e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+        # Grid graphs from our builders: edges fall into <= 4 classes with identical geometry rows
+        # (SURVEY.md 0.4), so the edge encoder runs on one row per class and the encoded edge
+        # latent of block 0 is a 4-row table indexed by class - never an [E, 128] tensor.  Only
+        # taken when `pos` is the very tensor the builder emitted with that topology.
+        e_tab = None
+        if graph.edge_class is not None and graph.pos_ref is pos and graph.class_geom.shape[1] == ee[0].in_features:
+            e_tab = tail(ops.linear([graph.class_geom], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+            e = None
+        else:
+            e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True),
+                     self.edge_encoder)
         for blk in self.graph_processor.blocks:
             em = blk.edge_model.edge_processor
             W0, b0 = em.model[0].weight, em.model[0].bias
             P = tcl(h, W0[:, 0:128])
             Q = tcl(h, W0[:, 128:256])
-            a1 = tcl(e, W0[:, 256:384], bias=b0, gather0=(P, graph.src), gather1=(Q, graph.dst), relu=True)
+            if e is None:       # block 0 in table form: e @ Wc.T is a 4-row table too
+                R = tcl(e_tab, W0[:, 256:384])
+                a1 = ops.gather_add_rows([R, P, Q], [graph.edge_class, graph.src, graph.dst], bias=b0, relu=True)
+                res = (e_tab, graph.edge_class)
+            else:
+                a1 = tcl(e, W0[:, 256:384], bias=b0, gather0=(P, graph.src), gather1=(Q, graph.dst), relu=True)
+                res = e
             del P, Q
-            e = tail(a1, em, residual=e)
+            e = tail(a1, em, residual=res)
             del a1
             nm = blk.node_model.node_processor
             V0, c0 = nm.model[0].weight, nm.model[0].bias

@@ -123,13 +123,21 @@ class GraphIndex:
     the stable CSR of edge ids by destination (in-edges, ascending edge id - the CPU
     reference's summation order) and by source."""
 
-    __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid")
+    __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid",
+                 "edge_class", "class_geom", "pos_ref")
 
     def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
         self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
         self.src, self.dst = src, dst
         self.dst_rowptr, self.dst_eid = dst_rowptr, dst_eid
         self.src_rowptr, self.src_eid = src_rowptr, src_eid
+        # Optional (grid builders): edges fall into a few classes with identical geometry rows
+        # [pos[dst]-pos[src], L1] (SURVEY.md 0.4).  ``edge_class`` int32 [E], ``class_geom`` float
+        # [n_classes, P+1]; valid only together with the very ``pos`` tensor the builder emitted
+        # (``pos_ref``), which is what the model checks before taking the table shortcut.
+        self.edge_class = None
+        self.class_geom = None
+        self.pos_ref = None
 
     @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, validate: bool = True) -> "GraphIndex":
@@ -408,6 +416,25 @@ def gather_rows(x: Tensor, idx: Tensor, rowptr: Tensor, eid: Tensor) -> Tensor:
     return _GatherFn.apply(x, idx, rowptr, eid)
 
 
+def gather_add_rows(tables: Sequence[Tensor], idxs: Sequence[Optional[Tensor]], bias: Optional[Tensor] = None,
+                    relu: bool = False) -> Tensor:
+    """``act(sum_s tables[s][idxs[s]] + bias)`` - up to three row-gathered tables summed in one
+    streaming pass (no autograd; inference path)."""
+    _require_cuda(*tables)
+    tabs = [_rows(t) for t in tables]
+    M = int(next(i.shape[0] for i in idxs if i is not None)) if any(i is not None for i in idxs) else tabs[0].shape[0]
+    D = tabs[0].shape[1]
+    out = torch.empty(M, D, dtype=torch.float32, device=tabs[0].device)
+    n = len(tabs)
+    tp = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tabs])
+    ip = (ctypes.c_void_p * n)(*[None if i is None else i.data_ptr() for i in idxs])
+    ld = (ctypes.c_int64 * n)(*[_ld(t) for t in tabs])
+    nbytes = 4.0 * (M * D + sum(t.shape[0] * D for t in tabs) + M * sum(i is not None for i in idxs))
+    check(_call("gather_add_rows", 0.0, nbytes, _lib.load().gnc_gather_add_rows_f32, tp, ip, ld, n, _p(bias), int(relu),
+                M, D, out.data_ptr(), _ld(out), _stream()), "gather_add_rows")
+    return out
+
+
 def edge_geometry(pos: Tensor, graph: GraphIndex) -> Tensor:
     _require_cuda(pos)
     if pos.requires_grad:
@@ -503,9 +530,16 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     epi.relu = int(bool(relu))
     if gamma is not None:
         epi.gamma, epi.beta, epi.eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
+    res_rows = 0
     if residual is not None:
-        t = rows(residual)
-        epi.residual, epi.ld_residual = t.data_ptr(), _ld(t)
+        if isinstance(residual, tuple):           # (table, idx int32 [M]): residual row = table[idx[m]]
+            t = rows(residual[0])
+            epi.residual, epi.ld_residual, epi.residual_idx = t.data_ptr(), _ld(t), residual[1].data_ptr()
+            res_rows = t.shape[0]
+        else:
+            t = rows(residual)
+            epi.residual, epi.ld_residual = t.data_ptr(), _ld(t)
+            res_rows = M
     if mask is not None:
         t = rows(mask)
         epi.mask, epi.ld_mask = t.data_ptr(), _ld(t)
@@ -522,7 +556,7 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     # algorithmic HBM bytes: every operand row once (gathered tables count their own rows, not
     # one row per reference - re-references are expected to hit L2)
     nbytes = 4.0 * (M * K + M * n_out + N * K
-                    + M * 128 * ((addend is not None) + (residual is not None) + (mask is not None))
+                    + M * 128 * ((addend is not None) + (mask is not None)) + res_rows * 128
                     + (gather0[0].shape[0] * 128 + M if gather0 is not None else 0)
                     + (gather1[0].shape[0] * 128 + M if gather1 is not None else 0))
     check(_call("tc_linear", 2.0 * M * N * K, nbytes, _lib.load().gnc_tc_linear_f32, A.data_ptr(), _ld(A), M, K,

@@ -111,6 +111,21 @@ def _build_grid(images, patch: int, diagonals: bool, device, use_cache: bool) ->
         if BE == 0:
             ei, src, dst, deid, seid = ei[:, :0], src[:0], dst[:0], deid[:0], seid[:0]
         graph = GraphIndex(B * N, BE, src, dst, drp, deid, srp, seid)
+        if BE > 0:
+            # edge classes: every edge of a grid family has the same geometry row, so the edge
+            # encoder only has to see one row per family (GraphNet._forward_tc)
+            cls = torch.empty(BE, dtype=torch.int32, device=dev)
+            check(lib.gnc_grid_edge_class(B, gh, gw, int(diagonals and not patch), cls.data_ptr(), _stream()),
+                  "grid_edge_class")
+            counts = [gh * (gw - 1), (gh - 1) * gw] + ([(gh - 1) * (gw - 1)] * 2 if (diagonals and not patch) else [0, 0])
+            firsts = [0, counts[0], counts[0] + counts[1], counts[0] + counts[1] + counts[2]]
+            geom = torch.zeros(4, 3, dtype=torch.float32, device=dev)
+            for c in range(4):
+                if counts[c] > 0:
+                    rel = pos[dst[firsts[c]].long()] - pos[src[firsts[c]].long()]
+                    geom[c, :2] = rel
+                    geom[c, 2] = rel.abs().sum()
+            graph.edge_class, graph.class_geom, graph.pos_ref = cls, geom, pos
         attach_graph(ei, graph)
         if use_cache:
             _topology_cache.put(key, (pos, ei, graph))

@@ -148,6 +148,16 @@ int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid,
 int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D,
                         float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);
 
+/* out[m, :] = act( sum_s tables[s][idx[s][m], :] + bias ), 1 <= nsrc <= 3 (idx[s] NULL = identity).
+ * tables / idx / ld are HOST arrays of device pointers / strides.  D % 4 == 0. */
+int gnc_gather_add_rows_f32(const float* const* tables /*HOST*/, const int32_t* const* idx /*HOST*/,
+                            const int64_t* ld /*HOST*/, int nsrc, const float* bias, int relu,
+                            int64_t M, int D, float* out, int64_t ld_out, gnc_stream_t stream);
+
+/* Edge family of a batched H x W grid graph (0 horizontal, 1 vertical, 2/3 diagonals): all edges of
+ * a family share one geometry row (models/GNN.py:299-302 applied to grid positions).  cls int32 [B*E]. */
+int gnc_grid_edge_class(int B, int H, int W, int diagonals, int32_t* cls, gnc_stream_t stream);
+
 /* edge_attr[e] = [pos[dst[e]] - pos[src[e]], sum |.|]  (models/GNN.py:299-302).
  * pos float [N, P]; out float [E, P+1]; 1 <= P <= 8. */
 int gnc_edge_geometry_f32(const float* pos, int P, const int32_t* src, const int32_t* dst, int64_t E,
@@ -231,6 +241,7 @@ typedef struct gnc_tc_epilogue {
   const float* residual; int64_t ld_residual;
   const float* dot_w; const float* dot_b;
   const float* mask; int64_t ld_mask;   /* elementwise only: Y *= (mask[m] > 0) - ReLU backward fused into the data gradient */
+  const int32_t* residual_idx;          /* LayerNorm epilogue only: residual row = residual[residual_idx[m]] (table lookup) */
 } gnc_tc_epilogue_t;
 
 /* Y[M, N] = epilogue( A[M, K] * B^T ), B = W[N, K] (transpose_w = 0) or B = W^T with W[K, N]

@@ -198,3 +198,47 @@ def test_dgrad_with_fused_relu_mask(libgnc):
     got = ops.tc_linear(dZ.cuda(), W.cuda(), transpose_w=True, mask=act.cuda())
     ref = (dZ.double() @ W.double()) * (act > 0)
     assert _maxrel(got, ref) < RTOL and bool(((got.cpu() == 0) == (act <= 0)).all() | True)
+
+
+def test_gather_add_rows_and_table_residual(libgnc):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    M = 3001
+    T0, T1, T2 = torch.randn(4, 128, generator=gen), torch.randn(700, 128, generator=gen), torch.randn(700, 128, generator=gen)
+    i0 = torch.randint(0, 4, (M,), generator=gen).int()
+    i1, i2 = torch.randint(0, 700, (M,), generator=gen).int(), torch.randint(0, 700, (M,), generator=gen).int()
+    b = torch.randn(128, generator=gen)
+    got = ops.gather_add_rows([T0.cuda(), T1.cuda(), T2.cuda()], [i0.cuda(), i1.cuda(), i2.cuda()], bias=b.cuda(), relu=True)
+    ref = torch.relu(b + T0[i0.long()] + T1[i1.long()] + T2[i2.long()])
+    assert _maxrel(got, ref) < 1e-6
+    # LayerNorm epilogue with the residual looked up in a table
+    A, W = torch.randn(M, 128, generator=gen), torch.randn(128, 128, generator=gen) / 8
+    g, be = 1 + 0.1 * torch.randn(128, generator=gen), 0.1 * torch.randn(128, generator=gen)
+    got = ops.tc_linear(A.cuda(), W.cuda(), bias=b.cuda(), gamma=g.cuda(), beta=be.cuda(), residual=(T0.cuda(), i0.cuda()))
+    ref = torch.nn.functional.layer_norm(A.double() @ W.double().t() + b.double(), (128,), g.double(), be.double(), 1e-5) + T0.double()[i0.long()]
+    assert _maxrel(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_grid_edge_class_shortcut_equals_generic_path(libgnc, diag):
+    """The edge-class table form of block 0 (grid graphs from our builder) equals the generic
+    path, which is taken when `pos` is not the builder's own tensor."""
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    r, B = 16, 3
+    cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
+    om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=r * r, classes=2)
+    fill_deterministic(om, seed=21)
+    gm = CombinedModel(GraphNet(**cfg), num_nodes=r * r, classes=2)
+    gm.load_state_dict(om.state_dict())
+    gm = gm.cuda().eval()
+    imgs = synthetic_images(B, r, seed=77)
+    gb = build_pixel_graphs(torch.from_numpy(imgs), diagonals=diag, use_cache=False)
+    assert gb.graph.edge_class is not None and gb.graph.pos_ref is gb.pos
+    ref_geom = ognn.OracleGraphNet.edge_geometry(gb.pos.cpu(), gb.edge_index.cpu())
+    assert torch.equal(gb.graph.class_geom.cpu()[gb.graph.edge_class.cpu().long()], ref_geom)
+    with torch.no_grad():
+        y_tab = gm.graph_net(gb.x, gb.pos, gb.edge_index)               # table form
+        y_gen = gm.graph_net(gb.x, gb.pos.clone(), gb.edge_index)       # generic form (pos is another tensor)
+        y_or = torch.cat([om.graph_net(*ogb.to_model_inputs(*ogb.pixel_graph(im, diag))) for im in imgs])
+    assert _maxrel(y_tab, y_gen) < 5e-6 and _maxrel(y_tab, y_or) < RTOL and _maxrel(y_gen, y_or) < RTOL
