@@ -77,6 +77,8 @@ SIGNATURES = {
                                       _P, _P, c_int, _P, c_int64, _P]),
     "gnc_tc_linear_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, POINTER(GncTcEpilogue),
                                   _P, c_int64, _P]),
+    "gnc_tc_linear_multi_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p),
+                                        c_int64, _P]),
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
     "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,
                                  _P]),

@@ -84,6 +84,10 @@ struct Params {
   const float* dot_w; const float* dot_b;
   float* Y; long long ldy;
   long long num_tiles;
+  // co-scheduled weight sets (plain epilogue): CTA b uses set b % nsets and walks the tiles of
+  // group b / nsets, so the nsets CTAs of a group read the same A tiles at the same time (L2 reuse)
+  int nsets;
+  const float* W_alt[2]; long long ldw_alt[2]; float* Y_alt[2];
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------
@@ -203,6 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   uint8_t* sm = smem_raw + (base - raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wsel = p.nsets > 1 ? (int)(blockIdx.x % p.nsets) : 0;
+  const float* Wsel = wsel == 0 ? p.W : p.W_alt[wsel - 1];
+  const long long ldw_sel = wsel == 0 ? p.ldw : p.ldw_alt[wsel - 1];
+  float* Ysel = wsel == 0 ? p.Y : p.Y_alt[wsel - 1];
   float* s_const = reinterpret_cast<float*>(sm + kOffConst);
   const uint32_t bar0 = base + kOffBar;
   // barrier slots (8 bytes each): a_full[4] a_empty[4] d_full[2] d_empty[2]; then the TMEM base pointer
@@ -229,12 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
     const int k0 = kb * kKB + c * 4;
     float4 v;
     if (!p.transpose_w) {
-      v = __ldg(reinterpret_cast<const float4*>(p.W + (long long)n * p.ldw + k0));
+      v = __ldg(reinterpret_cast<const float4*>(Wsel + (long long)n * ldw_sel + k0));
     } else {
-      v.x = __ldg(p.W + (long long)(k0 + 0) * p.ldw + n);
-      v.y = __ldg(p.W + (long long)(k0 + 1) * p.ldw + n);
-      v.z = __ldg(p.W + (long long)(k0 + 2) * p.ldw + n);
-      v.w = __ldg(p.W + (long long)(k0 + 3) * p.ldw + n);
+      v.x = __ldg(Wsel + (long long)(k0 + 0) * ldw_sel + n);
+      v.y = __ldg(Wsel + (long long)(k0 + 1) * ldw_sel + n);
+      v.z = __ldg(Wsel + (long long)(k0 + 2) * ldw_sel + n);
+      v.w = __ldg(Wsel + (long long)(k0 + 3) * ldw_sel + n);
     }
     float4 hi, lo;
     split4(v, hi, lo);
@@ -254,7 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long first = blockIdx.x, step = gridDim.x;
+  const long long first = p.nsets > 1 ? blockIdx.x / p.nsets : blockIdx.x;
+  const long long step = p.nsets > 1 ? gridDim.x / p.nsets : gridDim.x;
   const long long n_my = (p.num_tiles > first) ? (p.num_tiles - first + step - 1) / step : 0;
 
   if (warp < kLoaderWarps) {
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
               v[j].x = ext[j].x > 0.f ? v[j].x : 0.f; v[j].y = ext[j].y > 0.f ? v[j].y : 0.f;
               v[j].z = ext[j].z > 0.f ? v[j].z : 0.f; v[j].w = ext[j].w > 0.f ? v[j].w : 0.f;
             }
-            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
+            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(Ysel + grow[j] * p.ldy + col), v[j]);
           }
           if (has_ext && ch < 3) load_ext(ch + 1, ext); // next chunk's addends fly during the next TMEM read
         }
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
             acc = fmaf(fmaxf(r[cidx] + s_bias[ch * 32 + cidx], 0.f), s_dotw[ch * 32 + cidx], acc);
         }
         const long long g = wrow0 + lane;
-        if (g < p.M) p.Y[g * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
+        if (g < p.M) Ysel[g * p.ldy] = acc + (p.dot_b ? __ldg(p.dot_b) : 0.f);
       } else {
         // LayerNorm.  Pass 1 over the accumulator: shifted one-pass statistics (shift = first
         // element of the row, so the cancellation in E[d^2] - E[d]^2 is of order std^2);
@@ -547,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + grow[j] * p.ldy + col), v[j]);
+            if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(Ysel + grow[j] * p.ldy + col), v[j]);
         }
       }
     }
@@ -571,6 +580,11 @@ static int launch(const Params& p, cudaStream_t st) {
     configured = true;
   }
   long long grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (p.nsets > 1) {
+    long long groups = kNumSMs / p.nsets;
+    if (groups > p.num_tiles) groups = p.num_tiles;
+    grid = groups * p.nsets;
+  }
   tc_linear_kernel<MODE><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(p);
   return check_launch("tc_linear_kernel");
 }
@@ -599,6 +613,8 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
   p.mask = epi->mask; p.ld_mask = epi->ld_mask;
   p.dot_w = epi->dot_w; p.dot_b = epi->dot_b;
   p.Y = Y; p.ldy = ldy;
+  p.nsets = 1;
+  p.W_alt[0] = p.W_alt[1] = nullptr; p.ldw_alt[0] = p.ldw_alt[1] = 0; p.Y_alt[0] = p.Y_alt[1] = nullptr;
   p.num_tiles = (M + tc::kTileM - 1) / tc::kTileM;
   GNC_REQUIRE(!p.g0 || p.i0, "tc_linear: gather0 needs gather0_idx");
   GNC_REQUIRE(!p.g1 || p.i1, "tc_linear: gather1 needs gather1_idx");
@@ -619,4 +635,27 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
     return tc::launch<tc::MODE_LAYERNORM>(p, st);
   }
   return tc::launch<tc::MODE_ELEMENTWISE>(p, st);
+}
+
+// Y_s[M, 128] = A[M, 128] * W_s^T for 2 or 3 weight sets in ONE launch: the CTAs of a group walk
+// the same row tiles at the same time, so A is fetched from HBM once and served to the other sets
+// from L2 (the P / Q / T products of a GraphNet block all read the node latents).
+extern "C" int gnc_tc_linear_multi_f32(const float* A, int64_t lda, int64_t M, int nsets, const float* const* W,
+                                       const int64_t* ldw, float* const* Y, int64_t ldy, gnc_stream_t stream) {
+  GNC_REQUIRE(nsets >= 2 && nsets <= 3 && A && W && ldw && Y && M >= 0 && lda >= tc::kD && ldy >= tc::kD,
+              "tc_linear_multi: need 2 or 3 weight sets");
+  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(lda % 4 == 0 && aligned16(A) && ldy % 4 == 0, "tc_linear_multi: rows must be 16-byte aligned");
+  tc::Params p = {};
+  p.A = A; p.lda = lda; p.M = M; p.transpose_w = 0;
+  p.eps = 1e-5f; p.ldy = ldy;
+  p.num_tiles = (M + tc::kTileM - 1) / tc::kTileM;
+  p.nsets = nsets;
+  for (int s = 0; s < nsets; ++s) {
+    GNC_REQUIRE(W[s] && Y[s] && aligned16(W[s]) && aligned16(Y[s]) && ldw[s] % 4 == 0 && ldw[s] >= tc::kD,
+                "tc_linear_multi: bad weight / output pointer");
+    if (s == 0) { p.W = W[0]; p.ldw = ldw[0]; p.Y = Y[0]; }
+    else { p.W_alt[s - 1] = W[s]; p.ldw_alt[s - 1] = ldw[s]; p.Y_alt[s - 1] = Y[s]; }
+  }
+  return tc::launch<tc::MODE_ELEMENTWISE>(p, (cudaStream_t)stream);
 }

@@ -228,9 +228,11 @@ class GraphNet(nn.Module):
                      self.edge_encoder)
         for blk in self.graph_processor.blocks:
             em = blk.edge_model.edge_processor
+            nm = blk.node_model.node_processor
             W0, b0 = em.model[0].weight, em.model[0].bias
-            P = tcl(h, W0[:, 0:128])
-            Q = tcl(h, W0[:, 128:256])
+            V0, c0 = nm.model[0].weight, nm.model[0].bias
+            # the three node-side products of the block read the same h: one co-scheduled launch
+            P, Q, T = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256], V0[:, 0:128]])
             if e is None:       # block 0 in table form: e @ Wc.T is a 4-row table too
                 R = tcl(e_tab, W0[:, 256:384])
                 a1 = ops.gather_add_rows([R, P, Q], [graph.edge_class, graph.src, graph.dst], bias=b0, relu=True)
@@ -241,10 +243,7 @@ class GraphNet(nn.Module):
             del P, Q
             e = tail(a1, em, residual=res)
             del a1
-            nm = blk.node_model.node_processor
-            V0, c0 = nm.model[0].weight, nm.model[0].bias
             agg = ops.aggregate(e, graph)
-            T = tcl(h, V0[:, 0:128])
             n1 = tcl(agg, V0[:, 128:256], bias=c0, addend=T, relu=True)
             del agg, T
             h = tail(n1, nm, residual=h)

@@ -565,6 +565,23 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     return out
 
 
+def tc_linear_multi(A: Tensor, weights: Sequence[Tensor]) -> list:
+    """``[A @ W.T for W in weights]`` (2 or 3 width-128 weights, e.g. column slices of wider
+    matrices) in one launch whose CTAs share the A tiles through L2."""
+    _require_cuda(A, *weights)
+    A = _rows(A)
+    M = A.shape[0]
+    n = len(weights)
+    Ws = [w if w.stride(1) == 1 else w.contiguous() for w in weights]
+    outs = [torch.empty(M, 128, dtype=torch.float32, device=A.device) for _ in range(n)]
+    wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in Ws])
+    ld = (ctypes.c_int64 * n)(*[w.stride(0) for w in Ws])
+    yp = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    check(_call("tc_linear", 2.0 * M * 128 * 128 * n, 4.0 * 128 * (M + n * M + n * 128), _lib.load().gnc_tc_linear_multi_f32,
+                A.data_ptr(), _ld(A), M, n, wp, ld, yp, 128, _stream()), "tc_linear_multi")
+    return outs
+
+
 class _TcLinearFn(torch.autograd.Function):
     """``act(A @ W.T + b + addend + P[src] + Q[dst])`` on the tensor-core engine, with its
     backward: weight + bias gradients in one tcgen05 pass (gnc_tc_wgrad_f32), data gradient on

@@ -251,6 +251,12 @@ int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K,
                       const float* W, int64_t ldw, int N, int transpose_w,
                       const gnc_tc_epilogue_t* epi /*HOST*/, float* Y, int64_t ldy, gnc_stream_t stream);
 
+/* Y_s[M, 128] = A[M, 128] * W_s[128, 128]^T for nsets = 2 or 3 weight sets in one launch (A is read
+ * from HBM once; the other sets hit L2).  W / ldw / Y are HOST arrays.  No epilogue terms. */
+int gnc_tc_linear_multi_f32(const float* A, int64_t lda, int64_t M, int nsets,
+                            const float* const* W /*HOST*/, const int64_t* ldw /*HOST*/,
+                            float* const* Y /*HOST*/, int64_t ldy, gnc_stream_t stream);
+
 /* dW[N, K] (+)= dZ[M, N]^T * X[M, K] on the tensor-core engine (N = K = 128 only); both operands
  * stream once, partial products are flushed from TMEM into fp32 registers every 128 rows and the
  * per-CTA results are reduced deterministically.  db (may be NULL): db[N] (+)= column sums of dZ
