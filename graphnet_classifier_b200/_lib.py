@@ -30,6 +30,17 @@ class GncTcEpilogue(Structure):
                 ("residual_idx", c_void_p)]
 
 
+class GncTcChain(Structure):
+    """struct gnc_tc_chain (include/gnc.h)."""
+    _fields_ = [("nlayers", c_int32), ("_pad0", c_int32),
+                ("W", c_void_p * 3), ("ldw", c_int64 * 3), ("bias", c_void_p * 3),
+                ("gather0", c_void_p), ("gather0_idx", c_void_p), ("ld_gather0", c_int64),
+                ("gather1", c_void_p), ("gather1_idx", c_void_p), ("ld_gather1", c_int64),
+                ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
+                ("residual", c_void_p), ("residual_idx", c_void_p), ("ld_residual", c_int64),
+                ("dot_w", c_void_p), ("dot_b", c_void_p)]
+
+
 class GncError(RuntimeError):
     pass
 
@@ -79,6 +90,8 @@ SIGNATURES = {
                                   _P, c_int64, _P]),
     "gnc_tc_linear_multi_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p),
                                         c_int64, _P]),
+    "gnc_tc_mlp_chain_f32": (c_int, [_P, c_int64, c_int64, POINTER(GncTcChain), _P, c_int64, _P]),
+    "gnc_debug_chain_trace": (c_int, [_P, c_int]),
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
     "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,
                                  _P]),

@@ -1,0 +1,702 @@
+// Chained width-128 MLP on tcgen05: two or three Linear(128,128) layers (+ ReLU between them, LayerNorm +
+// residual or the decoder dot product at the end) evaluated in ONE kernel, the hidden activations
+// never leaving the SM:
+//
+//   Y = tail( W2 relu( W1 relu( W0 A + b0 + G0[i0] + G1[i1] ) + b1 ) + b2 )
+//
+// This is the whole EdgeProcessor / NodeProcessor MLP of a GraphNet block (models/GNN.py:57-64, 95-104,
+// models/MLP.py:24-37) in the restructured form of DESIGN.md section 4: the gathered addends are the
+// per-node products P[row], Q[col] (edge model) or the plain addend T (node model).
+//
+// fp32 parity.  Operands are split into two fp16 pieces, a = a1 + a2 (22 significant bits), after an exact
+// power-of-two scaling that keeps the second piece out of the fp16 subnormal range (weights x 2^8,
+// activations x 2^4; the accumulator is scaled back by 2^-12 in the epilogue), and each product is three
+// kind::f16 MMAs (a1 w2, a2 w1, a1 w1; the dropped a2 w2 is below 2^-22) accumulated in fp32 in TMEM.
+// Measured 4.7e-7 rel-L2 per GEMM for |a| from 1e-2 to 2e2 (scripts/probes/pair_probe.cu) - tighter than
+// 3xTF32 (9e-7) or bf16x3 with six products (8e-7) at HALF their tensor-pipe work and 2/3 of the bf16x3
+// weight footprint.  Domain: |activation| < 4094 (fp16 overflow beyond it gives inf / NaN outputs).
+//
+// CTA pair.  Two CTAs of a cluster share every MMA (tcgen05.mma.cta_group::2, M = 256, N = 128): each CTA
+// keeps the 64 output features n = 64 * rank .. 64 * rank + 63 of every layer in shared memory (32 KB per
+// layer) and its own 128 rows of A and D in tensor memory, which leaves ~120 KB of shared memory per SM
+// for the staging rings that hide the memory latency.  The leader CTA's single MMA thread issues for both.
+//
+// Per CTA: 16 warps.
+//   warps 0-3   loaders  : cp.async 32 x 32 fp32 chunks of A (global -> swizzled smem), read back with
+//                          thread = row, split, tcgen05.st into the A operand (2 pieces x 64 packed columns).
+//   warp  4     MMA      : (leader) per layer and 32-wide K chunk: wait for the chunk, 6 MMAs.  Layer
+//                          l+1's chunk c is produced by layer l's epilogue from accumulator columns
+//                          32c..32c+31, so its MMAs overlap the rest of that epilogue.  Accumulators
+//                          ping-pong between two 128-column TMEM buffers.
+//   warps 8-15  epilogue : warp (q, h) owns rows 32q..32q+31 and columns 32c + 16h .. + 15 of every
+//                          chunk.  Hidden layers: tcgen05.ld -> bias (+ addends staged through smem by
+//                          the warp's own cp.async) -> ReLU -> split -> tcgen05.st as the next A.  Last
+//                          layer: 64 values per thread in registers, exact two-pass LayerNorm statistics
+//                          (halves combined through smem), residual, transpose through smem, coalesced
+//                          stores.
+#include "common.cuh"
+
+namespace gnc {
+namespace chain {
+
+constexpr int kD = 128;
+constexpr int kTileM = 256;                       // rows per CTA-pair tile
+constexpr int kMaxLayers = 3;
+constexpr int kImgBytes = 64 * 128;               // one (piece, K-block) image: 64 weight rows x 64 fp16
+constexpr int kLayerBytes = 4 * kImgBytes;        // 2 pieces x 2 K-blocks = 32 KB
+constexpr int kLoaderWarps = 4, kLoadBufs = 3;
+constexpr float kScaleW = 256.f, kScaleA = 16.f;  // exact power-of-two operand scalings
+constexpr float kUnscaleD = 1.f / (kScaleW * kScaleA);
+constexpr int kMmaWarp = 4;
+constexpr int kEpiWarp0 = 8, kEpiWarps = 8;
+constexpr int kThreads = 512;
+constexpr int kRegsLoader = 72, kRegsMma = 40, kRegsEpi = 200;
+static_assert(32 * (4 * kRegsLoader + 4 * kRegsMma + kEpiWarps * kRegsEpi) <= kThreads * 128, "setmaxnreg budget");
+
+constexpr int kChunkBytes = 32 * 128;             // loader chunk: 32 rows x 32 fp32
+constexpr int kSlotBytes = 32 * 64;               // epilogue tile: 32 rows x 16 fp32
+constexpr int kOffW = 0;
+constexpr int kEpiSlots = 4;                      // per epilogue warp: addends (P, Q) x 2 steps, or 4 residual steps
+constexpr int kOffLd = kOffW + kMaxLayers * kLayerBytes;                    //  98304
+constexpr int kOffEp = kOffLd + kLoaderWarps * kLoadBufs * kChunkBytes;      // 147456
+constexpr int kOffConst = kOffEp + kEpiWarps * kEpiSlots * kSlotBytes;       // 212992: bias[3], gamma, beta
+constexpr int kOffXchg = kOffConst + 5 * kD * 4;                             // 215552: 2 x [8 warps][32 lanes]
+constexpr int kOffBar = kOffXchg + 2 * kEpiWarps * 32 * 4;                   // 217600
+constexpr int kSmemBytes = kOffBar + 256 + 1024;                             // 218880
+
+constexpr uint32_t kTmemD = 0;                    // two accumulators: [0,128) [128,256)
+constexpr uint32_t kTmemA = 256;                  // A pieces: [256,320) [320,384); [384,512) is free
+
+struct Params {
+  const float* A; long long lda; long long M;
+  int nlayers;
+  const float* W[kMaxLayers]; long long ldw[kMaxLayers]; const float* bias[kMaxLayers];
+  const float* g0; const int32_t* i0; long long ld_g0;
+  const float* g1; const int32_t* i1; long long ld_g1;
+  const float* gamma; const float* beta; float eps;
+  const float* residual; const int32_t* res_idx; long long ld_res;
+  const float* dot_w; const float* dot_b;
+  float* Y; long long ldy;
+  long long num_tiles;
+  unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
+};
+constexpr int kTraceRoles = 4;                // 0 MMA thread, 1 epilogue warp (q0,h0), 2 loader warp 0, 3 epilogue warp (q0,h1)
+
+// ---- PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+// address of the same barrier in the leader CTA's shared memory (cluster window)
+__device__ __forceinline__ uint32_t map_to_leader(uint32_t local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  // default (.release.cta) semantics: the data handed over lives in tensor memory and is ordered by the
+  // tcgen05 fences; the .release.cluster form costs a MEMBAR.ALL.GPU per arrive (measured: ~1400 cycles a chunk)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "CW_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni CW_DONE;\n\t"
+      "bra.uni CW_LOOP;\n\t"
+      "CW_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// A (fp16 pairs, K-major) from tensor memory, B from shared memory, both CTAs of the pair
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* u) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(u[0]),
+               "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16: fp16 x fp16 -> fp32, A and B K-major, M = 256 (the pair), N = 128.  (Issuing each layer as two
+// N = 64 column halves, to overlap the first half's epilogue with the second half's MMAs, was measured:
+// 12.6 ms instead of 9.2 ms on 16.6 M rows - the N = 64 shape runs well below the N = 128 rate.)
+constexpr uint32_t kInstrDesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+
+// (x0, x1), already scaled -> two packed fp16 pairs (low half = x0) with p1 + p2 == x to 22 bits
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& p1, uint32_t& p2) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(x1), "f"(x0));
+  float h0, h1;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(h0), "=f"(h1) : "r"(p1));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+template <int REGS>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+// (clock << 8 | tag) records for one thread of a role; only CTA 0 traces
+struct Tracer {
+  unsigned long long* buf; int cap; int n;
+  __device__ __forceinline__ void init(const Params& p, int role, bool on) {
+    buf = (on && p.trace && blockIdx.x == 0) ? p.trace + (size_t)role * p.trace_cap : nullptr;
+    cap = p.trace_cap; n = 0;
+  }
+  __device__ __forceinline__ void ev(int tag) {
+    if (buf && n < cap) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
+  }
+};
+
+// ---- the kernel -------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain_kernel(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nl = p.nlayers;
+  float* s_const = reinterpret_cast<float*>(sm + kOffConst);   // bias[0..2], gamma (or dot_w), beta
+  const uint32_t bar0 = base + kOffBar;
+  // barrier slots (8 bytes): a0_full[4] ae_full[4] a_empty[4] d_full[2]; then the TMEM base pointer
+  auto a0_full = [&](int c) { return bar0 + 8u * c; };
+  auto ae_full = [&](int c) { return bar0 + 32u + 8u * c; };
+  auto a_empty = [&](int c) { return bar0 + 64u + 8u * c; };
+  auto d_full = [&](int d) { return bar0 + 96u + 8u * d; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 128);
+
+  // ---- one-time setup ----------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(a0_full(c), 2 * kLoaderWarps * 32);   // every loader thread of both CTAs
+      mbar_init(ae_full(c), 2 * kEpiWarps * 32);      // every epilogue thread of both CTAs
+      mbar_init(a_empty(c), 1);
+    }
+    for (int d = 0; d < 4; ++d) mbar_init(d_full(d), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // resident B operands: scaled two-piece fp16 images of this CTA's 64 output features of every layer
+  for (int l = 0; l < nl; ++l) {
+    const float* W = p.W[l];
+    const long long ldw = p.ldw[l];
+    for (int item = threadIdx.x; item < 64 * 16; item += kThreads) {
+      const int c = item & 15, nloc = item >> 4;      // 16-byte chunk = 8 k-values; local weight row
+      const int n_glob = 64 * (int)rank + nloc;
+      const float* src = W + (long long)n_glob * ldw + c * 8;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+      uint32_t p1[4], p2[4];
+      split2(v0.x * kScaleW, v0.y * kScaleW, p1[0], p2[0]);
+      split2(v0.z * kScaleW, v0.w * kScaleW, p1[1], p2[1]);
+      split2(v1.x * kScaleW, v1.y * kScaleW, p1[2], p2[2]);
+      split2(v1.z * kScaleW, v1.w * kScaleW, p1[3], p2[3]);
+      const int kb = c >> 3, cc = c & 7;
+      uint8_t* img = sm + kOffW + l * kLayerBytes + kb * kImgBytes + (nloc >> 3) * 1024 + (nloc & 7) * 128 + ((cc ^ (nloc & 7)) << 4);
+      *reinterpret_cast<uint4*>(img) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<uint4*>(img + 2 * kImgBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+    }
+  }
+  for (int i = threadIdx.x; i < kD; i += kThreads) {
+    // hidden-layer biases are kept x kScaleA: their epilogue emits the next A operand already scaled
+    for (int l = 0; l < kMaxLayers; ++l) s_const[l * kD + i] = (l < nl && p.bias[l]) ? __ldg(p.bias[l] + i) * (l < nl - 1 ? kScaleA : 1.f) : 0.f;
+    s_const[3 * kD + i] = p.dot_w ? __ldg(p.dot_w + i) : (p.gamma ? __ldg(p.gamma + i) : 1.f);
+    s_const[4 * kD + i] = p.beta ? __ldg(p.beta + i) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs: barriers initialised, weights resident, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const long long n_my = (p.num_tiles > pair) ? (p.num_tiles - pair + npairs - 1) / npairs : 0;
+
+  if (warp < kLoaderWarps) {
+    // ======================= loaders =======================
+    reg_dec<kRegsLoader>();
+    const int q = warp;
+    const uint32_t buf0 = base + kOffLd + (uint32_t)(warp * kLoadBufs) * kChunkBytes;
+    const int rl = lane >> 3, cj = lane & 7;          // copy domain: 8 lanes per 128-byte row piece
+    const long long total = n_my * 4;
+    const uint32_t a0_remote = map_to_leader(a0_full(0));   // the cluster window is linear: + 8 c
+    Tracer tr; tr.init(p, 2, warp == 0 && lane == 0);
+    auto issue = [&](long long it, int b) {
+      if (it < total) {
+        const long long tile = pair + (it >> 2) * npairs;
+        const int c = (int)(it & 3);
+        const long long row0 = tile * kTileM + rank * 128 + q * 32;
+        const uint32_t dst0 = buf0 + (uint32_t)b * kChunkBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rl;
+          const long long row = row0 + r;
+          const long long rc = row < p.M ? row : p.M - 1;
+          cp_async16(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), p.A + rc * p.lda + c * 32 + cj * 4, row < p.M ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+    int b = 0;
+    for (long long it = 0; it < total; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
+      __syncwarp();
+      const int c = (int)(it & 3);
+      const uint32_t tph = (uint32_t)((it >> 2) & 1);
+      tr.ev(0x60 + c);
+      mbar_wait(a_empty(c), tph ^ 1u);              // last layer of the previous tile has read chunk c
+      tc_fence_after();
+      tr.ev(0x64 + c);
+      const uint8_t* buf = sm + kOffLd + (warp * kLoadBufs + b) * kChunkBytes + lane * 128;
+      const uint32_t ta = tmem_base + kTmemA + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t p1[8], p2[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + j) ^ (lane & 7)) << 4));
+          split2(x.x * kScaleA, x.y * kScaleA, p1[2 * j], p2[2 * j]);
+          split2(x.z * kScaleA, x.w * kScaleA, p1[2 * j + 1], p2[2 * j + 1]);
+        }
+        tmem_st8(ta + half * 8, p1);
+        tmem_st8(ta + 64 + half * 8, p2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_remote(a0_remote + 8u * c);
+      tr.ev(0x68 + c);
+      __syncwarp();
+      issue(it + kLoadBufs, b);
+      b = (b + 1 == kLoadBufs) ? 0 : b + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp < kEpiWarp0) {
+    // ======================= MMA issuer (leader CTA, warp 4, one thread) =======================
+    reg_dec<kRegsMma>();
+    if (rank == 0 && warp == kMmaWarp && lane == 0) {
+      const uint64_t desc0 = make_desc(base + kOffW);
+      Tracer tr; tr.init(p, 0, true);
+      uint32_t n_ae = 0;                            // completed phases of the ae_full barriers
+      long long s = 0;                              // layer sequence number: accumulator = s & 1
+#pragma unroll 1
+      for (long long t = 0; t < n_my; ++t) {
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l, ++s) {
+          const uint64_t desc_l = desc0 + (uint64_t)((l * kLayerBytes) >> 4);
+          const uint32_t d_tmem = tmem_base + kTmemD + (uint32_t)(s & 1) * kD;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            if (l == 0) mbar_wait(a0_full(c), (uint32_t)(t & 1));
+            else mbar_wait(ae_full(c), n_ae & 1u);
+            tc_fence_after();
+            tr.ev(0x10 + l * 4 + c);
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int ks = 2 * c + k2;              // K = 16 step
+              const uint32_t a1 = tmem_base + kTmemA + (uint32_t)ks * 8, a2 = a1 + 64;
+              const uint64_t w1 = desc_l + (uint64_t)(((ks >> 2) * kImgBytes + (ks & 3) * 32) >> 4);
+              const uint64_t w2 = w1 + (uint64_t)((2 * kImgBytes) >> 4);
+              umma_f16_pair(d_tmem, a1, w2, kInstrDesc, ks != 0);       // smallest terms first
+              umma_f16_pair(d_tmem, a2, w1, kInstrDesc, 1);
+              umma_f16_pair(d_tmem, a1, w1, kInstrDesc, 1);
+            }
+            if (l == nl - 1) umma_commit_pair(a_empty(c));   // chunk c of the A operand may take the next tile
+          }
+          umma_commit_pair(d_full((int)(s & 1)));
+          tr.ev(0x20 + l);
+          if (l > 0) ++n_ae;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    reg_inc<kRegsEpi>();
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3, hf = ew >> 2;           // TMEM lane quarter, column half of every chunk
+    uint8_t* slots = sm + kOffEp + ew * kEpiSlots * kSlotBytes;       // 4 tiles of 32 rows x 16 fp32
+    float* xchg = reinterpret_cast<float*>(sm + kOffXchg);           // [2][8][32]
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rl = lane >> 2, cc = lane & 3;        // coalesced domain: 4 lanes per 64-byte row piece, 8 rows per pass
+    const bool has_add = p.g0 || p.g1;
+    const uint32_t ae_remote = map_to_leader(ae_full(0));
+    Tracer tr; tr.init(p, ew == 0 ? 1 : 3, (ew == 0 || ew == 4) && lane == 0);
+    // tile slot offset of (row r, 16-byte chunk ch): 64-byte rows, chunks rotated so that thread = row reads are conflict-free
+    auto slot_off = [](int r, int ch) { return (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)); };
+
+    // Addend and residual rows are staged by this warp's own cp.async into its four 2 KB slots (no
+    // registers, no scoreboard coupling).  Addends: step c uses slots 2 (c & 1) (gather0) and 2 (c & 1) + 1
+    // (gather1), two steps in flight.  Residual: step c uses slot c, all four steps in flight from the end
+    // of the first hidden layer; the slot just consumed doubles as the transpose tile of the output.
+    // Row indices are loaded one tile ahead.
+    const uint32_t slots_u = base + kOffEp + (uint32_t)ew * kEpiSlots * kSlotBytes;
+    int ix0[4], ix1[4], ixr[4];                     // rows of gather0 / gather1 / residual for copy rows rl + 8 i
+    int nx0[4], nx1[4], nxr[4];                     // the same for the next tile
+    auto load_indices = [&](long long tile, int* a0, int* a1, int* ar) {
+      const long long r0 = tile * kTileM + rank * 128 + q * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        long long g = r0 + rl + 8 * i;
+        g = g < p.M ? g : p.M - 1;
+        a0[i] = (p.g0 && p.i0) ? __ldg(p.i0 + g) : (int)g;
+        a1[i] = (p.g1 && p.i1) ? __ldg(p.i1 + g) : (int)g;
+        ar[i] = (p.residual && p.res_idx) ? __ldg(p.res_idx + g) : (int)g;
+      }
+    };
+    auto fetch_add = [&](int c) {
+      const int col = 32 * c + 16 * hf + 4 * cc;
+      const uint32_t dst = slots_u + (uint32_t)(2 * (c & 1)) * kSlotBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = slot_off(rl + 8 * i, cc);
+        if (p.g0) cp_async16(dst + off, p.g0 + (long long)ix0[i] * p.ld_g0 + col, 16u);
+        if (p.g1) cp_async16(dst + kSlotBytes + off, p.g1 + (long long)ix1[i] * p.ld_g1 + col, 16u);
+      }
+      cp_async_commit();
+    };
+    auto fetch_res = [&](int c) {                   // into slot c
+      const int col = 32 * c + 16 * hf + 4 * cc;
+      const uint32_t dst = slots_u + (uint32_t)c * kSlotBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cp_async16(dst + slot_off(rl + 8 * i, cc), p.residual + (long long)ixr[i] * p.ld_res + col, 16u);
+      cp_async_commit();
+    };
+    auto fetch_res_all = [&]() {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) fetch_res(c);
+    };
+    auto first_fetch = [&]() {                      // what the tile needs first
+      if (has_add) { fetch_add(0); fetch_add(1); }
+      else if (p.residual) fetch_res_all();
+    };
+    // thread = row read of this lane's 16 floats from a slot
+    auto read_slot = [&](const uint8_t* slot, float* v) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const float4 x = *reinterpret_cast<const float4*>(slot + slot_off(lane, ch));
+        v[4 * ch] = x.x; v[4 * ch + 1] = x.y; v[4 * ch + 2] = x.z; v[4 * ch + 3] = x.w;
+      }
+    };
+    // 16 accumulator columns -> A operand chunk c of the next layer.  The accumulator holds kScaleW * kScaleA
+    // times the product and the next operand wants kScaleA times the activation:
+    //   kScaleA * relu(acc / (kScaleW kScaleA) + b [+ ext]) = relu(acc / kScaleW + kScaleA b [+ kScaleA ext])
+    // (exact power-of-two scalings; s_bias holds kScaleA * b, vc already includes kScaleA * ext).
+    auto emit_chunk = [&](const float* vc, const float* s_bias, int c, bool has_ext, const float* ext) {
+      const int col0 = 32 * c + 16 * hf;
+      uint32_t p1[8], p2[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j4);
+        float y0 = fmaf(vc[4 * j4], 1.f / kScaleW, b4.x), y1 = fmaf(vc[4 * j4 + 1], 1.f / kScaleW, b4.y);
+        float y2 = fmaf(vc[4 * j4 + 2], 1.f / kScaleW, b4.z), y3 = fmaf(vc[4 * j4 + 3], 1.f / kScaleW, b4.w);
+        if (has_ext) {
+          y0 = fmaf(ext[4 * j4], kScaleA, y0); y1 = fmaf(ext[4 * j4 + 1], kScaleA, y1);
+          y2 = fmaf(ext[4 * j4 + 2], kScaleA, y2); y3 = fmaf(ext[4 * j4 + 3], kScaleA, y3);
+        }
+        split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), p1[2 * j4], p2[2 * j4]);
+        split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+      }
+      const uint32_t ta = lane_addr + kTmemA + (uint32_t)(16 * c + 8 * hf);
+      tmem_st8(ta, p1);
+      tmem_st8(ta + 64, p2);
+      tr.ev(0x74);
+      tmem_st_wait();
+      tr.ev(0x75);
+      tc_fence_before();
+      mbar_arrive_remote(ae_remote + 8u * c);
+    };
+
+    if (n_my > 0) {
+      load_indices(pair, ix0, ix1, ixr);
+      first_fetch();
+    }
+    long long s = 0;
+#pragma unroll 1
+    for (long long t = 0; t < n_my; ++t) {
+      const long long tile = pair + t * npairs;
+      const long long row0 = tile * kTileM + rank * 128 + q * 32;
+      // ---- hidden layers: accumulator -> bias (+ addends) -> ReLU -> split -> next A operand
+#pragma unroll 1
+      for (int l = 0; l < nl - 1; ++l, ++s) {
+        const uint32_t d_addr = lane_addr + kTmemD + (uint32_t)(s & 1) * kD;
+        const float* s_bias = s_const + l * kD;
+        mbar_wait(d_full((int)(s & 1)), (uint32_t)((s >> 1) & 1));
+        tc_fence_after();
+        tr.ev(0x30 + l);
+        if (l == 0 && has_add) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[16];
+            tmem_ld16(d_addr + 32 * c + 16 * hf, v);
+            float ext[16];
+            tr.ev(0x70);
+            if (c < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");   // steps c and c + 1 are in flight
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            tr.ev(0x71);
+            const uint8_t* sp = slots + 2 * (c & 1) * kSlotBytes;
+            if (p.g0) read_slot(sp, ext);
+            if (p.g1) {
+              float e1[16];
+              read_slot(sp + kSlotBytes, e1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ext[j] = p.g0 ? ext[j] + e1[j] : e1[j];
+            }
+            __syncwarp();
+            if (c + 2 < 4) fetch_add(c + 2);
+            else if (c == 3 && p.residual) fetch_res_all();
+            tr.ev(0x72);
+            tmem_ld_wait();
+            tr.ev(0x73);
+            emit_chunk(v, s_bias, c, true, ext);
+            tr.ev(0x40 + l * 4 + c);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[16];
+            tmem_ld16(d_addr + 32 * c + 16 * hf, v);
+            tmem_ld_wait();
+            emit_chunk(v, s_bias, c, false, v);
+            tr.ev(0x40 + l * 4 + c);
+          }
+        }
+      }
+      // ---- last layer
+      {
+        mbar_wait(d_full((int)(s & 1)), (uint32_t)((s >> 1) & 1));
+        tc_fence_after();
+        tr.ev(0x50);
+        if (t + 1 < n_my) load_indices(tile + npairs, nx0, nx1, nxr);   // consumed at the end of this tile
+        const uint32_t d_addr = lane_addr + kTmemD + (uint32_t)(s & 1) * kD;
+        ++s;
+        const float* s_bias = s_const + (nl - 1) * kD;
+        float x[64];                                  // x[16 c + j] = column 32 c + 16 hf + j
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(d_addr + 32 * c + 16 * hf, x + 16 * c);
+        tmem_ld_wait();
+        tr.ev(0x51);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 16 * hf + 4 * j4);
+            x[16 * c + 4 * j4] = fmaf(x[16 * c + 4 * j4], kUnscaleD, b4.x);
+            x[16 * c + 4 * j4 + 1] = fmaf(x[16 * c + 4 * j4 + 1], kUnscaleD, b4.y);
+            x[16 * c + 4 * j4 + 2] = fmaf(x[16 * c + 4 * j4 + 2], kUnscaleD, b4.z);
+            x[16 * c + 4 * j4 + 3] = fmaf(x[16 * c + 4 * j4 + 3], kUnscaleD, b4.w);
+          }
+        float* xa = xchg + (ew * 32 + lane);                        // slot 0: this warp's partials
+        float* xb = xchg + (kEpiWarps * 32) + (ew * 32 + lane);     // slot 1
+        const int partner = (ew ^ 4) * 32 + lane;
+        if (p.dot_w) {
+          // decoder tail: y = relu(x) . w + b, halves combined through smem (slot alternates per tile)
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc = fmaf(fmaxf(x[16 * c + j], 0.f), s_const[3 * kD + 32 * c + 16 * hf + j], acc);
+          float* mine = (t & 1) ? xb : xa;
+          *mine = acc;
+          named_bar_sync(1 + q, 64);
+          if (hf == 0) {
+            const float other = xchg[((t & 1) ? kEpiWarps * 32 : 0) + partner];
+            const long long g = row0 + lane;
+            if (g < p.M) p.Y[g * p.ldy] = acc + other + (p.dot_b ? __ldg(p.dot_b) : 0.f);
+          }
+        } else {
+          if (p.gamma) {
+            float s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) s1 += x[j];
+            *xa = s1;
+            named_bar_sync(1 + q, 64);
+            const float mu = (s1 + xchg[partner]) * (1.0f / kD);
+            float s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { x[j] -= mu; s2 = fmaf(x[j], x[j], s2); }
+            *xb = s2;
+            named_bar_sync(1 + q, 64);
+            const float var = (s2 + xchg[kEpiWarps * 32 + partner]) * (1.0f / kD);
+            const float rstd = 1.0f / sqrtf(var + p.eps);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const int col = 32 * c + 16 * hf + 4 * j4;
+                const float4 g4 = *reinterpret_cast<const float4*>(s_const + 3 * kD + col);
+                const float4 e4 = *reinterpret_cast<const float4*>(s_const + 4 * kD + col);
+                float* xx = x + 16 * c + 4 * j4;
+                xx[0] = fmaf(xx[0] * rstd, g4.x, e4.x); xx[1] = fmaf(xx[1] * rstd, g4.y, e4.y);
+                xx[2] = fmaf(xx[2] * rstd, g4.z, e4.z); xx[3] = fmaf(xx[3] * rstd, g4.w, e4.w);
+              }
+          }
+          tr.ev(0x53);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint8_t* slot = slots + c * kSlotBytes;
+            if (p.residual) {
+              // steps c .. 3 are in flight
+              if (c == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+              else if (c == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+              else if (c == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+              else asm volatile("cp.async.wait_group 0;" ::: "memory");
+              __syncwarp();
+              float rsd[16];
+              read_slot(slot, rsd);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x[16 * c + j] += rsd[j];
+              __syncwarp();
+            }
+            // transpose through the same slot: thread = row writes, 4 lanes per row read and store 64 contiguous bytes
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<float4*>(slot + slot_off(lane, ch)) =
+                  make_float4(x[16 * c + 4 * ch], x[16 * c + 4 * ch + 1], x[16 * c + 4 * ch + 2], x[16 * c + 4 * ch + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rl + 8 * i;
+              const long long g = row0 + r;
+              const float4 o = *reinterpret_cast<const float4*>(slot + slot_off(r, cc));
+              if (g < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + g * p.ldy + 32 * c + 16 * hf + 4 * cc), o);
+            }
+            __syncwarp();
+            tr.ev(0x54 + c);
+          }
+        }
+      }
+      tr.ev(0x52);
+      if (t + 1 < n_my) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ix0[i] = nx0[i]; ix1[i] = nx1[i]; ixr[i] = nxr[i]; }
+        first_fetch();
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+
+  // ---- teardown ---------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer may still be arriving on the leader's barriers
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0;
+
+static int launch(const Params& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  tc_chain_kernel<<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
+  return check_launch("tc_chain_kernel");
+}
+
+}  // namespace chain
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* ch, float* Y, int64_t ldy,
+                                    gnc_stream_t stream) {
+  GNC_REQUIRE(A && ch && Y && M >= 0 && lda >= chain::kD, "tc_mlp_chain: bad arguments");
+  GNC_REQUIRE(ch->nlayers >= 2 && ch->nlayers <= chain::kMaxLayers, "tc_mlp_chain: 2 or 3 layers");
+  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(lda % 4 == 0 && aligned16(A), "tc_mlp_chain: A rows must be 16-byte aligned");
+  chain::Params p = {};
+  p.A = A; p.lda = lda; p.M = M; p.nlayers = ch->nlayers;
+  for (int l = 0; l < ch->nlayers; ++l) {
+    GNC_REQUIRE(ch->W[l] && aligned16(ch->W[l]) && ch->ldw[l] >= chain::kD && ch->ldw[l] % 4 == 0, "tc_mlp_chain: bad weight pointer / stride");
+    p.W[l] = ch->W[l]; p.ldw[l] = ch->ldw[l]; p.bias[l] = ch->bias[l];
+  }
+  auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0 && ld >= chain::kD); };
+  GNC_REQUIRE(ok4(ch->gather0, ch->ld_gather0) && ok4(ch->gather1, ch->ld_gather1) && ok4(ch->residual, ch->ld_residual),
+              "tc_mlp_chain: addend / residual rows must be 16-byte aligned, 128 wide");
+  p.g0 = ch->gather0; p.i0 = ch->gather0_idx; p.ld_g0 = ch->ld_gather0;
+  p.g1 = ch->gather1; p.i1 = ch->gather1_idx; p.ld_g1 = ch->ld_gather1;
+  p.gamma = ch->gamma; p.beta = ch->beta; p.eps = ch->eps;
+  p.residual = ch->residual; p.res_idx = ch->residual_idx; p.ld_res = ch->ld_residual;
+  p.dot_w = ch->dot_w; p.dot_b = ch->dot_b;
+  GNC_REQUIRE(!p.gamma || p.beta, "tc_mlp_chain: LayerNorm needs gamma and beta");
+  if (p.dot_w) {
+    GNC_REQUIRE(!p.gamma && !p.residual && ldy >= 1, "tc_mlp_chain: the dot tail excludes LayerNorm / residual");
+  } else {
+    GNC_REQUIRE(ldy >= chain::kD && ldy % 4 == 0 && aligned16(Y), "tc_mlp_chain: Y rows must be 16-byte aligned");
+  }
+  p.Y = Y; p.ldy = ldy;
+  p.num_tiles = (M + chain::kTileM - 1) / chain::kTileM;
+  p.trace = chain::g_trace; p.trace_cap = chain::g_trace_cap;
+  return chain::launch(p, (cudaStream_t)stream);
+}
+
+// Debug: CTA 0 of subsequent gnc_tc_mlp_chain_f32 launches records (clock64 << 8 | tag) events for
+// chain::kTraceRoles roles into buf[role * cap + i] (device memory, zeroed by the caller).  NULL disables.
+extern "C" int gnc_debug_chain_trace(unsigned long long* buf, int cap) {
+  chain::g_trace = buf; chain::g_trace_cap = cap;
+  return GNC_OK;
+}

@@ -23,7 +23,7 @@ from torch import Tensor
 import os
 
 from . import _lib
-from ._lib import GncSeg, GncTcEpilogue, check
+from ._lib import GncSeg, GncTcChain, GncTcEpilogue, check
 
 # Dense engine for width-128 layers: "tc" = tcgen05 3xTF32 kernels (csrc/tc_linear.cu),
 # "fp32" = CUDA-core GEMM (csrc/dense.cu).  Both meet the 1e-5 parity bar; "fp32" is the
@@ -580,6 +580,72 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor]) -> list:
     check(_call("tc_linear", 2.0 * M * 128 * 128 * n, 4.0 * 128 * (M + n * M + n * 128), _lib.load().gnc_tc_linear_multi_f32,
                 A.data_ptr(), _ld(A), M, n, wp, ld, yp, 128, _stream()), "tc_linear_multi")
     return outs
+
+
+def tc_mlp_chain(A: Tensor, layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
+                 beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
+                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
+    all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
+    ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
+    layer (``idx=None``: row m); the tail is ``LayerNorm(gamma, beta) + residual`` (``residual`` a
+    tensor or ``(table, idx)``) or the decoder's ``relu(.) . dot_w + dot_b``.
+    See include/gnc.h ``gnc_tc_chain_t``."""
+    _require_cuda(A)
+    A = _rows(A)
+    M = A.shape[0]
+    ch = GncTcChain()
+    keep = []
+    ch.nlayers = len(layers)
+    for l, (W, b) in enumerate(layers):
+        _require_cuda(W)
+        if W.stride(1) != 1:
+            W = W.contiguous()
+        keep.append(W)
+        ch.W[l], ch.ldw[l] = W.data_ptr(), W.stride(0)
+        ch.bias[l] = None if b is None else b.data_ptr()
+    nbytes = 4.0 * 128 * (M + len(layers) * 128)
+
+    def rows(t):
+        t = _rows(t)
+        keep.append(t)
+        return t
+
+    for name, g in (("gather0", gather0), ("gather1", gather1)):
+        if g is None:
+            continue
+        t = rows(g[0])
+        setattr(ch, name, t.data_ptr())
+        setattr(ch, "ld_" + name, _ld(t))
+        if g[1] is not None:
+            setattr(ch, name + "_idx", g[1].data_ptr())
+        nbytes += 4.0 * (t.shape[0] * 128 + (M if g[1] is not None else 0))
+    if gamma is not None:
+        ch.gamma, ch.beta = gamma.data_ptr(), beta.data_ptr()
+    ch.eps = float(eps)
+    if residual is not None:
+        if isinstance(residual, tuple):
+            t = rows(residual[0])
+            ch.residual, ch.ld_residual, ch.residual_idx = t.data_ptr(), _ld(t), residual[1].data_ptr()
+        else:
+            t = rows(residual)
+            ch.residual, ch.ld_residual = t.data_ptr(), _ld(t)
+        nbytes += 4.0 * t.shape[0] * 128
+    n_out = 128
+    if dot_w is not None:
+        dw = dot_w.reshape(-1)
+        if dw.stride(0) != 1:
+            dw = dw.contiguous()
+        keep.append(dw)
+        ch.dot_w = dw.data_ptr()
+        ch.dot_b = None if dot_b is None else dot_b.data_ptr()
+        n_out = 1
+    if out is None:
+        out = torch.empty(M, n_out, dtype=torch.float32, device=A.device)
+    nbytes += 4.0 * M * n_out
+    check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * len(layers), nbytes, _lib.load().gnc_tc_mlp_chain_f32,
+                A.data_ptr(), _ld(A), M, ctypes.byref(ch), out.data_ptr(), _ld(out), _stream()), "tc_mlp_chain")
+    return out
 
 
 class _TcLinearFn(torch.autograd.Function):

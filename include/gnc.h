@@ -257,6 +257,31 @@ int gnc_tc_linear_multi_f32(const float* A, int64_t lda, int64_t M, int nsets,
                             const float* const* W /*HOST*/, const int64_t* ldw /*HOST*/,
                             float* const* Y /*HOST*/, int64_t ldy, gnc_stream_t stream);
 
+/* Chained MLP on the tensor-core engine (csrc/tc_chain.cu): nlayers = 2 or 3 Linear(128,128) layers,
+ * ReLU after every layer but the last, hidden activations never written to memory:
+ *   z0 = W[0] a + bias[0] + gather0[gather0_idx[m]] + gather1[gather1_idx[m]]      (idx NULL: row m itself)
+ *   z_l = W[l] relu(z_{l-1}) + bias[l]
+ *   dot_w != NULL : Y[m, 0] = relu(z_last) . dot_w + *dot_b                        (decoder, models/GNN.py:289-295)
+ *   otherwise     : Y = LayerNorm(z_last; gamma, beta, eps) (gamma NULL: identity) + residual[residual_idx[m]]
+ * i.e. one EdgeProcessor / NodeProcessor MLP of models/GNN.py:57-64, 95-104 per launch.  Operands are
+ * split into three bf16 pieces (six MMAs per product): fp32-accurate like gnc_tc_linear_f32. */
+typedef struct gnc_tc_chain {
+  int32_t nlayers; int32_t _pad0;
+  const float* W[3]; int64_t ldw[3]; const float* bias[3];
+  const float* gather0; const int32_t* gather0_idx; int64_t ld_gather0;
+  const float* gather1; const int32_t* gather1_idx; int64_t ld_gather1;
+  const float* gamma; const float* beta; float eps; int32_t _pad1;
+  const float* residual; const int32_t* residual_idx; int64_t ld_residual;
+  const float* dot_w; const float* dot_b;
+} gnc_tc_chain_t;
+
+int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,
+                         float* Y, int64_t ldy, gnc_stream_t stream);
+
+/* Debug aid: timeline (clock64 << 8 | tag) of CTA 0's roles in later gnc_tc_mlp_chain_f32 launches,
+ * buf = device uint64 [4 * cap] zeroed by the caller; NULL switches it off (scripts/chain_trace.py). */
+int gnc_debug_chain_trace(unsigned long long* buf, int cap);
+
 /* dW[N, K] (+)= dZ[M, N]^T * X[M, K] on the tensor-core engine (N = K = 128 only); both operands
  * stream once, partial products are flushed from TMEM into fp32 registers every 128 rows and the
  * per-CTA results are reduced deterministically.  db (may be NULL): db[N] (+)= column sums of dZ

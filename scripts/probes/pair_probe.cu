@@ -54,11 +54,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // kind::f16, bf16 x bf16 -> fp32, K-major A and B, M = 256 (pair), N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 
-__device__ __forceinline__ void umma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc) {
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+__device__ __forceinline__ void umma_bf16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc, uint32_t idesc = kIdesc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc),
-      "r"(kIdesc), "r"(acc) : "memory");
+      "r"(idesc), "r"(acc) : "memory");
+}
+// (x0, x1) * scale -> two packed fp16 pairs, p1 + p2 == x * scale to 22 bits
+__device__ __forceinline__ void split2h(float x0, float x1, float scale, uint32_t& p1, uint32_t& p2) {
+  x0 *= scale; x1 *= scale;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(x1), "f"(x0));
+  float h0, h1;
+  asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(h0), "=f"(h1) : "r"(p1));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(x1 - h1), "f"(x0 - h0));
 }
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -121,7 +130,8 @@ pair_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, floa
     uint32_t p1[4], p2[4], p3[4];
     for (int j = 0; j < 4; ++j) {
       const float x0 = W[n * kD + c * 8 + 2 * j], x1 = W[n * kD + c * 8 + 2 * j + 1];
-      split3(x0, x1, p1[j], p2[j], p3[j]);
+      if (pieces == 12) { split2h(x0, x1, 256.f, p1[j], p2[j]); p3[j] = 0; }
+      else split3(x0, x1, p1[j], p2[j], p3[j]);
     }
     const uint32_t off = (uint32_t)kb * kImgBytes + (uint32_t)((nl >> 3) * 1024 + (nl & 7) * 128 + ((cc ^ (nl & 7)) << 4));
     *reinterpret_cast<uint4*>(sm + 0 * 2 * kImgBytes + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
@@ -143,7 +153,10 @@ pair_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, floa
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int g = 0; g < 4; ++g) {                      // 32 k-values -> 16 packed columns per piece
       uint32_t p1[16], p2[16], p3[16];
-      for (int j = 0; j < 16; ++j) split3(a[g * 32 + 2 * j], a[g * 32 + 2 * j + 1], p1[j], p2[j], p3[j]);
+      for (int j = 0; j < 16; ++j) {
+        if (pieces == 12) { split2h(a[g * 32 + 2 * j], a[g * 32 + 2 * j + 1], 16.f, p1[j], p2[j]); p3[j] = 0; }
+        else split3(a[g * 32 + 2 * j], a[g * 32 + 2 * j + 1], p1[j], p2[j], p3[j]);
+      }
       tmem_st16(lane_addr + kTmemA + 0 * 64 + g * 16, p1);
       tmem_st16(lane_addr + kTmemA + 1 * 64 + g * 16, p2);
       tmem_st16(lane_addr + kTmemA + 2 * 64 + g * 16, p3);
@@ -164,8 +177,9 @@ pair_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, floa
       // (a_i, w_j) products, smallest first
       const int combos[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
       for (int q = 0; q < 6; ++q) {
-        if (combos[q][0] >= pieces || combos[q][1] >= pieces) continue;
-        umma_bf16_ts2(tmem_base, apiece(combos[q][0]), bdesc(combos[q][1]), first ? 0u : 1u);
+        if (pieces == 12) { if (q < 3) continue; }          // fp16: a1w2, a2w1, a1w1 only
+        else if (combos[q][0] >= pieces || combos[q][1] >= pieces) continue;
+        umma_bf16_ts2(tmem_base, apiece(combos[q][0]), bdesc(combos[q][1]), first ? 0u : 1u, pieces == 12 ? kIdescF16 : kIdesc);
         first = false;
       }
     }
@@ -180,7 +194,7 @@ pair_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, floa
       float r[32];
       tmem_ld32(lane_addr + ch * 32, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      for (int j = 0; j < 32; ++j) Y[row * kD + ch * 32 + j] = r[j];
+      for (int j = 0; j < 32; ++j) Y[row * kD + ch * 32 + j] = pieces == 12 ? r[j] * (1.0f / 4096.f) : r[j];
     }
   }
   tc_fence_before();
@@ -204,7 +218,11 @@ int main() {
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(pair_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-  for (int pieces = 1; pieces <= 3; ++pieces) {
+  const int modes[4] = {1, 2, 3, 12};
+  for (int mi = 0; mi < 4 * 3; ++mi) {
+    const int pieces = modes[mi % 4];
+    if (mi == 4) { for (auto& v : A) v *= 0.01f; cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); printf("-- A scaled by 0.01\n"); }
+    if (mi == 8) { for (auto& v : A) v *= 1e4f; cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); printf("-- A scaled by 100 (|a| <= 200)\n"); }
     cudaMemset(dY, 0, Y.size() * 4);
     pair_probe_kernel<<<M / 128, 128, kSmem>>>(dA, dW, dY, pieces);
     cudaError_t e = cudaDeviceSynchronize();

@@ -1,0 +1,113 @@
+"""GPU: the chained-MLP tensor-core kernel (csrc/tc_chain.cu: CTA pairs, bf16x3 operands, hidden
+activations kept in tensor memory) against float64, per tail and addend form, at the north_star
+tolerance (1e-5)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _maxrel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _mlp64(A, layers, pre=None):
+    z = A.double() @ layers[0][0].double().t() + layers[0][1].double()
+    if pre is not None:
+        z = z + pre
+    for W, b in layers[1:]:
+        z = torch.relu(z) @ W.double().t() + b.double()
+    return z
+
+
+def _layers(gen, n, scale=11.0):
+    return [(torch.randn(128, 128, generator=gen) / scale, torch.randn(128, generator=gen) * 0.3) for _ in range(n)]
+
+
+@pytest.mark.parametrize("M", [1, 127, 256, 257, 1000, 256 * 74 + 131, 256 * 74 * 3 + 5])
+@pytest.mark.parametrize("nlayers", [2, 3])
+def test_chain_layernorm_residual(libgnc, M, nlayers):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M * 7 + nlayers)
+    A = torch.randn(M, 128, generator=gen) * 2
+    layers = _layers(gen, nlayers)
+    gamma, beta = torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.2
+    res = torch.randn(M, 128, generator=gen)
+    cl = [(W.cuda(), b.cuda()) for W, b in layers]
+    z = _mlp64(A, layers)
+    ref = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5) + res.double()
+    got = ops.tc_mlp_chain(A.cuda(), cl, gamma=gamma.cuda(), beta=beta.cuda(), eps=1e-5, residual=res.cuda())
+    assert _rel(got, ref) < 3e-6 and _maxrel(got, ref) < RTOL
+    # no LayerNorm, no residual: the raw chain
+    got = ops.tc_mlp_chain(A.cuda(), cl)
+    assert _rel(got, z) < 3e-6 and _maxrel(got, z) < RTOL
+
+
+def test_chain_gathered_addends_weight_slices_and_table_residual(libgnc):
+    """The edge-processor form: z0 = e Wc^T + b + P[src] + Q[dst] with Wc a column slice (ldw = 384);
+    residual through a table lookup (the block-0 edge-class form)."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    M, R = 5000, 900
+    A = torch.randn(M, 128, generator=gen)
+    W0 = torch.randn(128, 384, generator=gen) / 20
+    b0 = torch.randn(128, generator=gen) * 0.1
+    rest = _layers(gen, 2)
+    P, Q = torch.randn(R, 128, generator=gen), torch.randn(R, 128, generator=gen)
+    i0, i1 = torch.randint(0, R, (M,), generator=gen), torch.randint(0, R, (M,), generator=gen)
+    gamma, beta = torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.2
+    tab, ti = torch.randn(4, 128, generator=gen), torch.randint(0, 4, (M,), generator=gen)
+    W0c = W0.cuda()
+    layers = [(W0[:, 256:384], b0)] + rest
+    cl = [(W0c[:, 256:384], b0.cuda())] + [(W.cuda(), b.cuda()) for W, b in rest]
+    z = _mlp64(A, layers, pre=P.double()[i0] + Q.double()[i1])
+    ln = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5)
+    got = ops.tc_mlp_chain(A.cuda(), cl, gather0=(P.cuda(), i0.int().cuda()), gather1=(Q.cuda(), i1.int().cuda()),
+                           gamma=gamma.cuda(), beta=beta.cuda(), residual=A.cuda())
+    assert _maxrel(got, ln + A.double()) < RTOL
+    got = ops.tc_mlp_chain(A.cuda(), cl, gather0=(P.cuda(), i0.int().cuda()), gather1=(Q.cuda(), i1.int().cuda()),
+                           gamma=gamma.cuda(), beta=beta.cuda(), residual=(tab.cuda(), ti.int().cuda()))
+    assert _maxrel(got, ln + tab.double()[ti]) < RTOL
+    # the node-processor form: one plain addend (identity index), residual = another tensor
+    T, h = torch.randn(M, 128, generator=gen), torch.randn(M, 128, generator=gen)
+    z = _mlp64(A, layers, pre=T.double())
+    ln = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5)
+    got = ops.tc_mlp_chain(A.cuda(), cl, gather0=(T.cuda(), None), gamma=gamma.cuda(), beta=beta.cuda(), residual=h.cuda())
+    assert _maxrel(got, ln + h.double()) < RTOL
+    got = ops.tc_mlp_chain(A.cuda(), cl, gather1=(T.cuda(), None), gamma=gamma.cuda(), beta=beta.cuda())
+    assert _maxrel(got, ln) < RTOL
+
+
+@pytest.mark.parametrize("M", [77, 256 * 80 + 3])
+def test_chain_decoder_dot_tail(libgnc, M):
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    A = torch.randn(M, 128, generator=gen)
+    layers = _layers(gen, 2)
+    w, b = torch.randn(1, 128, generator=gen) / 11, torch.randn(1, generator=gen)
+    cl = [(W.cuda(), bb.cuda()) for W, bb in layers]
+    ref = torch.relu(_mlp64(A, layers)) @ w.double().t() + b.double()
+    got = ops.tc_mlp_chain(A.cuda(), cl, dot_w=w.cuda(), dot_b=b.cuda())
+    assert got.shape == (M, 1) and _maxrel(got, ref) < RTOL
+
+
+def test_chain_matches_per_layer_engine_at_scale(libgnc):
+    """2 M rows (every CTA pair runs many tiles): chained result == the per-layer 3xTF32 engine to 1e-5."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    M = 256 * 74 * 110 + 19
+    A = torch.randn(M, 128, generator=gen).cuda()
+    layers = [(W.cuda(), b.cuda()) for W, b in _layers(gen, 3)]
+    gamma, beta = (torch.rand(128, generator=gen) + 0.5).cuda(), (torch.randn(128, generator=gen) * 0.2).cuda()
+    a1 = ops.tc_linear(A, layers[0][0], bias=layers[0][1], relu=True)
+    a2 = ops.tc_linear(a1, layers[1][0], bias=layers[1][1], relu=True)
+    ref = ops.tc_linear(a2, layers[2][0], bias=layers[2][1], gamma=gamma, beta=beta, eps=1e-5, residual=A)
+    got = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A)
+    assert _maxrel(got, ref) < RTOL
