@@ -300,6 +300,24 @@ def run_ours(args):
             "note": "bytes = every operand/result row once per launch, summed over the step's launches; "
                     "time = CUDA events around each launch on the launching stream",
         }
+    elif dom_name == "tc_mlp_chain":
+        # a whole 2-3 layer MLP per launch, hidden activations on chip: 64-96 fp32-FLOP per byte of
+        # unavoidable traffic and three fp16 tensor-core passes per product -> bound by the tensor pipe
+        tf = 3.0 * dom["flops"] / dom_s / 1e12
+        gbs = dom["bytes"] / dom_s / 1e9
+        roofline = {
+            "kernel": "tc_chain_kernel (tcgen05 kind::f16 cta_group::2, two-piece fp16 split, 3 MMAs per product, "
+                      "hidden activations in TMEM)", "bound": "tensor",
+            "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
+            "traffic": None,
+            "peak_source": pk["source"] + ": dense bf16 cuBLAS, sustained (kernel timed inside a long step)",
+            "executed_tensor_flops_per_step": 3.0 * dom["flops"], "fp32_equivalent_tflops": dom["flops"] / dom_s / 1e12,
+            "launches_per_step": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"],
+            "share_of_step": dom["ms"] / prof_ms if prof_ms else None,
+            "hbm_algorithmic_gbs": gbs, "hbm_frac": gbs / pk["hbm"], "algorithmic_bytes_per_step": dom["bytes"],
+            "note": "achieved = executed tensor FLOPs (3 fp16 MMAs per fp32-accurate product) / CUDA-event time of "
+                    "the launches; hbm_* = every operand/result row once per launch over the same time",
+        }
     else:
         tf = dom["flops"] / dom_s / 1e12 if dom_s > 0 else 0.0
         roofline = {

@@ -207,25 +207,28 @@ class GraphNet(nn.Module):
         ``agg @ Vb.T + h @ Va.T + c``; every contraction is then a [rows,128] x [128,128] tile."""
         tcl = ops.tc_linear
 
-        def tail(a1, mlp, residual=None):
+        def chain(a, first, mlp, n_tail=2, **kw):
+            """One launch for [first +] the last ``n_tail`` Linear layers of ``mlp`` and its LayerNorm:
+            the hidden activations stay on chip (csrc/tc_chain.cu)."""
             m = mlp.model
-            a2 = tcl(a1, m[2].weight, bias=m[2].bias, relu=True)
-            return tcl(a2, m[4].weight, bias=m[4].bias, gamma=m[5].weight, beta=m[5].bias, eps=m[5].eps,
-                       residual=residual)
+            layers = ([first] if first is not None else []) + [(m[i].weight, m[i].bias) for i in (2, 4)[2 - n_tail:]]
+            if len(m) > 5:
+                kw.update(gamma=m[5].weight, beta=m[5].bias, eps=m[5].eps)
+            return ops.tc_mlp_chain(a, layers, **kw)
 
         ne, ee = self.node_encoder.model, self.edge_encoder.model
-        h = tail(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), self.node_encoder)
+        h = chain(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), None, self.node_encoder)
         # Grid graphs from our builders: edges fall into <= 4 classes with identical geometry rows
         # (SURVEY.md 0.4), so the edge encoder runs on one row per class and the encoded edge
         # latent of block 0 is a 4-row table indexed by class - never an [E, 128] tensor.  Only
         # taken when `pos` is the very tensor the builder emitted with that topology.
         e_tab = None
         if graph.edge_class is not None and graph.pos_ref is pos and graph.class_geom.shape[1] == ee[0].in_features:
-            e_tab = tail(ops.linear([graph.class_geom], ee[0].weight, ee[0].bias, relu=True), self.edge_encoder)
+            e_tab = chain(ops.linear([graph.class_geom], ee[0].weight, ee[0].bias, relu=True), None, self.edge_encoder)
             e = None
         else:
-            e = tail(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True),
-                     self.edge_encoder)
+            e = chain(ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True), None,
+                      self.edge_encoder)
         for blk in self.graph_processor.blocks:
             em = blk.edge_model.edge_processor
             nm = blk.node_model.node_processor
@@ -236,21 +239,18 @@ class GraphNet(nn.Module):
             if e is None:       # block 0 in table form: e @ Wc.T is a 4-row table too
                 R = tcl(e_tab, W0[:, 256:384])
                 a1 = ops.gather_add_rows([R, P, Q], [graph.edge_class, graph.src, graph.dst], bias=b0, relu=True)
-                res = (e_tab, graph.edge_class)
-            else:
-                a1 = tcl(e, W0[:, 256:384], bias=b0, gather0=(P, graph.src), gather1=(Q, graph.dst), relu=True)
-                res = e
+                e = chain(a1, None, em, residual=(e_tab, graph.edge_class))
+                del a1
+            else:               # the whole edge MLP in one launch: e Wc^T + P[row] + Q[col] + b0 -> ... -> LN + e
+                e = chain(e, (W0[:, 256:384], b0), em, gather0=(P, graph.src), gather1=(Q, graph.dst), residual=e)
             del P, Q
-            e = tail(a1, em, residual=res)
-            del a1
             agg = ops.aggregate(e, graph)
-            n1 = tcl(agg, V0[:, 128:256], bias=c0, addend=T, relu=True)
+            # the whole node MLP in one launch: agg Vb^T + (h Va^T) + c0 -> ... -> LN + h
+            h = chain(agg, (V0[:, 128:256], c0), nm, gather0=(T, None), residual=h)
             del agg, T
-            h = tail(n1, nm, residual=h)
-            del n1
         dec = self.node_decoder.model
-        d1 = tcl(h, dec[0].weight, bias=dec[0].bias, relu=True)
-        return tcl(d1, dec[2].weight, bias=dec[2].bias, relu=True, dot_w=dec[4].weight, dot_b=dec[4].bias)
+        return ops.tc_mlp_chain(h, [(dec[0].weight, dec[0].bias), (dec[2].weight, dec[2].bias)],
+                                dot_w=dec[4].weight, dot_b=dec[4].bias)
 
     def _forward_tc_train(self, x, pos, graph: GraphIndex):
         """Differentiable form of ``_forward_tc``: the same restructured contractions through
