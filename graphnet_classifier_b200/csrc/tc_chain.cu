@@ -184,19 +184,42 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int REGS>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-// (clock << 8 | tag) records for one thread of a role; only CTA 0 traces
+// (clock << 8 | tag) records for one thread of a role; only CTA 0 traces.  Compiled out (ON = false) of
+// the specialised instantiations.
+template <bool ON>
 struct Tracer {
   unsigned long long* buf; int cap; int n;
   __device__ __forceinline__ void init(const Params& p, int role, bool on) {
-    buf = (on && p.trace && blockIdx.x == 0) ? p.trace + (size_t)role * p.trace_cap : nullptr;
-    cap = p.trace_cap; n = 0;
+    if (ON) {
+      buf = (on && p.trace && blockIdx.x == 0) ? p.trace + (size_t)role * p.trace_cap : nullptr;
+      cap = p.trace_cap; n = 0;
+    }
   }
   __device__ __forceinline__ void ev(int tag) {
-    if (buf && n < cap) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
+    if (ON) {
+      if (buf && n < cap) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
+    }
   }
 };
 
+// Compile-time view of a launch.  0 = absent, 1 = present, 2 = decided at run time.  The epilogue is
+// bound by instruction issue, and the run-time-generic form spends ~45 % of its instructions on
+// predication and re-derived addresses, so the shapes the GraphNet forward uses are specialised.
+template <int SPEC> struct Spec { static constexpr int nl = 0, g0 = 2, i0 = 2, g1 = 2, i1 = 2, res = 2, ridx = 2, ln = 2, dot = 2; static constexpr bool trace = true; };
+// edge processor: 3 layers, P[row] + Q[col], LayerNorm, residual          (models/GNN.py:57-64)
+template <> struct Spec<1> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+// node processor: 3 layers, one plain addend, LayerNorm, residual          (models/GNN.py:95-104)
+template <> struct Spec<2> { static constexpr int nl = 3, g0 = 1, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+// last two layers of a processor MLP: LayerNorm, residual (direct or through a table)
+template <> struct Spec<3> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 2, ln = 1, dot = 0; static constexpr bool trace = false; };
+// last two layers of an encoder MLP: LayerNorm, no residual                  (models/GNN.py:262-287)
+template <> struct Spec<4> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+// decoder: two layers and the dot-product tail                               (models/GNN.py:289-295)
+template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 1; static constexpr bool trace = false; };
+#define GNC_FLAG(field, runtime) (Spec<SPEC>::field == 2 ? (runtime) : (Spec<SPEC>::field != 0))
+
 // ---- the kernel -------------------------------------------------------------------
+template <int SPEC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -205,7 +228,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int nl = p.nlayers;
+  const int nl = Spec<SPEC>::nl ? Spec<SPEC>::nl : p.nlayers;
+  const bool has_g0 = GNC_FLAG(g0, p.g0 != nullptr), has_i0 = GNC_FLAG(i0, p.i0 != nullptr);
+  const bool has_g1 = GNC_FLAG(g1, p.g1 != nullptr), has_i1 = GNC_FLAG(i1, p.i1 != nullptr);
+  const bool has_res = GNC_FLAG(res, p.residual != nullptr), has_ridx = GNC_FLAG(ridx, p.res_idx != nullptr);
+  const bool has_ln = GNC_FLAG(ln, p.gamma != nullptr), has_dot = GNC_FLAG(dot, p.dot_w != nullptr);
+  using Trace = Tracer<Spec<SPEC>::trace>;
   float* s_const = reinterpret_cast<float*>(sm + kOffConst);   // bias[0..2], gamma (or dot_w), beta
   const uint32_t bar0 = base + kOffBar;
   // barrier slots (8 bytes): a0_full[4] ae_full[4] a_empty[4] d_full[2]; then the TMEM base pointer
@@ -253,8 +281,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   for (int i = threadIdx.x; i < kD; i += kThreads) {
     // hidden-layer biases are kept x kScaleA: their epilogue emits the next A operand already scaled
     for (int l = 0; l < kMaxLayers; ++l) s_const[l * kD + i] = (l < nl && p.bias[l]) ? __ldg(p.bias[l] + i) * (l < nl - 1 ? kScaleA : 1.f) : 0.f;
-    s_const[3 * kD + i] = p.dot_w ? __ldg(p.dot_w + i) : (p.gamma ? __ldg(p.gamma + i) : 1.f);
-    s_const[4 * kD + i] = p.beta ? __ldg(p.beta + i) : 0.f;
+    s_const[3 * kD + i] = has_dot ? __ldg(p.dot_w + i) : (has_ln ? __ldg(p.gamma + i) : 1.f);
+    s_const[4 * kD + i] = has_ln ? __ldg(p.beta + i) : 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -274,7 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     const int rl = lane >> 3, cj = lane & 7;          // copy domain: 8 lanes per 128-byte row piece
     const long long total = n_my * 4;
     const uint32_t a0_remote = map_to_leader(a0_full(0));   // the cluster window is linear: + 8 c
-    Tracer tr; tr.init(p, 2, warp == 0 && lane == 0);
+    Trace tr; tr.init(p, 2, warp == 0 && lane == 0);
     auto issue = [&](long long it, int b) {
       if (it < total) {
         const long long tile = pair + (it >> 2) * npairs;
@@ -331,7 +359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     reg_dec<kRegsMma>();
     if (rank == 0 && warp == kMmaWarp && lane == 0) {
       const uint64_t desc0 = make_desc(base + kOffW);
-      Tracer tr; tr.init(p, 0, true);
+      Trace tr; tr.init(p, 0, true);
       uint32_t n_ae = 0;                            // completed phases of the ae_full barriers
       long long s = 0;                              // layer sequence number: accumulator = s & 1
 #pragma unroll 1
@@ -374,9 +402,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     float* xchg = reinterpret_cast<float*>(sm + kOffXchg);           // [2][8][32]
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rl = lane >> 2, cc = lane & 3;        // coalesced domain: 4 lanes per 64-byte row piece, 8 rows per pass
-    const bool has_add = p.g0 || p.g1;
+    const bool has_add = has_g0 || has_g1;
     const uint32_t ae_remote = map_to_leader(ae_full(0));
-    Tracer tr; tr.init(p, ew == 0 ? 1 : 3, (ew == 0 || ew == 4) && lane == 0);
+    Trace tr; tr.init(p, ew == 0 ? 1 : 3, (ew == 0 || ew == 4) && lane == 0);
     // tile slot offset of (row r, 16-byte chunk ch): 64-byte rows, chunks rotated so that thread = row reads are conflict-free
     auto slot_off = [](int r, int ch) { return (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)); };
 
@@ -394,9 +422,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       for (int i = 0; i < 4; ++i) {
         long long g = r0 + rl + 8 * i;
         g = g < p.M ? g : p.M - 1;
-        a0[i] = (p.g0 && p.i0) ? __ldg(p.i0 + g) : (int)g;
-        a1[i] = (p.g1 && p.i1) ? __ldg(p.i1 + g) : (int)g;
-        ar[i] = (p.residual && p.res_idx) ? __ldg(p.res_idx + g) : (int)g;
+        a0[i] = (has_g0 && has_i0) ? __ldg(p.i0 + g) : (int)g;
+        a1[i] = (has_g1 && has_i1) ? __ldg(p.i1 + g) : (int)g;
+        ar[i] = (has_res && has_ridx) ? __ldg(p.res_idx + g) : (int)g;
       }
     };
     auto fetch_add = [&](int c) {
@@ -405,8 +433,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t off = slot_off(rl + 8 * i, cc);
-        if (p.g0) cp_async16(dst + off, p.g0 + (long long)ix0[i] * p.ld_g0 + col, 16u);
-        if (p.g1) cp_async16(dst + kSlotBytes + off, p.g1 + (long long)ix1[i] * p.ld_g1 + col, 16u);
+        if (has_g0) cp_async16(dst + off, p.g0 + (long long)ix0[i] * p.ld_g0 + col, 16u);
+        if (has_g1) cp_async16(dst + kSlotBytes + off, p.g1 + (long long)ix1[i] * p.ld_g1 + col, 16u);
       }
       cp_async_commit();
     };
@@ -423,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     };
     auto first_fetch = [&]() {                      // what the tile needs first
       if (has_add) { fetch_add(0); fetch_add(1); }
-      else if (p.residual) fetch_res_all();
+      else if (has_res) fetch_res_all();
     };
     // thread = row read of this lane's 16 floats from a slot
     auto read_slot = [&](const uint8_t* slot, float* v) {
@@ -471,6 +499,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     for (long long t = 0; t < n_my; ++t) {
       const long long tile = pair + t * npairs;
       const long long row0 = tile * kTileM + rank * 128 + q * 32;
+      const bool tile_full = row0 + 32 <= p.M;      // warp-uniform: no per-row guards on the stores
       // ---- hidden layers: accumulator -> bias (+ addends) -> ReLU -> split -> next A operand
 #pragma unroll 1
       for (int l = 0; l < nl - 1; ++l, ++s) {
@@ -491,16 +520,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
             __syncwarp();
             tr.ev(0x71);
             const uint8_t* sp = slots + 2 * (c & 1) * kSlotBytes;
-            if (p.g0) read_slot(sp, ext);
-            if (p.g1) {
+            if (has_g0) read_slot(sp, ext);
+            if (has_g1) {
               float e1[16];
               read_slot(sp + kSlotBytes, e1);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) ext[j] = p.g0 ? ext[j] + e1[j] : e1[j];
+              for (int j = 0; j < 16; ++j) ext[j] = has_g0 ? ext[j] + e1[j] : e1[j];
             }
             __syncwarp();
             if (c + 2 < 4) fetch_add(c + 2);
-            else if (c == 3 && p.residual) fetch_res_all();
+            else if (c == 3 && has_res) fetch_res_all();
             tr.ev(0x72);
             tmem_ld_wait();
             tr.ev(0x73);
@@ -545,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         float* xa = xchg + (ew * 32 + lane);                        // slot 0: this warp's partials
         float* xb = xchg + (kEpiWarps * 32) + (ew * 32 + lane);     // slot 1
         const int partner = (ew ^ 4) * 32 + lane;
-        if (p.dot_w) {
+        if (has_dot) {
           // decoder tail: y = relu(x) . w + b, halves combined through smem (slot alternates per tile)
           float acc = 0.f;
 #pragma unroll
@@ -561,7 +590,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
             if (g < p.M) p.Y[g * p.ldy] = acc + other + (p.dot_b ? __ldg(p.dot_b) : 0.f);
           }
         } else {
-          if (p.gamma) {
+          if (has_ln) {
             float s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) s1 += x[j];
@@ -591,7 +620,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint8_t* slot = slots + c * kSlotBytes;
-            if (p.residual) {
+            if (has_res) {
               // steps c .. 3 are in flight
               if (c == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
               else if (c == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -610,12 +639,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
               *reinterpret_cast<float4*>(slot + slot_off(lane, ch)) =
                   make_float4(x[16 * c + 4 * ch], x[16 * c + 4 * ch + 1], x[16 * c + 4 * ch + 2], x[16 * c + 4 * ch + 3]);
             __syncwarp();
+            float4 o[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = rl + 8 * i;
-              const long long g = row0 + r;
-              const float4 o = *reinterpret_cast<const float4*>(slot + slot_off(r, cc));
-              if (g < p.M) stg_stream(reinterpret_cast<float4*>(p.Y + g * p.ldy + 32 * c + 16 * hf + 4 * cc), o);
+            for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(slot + slot_off(rl + 8 * i, cc));
+            float* yrow = p.Y + (row0 + rl) * p.ldy + 32 * c + 16 * hf + 4 * cc;
+            if (tile_full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (row0 + rl + 8 * i < p.M) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
             }
             __syncwarp();
             tr.ev(0x54 + c);
@@ -645,16 +679,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0;
 
-static int launch(const Params& p, cudaStream_t st) {
+template <int SPEC>
+static int launch_spec(const Params& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tc_chain_kernel<SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  tc_chain_kernel<<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
+  tc_chain_kernel<SPEC><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
   return check_launch("tc_chain_kernel");
+}
+
+// picks the specialised instantiation when the launch has exactly its shape (Spec<> above)
+static int launch(const Params& p, cudaStream_t st) {
+  if (!p.trace) {
+    const bool ln = p.gamma != nullptr, dot = p.dot_w != nullptr, res = p.residual != nullptr;
+    if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot) return launch_spec<1>(p, st);
+    if (p.nlayers == 3 && p.g0 && !p.i0 && !p.g1 && res && !p.res_idx && ln && !dot) return launch_spec<2>(p, st);
+    if (p.nlayers == 2 && !p.g0 && !p.g1 && res && ln && !dot) return launch_spec<3>(p, st);
+    if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && ln && !dot) return launch_spec<4>(p, st);
+    if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && !ln && dot) return launch_spec<5>(p, st);
+  }
+  return launch_spec<0>(p, st);
 }
 
 }  // namespace chain
