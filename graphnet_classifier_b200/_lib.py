@@ -91,6 +91,8 @@ SIGNATURES = {
     "gnc_tc_linear_multi_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p),
                                         c_int64, _P]),
     "gnc_tc_mlp_chain_f32": (c_int, [_P, c_int64, c_int64, POINTER(GncTcChain), _P, c_int64, _P]),
+    "gnc_tc_multi_chain_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p),
+                                       POINTER(c_void_p), c_int64, _P]),
     "gnc_debug_chain_trace": (c_int, [_P, c_int]),
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
     "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,

@@ -77,6 +77,8 @@ struct Params {
   const float* residual; const int32_t* res_idx; long long ld_res;
   const float* dot_w; const float* dot_b;
   float* Y; long long ldy;
+  float* Ym[kMaxLayers];                      // multi mode: one output per weight set
+  int multi;
   long long num_tiles;
   unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
 };
@@ -205,17 +207,19 @@ struct Tracer {
 // Compile-time view of a launch.  0 = absent, 1 = present, 2 = decided at run time.  The epilogue is
 // bound by instruction issue, and the run-time-generic form spends ~45 % of its instructions on
 // predication and re-derived addresses, so the shapes the GraphNet forward uses are specialised.
-template <int SPEC> struct Spec { static constexpr int nl = 0, g0 = 2, i0 = 2, g1 = 2, i1 = 2, res = 2, ridx = 2, ln = 2, dot = 2; static constexpr bool trace = true; };
+template <int SPEC> struct Spec { static constexpr int nl = 0, g0 = 2, i0 = 2, g1 = 2, i1 = 2, res = 2, ridx = 2, ln = 2, dot = 2; static constexpr bool trace = true, multi = false; };
 // edge processor: 3 layers, P[row] + Q[col], LayerNorm, residual          (models/GNN.py:57-64)
-template <> struct Spec<1> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+template <> struct Spec<1> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
 // node processor: 3 layers, one plain addend, LayerNorm, residual          (models/GNN.py:95-104)
-template <> struct Spec<2> { static constexpr int nl = 3, g0 = 1, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+template <> struct Spec<2> { static constexpr int nl = 3, g0 = 1, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
 // last two layers of a processor MLP: LayerNorm, residual (direct or through a table)
-template <> struct Spec<3> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 2, ln = 1, dot = 0; static constexpr bool trace = false; };
+template <> struct Spec<3> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 2, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
 // last two layers of an encoder MLP: LayerNorm, no residual                  (models/GNN.py:262-287)
-template <> struct Spec<4> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false; };
+template <> struct Spec<4> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
 // decoder: two layers and the dot-product tail                               (models/GNN.py:289-295)
-template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 1; static constexpr bool trace = false; };
+template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 1; static constexpr bool trace = false, multi = false; };
+// multi mode: nl independent products of the SAME rows, Y_l = A W_l^T (the P / Q / T products of a block)
+template <> struct Spec<6> { static constexpr int nl = 0, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 0; static constexpr bool trace = false, multi = true; };
 #define GNC_FLAG(field, runtime) (Spec<SPEC>::field == 2 ? (runtime) : (Spec<SPEC>::field != 0))
 
 // ---- the kernel -------------------------------------------------------------------
@@ -234,14 +238,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   const bool has_res = GNC_FLAG(res, p.residual != nullptr), has_ridx = GNC_FLAG(ridx, p.res_idx != nullptr);
   const bool has_ln = GNC_FLAG(ln, p.gamma != nullptr), has_dot = GNC_FLAG(dot, p.dot_w != nullptr);
   using Trace = Tracer<Spec<SPEC>::trace>;
+  constexpr bool kMulti = Spec<SPEC>::multi;
   float* s_const = reinterpret_cast<float*>(sm + kOffConst);   // bias[0..2], gamma (or dot_w), beta
   const uint32_t bar0 = base + kOffBar;
-  // barrier slots (8 bytes): a0_full[4] ae_full[4] a_empty[4] d_full[2]; then the TMEM base pointer
+  // barrier slots (8 bytes): a0_full[4] ae_full[4] a_empty[4] d_full[2] (+2 spare) d_free[2]; then the TMEM base pointer
   auto a0_full = [&](int c) { return bar0 + 8u * c; };
   auto ae_full = [&](int c) { return bar0 + 32u + 8u * c; };
   auto a_empty = [&](int c) { return bar0 + 64u + 8u * c; };
   auto d_full = [&](int d) { return bar0 + 96u + 8u * d; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 128);
+  auto d_free = [&](int d) { return bar0 + 128u + 8u * d; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 144);
 
   // ---- one-time setup ----------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -251,6 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       mbar_init(a_empty(c), 1);
     }
     for (int d = 0; d < 4; ++d) mbar_init(d_full(d), 1);
+    for (int d = 0; d < 2; ++d) mbar_init(d_free(d), 2 * kEpiWarps * 32);   // multi mode: accumulator drained
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -280,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   }
   for (int i = threadIdx.x; i < kD; i += kThreads) {
     // hidden-layer biases are kept x kScaleA: their epilogue emits the next A operand already scaled
-    for (int l = 0; l < kMaxLayers; ++l) s_const[l * kD + i] = (l < nl && p.bias[l]) ? __ldg(p.bias[l] + i) * (l < nl - 1 ? kScaleA : 1.f) : 0.f;
+    for (int l = 0; l < kMaxLayers; ++l) s_const[l * kD + i] = (l < nl && p.bias[l]) ? __ldg(p.bias[l] + i) * ((l < nl - 1 && !kMulti) ? kScaleA : 1.f) : 0.f;
     s_const[3 * kD + i] = has_dot ? __ldg(p.dot_w + i) : (has_ln ? __ldg(p.gamma + i) : 1.f);
     s_const[4 * kD + i] = has_ln ? __ldg(p.beta + i) : 0.f;
   }
@@ -368,10 +375,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         for (int l = 0; l < nl; ++l, ++s) {
           const uint64_t desc_l = desc0 + (uint64_t)((l * kLayerBytes) >> 4);
           const uint32_t d_tmem = tmem_base + kTmemD + (uint32_t)(s & 1) * kD;
+          if (kMulti && s >= 2) {      // the products do not depend on each other: only the accumulator must be free
+            mbar_wait(d_free((int)(s & 1)), (uint32_t)(((s >> 1) - 1) & 1));
+            tc_fence_after();
+          }
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             if (l == 0) mbar_wait(a0_full(c), (uint32_t)(t & 1));
-            else mbar_wait(ae_full(c), n_ae & 1u);
+            else if (!kMulti) mbar_wait(ae_full(c), n_ae & 1u);
             tc_fence_after();
             tr.ev(0x10 + l * 4 + c);
 #pragma unroll
@@ -500,6 +511,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       const long long tile = pair + t * npairs;
       const long long row0 = tile * kTileM + rank * 128 + q * 32;
       const bool tile_full = row0 + 32 <= p.M;      // warp-uniform: no per-row guards on the stores
+      if (kMulti) {
+        // ---- independent products: every accumulator goes straight to its own output
+        const uint32_t dfree_remote = map_to_leader(d_free(0));
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l, ++s) {
+          mbar_wait(d_full((int)(s & 1)), (uint32_t)((s >> 1) & 1));
+          tc_fence_after();
+          const uint32_t d_addr = lane_addr + kTmemD + (uint32_t)(s & 1) * kD;
+          float x[64];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld16(d_addr + 32 * c + 16 * hf, x + 16 * c);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive_remote(dfree_remote + 8u * (uint32_t)(s & 1));     // accumulator drained
+          const float* s_bias = s_const + l * kD;
+          float* Yl = p.Ym[l];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint8_t* slot = slots + c * kSlotBytes;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 16 * hf + 4 * ch);
+              *reinterpret_cast<float4*>(slot + slot_off(lane, ch)) =
+                  make_float4(fmaf(x[16 * c + 4 * ch], kUnscaleD, b4.x), fmaf(x[16 * c + 4 * ch + 1], kUnscaleD, b4.y),
+                              fmaf(x[16 * c + 4 * ch + 2], kUnscaleD, b4.z), fmaf(x[16 * c + 4 * ch + 3], kUnscaleD, b4.w));
+            }
+            __syncwarp();
+            float4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(slot + slot_off(rl + 8 * i, cc));
+            float* yrow = Yl + (row0 + rl) * p.ldy + 32 * c + 16 * hf + 4 * cc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (tile_full || row0 + rl + 8 * i < p.M) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       // ---- hidden layers: accumulator -> bias (+ addends) -> ReLU -> split -> next A operand
 #pragma unroll 1
       for (int l = 0; l < nl - 1; ++l, ++s) {
@@ -694,6 +744,7 @@ static int launch_spec(const Params& p, cudaStream_t st) {
 
 // picks the specialised instantiation when the launch has exactly its shape (Spec<> above)
 static int launch(const Params& p, cudaStream_t st) {
+  if (p.multi) return launch_spec<6>(p, st);
   if (!p.trace) {
     const bool ln = p.gamma != nullptr, dot = p.dot_w != nullptr, res = p.residual != nullptr;
     if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot) return launch_spec<1>(p, st);
@@ -747,4 +798,25 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
 extern "C" int gnc_debug_chain_trace(unsigned long long* buf, int cap) {
   chain::g_trace = buf; chain::g_trace_cap = cap;
   return GNC_OK;
+}
+
+// Y_l[M, 128] = A[M, 128] * W_l[128, 128]^T (+ bias_l) for nsets = 2 or 3 weight sets in ONE launch of the
+// chained kernel in multi mode: A is read from memory once and stays in tensor memory for all products.
+extern "C" int gnc_tc_multi_chain_f32(const float* A, int64_t lda, int64_t M, int nsets, const float* const* W,
+                                      const int64_t* ldw, const float* const* bias, float* const* Y, int64_t ldy,
+                                      gnc_stream_t stream) {
+  GNC_REQUIRE(nsets >= 2 && nsets <= chain::kMaxLayers && A && W && ldw && Y && M >= 0 && lda >= chain::kD && ldy >= chain::kD,
+              "tc_multi_chain: need 2 or 3 weight sets");
+  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(lda % 4 == 0 && aligned16(A) && ldy % 4 == 0, "tc_multi_chain: rows must be 16-byte aligned");
+  chain::Params p = {};
+  p.A = A; p.lda = lda; p.M = M; p.nlayers = nsets; p.multi = 1; p.ldy = ldy; p.eps = 1e-5f;
+  for (int l = 0; l < nsets; ++l) {
+    GNC_REQUIRE(W[l] && Y[l] && aligned16(W[l]) && aligned16(Y[l]) && ldw[l] % 4 == 0 && ldw[l] >= chain::kD,
+                "tc_multi_chain: bad weight / output pointer");
+    p.W[l] = W[l]; p.ldw[l] = ldw[l]; p.bias[l] = bias ? bias[l] : nullptr; p.Ym[l] = Y[l];
+  }
+  p.Y = Y[0];
+  p.num_tiles = (M + chain::kTileM - 1) / chain::kTileM;
+  return chain::launch(p, (cudaStream_t)stream);
 }

@@ -565,9 +565,11 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     return out
 
 
-def tc_linear_multi(A: Tensor, weights: Sequence[Tensor]) -> list:
+def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain") -> list:
     """``[A @ W.T for W in weights]`` (2 or 3 width-128 weights, e.g. column slices of wider
-    matrices) in one launch whose CTAs share the A tiles through L2."""
+    matrices) in one launch.  ``engine="chain"``: the chained kernel in multi mode (A stays in tensor
+    memory for all products, fp16 two-piece operands); ``"tf32"``: the co-scheduled 3xTF32 launch
+    whose CTAs share the A tiles through L2."""
     _require_cuda(A, *weights)
     A = _rows(A)
     M = A.shape[0]
@@ -577,8 +579,13 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor]) -> list:
     wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in Ws])
     ld = (ctypes.c_int64 * n)(*[w.stride(0) for w in Ws])
     yp = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
-    check(_call("tc_linear", 2.0 * M * 128 * 128 * n, 4.0 * 128 * (M + n * M + n * 128), _lib.load().gnc_tc_linear_multi_f32,
-                A.data_ptr(), _ld(A), M, n, wp, ld, yp, 128, _stream()), "tc_linear_multi")
+    nbytes = 4.0 * 128 * (M + n * M + n * 128)
+    if engine == "chain":
+        check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * n, nbytes, _lib.load().gnc_tc_multi_chain_f32,
+                    A.data_ptr(), _ld(A), M, n, wp, ld, None, yp, 128, _stream()), "tc_multi_chain")
+    else:
+        check(_call("tc_linear", 2.0 * M * 128 * 128 * n, nbytes, _lib.load().gnc_tc_linear_multi_f32,
+                    A.data_ptr(), _ld(A), M, n, wp, ld, yp, 128, _stream()), "tc_linear_multi")
     return outs
 
 

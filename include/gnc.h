@@ -278,6 +278,14 @@ typedef struct gnc_tc_chain {
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,
                          float* Y, int64_t ldy, gnc_stream_t stream);
 
+/* Y_l[M, 128] = A[M, 128] * W_l[128, 128]^T (+ bias_l, bias may be NULL) for nsets = 2 or 3 weight sets in one
+ * launch of the chained kernel: A is read once and stays in tensor memory for all products (the P / Q / T
+ * products of a GraphNet block).  W / ldw / bias / Y are HOST arrays. */
+int gnc_tc_multi_chain_f32(const float* A, int64_t lda, int64_t M, int nsets,
+                           const float* const* W /*HOST*/, const int64_t* ldw /*HOST*/,
+                           const float* const* bias /*HOST, may be NULL*/, float* const* Y /*HOST*/,
+                           int64_t ldy, gnc_stream_t stream);
+
 /* Debug aid: timeline (clock64 << 8 | tag) of CTA 0's roles in later gnc_tc_mlp_chain_f32 launches,
  * buf = device uint64 [4 * cap] zeroed by the caller; NULL switches it off (scripts/chain_trace.py). */
 int gnc_debug_chain_trace(unsigned long long* buf, int cap);

@@ -244,15 +244,16 @@ def test_grid_edge_class_shortcut_equals_generic_path(libgnc, diag):
     assert _maxrel(y_tab, y_gen) < 5e-6 and _maxrel(y_tab, y_or) < RTOL and _maxrel(y_gen, y_or) < RTOL
 
 
+@pytest.mark.parametrize("engine", ["chain", "tf32"])
 @pytest.mark.parametrize("M", [77, 128 * 49 + 3, 128 * 500])
-def test_tc_linear_multi(libgnc, M):
+def test_tc_linear_multi(libgnc, M, engine):
     from graphnet_classifier_b200 import ops
     gen = torch.Generator().manual_seed(M)
     A = torch.randn(M, 128, generator=gen)
     W0, V0 = torch.randn(128, 384, generator=gen) / 12, torch.randn(128, 256, generator=gen) / 12
     Wc, Vc = W0.cuda(), V0.cuda()
-    P, Q, T = ops.tc_linear_multi(A.cuda(), [Wc[:, 0:128], Wc[:, 128:256], Vc[:, 0:128]])
+    P, Q, T = ops.tc_linear_multi(A.cuda(), [Wc[:, 0:128], Wc[:, 128:256], Vc[:, 0:128]], engine=engine)
     for got, W in ((P, W0[:, 0:128]), (Q, W0[:, 128:256]), (T, V0[:, 0:128])):
         assert _maxrel(got, A.double() @ W.double().t()) < RTOL
-    P2, Q2 = ops.tc_linear_multi(A.cuda(), [Wc[:, 0:128], Wc[:, 128:256]])
+    P2, Q2 = ops.tc_linear_multi(A.cuda(), [Wc[:, 0:128], Wc[:, 128:256]], engine=engine)
     assert torch.equal(P2, P) and torch.equal(Q2, Q)
