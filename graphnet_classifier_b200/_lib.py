@@ -38,7 +38,8 @@ class GncTcChain(Structure):
                 ("gather1", c_void_p), ("gather1_idx", c_void_p), ("ld_gather1", c_int64),
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
                 ("residual", c_void_p), ("residual_idx", c_void_p), ("ld_residual", c_int64),
-                ("dot_w", c_void_p), ("dot_b", c_void_p)]
+                ("dot_w", c_void_p), ("dot_b", c_void_p),
+                ("gather2", c_void_p), ("gather2_idx", c_void_p), ("ld_gather2", c_int64), ("pre_bias", c_void_p)]
 
 
 class GncError(RuntimeError):

@@ -79,6 +79,9 @@ struct Params {
   float* Y; long long ldy;
   float* Ym[kMaxLayers];                      // multi mode: one output per weight set
   int multi;
+  // pre-stage mode (A == NULL): the first operand is relu(g2[i2[m]] + g0[i0[m]] + g1[i1[m]] + pre_bias), built by
+  // the epilogue warps - block 0 of the grid-graph path, whose edge latents are a 4-row table (models/GNN.py:57-64)
+  const float* g2; const int32_t* i2; long long ld_g2; const float* pre_bias;
   long long num_tiles;
   unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
 };
@@ -207,19 +210,21 @@ struct Tracer {
 // Compile-time view of a launch.  0 = absent, 1 = present, 2 = decided at run time.  The epilogue is
 // bound by instruction issue, and the run-time-generic form spends ~45 % of its instructions on
 // predication and re-derived addresses, so the shapes the GraphNet forward uses are specialised.
-template <int SPEC> struct Spec { static constexpr int nl = 0, g0 = 2, i0 = 2, g1 = 2, i1 = 2, res = 2, ridx = 2, ln = 2, dot = 2; static constexpr bool trace = true, multi = false; };
+template <int SPEC> struct Spec { static constexpr int nl = 0, g0 = 2, i0 = 2, g1 = 2, i1 = 2, res = 2, ridx = 2, ln = 2, dot = 2; static constexpr bool trace = true, multi = false, pre = false; };
 // edge processor: 3 layers, P[row] + Q[col], LayerNorm, residual          (models/GNN.py:57-64)
-template <> struct Spec<1> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
+template <> struct Spec<1> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = false; };
 // node processor: 3 layers, one plain addend, LayerNorm, residual          (models/GNN.py:95-104)
-template <> struct Spec<2> { static constexpr int nl = 3, g0 = 1, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
+template <> struct Spec<2> { static constexpr int nl = 3, g0 = 1, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = false; };
 // last two layers of a processor MLP: LayerNorm, residual (direct or through a table)
-template <> struct Spec<3> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 2, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
+template <> struct Spec<3> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 1, ridx = 2, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = false; };
 // last two layers of an encoder MLP: LayerNorm, no residual                  (models/GNN.py:262-287)
-template <> struct Spec<4> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false; };
+template <> struct Spec<4> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = false; };
 // decoder: two layers and the dot-product tail                               (models/GNN.py:289-295)
-template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 1; static constexpr bool trace = false, multi = false; };
+template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 1; static constexpr bool trace = false, multi = false, pre = false; };
 // multi mode: nl independent products of the SAME rows, Y_l = A W_l^T (the P / Q / T products of a block)
-template <> struct Spec<6> { static constexpr int nl = 0, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 0; static constexpr bool trace = false, multi = true; };
+template <> struct Spec<6> { static constexpr int nl = 0, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 0; static constexpr bool trace = false, multi = true, pre = false; };
+// pre-stage + two layers + LayerNorm + table residual: the block-0 edge processor of the grid-graph path
+template <> struct Spec<7> { static constexpr int nl = 2, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 1, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = true; };
 #define GNC_FLAG(field, runtime) (Spec<SPEC>::field == 2 ? (runtime) : (Spec<SPEC>::field != 0))
 
 // ---- the kernel -------------------------------------------------------------------
@@ -239,6 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   const bool has_ln = GNC_FLAG(ln, p.gamma != nullptr), has_dot = GNC_FLAG(dot, p.dot_w != nullptr);
   using Trace = Tracer<Spec<SPEC>::trace>;
   constexpr bool kMulti = Spec<SPEC>::multi;
+  constexpr bool kPre = Spec<SPEC>::pre;
   float* s_const = reinterpret_cast<float*>(sm + kOffConst);   // bias[0..2], gamma (or dot_w), beta
   const uint32_t bar0 = base + kOffBar;
   // barrier slots (8 bytes): a0_full[4] ae_full[4] a_empty[4] d_full[2] (+2 spare) d_free[2]; then the TMEM base pointer
@@ -288,6 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   for (int i = threadIdx.x; i < kD; i += kThreads) {
     // hidden-layer biases are kept x kScaleA: their epilogue emits the next A operand already scaled
     for (int l = 0; l < kMaxLayers; ++l) s_const[l * kD + i] = (l < nl && p.bias[l]) ? __ldg(p.bias[l] + i) * ((l < nl - 1 && !kMulti) ? kScaleA : 1.f) : 0.f;
+    if (kPre) s_const[2 * kD + i] = p.pre_bias ? __ldg(p.pre_bias + i) * kScaleA : 0.f;
     s_const[3 * kD + i] = has_dot ? __ldg(p.dot_w + i) : (has_ln ? __ldg(p.gamma + i) : 1.f);
     s_const[4 * kD + i] = has_ln ? __ldg(p.beta + i) : 0.f;
   }
@@ -307,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     const int q = warp;
     const uint32_t buf0 = base + kOffLd + (uint32_t)(warp * kLoadBufs) * kChunkBytes;
     const int rl = lane >> 3, cj = lane & 7;          // copy domain: 8 lanes per 128-byte row piece
-    const long long total = n_my * 4;
+    const long long total = kPre ? 0 : n_my * 4;     // pre-stage mode: the epilogue builds the first operand
     const uint32_t a0_remote = map_to_leader(a0_full(0));   // the cluster window is linear: + 8 c
     Trace tr; tr.init(p, 2, warp == 0 && lane == 0);
     auto issue = [&](long long it, int b) {
@@ -381,7 +388,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           }
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            if (l == 0) mbar_wait(a0_full(c), (uint32_t)(t & 1));
+            if (l == 0 && !kPre) mbar_wait(a0_full(c), (uint32_t)(t & 1));
             else if (!kMulti) mbar_wait(ae_full(c), n_ae & 1u);
             tc_fence_after();
             tr.ev(0x10 + l * 4 + c);
@@ -399,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           }
           umma_commit_pair(d_full((int)(s & 1)));
           tr.ev(0x20 + l);
-          if (l > 0) ++n_ae;
+          if (l > 0 || kPre) ++n_ae;
         }
       }
     }
@@ -438,6 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         ar[i] = (has_res && has_ridx) ? __ldg(p.res_idx + g) : (int)g;
       }
     };
+    int pre_row = 0, pre_row_next = 0;              // pre-stage: this lane's row of the g2 table
     auto fetch_add = [&](int c) {
       const int col = 32 * c + 16 * hf + 4 * cc;
       const uint32_t dst = slots_u + (uint32_t)(2 * (c & 1)) * kSlotBytes;
@@ -501,8 +509,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       mbar_arrive_remote(ae_remote + 8u * c);
     };
 
+    auto load_pre_row = [&](long long tile) {
+      long long g = tile * kTileM + rank * 128 + q * 32 + lane;
+      g = g < p.M ? g : p.M - 1;
+      return (int)__ldg(p.i2 + g);
+    };
     if (n_my > 0) {
       load_indices(pair, ix0, ix1, ixr);
+      if (kPre) pre_row = load_pre_row(pair);
       first_fetch();
     }
     long long s = 0;
@@ -550,6 +564,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         }
         continue;
       }
+      if (kPre) {
+        // ---- pre-stage: first operand = relu(g2[i2] + g0[i0] + g1[i1] + bias), no accumulator involved
+        const float* s_bias = s_const + 2 * kD;
+        const float* trow = p.g2 + (long long)pre_row * p.ld_g2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float ext[16];
+          if (c < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          const uint8_t* sp = slots + 2 * (c & 1) * kSlotBytes;
+          read_slot(sp, ext);
+          {
+            float e1[16];
+            read_slot(sp + kSlotBytes, e1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ext[j] += e1[j];
+          }
+          __syncwarp();
+          if (c + 2 < 4) fetch_add(c + 2);
+          else if (c == 3 && has_res) fetch_res_all();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(trow + 32 * c + 16 * hf + 4 * j4));
+            ext[4 * j4] += r4.x; ext[4 * j4 + 1] += r4.y; ext[4 * j4 + 2] += r4.z; ext[4 * j4 + 3] += r4.w;
+          }
+          float zero[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) zero[j] = 0.f;
+          mbar_wait(a_empty(c), (uint32_t)((t & 1) ^ 1));     // the previous tile's last layer has read chunk c
+          tc_fence_after();
+          emit_chunk(zero, s_bias, c, true, ext);
+        }
+      }
       // ---- hidden layers: accumulator -> bias (+ addends) -> ReLU -> split -> next A operand
 #pragma unroll 1
       for (int l = 0; l < nl - 1; ++l, ++s) {
@@ -558,7 +606,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         mbar_wait(d_full((int)(s & 1)), (uint32_t)((s >> 1) & 1));
         tc_fence_after();
         tr.ev(0x30 + l);
-        if (l == 0 && has_add) {
+        if (l == 0 && has_add && !kPre) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float v[16];
@@ -602,7 +650,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         mbar_wait(d_full((int)(s & 1)), (uint32_t)((s >> 1) & 1));
         tc_fence_after();
         tr.ev(0x50);
-        if (t + 1 < n_my) load_indices(tile + npairs, nx0, nx1, nxr);   // consumed at the end of this tile
+        if (t + 1 < n_my) {                           // consumed at the end of this tile
+          load_indices(tile + npairs, nx0, nx1, nxr);
+          if (kPre) pre_row_next = load_pre_row(tile + npairs);
+        }
         const uint32_t d_addr = lane_addr + kTmemD + (uint32_t)(s & 1) * kD;
         ++s;
         const float* s_bias = s_const + (nl - 1) * kD;
@@ -710,6 +761,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       if (t + 1 < n_my) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ix0[i] = nx0[i]; ix1[i] = nx1[i]; ixr[i] = nxr[i]; }
+        pre_row = pre_row_next;
         first_fetch();
       }
     }
@@ -745,6 +797,7 @@ static int launch_spec(const Params& p, cudaStream_t st) {
 // picks the specialised instantiation when the launch has exactly its shape (Spec<> above)
 static int launch(const Params& p, cudaStream_t st) {
   if (p.multi) return launch_spec<6>(p, st);
+  if (!p.A) return launch_spec<7>(p, st);
   if (!p.trace) {
     const bool ln = p.gamma != nullptr, dot = p.dot_w != nullptr, res = p.residual != nullptr;
     if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot) return launch_spec<1>(p, st);
@@ -763,17 +816,27 @@ using namespace gnc;
 
 extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* ch, float* Y, int64_t ldy,
                                     gnc_stream_t stream) {
-  GNC_REQUIRE(A && ch && Y && M >= 0 && lda >= chain::kD, "tc_mlp_chain: bad arguments");
+  GNC_REQUIRE(ch && Y && M >= 0, "tc_mlp_chain: bad arguments");
   GNC_REQUIRE(ch->nlayers >= 2 && ch->nlayers <= chain::kMaxLayers, "tc_mlp_chain: 2 or 3 layers");
   if (M == 0) return GNC_OK;
-  GNC_REQUIRE(lda % 4 == 0 && aligned16(A), "tc_mlp_chain: A rows must be 16-byte aligned");
   chain::Params p = {};
   p.A = A; p.lda = lda; p.M = M; p.nlayers = ch->nlayers;
+  auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0 && ld >= chain::kD); };
+  if (A) {
+    GNC_REQUIRE(lda >= chain::kD && lda % 4 == 0 && aligned16(A), "tc_mlp_chain: A rows must be 16-byte aligned");
+    GNC_REQUIRE(!ch->gather2, "tc_mlp_chain: gather2 belongs to the pre-stage form (A == NULL)");
+  } else {
+    // pre-stage form: the first operand is relu(gather2[idx2] + gather0[idx0] + gather1[idx1] + pre_bias)
+    GNC_REQUIRE(ch->nlayers == 2 && ch->gather0 && ch->gather0_idx && ch->gather1 && ch->gather1_idx && ch->gather2 &&
+                ch->gather2_idx && ch->gamma && ch->residual && ch->residual_idx && !ch->dot_w,
+                "tc_mlp_chain: the pre-stage form takes three indexed gathers, two layers, LayerNorm and an indexed residual");
+    GNC_REQUIRE(ok4(ch->gather2, ch->ld_gather2), "tc_mlp_chain: gather2 rows must be 16-byte aligned, 128 wide");
+    p.g2 = ch->gather2; p.i2 = ch->gather2_idx; p.ld_g2 = ch->ld_gather2; p.pre_bias = ch->pre_bias;
+  }
   for (int l = 0; l < ch->nlayers; ++l) {
     GNC_REQUIRE(ch->W[l] && aligned16(ch->W[l]) && ch->ldw[l] >= chain::kD && ch->ldw[l] % 4 == 0, "tc_mlp_chain: bad weight pointer / stride");
     p.W[l] = ch->W[l]; p.ldw[l] = ch->ldw[l]; p.bias[l] = ch->bias[l];
   }
-  auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0 && ld >= chain::kD); };
   GNC_REQUIRE(ok4(ch->gather0, ch->ld_gather0) && ok4(ch->gather1, ch->ld_gather1) && ok4(ch->residual, ch->ld_residual),
               "tc_mlp_chain: addend / residual rows must be 16-byte aligned, 128 wide");
   p.g0 = ch->gather0; p.i0 = ch->gather0_idx; p.ld_g0 = ch->ld_gather0;

@@ -237,10 +237,10 @@ class GraphNet(nn.Module):
             # the three node-side products of the block read the same h: one co-scheduled launch
             P, Q, T = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256], V0[:, 0:128]])
             if e is None:       # block 0 in table form: e @ Wc.T is a 4-row table too
+                # relu(R[class] + P[row] + Q[col] + b0) is built inside the launch as its first operand
                 R = tcl(e_tab, W0[:, 256:384])
-                a1 = ops.gather_add_rows([R, P, Q], [graph.edge_class, graph.src, graph.dst], bias=b0, relu=True)
-                e = chain(a1, None, em, residual=(e_tab, graph.edge_class))
-                del a1
+                e = chain(None, None, em, pre=(R, graph.edge_class, b0), gather0=(P, graph.src), gather1=(Q, graph.dst),
+                          residual=(e_tab, graph.edge_class))
             else:               # the whole edge MLP in one launch: e Wc^T + P[row] + Q[col] + b0 -> ... -> LN + e
                 e = chain(e, (W0[:, 256:384], b0), em, gather0=(P, graph.src), gather1=(Q, graph.dst), residual=e)
             del P, Q

@@ -589,20 +589,32 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain")
     return outs
 
 
-def tc_mlp_chain(A: Tensor, layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
+def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
-                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None) -> Tensor:
     """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
     all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
     ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
     layer (``idx=None``: row m); the tail is ``LayerNorm(gamma, beta) + residual`` (``residual`` a
     tensor or ``(table, idx)``) or the decoder's ``relu(.) . dot_w + dot_b``.
+    ``A=None`` with ``pre=(table, idx int32 [M], bias)`` is the pre-stage form: the first operand is
+    ``relu(table[idx] + gather0 + gather1 + bias)`` and ``layers`` are the two layers after it.
     See include/gnc.h ``gnc_tc_chain_t``."""
-    _require_cuda(A)
-    A = _rows(A)
-    M = A.shape[0]
     ch = GncTcChain()
     keep = []
+    if A is None:
+        tab, tidx, tbias = pre
+        tab = _rows(tab)
+        keep.append(tab)
+        M = tidx.shape[0]
+        ch.gather2, ch.gather2_idx, ch.ld_gather2 = tab.data_ptr(), tidx.data_ptr(), _ld(tab)
+        ch.pre_bias = None if tbias is None else tbias.data_ptr()
+        a_ptr, a_ld, dev = None, 0, tab.device
+    else:
+        _require_cuda(A)
+        A = _rows(A)
+        M = A.shape[0]
+        a_ptr, a_ld, dev = A.data_ptr(), _ld(A), A.device
     ch.nlayers = len(layers)
     for l, (W, b) in enumerate(layers):
         _require_cuda(W)
@@ -611,7 +623,7 @@ def tc_mlp_chain(A: Tensor, layers: Sequence, *, gather0=None, gather1=None, gam
         keep.append(W)
         ch.W[l], ch.ldw[l] = W.data_ptr(), W.stride(0)
         ch.bias[l] = None if b is None else b.data_ptr()
-    nbytes = 4.0 * 128 * (M + len(layers) * 128)
+    nbytes = 4.0 * 128 * ((M if A is not None else 0) + len(layers) * 128)
 
     def rows(t):
         t = _rows(t)
@@ -648,10 +660,10 @@ def tc_mlp_chain(A: Tensor, layers: Sequence, *, gather0=None, gather1=None, gam
         ch.dot_b = None if dot_b is None else dot_b.data_ptr()
         n_out = 1
     if out is None:
-        out = torch.empty(M, n_out, dtype=torch.float32, device=A.device)
+        out = torch.empty(M, n_out, dtype=torch.float32, device=dev)
     nbytes += 4.0 * M * n_out
     check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * len(layers), nbytes, _lib.load().gnc_tc_mlp_chain_f32,
-                A.data_ptr(), _ld(A), M, ctypes.byref(ch), out.data_ptr(), _ld(out), _stream()), "tc_mlp_chain")
+                a_ptr, a_ld, M, ctypes.byref(ch), out.data_ptr(), _ld(out), _stream()), "tc_mlp_chain")
     return out
 
 

@@ -273,6 +273,11 @@ typedef struct gnc_tc_chain {
   const float* gamma; const float* beta; float eps; int32_t _pad1;
   const float* residual; const int32_t* residual_idx; int64_t ld_residual;
   const float* dot_w; const float* dot_b;
+  /* pre-stage form (A == NULL, nlayers = 2): the first operand is
+   *   relu(gather2[gather2_idx[m]] + gather0[gather0_idx[m]] + gather1[gather1_idx[m]] + pre_bias)
+   * and W[0], W[1] are the two layers after it - the block-0 edge processor when the encoded edge latents
+   * are a small table indexed by edge class. */
+  const float* gather2; const int32_t* gather2_idx; int64_t ld_gather2; const float* pre_bias;
 } gnc_tc_chain_t;
 
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,

@@ -111,3 +111,26 @@ def test_chain_matches_per_layer_engine_at_scale(libgnc):
     ref = ops.tc_linear(a2, layers[2][0], bias=layers[2][1], gamma=gamma, beta=beta, eps=1e-5, residual=A)
     got = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A)
     assert _maxrel(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("M", [300, 256 * 74 * 2 + 77])
+def test_chain_prestage_table_form(libgnc, M):
+    """Block 0 of the grid-graph path: first operand relu(R[class] + P[src] + Q[dst] + b0) built in the launch,
+    two layers, LayerNorm, residual through the class table."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    Rn = 500
+    R, e_tab = torch.randn(4, 128, generator=gen), torch.randn(4, 128, generator=gen)
+    P, Q = torch.randn(Rn, 128, generator=gen), torch.randn(Rn, 128, generator=gen)
+    cls = torch.randint(0, 4, (M,), generator=gen)
+    i0, i1 = torch.randint(0, Rn, (M,), generator=gen), torch.randint(0, Rn, (M,), generator=gen)
+    b0 = torch.randn(128, generator=gen) * 0.2
+    layers = _layers(gen, 2)
+    gamma, beta = torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.2
+    a1 = torch.relu(R.double()[cls] + P.double()[i0] + Q.double()[i1] + b0.double())
+    z = torch.relu(a1 @ layers[0][0].double().t() + layers[0][1].double()) @ layers[1][0].double().t() + layers[1][1].double()
+    ref = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5) + e_tab.double()[cls]
+    got = ops.tc_mlp_chain(None, [(W.cuda(), b.cuda()) for W, b in layers], pre=(R.cuda(), cls.int().cuda(), b0.cuda()),
+                           gather0=(P.cuda(), i0.int().cuda()), gather1=(Q.cuda(), i1.int().cuda()),
+                           gamma=gamma.cuda(), beta=beta.cuda(), residual=(e_tab.cuda(), cls.int().cuda()))
+    assert _maxrel(got, ref) < RTOL
