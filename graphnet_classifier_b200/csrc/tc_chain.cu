@@ -225,6 +225,8 @@ template <> struct Spec<5> { static constexpr int nl = 2, g0 = 0, i0 = 0, g1 = 0
 template <> struct Spec<6> { static constexpr int nl = 0, g0 = 0, i0 = 0, g1 = 0, i1 = 0, res = 0, ridx = 0, ln = 0, dot = 0; static constexpr bool trace = false, multi = true, pre = false; };
 // pre-stage + two layers + LayerNorm + table residual: the block-0 edge processor of the grid-graph path
 template <> struct Spec<7> { static constexpr int nl = 2, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 1, ln = 1, dot = 0; static constexpr bool trace = false, multi = false, pre = true; };
+// Spec<1> with the timeline recorder compiled in (scripts/chain_trace.py)
+template <> struct Spec<8> { static constexpr int nl = 3, g0 = 1, i0 = 1, g1 = 1, i1 = 1, res = 1, ridx = 0, ln = 1, dot = 0; static constexpr bool trace = true, multi = false, pre = false; };
 #define GNC_FLAG(field, runtime) (Spec<SPEC>::field == 2 ? (runtime) : (Spec<SPEC>::field != 0))
 
 // ---- the kernel -------------------------------------------------------------------
@@ -692,15 +694,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           }
         } else {
           if (has_ln) {
-            float s1 = 0.f;
+            // four independent partial sums: the reductions are dependency chains, not issue-bound
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) s1 += x[j];
+            for (int j = 0; j < 64; j += 4) { t0 += x[j]; t1 += x[j + 1]; t2 += x[j + 2]; t3 += x[j + 3]; }
+            const float s1 = (t0 + t1) + (t2 + t3);
             *xa = s1;
             named_bar_sync(1 + q, 64);
             const float mu = (s1 + xchg[partner]) * (1.0f / kD);
-            float s2 = 0.f;
+            t0 = t1 = t2 = t3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { x[j] -= mu; s2 = fmaf(x[j], x[j], s2); }
+            for (int j = 0; j < 64; j += 4) {
+              x[j] -= mu; x[j + 1] -= mu; x[j + 2] -= mu; x[j + 3] -= mu;
+              t0 = fmaf(x[j], x[j], t0); t1 = fmaf(x[j + 1], x[j + 1], t1);
+              t2 = fmaf(x[j + 2], x[j + 2], t2); t3 = fmaf(x[j + 3], x[j + 3], t3);
+            }
+            const float s2 = (t0 + t1) + (t2 + t3);
             *xb = s2;
             named_bar_sync(1 + q, 64);
             const float var = (s2 + xchg[kEpiWarps * 32 + partner]) * (1.0f / kD);
@@ -723,10 +732,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
             uint8_t* slot = slots + c * kSlotBytes;
             if (has_res) {
               // steps c .. 3 are in flight
+              // (from step 2 on the next tile's first addend step may be pending behind them)
+              const bool early = has_add && t + 1 < n_my;
               if (c == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
               else if (c == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
-              else if (c == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-              else asm volatile("cp.async.wait_group 0;" ::: "memory");
+              else if (c == 2) { if (early) asm volatile("cp.async.wait_group 2;" ::: "memory"); else asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+              else { if (early) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory"); }
               __syncwarp();
               float rsd[16];
               read_slot(slot, rsd);
@@ -753,6 +764,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
                 if (row0 + rl + 8 * i < p.M) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
             }
             __syncwarp();
+            if (has_add && t + 1 < n_my && (c == 1 || c == 3)) {
+              // slots 2 (c >> 1), 2 (c >> 1) + 1 are free again: the next tile's addend step c >> 1 can go now
+              if (c == 1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ix0[i] = nx0[i]; ix1[i] = nx1[i]; }
+              }
+              fetch_add(c >> 1);
+            }
             tr.ev(0x54 + c);
           }
         }
@@ -762,7 +781,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
         for (int i = 0; i < 4; ++i) { ix0[i] = nx0[i]; ix1[i] = nx1[i]; ixr[i] = nxr[i]; }
         pre_row = pre_row_next;
-        first_fetch();
+        if (!(has_add && !has_dot)) first_fetch();      // with addends the two steps were issued inside the last layer
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -798,6 +817,8 @@ static int launch_spec(const Params& p, cudaStream_t st) {
 static int launch(const Params& p, cudaStream_t st) {
   if (p.multi) return launch_spec<6>(p, st);
   if (!p.A) return launch_spec<7>(p, st);
+  if (p.trace && p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && p.residual && !p.res_idx && p.gamma && !p.dot_w)
+    return launch_spec<8>(p, st);
   if (!p.trace) {
     const bool ln = p.gamma != nullptr, dot = p.dot_w != nullptr, res = p.residual != nullptr;
     if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot) return launch_spec<1>(p, st);
