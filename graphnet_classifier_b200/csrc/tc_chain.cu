@@ -34,6 +34,8 @@
 //                          layer: 64 values per thread in registers, exact two-pass LayerNorm statistics
 //                          (halves combined through smem), residual, transpose through smem, coalesced
 //                          stores.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gnc {
@@ -113,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "CW_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
       "@p bra.uni CW_DONE;\n\t"
       "bra.uni CW_LOOP;\n\t"
       "CW_DONE:\n\t"
@@ -800,6 +802,477 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0;
 
+
+// ---- two tiles in flight ----------------------------------------------------------------------------------
+// The single-tile kernel above is bound by its epilogue warps: the MMA thread waits for them at every layer
+// boundary and they wait for it.  With fp16 two-piece operands a tile needs 128 accumulator + 128 operand
+// columns, so TWO tiles fit in tensor memory (slot S: D at 256 S, a1 | a2 at 256 S + 128) and every epilogue of
+// one tile runs under the MMAs of the other:
+//   MMA      : L0(X) L0(Y) | L1(X) L1(Y) | L2(X) L2(Y) | L0(X') ...
+//   epilogue :       E0(X) | E0(Y) E1(X) | E1(Y) EL(X) | EL(Y) ...
+// A tile has ONE accumulator: an epilogue first copies all of it to registers (64 values per thread) - its
+// arrival for chunk 0 of the next operand (hidden layers) or on d_free (last layer) is what lets the next MMA of
+// that slot overwrite it.  Specialised for the two block MLPs: 3 layers, gather0 (+ gather1), LayerNorm, residual
+// by row (Spec<1>, Spec<2>).  All cp.async groups of a warp are consumed in the order they were issued, so one
+// issued / consumed counter pair tells every wait how many younger groups may stay in flight.
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+  }
+}
+
+template <int SPEC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain2_kernel(const Params p) {
+  static_assert(Spec<SPEC>::nl == 3 && Spec<SPEC>::g0 == 1 && Spec<SPEC>::res == 1 && Spec<SPEC>::ridx == 0 &&
+                Spec<SPEC>::ln == 1 && Spec<SPEC>::dot == 0, "two-tile form: 3 layers, addends, LayerNorm, residual by row");
+  constexpr int nl = 3;
+  constexpr bool has_i0 = Spec<SPEC>::i0 != 0, has_g1 = Spec<SPEC>::g1 != 0, has_i1 = Spec<SPEC>::i1 != 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  float* s_const = reinterpret_cast<float*>(sm + kOffConst);   // bias[0..2] (hidden ones x kScaleA), gamma, beta
+  const uint32_t bar0 = base + kOffBar;
+  // per slot S (112 bytes): a0_full[4] ae_full[4] a_empty[4] d_full d_free; then the TMEM base pointer
+  auto a0_full = [&](int S, int c) { return bar0 + 112u * S + 8u * c; };
+  auto ae_full = [&](int S, int c) { return bar0 + 112u * S + 32u + 8u * c; };
+  auto a_empty = [&](int S, int c) { return bar0 + 112u * S + 64u + 8u * c; };
+  auto d_full = [&](int S) { return bar0 + 112u * S + 96u; };
+  auto d_free = [&](int S) { return bar0 + 112u * S + 104u; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 224);
+
+  if (threadIdx.x == 0) {
+    for (int S = 0; S < 2; ++S) {
+      for (int c = 0; c < 4; ++c) {
+        mbar_init(a0_full(S, c), 2 * kLoaderWarps * 32);
+        mbar_init(ae_full(S, c), 2 * kEpiWarps * 32);
+        mbar_init(a_empty(S, c), 1);
+      }
+      mbar_init(d_full(S), 1);
+      mbar_init(d_free(S), 2 * kEpiWarps * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int l = 0; l < nl; ++l) {
+    const float* W = p.W[l];
+    const long long ldw = p.ldw[l];
+    for (int item = threadIdx.x; item < 64 * 16; item += kThreads) {
+      const int c = item & 15, nloc = item >> 4;
+      const float* src = W + (long long)(64 * (int)rank + nloc) * ldw + c * 8;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+      uint32_t p1[4], p2[4];
+      split2(v0.x * kScaleW, v0.y * kScaleW, p1[0], p2[0]);
+      split2(v0.z * kScaleW, v0.w * kScaleW, p1[1], p2[1]);
+      split2(v1.x * kScaleW, v1.y * kScaleW, p1[2], p2[2]);
+      split2(v1.z * kScaleW, v1.w * kScaleW, p1[3], p2[3]);
+      const int kb = c >> 3, cc = c & 7;
+      uint8_t* img = sm + kOffW + l * kLayerBytes + kb * kImgBytes + (nloc >> 3) * 1024 + (nloc & 7) * 128 + ((cc ^ (nloc & 7)) << 4);
+      *reinterpret_cast<uint4*>(img) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<uint4*>(img + 2 * kImgBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+    }
+  }
+  for (int i = threadIdx.x; i < kD; i += kThreads) {
+    for (int l = 0; l < nl; ++l) s_const[l * kD + i] = p.bias[l] ? __ldg(p.bias[l] + i) * (l < nl - 1 ? kScaleA : 1.f) : 0.f;
+    s_const[3 * kD + i] = __ldg(p.gamma + i);
+    s_const[4 * kD + i] = __ldg(p.beta + i);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const long long n_my = (p.num_tiles > pair) ? (p.num_tiles - pair + npairs - 1) / npairs : 0;   // tile j -> slot j & 1
+
+  if (warp < kLoaderWarps) {
+    // ======================= loaders =======================
+    reg_dec<kRegsLoader>();
+    const int q = warp;
+    const uint32_t buf0 = base + kOffLd + (uint32_t)(warp * kLoadBufs) * kChunkBytes;
+    const int rl = lane >> 3, cj = lane & 7;
+    const long long total = n_my * 4;
+    const uint32_t a0_remote = map_to_leader(a0_full(0, 0));
+    auto issue = [&](long long it, int b) {
+      if (it < total) {
+        const long long tile = pair + (it >> 2) * npairs;
+        const int c = (int)(it & 3);
+        const long long row0 = tile * kTileM + rank * 128 + q * 32;
+        const uint32_t dst0 = buf0 + (uint32_t)b * kChunkBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rl;
+          const long long row = row0 + r;
+          const long long rc = row < p.M ? row : p.M - 1;
+          cp_async16(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), p.A + rc * p.lda + c * 32 + cj * 4, row < p.M ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+    int b = 0;
+    for (long long it = 0; it < total; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
+      __syncwarp();
+      const int c = (int)(it & 3);
+      const long long j = it >> 2;
+      const int S = (int)(j & 1);
+      mbar_wait(a_empty(S, c), (uint32_t)(((j >> 1) & 1) ^ 1));   // the slot's previous tile has read chunk c
+      tc_fence_after();
+      const uint8_t* buf = sm + kOffLd + (warp * kLoadBufs + b) * kChunkBytes + lane * 128;
+      const uint32_t ta = tmem_base + (uint32_t)S * 256 + 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t p1[8], p2[8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
+          split2(x.x * kScaleA, x.y * kScaleA, p1[2 * jj], p2[2 * jj]);
+          split2(x.z * kScaleA, x.w * kScaleA, p1[2 * jj + 1], p2[2 * jj + 1]);
+        }
+        tmem_st8(ta + half * 8, p1);
+        tmem_st8(ta + 64 + half * 8, p2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_remote(a0_remote + 112u * (uint32_t)S + 8u * (uint32_t)c);
+      __syncwarp();
+      issue(it + kLoadBufs, b);
+      b = (b + 1 == kLoadBufs) ? 0 : b + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp < kEpiWarp0) {
+    // ======================= MMA issuer =======================
+    reg_dec<kRegsMma>();
+    if (rank == 0 && warp == kMmaWarp && lane == 0) {
+      const uint64_t desc0 = make_desc(base + kOffW);
+      const long long groups = (n_my + 1) >> 1;
+#pragma unroll 1
+      for (long long g = 0; g < groups; ++g) {
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+          const uint64_t desc_l = desc0 + (uint64_t)((l * kLayerBytes) >> 4);
+#pragma unroll 1
+          for (int S = 0; S < 2; ++S) {
+            if (2 * g + S >= n_my) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)S * 256;
+            const uint32_t a_base = d_tmem + 128;
+            if (l == 0 && g > 0) {                  // the slot's previous tile has copied its last accumulator out
+              mbar_wait(d_free(S), (uint32_t)((g - 1) & 1));
+              tc_fence_after();
+            }
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              // the slot's ae_full barriers complete (nl - 1) times per tile: phase index g (nl - 1) + (l - 1)
+              if (l == 0) mbar_wait(a0_full(S, c), (uint32_t)(g & 1));
+              else mbar_wait(ae_full(S, c), (uint32_t)((g * (nl - 1) + (l - 1)) & 1));
+              tc_fence_after();
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int ks = 2 * c + k2;
+                const uint32_t a1 = a_base + (uint32_t)ks * 8, a2 = a1 + 64;
+                const uint64_t w1 = desc_l + (uint64_t)(((ks >> 2) * kImgBytes + (ks & 3) * 32) >> 4);
+                const uint64_t w2 = w1 + (uint64_t)((2 * kImgBytes) >> 4);
+                umma_f16_pair(d_tmem, a1, w2, kInstrDesc, ks != 0);
+                umma_f16_pair(d_tmem, a2, w1, kInstrDesc, 1);
+                umma_f16_pair(d_tmem, a1, w1, kInstrDesc, 1);
+              }
+              if (l == nl - 1) umma_commit_pair(a_empty(S, c));
+            }
+            umma_commit_pair(d_full(S));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    reg_inc<kRegsEpi>();
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3, hf = ew >> 2;
+    uint8_t* slots = sm + kOffEp + ew * kEpiSlots * kSlotBytes;
+    const uint32_t slots_u = base + kOffEp + (uint32_t)ew * kEpiSlots * kSlotBytes;
+    float* xchg = reinterpret_cast<float*>(sm + kOffXchg);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rl = lane >> 2, cc = lane & 3;
+    const uint32_t ae_remote = map_to_leader(ae_full(0, 0)), dfree_remote = map_to_leader(d_free(0));
+    auto slot_off = [](int r, int ch) { return (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)); };
+    auto read_slot = [&](const uint8_t* slot, float* v) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const float4 x = *reinterpret_cast<const float4*>(slot + slot_off(lane, ch));
+        v[4 * ch] = x.x; v[4 * ch + 1] = x.y; v[4 * ch + 2] = x.z; v[4 * ch + 3] = x.w;
+      }
+    };
+    auto tile_row0 = [&](long long j) { return (pair + j * npairs) * kTileM + rank * 128 + q * 32; };
+
+    // ---- the cp.async stream (FIFO: consumed in issue order) ----
+    int issued = 0, consumed = 0;
+    auto wait_next = [&]() { cp_async_wait_pending(issued - consumed - 1); ++consumed; };
+    // Row pointers (lane's 16-byte column piece included) are formed once per tile: a step then costs one
+    // cp.async per row with the step's column offset as an immediate.
+    const float* pr0[4]; const float* pr1[4];       // gather rows of the tile whose addend steps are being issued
+    const float* nr0[4]; const float* nr1[4];       // ... of the tile after it
+    const float* pres[4];                           // residual rows of the tile whose residual steps are being issued
+    uint32_t soff[4];                               // this lane's destinations inside a slot
+#pragma unroll
+    for (int i = 0; i < 4; ++i) soff[i] = slot_off(rl + 8 * i, cc);
+    const int lane_col = 16 * hf + 4 * cc;
+    auto load_indices = [&](long long j, const float** a0, const float** a1) {
+      const long long r0 = tile_row0(j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        long long g = r0 + rl + 8 * i;
+        g = g < p.M ? g : p.M - 1;
+        a0[i] = p.g0 + (has_i0 ? (long long)__ldg(p.i0 + g) : g) * p.ld_g0 + lane_col;
+        if (has_g1) a1[i] = p.g1 + (has_i1 ? (long long)__ldg(p.i1 + g) : g) * p.ld_g1 + lane_col;
+      }
+    };
+    auto res_rows = [&](long long j) {
+      const long long r0 = tile_row0(j);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        long long g = r0 + rl + 8 * i;
+        g = g < p.M ? g : p.M - 1;
+        pres[i] = p.residual + g * p.ld_res + lane_col;
+      }
+    };
+    long long add_k = 0;                            // addend steps issued so far (step k -> slots 2 (k & 1), + 1)
+    auto fetch_add = [&](int c) {                   // step c of the tile pr0 / pr1 describe
+      const uint32_t dst = slots_u + (uint32_t)(2 * (add_k & 1)) * kSlotBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cp_async16(dst + soff[i], pr0[i] + 32 * c, 16u);
+        if (has_g1) cp_async16(dst + kSlotBytes + soff[i], pr1[i] + 32 * c, 16u);
+      }
+      cp_async_commit();
+      ++issued; ++add_k;
+    };
+    auto fetch_res = [&](int c) {                   // step c of the tile pres describes -> slot c
+      const uint32_t dst = slots_u + (uint32_t)c * kSlotBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cp_async16(dst + soff[i], pres[i] + 32 * c, 16u);
+      cp_async_commit();
+      ++issued;
+    };
+    auto emit_chunk = [&](const float* vc, const float* s_bias, int S, int c, const float* ext, bool has_ext) {
+      const int col0 = 32 * c + 16 * hf;
+      uint32_t p1[8], p2[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j4);
+        float y0 = fmaf(vc[4 * j4], 1.f / kScaleW, b4.x), y1 = fmaf(vc[4 * j4 + 1], 1.f / kScaleW, b4.y);
+        float y2 = fmaf(vc[4 * j4 + 2], 1.f / kScaleW, b4.z), y3 = fmaf(vc[4 * j4 + 3], 1.f / kScaleW, b4.w);
+        if (has_ext) {
+          y0 = fmaf(ext[4 * j4], kScaleA, y0); y1 = fmaf(ext[4 * j4 + 1], kScaleA, y1);
+          y2 = fmaf(ext[4 * j4 + 2], kScaleA, y2); y3 = fmaf(ext[4 * j4 + 3], kScaleA, y3);
+        }
+        split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), p1[2 * j4], p2[2 * j4]);
+        split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+      }
+      const uint32_t ta = lane_addr + (uint32_t)S * 256 + 128 + (uint32_t)(16 * c + 8 * hf);
+      tmem_st8(ta, p1);
+      tmem_st8(ta + 64, p2);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_remote(ae_remote + 112u * (uint32_t)S + 8u * (uint32_t)c);
+    };
+
+    uint32_t dcnt0 = 0, dcnt1 = 0;                  // d_full phases consumed per slot
+    auto wait_acc = [&](int S, float* v) {          // the slot's accumulator -> 64 registers
+      mbar_wait(d_full(S), (S ? dcnt1 : dcnt0) & 1u);
+      if (S) ++dcnt1; else ++dcnt0;
+      tc_fence_after();
+      const uint32_t d_addr = lane_addr + (uint32_t)S * 256;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(d_addr + 32 * c + 16 * hf, v + 16 * c);
+      tmem_ld_wait();
+    };
+
+    const long long groups = (n_my + 1) >> 1;
+    if (n_my > 0) {
+      load_indices(0, pr0, pr1);
+      fetch_add(0); fetch_add(1);
+      if (n_my > 1) load_indices(1, nr0, nr1);
+    }
+#pragma unroll 1
+    for (long long g = 0; g < groups; ++g) {
+      const long long jX = 2 * g, jY = 2 * g + 1;
+      const bool hasY = jY < n_my, hasNext = jY + 1 < n_my;
+      // ---- E0: addends + bias + ReLU -> the slot's next operand
+#pragma unroll 1
+      for (int S = 0; S < 2; ++S) {
+        if (S == 1 && !hasY) break;
+        float v[64];
+        wait_acc(S, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float ext[16];
+          wait_next();
+          __syncwarp();
+          const uint8_t* sp = slots + 2 * (c & 1) * kSlotBytes;      // add_k parity == c parity (4 steps per tile)
+          read_slot(sp, ext);
+          if (has_g1) {
+            float e1[16];
+            read_slot(sp + kSlotBytes, e1);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) ext[jj] += e1[jj];
+          }
+          __syncwarp();
+          // next issue of the stream: two addend steps stay in flight; after a tile's last two steps the
+          // stream moves to the next tile's addends, or (after the group's last tile) to the residuals of X
+          if (c < 2) {
+            fetch_add(c + 2);
+            if (c == 1) {                           // this tile's steps are all issued: indices of the next tile
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { pr0[i] = nr0[i]; if (has_g1) pr1[i] = nr1[i]; }
+            }
+          } else if (S == 0 && hasY) {
+            fetch_add(c - 2);                       // addends of Y, steps 0 and 1
+          } else {                                  // last tile of the group: residual steps of X (slots 2(c-2), +1 are free)
+            if (c == 2) res_rows(jX);
+            fetch_res(2 * (c - 2));
+            fetch_res(2 * (c - 2) + 1);
+          }
+          emit_chunk(v + 16 * c, s_const, S, c, ext, true);
+        }
+      }
+      // all addend steps of this group are issued: gather rows of the next group's tiles (X' straight into the
+      // live set - its first steps are issued inside this group's last layer -, Y' into the spare set)
+      if (hasNext) load_indices(jY + 1, pr0, pr1);
+      if (jY + 2 < n_my) load_indices(jY + 2, nr0, nr1);
+      // ---- E1: bias + ReLU -> next operand
+#pragma unroll 1
+      for (int S = 0; S < 2; ++S) {
+        if (S == 1 && !hasY) break;
+        float v[64];
+        wait_acc(S, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) emit_chunk(v + 16 * c, s_const + kD, S, c, v, false);
+      }
+      // ---- last layer: LayerNorm + residual + store
+#pragma unroll 1
+      for (int S = 0; S < 2; ++S) {
+        if (S == 1 && !hasY) break;
+        const long long row0 = tile_row0(2 * g + S);
+        const bool tile_full = row0 + 32 <= p.M;
+        if (S == 0 && hasY) res_rows(jY);             // X's residual steps are all issued: the stream continues with Y's
+        float x[64];
+        wait_acc(S, x);
+        tc_fence_before();
+        mbar_arrive_remote(dfree_remote + 112u * (uint32_t)S);      // accumulator copied out
+        const float* s_bias = s_const + 2 * kD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 16 * hf + 4 * j4);
+            float* xx = x + 16 * c + 4 * j4;
+            xx[0] = fmaf(xx[0], kUnscaleD, b4.x); xx[1] = fmaf(xx[1], kUnscaleD, b4.y);
+            xx[2] = fmaf(xx[2], kUnscaleD, b4.z); xx[3] = fmaf(xx[3], kUnscaleD, b4.w);
+          }
+        float* xa = xchg + (ew * 32 + lane);
+        float* xb = xchg + (kEpiWarps * 32) + (ew * 32 + lane);
+        const int partner = (ew ^ 4) * 32 + lane;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 64; jj += 4) { t0 += x[jj]; t1 += x[jj + 1]; t2 += x[jj + 2]; t3 += x[jj + 3]; }
+        const float s1 = (t0 + t1) + (t2 + t3);
+        *xa = s1;
+        named_bar_sync(1 + q, 64);
+        const float mu = (s1 + xchg[partner]) * (1.0f / kD);
+        t0 = t1 = t2 = t3 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 64; jj += 4) {
+          x[jj] -= mu; x[jj + 1] -= mu; x[jj + 2] -= mu; x[jj + 3] -= mu;
+          t0 = fmaf(x[jj], x[jj], t0); t1 = fmaf(x[jj + 1], x[jj + 1], t1);
+          t2 = fmaf(x[jj + 2], x[jj + 2], t2); t3 = fmaf(x[jj + 3], x[jj + 3], t3);
+        }
+        const float s2 = (t0 + t1) + (t2 + t3);
+        *xb = s2;
+        named_bar_sync(1 + q, 64);
+        const float var = (s2 + xchg[kEpiWarps * 32 + partner]) * (1.0f / kD);
+        const float rstd = 1.0f / sqrtf(var + p.eps);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int col = 32 * c + 16 * hf + 4 * j4;
+            const float4 g4 = *reinterpret_cast<const float4*>(s_const + 3 * kD + col);
+            const float4 e4 = *reinterpret_cast<const float4*>(s_const + 4 * kD + col);
+            float* xx = x + 16 * c + 4 * j4;
+            xx[0] = fmaf(xx[0] * rstd, g4.x, e4.x); xx[1] = fmaf(xx[1] * rstd, g4.y, e4.y);
+            xx[2] = fmaf(xx[2] * rstd, g4.z, e4.z); xx[3] = fmaf(xx[3] * rstd, g4.w, e4.w);
+          }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* slot = slots + c * kSlotBytes;
+          wait_next();                                              // residual step c of this tile
+          __syncwarp();
+          float rsd[16];
+          read_slot(slot, rsd);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) x[16 * c + jj] += rsd[jj];
+          __syncwarp();
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<float4*>(slot + slot_off(lane, ch)) =
+                make_float4(x[16 * c + 4 * ch], x[16 * c + 4 * ch + 1], x[16 * c + 4 * ch + 2], x[16 * c + 4 * ch + 3]);
+          __syncwarp();
+          float4 o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(slot + slot_off(rl + 8 * i, cc));
+          float* yrow = p.Y + (row0 + rl) * p.ldy + 32 * c + 16 * hf + 4 * cc;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (tile_full || row0 + rl + 8 * i < p.M) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
+          __syncwarp();
+          // the slot is free again: next group of the stream
+          if (S == 0 && hasY) fetch_res(c);                         // residual of Y, step c
+          else if (hasNext && (c == 1 || c == 3)) fetch_add(c >> 1); // slots 2 (c >> 1), + 1 free: next group's X, step c >> 1
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int SPEC>
+static int launch_spec2(const Params& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_chain2_kernel<SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  tc_chain2_kernel<SPEC><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
+  return check_launch("tc_chain2_kernel");
+}
+
 template <int SPEC>
 static int launch_spec(const Params& p, cudaStream_t st) {
   static bool configured = false;
@@ -821,8 +1294,11 @@ static int launch(const Params& p, cudaStream_t st) {
     return launch_spec<8>(p, st);
   if (!p.trace) {
     const bool ln = p.gamma != nullptr, dot = p.dot_w != nullptr, res = p.residual != nullptr;
-    if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot) return launch_spec<1>(p, st);
-    if (p.nlayers == 3 && p.g0 && !p.i0 && !p.g1 && res && !p.res_idx && ln && !dot) return launch_spec<2>(p, st);
+    static const bool two_tiles = []() { const char* e = getenv("GNC_CHAIN_TWO_TILES"); return !e || e[0] != '0'; }();
+    if (p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && res && !p.res_idx && ln && !dot)
+      return two_tiles ? launch_spec2<1>(p, st) : launch_spec<1>(p, st);
+    if (p.nlayers == 3 && p.g0 && !p.i0 && !p.g1 && res && !p.res_idx && ln && !dot)
+      return two_tiles ? launch_spec2<2>(p, st) : launch_spec<2>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && res && ln && !dot) return launch_spec<3>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && ln && !dot) return launch_spec<4>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && !ln && dot) return launch_spec<5>(p, st);

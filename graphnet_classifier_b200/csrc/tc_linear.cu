@@ -104,7 +104,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
       "@p bra.uni WAIT_DONE;\n\t"
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"

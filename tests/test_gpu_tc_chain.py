@@ -134,3 +134,33 @@ def test_chain_prestage_table_form(libgnc, M):
                            gather0=(P.cuda(), i0.int().cuda()), gather1=(Q.cuda(), i1.int().cuda()),
                            gamma=gamma.cuda(), beta=beta.cuda(), residual=(e_tab.cuda(), cls.int().cuda()))
     assert _maxrel(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("tiles_per_pair", [1, 2, 3, 6, 7])
+@pytest.mark.parametrize("form", ["edge", "node"])
+def test_two_tile_kernel_many_tiles(libgnc, tiles_per_pair, form):
+    """The two-tiles-in-flight kernel (edge / node processor shapes) with odd and even tile counts per CTA
+    pair and a ragged last tile, against the per-layer 3xTF32 engine and the single-tile kernel."""
+    import os
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(tiles_per_pair * 3 + len(form))
+    M = 256 * 74 * (tiles_per_pair - 1) + 256 * 40 + 57        # some pairs run one tile more than others
+    R = 3000
+    A = torch.randn(M, 128, generator=gen).cuda()
+    layers = [(W.cuda(), b.cuda()) for W, b in _layers(gen, 3)]
+    gamma, beta = (torch.rand(128, generator=gen) + 0.5).cuda(), (torch.randn(128, generator=gen) * 0.2).cuda()
+    if form == "edge":
+        P, Q = torch.randn(R, 128, generator=gen).cuda(), torch.randn(R, 128, generator=gen).cuda()
+        i0 = torch.randint(0, R, (M,), generator=gen).int().cuda()
+        i1 = torch.randint(0, R, (M,), generator=gen).int().cuda()
+        kw = dict(gather0=(P, i0), gather1=(Q, i1))
+        a1 = ops.tc_linear(A, layers[0][0], bias=layers[0][1], gather0=(P, i0), gather1=(Q, i1), relu=True)
+    else:
+        T = torch.randn(M, 128, generator=gen).cuda()
+        kw = dict(gather0=(T, None))
+        a1 = ops.tc_linear(A, layers[0][0], bias=layers[0][1], addend=T, relu=True)
+    a2 = ops.tc_linear(a1, layers[1][0], bias=layers[1][1], relu=True)
+    ref = ops.tc_linear(a2, layers[2][0], bias=layers[2][1], gamma=gamma, beta=beta, eps=1e-5, residual=A)
+    got = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A, **kw)
+    assert _maxrel(got, ref) < RTOL
+    assert torch.isfinite(got).all()
