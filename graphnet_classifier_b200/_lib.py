@@ -71,6 +71,9 @@ SIGNATURES = {
     "gnc_grid_edge_class": (c_int, [c_int, c_int, c_int, c_int, _P, _P]),
     "gnc_edge_geometry_f32": (c_int, [_P, c_int, _P, _P, c_int64, _P, _P]),
     "gnc_linear_fwd_f32": (c_int, [POINTER(GncSeg), c_int, c_int64, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
+    "gnc_linear_fwd_splitk_workspace": (c_int64, [c_int64, c_int, c_int64]),
+    "gnc_linear_fwd_splitk_f32": (c_int, [POINTER(GncSeg), c_int, c_int64, _P, c_int64, _P, c_int, c_int, _P, c_int64,
+                                          _P, c_int64, _P]),
     "gnc_linear_narrowk_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, _P, c_int, c_int, _P, c_int64, _P]),
     "gnc_linear_narrowk_wgrad_workspace": (c_int64, [c_int64, c_int, c_int]),
     "gnc_linear_narrowk_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64,

@@ -379,6 +379,34 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, long long spli
   *d = accumulate ? (*d + s) : s;
 }
 
+// Split-K forward (few output tiles, long reduction: the classifier head's fc1, models/GNN.py:315): how many
+// slices of the reduction run as separate CTAs, and the per-slice length.
+static void fwd_split(long long M, int N, long long K, long long* splits, long long* chunk) {
+  const long long tiles = ceil_div<long long>(M, BM) * ceil_div<long long>(N, BN);
+  long long s = (long long)(kNumSMs * 2) / tiles;
+  const long long smax = ceil_div<long long>(K, 8 * BK);      // at least 8 K-steps per slice
+  if (s > smax) s = smax;
+  if (s < 1) s = 1;
+  long long c = ceil_div<long long>(ceil_div<long long>(K, s), BK) * BK;
+  if (c < BK) c = BK;
+  *chunk = c;
+  *splits = ceil_div<long long>(K, c);
+}
+
+// Y[m, n] = act(sum over slices of ws[z][m, n] + bias[n]) in slice order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, long long splits, long long MN, int N,
+                                     const float* __restrict__ bias, int relu, float* __restrict__ Y, long long ldy) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float s = 0.f;
+  for (long long z = 0; z < splits; ++z) s += ws[z * MN + i];
+  const long long m = i / N;
+  const int n = (int)(i - m * N);
+  if (bias) s += __ldg(bias + n);
+  if (relu) s = fmaxf(s, 0.f);
+  Y[m * ldy + n] = s;
+}
+
 // ---- column reductions --------------------------------------------------------
 constexpr int kColBlocksMax = kNumSMs * 4;
 
@@ -751,6 +779,39 @@ int gnc_linear_fwd_f32(const gnc_seg_t* segs, int nseg, int64_t M, const float* 
   g.vec_store = (ldy % 4 == 0 && aligned16(Y)) ? 1 : 0;
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div<long long>(N, BN), 1);
   return launch_gemm<true, true, 0>(g, t_fast(g.A), t_fast(g.B), grid, (cudaStream_t)stream);
+}
+
+int64_t gnc_linear_fwd_splitk_workspace(int64_t M, int N, int64_t K) {
+  long long splits, chunk;
+  fwd_split(M, N, K, &splits, &chunk);
+  return splits > 1 ? splits * M * (int64_t)N : 0;
+}
+
+int gnc_linear_fwd_splitk_f32(const gnc_seg_t* segs, int nseg, int64_t M, const float* W, int64_t ldw, const float* bias,
+                              int N, int relu, float* Y, int64_t ldy, float* work, int64_t work_elems,
+                              gnc_stream_t stream) {
+  GNC_REQUIRE(M >= 0 && N > 0 && W && Y && ldy >= N, "linear_fwd_splitk: bad arguments");
+  if (M == 0) return GNC_OK;
+  GemmArgs g;
+  long long K = 0;
+  int rc = make_operand(segs, nseg, g.A, &K);
+  if (rc) return rc;
+  GNC_REQUIRE(ldw >= K, "linear_fwd_splitk: ldw < K");
+  long long splits, chunk;
+  fwd_split(M, N, K, &splits, &chunk);
+  if (splits <= 1) return gnc_linear_fwd_f32(segs, nseg, M, W, ldw, bias, N, relu, Y, ldy, stream);
+  const long long MN = (long long)M * N;
+  if (!work || work_elems < splits * MN) return fail(GNC_EWORKSPACE, "%s", "linear_fwd_splitk: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  single_operand(W, ldw, (int)K, g.B);
+  g.rows = M; g.cols = N; g.red = K; g.red_chunk = chunk;
+  g.C = work; g.ldc = N; g.c_split_stride = MN; g.bias = nullptr; g.relu = 0; g.accumulate = 0;
+  g.vec_store = (N % 4 == 0 && aligned16(work)) ? 1 : 0;
+  dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div<long long>(N, BN), (unsigned)splits);
+  rc = launch_gemm<true, true, 2>(g, t_fast(g.A), t_fast(g.B), grid, st);
+  if (rc) return rc;
+  splitk_reduce_kernel<<<(unsigned)ceil_div<long long>(MN, 256), 256, 0, st>>>(work, splits, MN, N, bias, relu, Y, ldy);
+  return check_launch("splitk_reduce_kernel");
 }
 
 int gnc_linear_dgrad_f32(const float* dZ, int64_t lddz, int64_t M, int N, const float* W, int64_t ldw, int K,

@@ -241,6 +241,14 @@ def _linear_fwd_raw(srcs, idxs, M, W, b, relu) -> Tensor:
         return Y
     segs = _make_segs(srcs, idxs)
     K = W.shape[1]
+    lib = _lib.load()
+    n_work = lib.gnc_linear_fwd_splitk_workspace(M, N, K) if K >= 2048 else 0
+    if n_work > 0:      # few output tiles, long reduction (the classifier head's fc1): split K over CTAs
+        work = _workspace(W.device, n_work)
+        check(_call("linear_fwd", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), lib.gnc_linear_fwd_splitk_f32,
+                    segs, len(srcs), M, W.data_ptr(), W.stride(0), _p(b), N, int(relu), Y.data_ptr(), _ld(Y),
+                    work.data_ptr(), work.numel(), _stream()), "linear_fwd_splitk")
+        return Y
     check(_call("linear_fwd", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N), _lib.load().gnc_linear_fwd_f32,
                 segs, len(srcs), M, W.data_ptr(), W.stride(0), _p(b), N, int(relu), Y.data_ptr(), _ld(Y), _stream()),
           "linear_fwd")

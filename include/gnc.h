@@ -171,6 +171,14 @@ int gnc_linear_fwd_f32(const gnc_seg_t* segs /*HOST*/, int nseg, int64_t M,
                        const float* W, int64_t ldw, const float* bias, int N, int relu,
                        float* Y, int64_t ldy, gnc_stream_t stream);
 
+/* The same with the reduction split over CTAs (few output tiles, long K: the classifier head's first layer,
+ * models/GNN.py:315, K = number of nodes) and a deterministic slice-order reduction.
+ * work: float [gnc_linear_fwd_splitk_workspace(M, N, K)] (0 = no split: work may be NULL). */
+int64_t gnc_linear_fwd_splitk_workspace(int64_t M, int N, int64_t K);
+int gnc_linear_fwd_splitk_f32(const gnc_seg_t* segs /*HOST*/, int nseg, int64_t M,
+                              const float* W, int64_t ldw, const float* bias, int N, int relu,
+                              float* Y, int64_t ldy, float* work, int64_t work_elems, gnc_stream_t stream);
+
 /* Thin first layers (1 <= K <= 8 inputs: pixel channels / edge geometry, models/GNN.py:233-234):
  * Y[M, N] = act(X[M, K] * W[N, K]^T + bias), one streaming pass.  N % 4 == 0. */
 int gnc_linear_narrowk_fwd_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, int64_t ldw,

@@ -184,3 +184,25 @@ def test_reference_train_loop_one_graph_per_step(libgnc, tmp_path):
     assert len(log) == 1
     text = open(os.path.join(tmp_path, log[0])).read()
     assert "Epochs: 2, Patience: 5" in text and "Epoch 2/2, avg_loss=" in text and "Best loss achieved:" in text
+
+
+def test_infer_graphed_equals_infer(libgnc):
+    """CUDA-graph replay of the small-batch call returns the eager call's logits, for
+    changing inputs and after a weight update."""
+    import numpy as np
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.pipeline import GraphClassifierPipeline
+    torch.manual_seed(3)
+    r = 32
+    model = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=r * r).cuda().eval()
+    pipe = GraphClassifierPipeline(model, resize_value=r)
+    rng = np.random.default_rng(5)
+    for B in (1, 3):
+        for _ in range(3):
+            img = torch.from_numpy(rng.integers(0, 256, (B, r, r, 3), dtype=np.uint8))
+            assert torch.equal(pipe.infer_graphed(img), pipe.infer(img))
+    with torch.no_grad():
+        for prm in model.parameters():
+            prm.mul_(1.01)
+    img = torch.from_numpy(rng.integers(0, 256, (1, r, r, 3), dtype=np.uint8))
+    assert torch.equal(pipe.infer_graphed(img), pipe.infer(img))
