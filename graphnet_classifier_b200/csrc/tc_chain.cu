@@ -181,6 +181,12 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& p1, uint32_
   asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(h0), "=f"(h1) : "r"(p1));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(x1 - h1), "f"(x0 - h0));
 }
+// ReLU that keeps NaN (fmaxf would turn the NaN of an out-of-range fp16 operand into a silent 0)
+__device__ __forceinline__ float relu_nan(float x) {
+  float y;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
@@ -500,8 +506,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           y0 = fmaf(ext[4 * j4], kScaleA, y0); y1 = fmaf(ext[4 * j4 + 1], kScaleA, y1);
           y2 = fmaf(ext[4 * j4 + 2], kScaleA, y2); y3 = fmaf(ext[4 * j4 + 3], kScaleA, y3);
         }
-        split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), p1[2 * j4], p2[2 * j4]);
-        split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+        split2(relu_nan(y0), relu_nan(y1), p1[2 * j4], p2[2 * j4]);
+        split2(relu_nan(y2), relu_nan(y3), p1[2 * j4 + 1], p2[2 * j4 + 1]);
       }
       const uint32_t ta = lane_addr + kTmemA + (uint32_t)(16 * c + 8 * hf);
       tmem_st8(ta, p1);
@@ -685,7 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc = fmaf(fmaxf(x[16 * c + j], 0.f), s_const[3 * kD + 32 * c + 16 * hf + j], acc);
+            for (int j = 0; j < 16; ++j) acc = fmaf(relu_nan(x[16 * c + j]), s_const[3 * kD + 32 * c + 16 * hf + j], acc);
           float* mine = (t & 1) ? xb : xa;
           *mine = acc;
           named_bar_sync(1 + q, 64);
@@ -1082,8 +1088,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           y0 = fmaf(ext[4 * j4], kScaleA, y0); y1 = fmaf(ext[4 * j4 + 1], kScaleA, y1);
           y2 = fmaf(ext[4 * j4 + 2], kScaleA, y2); y3 = fmaf(ext[4 * j4 + 3], kScaleA, y3);
         }
-        split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), p1[2 * j4], p2[2 * j4]);
-        split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+        split2(relu_nan(y0), relu_nan(y1), p1[2 * j4], p2[2 * j4]);
+        split2(relu_nan(y2), relu_nan(y3), p1[2 * j4 + 1], p2[2 * j4 + 1]);
       }
       const uint32_t ta = lane_addr + (uint32_t)S * 256 + 128 + (uint32_t)(16 * c + 8 * hf);
       tmem_st8(ta, p1);

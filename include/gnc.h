@@ -272,7 +272,10 @@ int gnc_tc_linear_multi_f32(const float* A, int64_t lda, int64_t M, int nsets,
  *   dot_w != NULL : Y[m, 0] = relu(z_last) . dot_w + *dot_b                        (decoder, models/GNN.py:289-295)
  *   otherwise     : Y = LayerNorm(z_last; gamma, beta, eps) (gamma NULL: identity) + residual[residual_idx[m]]
  * i.e. one EdgeProcessor / NodeProcessor MLP of models/GNN.py:57-64, 95-104 per launch.  Operands are
- * split into three bf16 pieces (six MMAs per product): fp32-accurate like gnc_tc_linear_f32. */
+ * split into two fp16 pieces after an exact power-of-two scaling (three MMAs per product): 4.7e-7 rel-L2
+ * per product, tighter than gnc_tc_linear_f32's 3xTF32.  DOMAIN: |A|, |hidden activations| < 4094 and
+ * |W| < 255 (fp16 range after the scaling); outside it the outputs are inf / NaN, never silently wrong.
+ * Models outside the domain use the per-layer engines (gnc_tc_linear_f32, gnc_linear_fwd_f32). */
 typedef struct gnc_tc_chain {
   int32_t nlayers; int32_t _pad0;
   const float* W[3]; int64_t ldw[3]; const float* bias[3];

@@ -164,3 +164,17 @@ def test_two_tile_kernel_many_tiles(libgnc, tiles_per_pair, form):
     got = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A, **kw)
     assert _maxrel(got, ref) < RTOL
     assert torch.isfinite(got).all()
+
+
+def test_chain_out_of_domain_is_loud(libgnc):
+    """fp16 two-piece operands cover |activation| < 4094 (include/gnc.h): beyond it the result must be
+    non-finite, never a finite wrong number."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    A = torch.randn(300, 128, generator=gen)
+    A[7, 5] = 6000.0
+    layers = [(W.cuda(), b.cuda()) for W, b in _layers(gen, 2)]
+    out = ops.tc_mlp_chain(A.cuda(), layers)
+    assert not torch.isfinite(out[7]).all()
+    ok = torch.ones(300, dtype=torch.bool); ok[7] = False
+    assert torch.isfinite(out[ok.cuda()]).all()
