@@ -98,6 +98,7 @@ SIGNATURES = {
     "gnc_tc_multi_chain_f32": (c_int, [_P, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p),
                                        POINTER(c_void_p), c_int64, _P]),
     "gnc_debug_chain_trace": (c_int, [_P, c_int]),
+    "gnc_debug_slic_run_length": (c_int, [c_int]),
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
     "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,
                                  _P]),

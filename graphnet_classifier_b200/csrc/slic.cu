@@ -9,7 +9,8 @@
 // RGB -> CIELAB (D65), colour scaled by 1/compactness, spatial distance scaled by 1/step,
 // regular-grid initial centres, `iters` Lloyd iterations (10 in scikit-image), each pixel
 // searching the 3x3 grid cells around it (centres move by less than one step), labels
-// 0..K-1.  Centre updates use 64-bit fixed-point atomics, so the result is deterministic.
+// 0..K-1.  Centre updates use 64-bit fixed-point atomics (one set per label run of a thread's 8 pixels, merged across the lanes of a warp), so
+// the result is deterministic.
 // Connectivity enforcement (scikit-image's post-pass) is NOT applied; the label-map ->
 // graph stage (gnc_build_superpixel_graph) treats labels that vanish correctly
 // (node id = rank among the labels present).
@@ -62,42 +63,131 @@ __global__ void slic_init_kernel(const float* __restrict__ lab, SlicDims d, floa
 
 constexpr double kFix = 1048576.0;   // 2^20 fixed-point scale for deterministic sums
 
-__global__ void slic_assign_kernel(const float* __restrict__ lab, SlicDims d, const float* __restrict__ centers,
-                                   int32_t* __restrict__ labels, long long* __restrict__ acc /*[B,K,6]*/) {
-  const long long npix = (long long)d.B * d.H * d.W;
+// Assignment + accumulation.  Each thread owns kRun consecutive pixels of one image row:
+//  * their Lab values arrive as 128-bit loads and their labels leave as 128-bit stores (a thread-per-pixel
+//    layout with 12-byte pixels makes every scalar access a 32-sector request);
+//  * the open runs of a warp's 32 lanes (32 * kRun consecutive pixels) are merged by a segmented warp
+//    reduction before they go to the global accumulators;
+//  * the fixed-point sums of the current label run stay in registers, so the 6 global 64-bit atomics are
+//    issued once per run, not once per pixel (superpixels are ~25 pixels wide; integer sums: order-independent).
+// kRun = 1 is the per-pixel form of the same arithmetic (debug switch, used by the tests as the reference).
+template <int kRun>
+__global__ void __launch_bounds__(256, 2) slic_assign_kernel(const float* __restrict__ lab, SlicDims d,
+                                                          const float* __restrict__ centers, int32_t* __restrict__ labels,
+                                                          long long* __restrict__ acc /*[B,K,6]*/) {
+  const int gpr = (d.W + kRun - 1) / kRun;                     // pixel groups per row
+  const long long ngroups = (long long)d.B * d.H * gpr;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const float inv_step = 1.0f / d.step;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
-    const int b = (int)(p / ((long long)d.H * d.W));
-    const int rem = (int)(p - (long long)b * d.H * d.W);
-    const int y = rem / d.W, x = rem - y * d.W;
-    const float L = lab[p * 3], A = lab[p * 3 + 1], Bc = lab[p * 3 + 2];
-    int gy = (int)((long long)y * d.ny / d.H), gx = (int)((long long)x * d.nx / d.W);
-    float best = 3.4e38f;
-    int best_k = gy * d.nx + gx;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = gy + dy;
-      if (yy < 0 || yy >= d.ny) continue;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = gx + dx;
-        if (xx < 0 || xx >= d.nx) continue;
-        const int k = yy * d.nx + xx;
-        const float* c = centers + ((long long)b * d.K + k) * 5;
-        const float dl = L - c[0], da = A - c[1], db = Bc - c[2];
-        const float sy = ((y + 0.5f) - c[3]) * inv_step, sx = ((x + 0.5f) - c[4]) * inv_step;
-        const float dist = dl * dl + da * da + db * db + sy * sy + sx * sx;
-        if (dist < best) { best = dist; best_k = k; }       // ties: lowest centre index (scan order)
+  const bool vec = kRun % 4 == 0 && (d.W % kRun == 0) && ((reinterpret_cast<uintptr_t>(lab) | reinterpret_cast<uintptr_t>(labels)) & 15u) == 0;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < ngroups; base += stride) {   // warp-uniform trip count
+    const long long gi0 = base + threadIdx.x;
+    const bool active = gi0 < ngroups;
+    const long long gi = active ? gi0 : ngroups - 1;
+    const long long row = gi / gpr;                            // b * H + y
+    const int x0 = (int)(gi - row * gpr) * kRun;
+    const int b = (int)(row / d.H);
+    const int y = (int)(row - (long long)b * d.H);
+    const int n = !active ? 0 : (d.W - x0 < kRun ? d.W - x0 : kRun);
+    const long long p0 = row * d.W + x0;
+    const int gy = (int)((long long)y * d.ny / d.H);
+    const float* cb = centers + (long long)b * d.K * 5;
+    float px[kRun * 3];
+    int out[kRun];
+    if (vec && active) {
+      const float4* src = reinterpret_cast<const float4*>(lab + p0 * 3);
+#pragma unroll
+      for (int j = 0; j < (kRun * 3) / 4; ++j) {
+        const float4 v = __ldg(src + j);
+        px[4 * j] = v.x; px[4 * j + 1] = v.y; px[4 * j + 2] = v.z; px[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRun * 3; ++j) px[j] = j < n * 3 ? lab[p0 * 3 + j] : 0.f;
+    }
+    int run_k = -1;                                            // key of the open run: b * K + k
+    long long sL = 0, sA = 0, sB = 0, sx = 0, cnt = 0;
+    auto flush_to = [&](int key, long long vL, long long vA, long long vB, long long vy, long long vx, long long vn) {
+      long long* a = acc + (long long)key * 6;
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 0), (unsigned long long)vL);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 1), (unsigned long long)vA);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 2), (unsigned long long)vB);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 3), (unsigned long long)vy);   // sum of 2*(y+0.5)
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 4), (unsigned long long)vx);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + 5), (unsigned long long)vn);
+    };
+    auto flush = [&]() {
+      if (acc && cnt > 0) flush_to(run_k, sL, sA, sB, cnt * (2 * y + 1), sx, cnt);
+    };
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) {
+      if (i < n) {
+        const int x = x0 + i;
+        const float L = px[3 * i], A = px[3 * i + 1], Bc = px[3 * i + 2];
+        const int gx = (int)((long long)x * d.nx / d.W);
+        float best = 3.4e38f;
+        int best_k = gy * d.nx + gx;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = gy + dy;
+          if (yy < 0 || yy >= d.ny) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = gx + dx;
+            if (xx < 0 || xx >= d.nx) continue;
+            const int k = yy * d.nx + xx;
+            const float* c = cb + (long long)k * 5;
+            const float dl = L - __ldg(c), da = A - __ldg(c + 1), db = Bc - __ldg(c + 2);
+            const float sy = ((y + 0.5f) - __ldg(c + 3)) * inv_step, sxx = ((x + 0.5f) - __ldg(c + 4)) * inv_step;
+            const float dist = dl * dl + da * da + db * db + sy * sy + sxx * sxx;
+            if (dist < best) { best = dist; best_k = k; }     // ties: lowest centre index (scan order)
+          }
+        }
+        out[i] = best_k;
+        if (acc) {
+          if (b * d.K + best_k != run_k) {
+            flush();
+            run_k = b * d.K + best_k; sL = sA = sB = sx = cnt = 0;
+          }
+          // v * 2^20 is exact in fp32, so this equals llrint((double)v * 2^20) without the (slow) fp64 pipe
+          sL += __float2ll_rn(L * (float)kFix);
+          sA += __float2ll_rn(A * (float)kFix);
+          sB += __float2ll_rn(Bc * (float)kFix);
+          sx += 2 * x + 1;                                     // 2*(x+0.5)
+          cnt += 1;
+        }
       }
     }
-    labels[p] = best_k;
+    // The open runs of neighbouring lanes usually carry the same label (a warp covers 32 * kRun consecutive
+    // pixels): segmented warp reduction, one set of atomics per segment instead of per lane.
     if (acc) {
-      long long* a = acc + ((long long)b * d.K + best_k) * 6;
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 0), (unsigned long long)(long long)llrint((double)L * kFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 1), (unsigned long long)(long long)llrint((double)A * kFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 2), (unsigned long long)(long long)llrint((double)Bc * kFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 3), (unsigned long long)(2 * y + 1));   // 2*(y+0.5)
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 4), (unsigned long long)(2 * x + 1));
-      atomicAdd(reinterpret_cast<unsigned long long*>(a + 5), 1ull);
+      const unsigned kFull = 0xffffffffu;
+      const int key = (cnt > 0) ? run_k : -1;
+      long long v[6] = {sL, sA, sB, cnt * (2 * y + 1), sx, cnt};
+      const int prev = __shfl_up_sync(kFull, key, 1);
+      const bool head = lane == 0 || prev != key;
+      const unsigned heads = __ballot_sync(kFull, head);
+      const unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+      const int end = higher ? __ffs(higher) - 2 : 31;         // last lane of this lane's segment
+#pragma unroll
+      for (int delta = 1; delta < 32; delta <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const long long t = __shfl_down_sync(kFull, v[j], delta);
+          if (lane + delta <= end) v[j] += t;
+        }
+      }
+      if (head && key >= 0) flush_to(key, v[0], v[1], v[2], v[3], v[4], v[5]);
+    }
+    if (vec && active) {
+      int4* dst = reinterpret_cast<int4*>(labels + p0);
+#pragma unroll
+      for (int j = 0; j < kRun / 4; ++j) dst[j] = make_int4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRun; ++i)
+        if (i < n) labels[p0 + i] = out[i];
     }
   }
 }
@@ -124,6 +214,8 @@ __global__ void slic_update_kernel(SlicDims d, long long* __restrict__ acc, floa
 
 using namespace gnc;
 
+static int g_slic_run = 8;     // pixels per thread in the assignment kernel (1 = the per-pixel form; debug)
+
 static SlicDims slic_dims(int B, int H, int W, int n_segments, float compactness) {
   SlicDims d;
   d.B = B; d.H = H; d.W = W;
@@ -138,6 +230,12 @@ static SlicDims slic_dims(int B, int H, int W, int n_segments, float compactness
 }
 
 extern "C" {
+
+// Debug: 1 = per-pixel form of the assignment kernel, anything else = runs of 8 pixels (same labels).
+int gnc_debug_slic_run_length(int run) {
+  g_slic_run = run == 1 ? 1 : 8;
+  return GNC_OK;
+}
 
 int gnc_slic_num_centers(int H, int W, int n_segments) {
   if (H <= 0 || W <= 0) return 0;
@@ -165,6 +263,9 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
   if (e != cudaSuccess) return fail(GNC_ECUDA, "slic memset: %s", cudaGetErrorString(e));
   long long blocks = ceil_div<long long>(npix, 256);
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  const int run = g_slic_run;
+  long long ablocks = ceil_div<long long>((long long)B * H * ceil_div<int>(W, run), 256);   // one thread per pixel run
+  if (ablocks > (long long)kNumSMs * 32) ablocks = (long long)kNumSMs * 32;
   int rc;
   slic_lab_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, npix, d.inv_compactness, lab);
   if ((rc = check_launch("slic_lab_kernel"))) return rc;
@@ -172,12 +273,14 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
   slic_init_kernel<<<kb, 128, 0, st>>>(lab, d, centers);
   if ((rc = check_launch("slic_init_kernel"))) return rc;
   for (int it = 0; it < iters; ++it) {
-    slic_assign_kernel<<<(unsigned)blocks, 256, 0, st>>>(lab, d, centers, labels, acc);
+    if (run == 1) slic_assign_kernel<1><<<(unsigned)ablocks, 256, 0, st>>>(lab, d, centers, labels, acc);
+    else slic_assign_kernel<8><<<(unsigned)ablocks, 256, 0, st>>>(lab, d, centers, labels, acc);
     if ((rc = check_launch("slic_assign_kernel"))) return rc;
     slic_update_kernel<<<kb, 128, 0, st>>>(d, acc, centers);
     if ((rc = check_launch("slic_update_kernel"))) return rc;
   }
-  slic_assign_kernel<<<(unsigned)blocks, 256, 0, st>>>(lab, d, centers, labels, nullptr);   // final labels
+  if (run == 1) slic_assign_kernel<1><<<(unsigned)ablocks, 256, 0, st>>>(lab, d, centers, labels, nullptr);   // final labels
+  else slic_assign_kernel<8><<<(unsigned)ablocks, 256, 0, st>>>(lab, d, centers, labels, nullptr);
   return check_launch("slic_assign_kernel");
 }
 

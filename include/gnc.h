@@ -120,6 +120,8 @@ int gnc_slic_num_centers(int H, int W, int n_segments);
 int64_t gnc_slic_workspace_bytes(int B, int H, int W, int n_segments);
 int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, float compactness, int iters,
                        int32_t* labels, void* work, gnc_stream_t stream);
+/* Debug aid: 1 = one set of centre atomics per pixel instead of per 8-pixel label run (same result). */
+int gnc_debug_slic_run_length(int run);
 
 /* Stable CSR of edge ids grouped by key (= edge_index row 0 or row 1): the order
  * index_add_ visits edges in (models/GNN.py:20).  key is read with an element

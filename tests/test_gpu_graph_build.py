@@ -215,3 +215,20 @@ def test_device_slic_properties_and_superpixel_pipeline(libgnc):
     x, pos, ei = image_to_graph_superpixel(Image.fromarray(imgs[0]), r, n_segments=16)
     assert x.shape[1] == 3 and pos.shape[1] == 2 and ei.shape[0] == 2 and x.shape[0] <= 16
     assert float(x.min()) >= 0.0 and float(x.max()) <= 1.0
+
+
+def test_slic_run_aggregation_equals_per_pixel_atomics(libgnc):
+    """The assignment kernel accumulates centre sums per 8-pixel label run; the per-pixel form (debug switch)
+    must give the same labels, also for widths that are not a multiple of 8."""
+    from graphnet_classifier_b200.utils.image_to_graph.slic import slic_labels
+    rng = np.random.default_rng(3)
+    for (B, H, W, S) in ((2, 64, 64, 16), (3, 50, 61, 12), (1, 256, 256, 100)):
+        low = rng.random((B, 6, 6, 3))
+        img = np.kron(low, np.ones((1, H // 6 + 1, W // 6 + 1, 1)))[:, :H, :W]
+        img = np.clip(img * 255 + rng.integers(-6, 7, (B, H, W, 3)), 0, 255).astype(np.uint8)
+        t = torch.from_numpy(img).cuda()
+        libgnc.gnc_debug_slic_run_length(1)
+        ref = slic_labels(t, n_segments=S, compactness=10.0)
+        libgnc.gnc_debug_slic_run_length(8)
+        got = slic_labels(t, n_segments=S, compactness=10.0)
+        assert torch.equal(ref, got)
