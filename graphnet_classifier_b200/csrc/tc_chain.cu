@@ -190,6 +190,27 @@ __device__ __forceinline__ float relu_nan(float x) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
+// L2 residency hints (two-tile kernel): the rows of A are read again ~2 tiles later as the residual; without a
+// hint the P / Q gathers and the output stream push ~70 % of them out of L2 in between (ncu: DRAM reads 1.36 x
+// algorithmic).  A rows are loaded evict_last, their second (last) read and the output stores are evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, uint32_t nbytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(nbytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
 template <int REGS>
@@ -913,6 +934,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     const int rl = lane >> 3, cj = lane & 7;
     const long long total = n_my * 4;
     const uint32_t a0_remote = map_to_leader(a0_full(0, 0));
+    const uint64_t pol_keep = l2_policy_evict_last();
     auto issue = [&](long long it, int b) {
       if (it < total) {
         const long long tile = pair + (it >> 2) * npairs;
@@ -924,7 +946,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           const int r = i * 4 + rl;
           const long long row = row0 + r;
           const long long rc = row < p.M ? row : p.M - 1;
-          cp_async16(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), p.A + rc * p.lda + c * 32 + cj * 4, row < p.M ? 16u : 0u);
+          cp_async16_hint(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), p.A + rc * p.lda + c * 32 + cj * 4, row < p.M ? 16u : 0u, pol_keep);
         }
       }
       cp_async_commit();
@@ -1039,6 +1061,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
     for (int i = 0; i < 4; ++i) soff[i] = slot_off(rl + 8 * i, cc);
     const int lane_col = 16 * hf + 4 * cc;
+    const uint64_t pol_drop = l2_policy_evict_first();
     auto load_indices = [&](long long j, const float** a0, const float** a1) {
       const long long r0 = tile_row0(j);
 #pragma unroll
@@ -1072,7 +1095,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     auto fetch_res = [&](int c) {                   // step c of the tile pres describes -> slot c
       const uint32_t dst = slots_u + (uint32_t)c * kSlotBytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cp_async16(dst + soff[i], pres[i] + 32 * c, 16u);
+      for (int i = 0; i < 4; ++i) cp_async16_hint(dst + soff[i], pres[i] + 32 * c, 16u, pol_drop);
       cp_async_commit();
       ++issued;
     };
@@ -1246,7 +1269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           float* yrow = p.Y + (row0 + rl) * p.ldy + 32 * c + 16 * hf + 4 * cc;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (tile_full || row0 + rl + 8 * i < p.M) stg_stream(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i]);
+            if (tile_full || row0 + rl + 8 * i < p.M) stg_hint(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i], pol_drop);
           __syncwarp();
           // the slot is free again: next group of the stream
           if (S == 0 && hasY) fetch_res(c);                         // residual of Y, step c
