@@ -39,22 +39,25 @@ struct GridBuildArgs {
 __device__ __forceinline__ void phase_pixel_features(const GridBuildArgs& a, int64_t it) {
   const int64_t nbytes = (int64_t)a.B * a.g.N * 3;
   if (a.vecA) {
-    const int64_t off = it * 16;
-    if (off + 16 <= nbytes) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.img + off));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-      float4* o = reinterpret_cast<float4*>(a.x + off);
+    // unit `it` = 16 input bytes, but the 32 units of a warp are walked word-interleaved: lane l takes the
+    // 32-bit words l, l + 32, l + 64, l + 96 of the warp's 512-byte block, so that every load is one coalesced
+    // 128-byte request and every store one coalesced 512-byte request (4 pixels' channels per float4)
+    const int64_t wbase = (it & ~(int64_t)31) * 4 + (it & 31);      // first word of this lane
+    const int64_t nwords = nbytes >> 2;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k) {
+      const int64_t w = wbase + 32 * k;
+      if (w < nwords) {
+        const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(a.img) + w);
         float4 f;
-        f.x = (float)(w[k] & 0xffu);
-        f.y = (float)((w[k] >> 8) & 0xffu);
-        f.z = (float)((w[k] >> 16) & 0xffu);
-        f.w = (float)(w[k] >> 24);
-        stg_stream(o + k, f);
+        f.x = (float)(q & 0xffu);
+        f.y = (float)((q >> 8) & 0xffu);
+        f.z = (float)((q >> 16) & 0xffu);
+        f.w = (float)(q >> 24);
+        stg_stream(reinterpret_cast<float4*>(a.x) + w, f);
+      } else if (w == nwords) {
+        for (int64_t p = nwords * 4; p < nbytes; ++p) a.x[p] = (float)a.img[p];   // < 4 trailing bytes
       }
-    } else {
-      for (int64_t p = off; p < nbytes; ++p) a.x[p] = (float)a.img[p];
     }
   } else {
     const int64_t off = it * 16;
@@ -171,7 +174,8 @@ static int launch_grid_build(const uint8_t* img, int B, int imgH, int imgW, int 
   const int64_t BN = (int64_t)B * a.g.N, BE = (int64_t)B * a.g.E;
   GNC_REQUIRE(BN < 2147483647LL && BE < 2147483647LL, "build graph: B*N and B*E must fit int32");
   a.vecA = (!patch && aligned16(img) && aligned16(x)) ? 1 : 0;
-  const int64_t nA = patch ? BN : ceil_div<int64_t>(BN * 3, 16);
+  // pixel features: whole warps of 16-byte units (the lanes of a warp share a 512-byte block, phase_pixel_features)
+  const int64_t nA = patch ? BN : (a.vecA ? ceil_div<int64_t>(ceil_div<int64_t>(BN * 3, 16), 32) * 32 : ceil_div<int64_t>(BN * 3, 16));
   a.endA = nA;
   a.endB = a.endA + (pos ? BN : 0);
   a.endC = a.endB + ((ei || all_csr) ? BE : 0);
