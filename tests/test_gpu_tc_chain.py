@@ -113,7 +113,7 @@ def test_chain_matches_per_layer_engine_at_scale(libgnc):
     assert _maxrel(got, ref) < RTOL
 
 
-@pytest.mark.parametrize("M", [300, 256 * 74 * 2 + 77])
+@pytest.mark.parametrize("M", [300, 256 * 74 * 2 + 77, 256 * 74 * 5 + 256 * 30 + 9])
 def test_chain_prestage_table_form(libgnc, M):
     """Block 0 of the grid-graph path: first operand relu(R[class] + P[src] + Q[dst] + b0) built in the launch,
     two layers, LayerNorm, residual through the class table."""
