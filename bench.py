@@ -309,7 +309,11 @@ def run_ours(args):
             "kernel": "tc_chain_kernel (tcgen05 kind::f16 cta_group::2, two-piece fp16 split, 3 MMAs per product, "
                       "hidden activations in TMEM)", "bound": "tensor",
             "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
-            "traffic": None,
+            # DRAM bytes of the largest launch of this kernel family at this workload (edge processor, 16.6 M rows,
+            # tc_chain2_kernel<1>): dram__bytes_read + dram__bytes_write of one ncu capture, profiles/
+            # r01_tc_chain2_edge_b512_full_summary.txt (31.75 GB) re-measured with the L2 eviction hints (20.64 + 8.49)
+            "traffic": 29.13e9 if (B == 512 and args.resize == 128) else None,
+            "traffic_algorithmic_bytes_same_launch": 4.0 * 128 * (2 * 16646144 + 2 * 8388608) if (B == 512 and args.resize == 128) else None,
             "peak_source": pk["source"] + ": dense bf16 cuBLAS, sustained (kernel timed inside a long step)",
             "executed_tensor_flops_per_step": 3.0 * dom["flops"], "fp32_equivalent_tflops": dom["flops"] / dom_s / 1e12,
             "launches_per_step": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"],
