@@ -39,7 +39,8 @@ class GncTcChain(Structure):
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("_pad1", c_int32),
                 ("residual", c_void_p), ("residual_idx", c_void_p), ("ld_residual", c_int64),
                 ("dot_w", c_void_p), ("dot_b", c_void_p),
-                ("gather2", c_void_p), ("gather2_idx", c_void_p), ("ld_gather2", c_int64), ("pre_bias", c_void_p)]
+                ("gather2", c_void_p), ("gather2_idx", c_void_p), ("ld_gather2", c_int64), ("pre_bias", c_void_p),
+                ("operand2", c_void_p), ("ld_operand2", c_int64), ("W_operand2", c_void_p), ("ldw_operand2", c_int64)]
 
 
 class GncError(RuntimeError):

@@ -84,6 +84,8 @@ struct Params {
   // pre-stage mode (A == NULL): the first operand is relu(g2[i2[m]] + g0[i0[m]] + g1[i1[m]] + pre_bias), built by
   // the epilogue warps - block 0 of the grid-graph path, whose edge latents are a 4-row table (models/GNN.py:57-64)
   const float* g2; const int32_t* i2; long long ld_g2; const float* pre_bias;
+  // second operand of the first layer: z0 += A2 W_A2^T (the node processor's cat([x, agg]) without a T tensor)
+  const float* A2; long long lda2; const float* W_A2; long long ldw_A2;
   long long num_tiles;
   unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
 };
@@ -1327,6 +1329,458 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   }
 }
 
+
+// ---- two tiles in flight, shapes without gathered addends -------------------------------------------------------
+// NL layers (2 or 3); K2: the first layer contracts two operands (z0 = A W0^T + A2 W_A2^T + b0, the node processor's
+// cat([x, agg]) @ V0^T of models/GNN.py:100 - no intermediate T = x Va^T tensor, no addend stage: the loader writes
+// the second operand into the same TMEM chunks once the first operand's MMAs have read them); RES: residual = the
+// tile's own rows of p.residual; TAIL 0: LayerNorm (if gamma) + residual -> Y, TAIL 1: relu . dot_w + dot_b.
+// Shared memory: (NL + K2) weight images, loader ring, two 2 KB slots per epilogue warp (residual ring / transpose).
+template <int NL, bool K2, bool RES, int TAIL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain2n_kernel(const Params p) {
+  constexpr int kImgs = NL + (K2 ? 1 : 0);
+  static_assert(kImgs <= 4 && NL >= 2, "at most four weight images");
+  constexpr int kOffLd2 = kImgs * kLayerBytes;
+  constexpr int kOffEp2 = kOffLd2 + kLoaderWarps * kLoadBufs * kChunkBytes;
+  constexpr int kOffConst2 = kOffEp2 + kEpiWarps * 2 * kSlotBytes;
+  constexpr int kOffXchg2 = kOffConst2 + 5 * kD * 4;
+  constexpr int kOffBar2 = kOffXchg2 + 2 * kEpiWarps * 32 * 4;
+  static_assert(kOffBar2 + 320 + 1024 <= 232448, "shared memory layout");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  float* s_const = reinterpret_cast<float*>(sm + kOffConst2);
+  const uint32_t bar0 = base + kOffBar2;
+  // per slot S (144 bytes): a0_full[4] ae_full[4] a_empty[4] a_mid[4] d_full d_free; then the TMEM base pointer
+  auto a0_full = [&](int S, int c) { return bar0 + 144u * S + 8u * c; };
+  auto ae_full = [&](int S, int c) { return bar0 + 144u * S + 32u + 8u * c; };
+  auto a_empty = [&](int S, int c) { return bar0 + 144u * S + 64u + 8u * c; };
+  auto a_mid = [&](int S, int c) { return bar0 + 144u * S + 96u + 8u * c; };
+  auto d_full = [&](int S) { return bar0 + 144u * S + 128u; };
+  auto d_free = [&](int S) { return bar0 + 144u * S + 136u; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar2 + 288);
+
+  if (threadIdx.x == 0) {
+    for (int S = 0; S < 2; ++S) {
+      for (int c = 0; c < 4; ++c) {
+        mbar_init(a0_full(S, c), 2 * kLoaderWarps * 32);
+        mbar_init(ae_full(S, c), 2 * kEpiWarps * 32);
+        mbar_init(a_empty(S, c), 1);
+        mbar_init(a_mid(S, c), 1);
+      }
+      mbar_init(d_full(S), 1);
+      mbar_init(d_free(S), 2 * kEpiWarps * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // weight images: [W[0]] [W_A2 if K2] [W[1]] ... [W[NL-1]]
+  for (int im = 0; im < kImgs; ++im) {
+    const int l = (K2 && im >= 1) ? im - 1 : im;
+    const float* W = (K2 && im == 1) ? p.W_A2 : p.W[l];
+    const long long ldw = (K2 && im == 1) ? p.ldw_A2 : p.ldw[l];
+    for (int item = threadIdx.x; item < 64 * 16; item += kThreads) {
+      const int c = item & 15, nloc = item >> 4;
+      const float* src = W + (long long)(64 * (int)rank + nloc) * ldw + c * 8;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+      uint32_t p1[4], p2[4];
+      split2(v0.x * kScaleW, v0.y * kScaleW, p1[0], p2[0]);
+      split2(v0.z * kScaleW, v0.w * kScaleW, p1[1], p2[1]);
+      split2(v1.x * kScaleW, v1.y * kScaleW, p1[2], p2[2]);
+      split2(v1.z * kScaleW, v1.w * kScaleW, p1[3], p2[3]);
+      const int kb = c >> 3, cc = c & 7;
+      uint8_t* img = sm + im * kLayerBytes + kb * kImgBytes + (nloc >> 3) * 1024 + (nloc & 7) * 128 + ((cc ^ (nloc & 7)) << 4);
+      *reinterpret_cast<uint4*>(img) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<uint4*>(img + 2 * kImgBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+    }
+  }
+  for (int i = threadIdx.x; i < kD; i += kThreads) {
+    for (int l = 0; l < NL; ++l) s_const[l * kD + i] = p.bias[l] ? __ldg(p.bias[l] + i) * (l < NL - 1 ? kScaleA : 1.f) : 0.f;
+    s_const[3 * kD + i] = TAIL == 1 ? __ldg(p.dot_w + i) : (p.gamma ? __ldg(p.gamma + i) : 1.f);
+    s_const[4 * kD + i] = (TAIL == 0 && p.gamma) ? __ldg(p.beta + i) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const long long n_my = (p.num_tiles > pair) ? (p.num_tiles - pair + npairs - 1) / npairs : 0;   // tile j -> slot j & 1
+  constexpr int kOps = K2 ? 2 : 1;                  // operands of the first layer
+
+  if (warp < kLoaderWarps) {
+    // ======================= loaders =======================
+    reg_dec<kRegsLoader>();
+    const int q = warp;
+    const uint32_t buf0 = base + kOffLd2 + (uint32_t)(warp * kLoadBufs) * kChunkBytes;
+    const int rl = lane >> 3, cj = lane & 7;
+    const long long total = n_my * 4 * kOps;
+    // item order = the MMA thread's order: per group of two tiles [op0 X][op0 Y][op1 X][op1 Y] (4 chunks each), so
+    // that the second operand of a tile is converted while the other tile's first operand is being multiplied
+    const long long full_groups = n_my >> 1;
+    auto decode = [&](long long it, long long& j, int& op, int& c) {
+      const long long per = 8 * kOps;
+      if (it < full_groups * per) {
+        const long long g = it / per;
+        const int r = (int)(it - g * per);
+        op = r >> 3; c = r & 3;
+        j = 2 * g + ((r >> 2) & 1);
+      } else {
+        const int r = (int)(it - full_groups * per);
+        op = r >> 2; c = r & 3;
+        j = 2 * full_groups;
+      }
+    };
+    const uint32_t a0_remote = map_to_leader(a0_full(0, 0));
+    const uint64_t pol_keep = l2_policy_evict_last();
+    auto issue = [&](long long it, int b) {
+      if (it < total) {
+        long long j; int op, c;
+        decode(it, j, op, c);
+        const long long tile = pair + j * npairs;
+        const long long row0 = tile * kTileM + rank * 128 + q * 32;
+        const float* src = op ? p.A2 : p.A;
+        const long long ld = op ? p.lda2 : p.lda;
+        const uint32_t dst0 = buf0 + (uint32_t)b * kChunkBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + rl;
+          const long long row = row0 + r;
+          const long long rc = row < p.M ? row : p.M - 1;
+          cp_async16_hint(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), src + rc * ld + c * 32 + cj * 4, row < p.M ? 16u : 0u, pol_keep);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+    int b = 0;
+    for (long long it = 0; it < total; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
+      __syncwarp();
+      long long j; int op, c;
+      decode(it, j, op, c);
+      const int S = (int)(j & 1);
+      const uint32_t u = (uint32_t)(j >> 1);          // tiles this slot has seen
+      if (op == 0) mbar_wait(a_empty(S, c), (u & 1u) ^ 1u);   // the slot's previous tile has read chunk c
+      else mbar_wait(a_mid(S, c), u & 1u);                    // this tile's first-operand MMAs have read chunk c
+      tc_fence_after();
+      const uint8_t* buf = sm + kOffLd2 + (warp * kLoadBufs + b) * kChunkBytes + lane * 128;
+      const uint32_t ta = tmem_base + (uint32_t)S * 256 + 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t p1[8], p2[8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
+          split2(x.x * kScaleA, x.y * kScaleA, p1[2 * jj], p2[2 * jj]);
+          split2(x.z * kScaleA, x.w * kScaleA, p1[2 * jj + 1], p2[2 * jj + 1]);
+        }
+        tmem_st8(ta + half * 8, p1);
+        tmem_st8(ta + 64 + half * 8, p2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_remote(a0_remote + 144u * (uint32_t)S + 8u * (uint32_t)c);
+      __syncwarp();
+      issue(it + kLoadBufs, b);
+      b = (b + 1 == kLoadBufs) ? 0 : b + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp < kEpiWarp0) {
+    // ======================= MMA issuer =======================
+    reg_dec<kRegsMma>();
+    if (rank == 0 && warp == kMmaWarp && lane == 0) {
+      const uint64_t desc0 = make_desc(base);
+      const long long groups = (n_my + 1) >> 1;
+      auto mma_chunk = [&](uint32_t d_tmem, uint32_t a_base, uint64_t desc_img, int c, bool first_of_layer) {
+#pragma unroll
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int ks = 2 * c + k2;
+          const uint32_t a1 = a_base + (uint32_t)ks * 8, a2 = a1 + 64;
+          const uint64_t w1 = desc_img + (uint64_t)(((ks >> 2) * kImgBytes + (ks & 3) * 32) >> 4);
+          const uint64_t w2 = w1 + (uint64_t)((2 * kImgBytes) >> 4);
+          umma_f16_pair(d_tmem, a1, w2, kInstrDesc, !(first_of_layer && ks == 0));
+          umma_f16_pair(d_tmem, a2, w1, kInstrDesc, 1);
+          umma_f16_pair(d_tmem, a1, w1, kInstrDesc, 1);
+        }
+      };
+#pragma unroll 1
+      for (long long g = 0; g < groups; ++g) {
+        // phases of a group: (layer 0, operand 0) [(layer 0, operand 1)] layer 1 ... - each over both slots
+#pragma unroll 1
+        for (int ph = 0; ph < NL + kOps - 1; ++ph) {
+          const int l = ph < kOps ? 0 : ph - kOps + 1;
+          const int op = ph < kOps ? ph : 0;
+#pragma unroll 1
+          for (int S = 0; S < 2; ++S) {
+            if (2 * g + S >= n_my) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)S * 256;
+            const uint32_t a_base = d_tmem + 128;
+            if (l == 0) {
+              if (op == 0 && g > 0) {               // the slot's previous tile has copied its last accumulator out
+                mbar_wait(d_free(S), (uint32_t)((g - 1) & 1));
+                tc_fence_after();
+              }
+              const uint64_t desc_img = desc0 + (uint64_t)((op * kLayerBytes) >> 4);
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                mbar_wait(a0_full(S, c), (uint32_t)((g * kOps + op) & 1));
+                tc_fence_after();
+                mma_chunk(d_tmem, a_base, desc_img, c, op == 0);
+                if (K2 && op == 0) umma_commit_pair(a_mid(S, c));        // the second operand may overwrite chunk c
+              }
+              if (op == kOps - 1) umma_commit_pair(d_full(S));
+            } else {
+              const uint64_t desc_img = desc0 + (uint64_t)(((l + (K2 ? 1 : 0)) * kLayerBytes) >> 4);
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                mbar_wait(ae_full(S, c), (uint32_t)((g * (NL - 1) + (l - 1)) & 1));
+                tc_fence_after();
+                mma_chunk(d_tmem, a_base, desc_img, c, true);
+                if (l == NL - 1) umma_commit_pair(a_empty(S, c));
+              }
+              umma_commit_pair(d_full(S));
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    reg_inc<kRegsEpi>();
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3, hf = ew >> 2;
+    uint8_t* slots = sm + kOffEp2 + ew * 2 * kSlotBytes;
+    const uint32_t slots_u = base + kOffEp2 + (uint32_t)ew * 2 * kSlotBytes;
+    float* xchg = reinterpret_cast<float*>(sm + kOffXchg2);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rl = lane >> 2, cc = lane & 3;
+    const uint32_t ae_remote = map_to_leader(ae_full(0, 0)), dfree_remote = map_to_leader(d_free(0));
+    auto slot_off = [](int r, int ch) { return (uint32_t)(r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)); };
+    auto read_slot = [&](const uint8_t* slot, float* v) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const float4 x = *reinterpret_cast<const float4*>(slot + slot_off(lane, ch));
+        v[4 * ch] = x.x; v[4 * ch + 1] = x.y; v[4 * ch + 2] = x.z; v[4 * ch + 3] = x.w;
+      }
+    };
+    auto tile_row0 = [&](long long j) { return (pair + j * npairs) * kTileM + rank * 128 + q * 32; };
+    uint32_t soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) soff[i] = slot_off(rl + 8 * i, cc);
+    const int lane_col = 16 * hf + 4 * cc;
+    const uint64_t pol_drop = l2_policy_evict_first();
+
+    // residual stream: step k (= 4 j + c over the pair's tiles) uses slot k & 1, two steps in flight, FIFO
+    long long res_issued = 0, res_consumed = 0;
+    const long long res_total = RES ? 4 * n_my : 0;
+    auto issue_res = [&]() {
+      if (res_issued < res_total) {
+        const long long j = res_issued >> 2;
+        const int c = (int)(res_issued & 3);
+        const long long r0 = tile_row0(j);
+        const uint32_t dst = slots_u + (uint32_t)(res_issued & 1) * kSlotBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          long long g = r0 + rl + 8 * i;
+          g = g < p.M ? g : p.M - 1;
+          cp_async16_hint(dst + soff[i], p.residual + g * p.ld_res + lane_col + 32 * c, 16u, pol_drop);
+        }
+      }
+      cp_async_commit();                            // always: uniform group counting
+      ++res_issued;
+    };
+    auto emit_chunk = [&](const float* vc, const float* s_bias, int S, int c) {
+      const int col0 = 32 * c + 16 * hf;
+      uint32_t p1[8], p2[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j4);
+        const float y0 = fmaf(vc[4 * j4], 1.f / kScaleW, b4.x), y1 = fmaf(vc[4 * j4 + 1], 1.f / kScaleW, b4.y);
+        const float y2 = fmaf(vc[4 * j4 + 2], 1.f / kScaleW, b4.z), y3 = fmaf(vc[4 * j4 + 3], 1.f / kScaleW, b4.w);
+        split2(relu_nan(y0), relu_nan(y1), p1[2 * j4], p2[2 * j4]);
+        split2(relu_nan(y2), relu_nan(y3), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+      }
+      const uint32_t ta = lane_addr + (uint32_t)S * 256 + 128 + (uint32_t)(16 * c + 8 * hf);
+      tmem_st8(ta, p1);
+      tmem_st8(ta + 64, p2);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_remote(ae_remote + 144u * (uint32_t)S + 8u * (uint32_t)c);
+    };
+    uint32_t dcnt0 = 0, dcnt1 = 0;
+    auto wait_acc = [&](int S, float* v) {
+      mbar_wait(d_full(S), (S ? dcnt1 : dcnt0) & 1u);
+      if (S) ++dcnt1; else ++dcnt0;
+      tc_fence_after();
+      const uint32_t d_addr = lane_addr + (uint32_t)S * 256;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(d_addr + 32 * c + 16 * hf, v + 16 * c);
+      tmem_ld_wait();
+    };
+
+    const long long groups = (n_my + 1) >> 1;
+    if (RES) { issue_res(); issue_res(); }
+#pragma unroll 1
+    for (long long g = 0; g < groups; ++g) {
+      const bool hasY = 2 * g + 1 < n_my;
+      // ---- hidden layers
+#pragma unroll 1
+      for (int l = 0; l < NL - 1; ++l) {
+#pragma unroll 1
+        for (int S = 0; S < 2; ++S) {
+          if (S == 1 && !hasY) break;
+          float v[64];
+          wait_acc(S, v);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) emit_chunk(v + 16 * c, s_const + l * kD, S, c);
+        }
+      }
+      // ---- last layer
+#pragma unroll 1
+      for (int S = 0; S < 2; ++S) {
+        if (S == 1 && !hasY) break;
+        const long long row0 = tile_row0(2 * g + S);
+        const bool tile_full = row0 + 32 <= p.M;
+        float x[64];
+        wait_acc(S, x);
+        tc_fence_before();
+        mbar_arrive_remote(dfree_remote + 144u * (uint32_t)S);
+        const float* s_bias = s_const + (NL - 1) * kD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 32 * c + 16 * hf + 4 * j4);
+            float* xx = x + 16 * c + 4 * j4;
+            xx[0] = fmaf(xx[0], kUnscaleD, b4.x); xx[1] = fmaf(xx[1], kUnscaleD, b4.y);
+            xx[2] = fmaf(xx[2], kUnscaleD, b4.z); xx[3] = fmaf(xx[3], kUnscaleD, b4.w);
+          }
+        float* xa = xchg + (ew * 32 + lane);
+        float* xb = xchg + (kEpiWarps * 32) + (ew * 32 + lane);
+        const int partner = (ew ^ 4) * 32 + lane;
+        if (TAIL == 1) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) acc = fmaf(relu_nan(x[16 * c + jj]), s_const[3 * kD + 32 * c + 16 * hf + jj], acc);
+          const long long tcount = 2 * g + S;         // slot alternates per tile: one barrier per tile
+          float* mine = (tcount & 1) ? xb : xa;
+          *mine = acc;
+          named_bar_sync(1 + q, 64);
+          if (hf == 0) {
+            const float other = xchg[((tcount & 1) ? kEpiWarps * 32 : 0) + partner];
+            const long long gr = row0 + lane;
+            if (gr < p.M) p.Y[gr * p.ldy] = acc + other + (p.dot_b ? __ldg(p.dot_b) : 0.f);
+          }
+          continue;
+        }
+        if (p.gamma) {
+          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 64; jj += 4) { t0 += x[jj]; t1 += x[jj + 1]; t2 += x[jj + 2]; t3 += x[jj + 3]; }
+          const float s1 = (t0 + t1) + (t2 + t3);
+          *xa = s1;
+          named_bar_sync(1 + q, 64);
+          const float mu = (s1 + xchg[partner]) * (1.0f / kD);
+          t0 = t1 = t2 = t3 = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 64; jj += 4) {
+            x[jj] -= mu; x[jj + 1] -= mu; x[jj + 2] -= mu; x[jj + 3] -= mu;
+            t0 = fmaf(x[jj], x[jj], t0); t1 = fmaf(x[jj + 1], x[jj + 1], t1);
+            t2 = fmaf(x[jj + 2], x[jj + 2], t2); t3 = fmaf(x[jj + 3], x[jj + 3], t3);
+          }
+          const float s2 = (t0 + t1) + (t2 + t3);
+          *xb = s2;
+          named_bar_sync(1 + q, 64);
+          const float var = (s2 + xchg[kEpiWarps * 32 + partner]) * (1.0f / kD);
+          const float rstd = 1.0f / sqrtf(var + p.eps);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int col = 32 * c + 16 * hf + 4 * j4;
+              const float4 g4 = *reinterpret_cast<const float4*>(s_const + 3 * kD + col);
+              const float4 e4 = *reinterpret_cast<const float4*>(s_const + 4 * kD + col);
+              float* xx = x + 16 * c + 4 * j4;
+              xx[0] = fmaf(xx[0] * rstd, g4.x, e4.x); xx[1] = fmaf(xx[1] * rstd, g4.y, e4.y);
+              xx[2] = fmaf(xx[2] * rstd, g4.z, e4.z); xx[3] = fmaf(xx[3] * rstd, g4.w, e4.w);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // residual step k = 4 (2 g + S) + c lives in slot k & 1 = c & 1; without a residual the slot is only the
+          // transpose tile of the output
+          uint8_t* slot = slots + (c & 1) * kSlotBytes;
+          if (RES) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");      // the older of the two groups in flight
+            ++res_consumed;
+            __syncwarp();
+            float rsd[16];
+            read_slot(slot, rsd);
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) x[16 * c + jj] += rsd[jj];
+            __syncwarp();
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<float4*>(slot + slot_off(lane, ch)) =
+                make_float4(x[16 * c + 4 * ch], x[16 * c + 4 * ch + 1], x[16 * c + 4 * ch + 2], x[16 * c + 4 * ch + 3]);
+          __syncwarp();
+          float4 o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = *reinterpret_cast<const float4*>(slot + soff[i]);
+          float* yrow = p.Y + (row0 + rl) * p.ldy + 32 * c + lane_col;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (tile_full || row0 + rl + 8 * i < p.M) stg_hint(reinterpret_cast<float4*>(yrow + (long long)(8 * i) * p.ldy), o[i], pol_drop);
+          __syncwarp();
+          if (RES) issue_res();                        // the slot is free: next step of the stream
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    (void)res_consumed;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int NL, bool K2, bool RES, int TAIL>
+static int launch_spec2n(const Params& p, cudaStream_t st) {
+  // (the kernel's own layout: weight images, loader ring, 2 slots per epilogue warp, constants, barriers, slack)
+  constexpr int kSmem2n = (NL + (K2 ? 1 : 0)) * kLayerBytes + kLoaderWarps * kLoadBufs * kChunkBytes + kEpiWarps * 2 * kSlotBytes +
+                          5 * kD * 4 + 2 * kEpiWarps * 32 * 4 + 320 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_chain2n_kernel<NL, K2, RES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2n);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain2n: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
+  tc_chain2n_kernel<NL, K2, RES, TAIL><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
+  return check_launch("tc_chain2n_kernel");
+}
+
 template <int SPEC>
 static int launch_spec2(const Params& p, cudaStream_t st) {
   static bool configured = false;
@@ -1360,6 +1814,7 @@ static int launch(const Params& p, cudaStream_t st) {
     static const bool two = []() { const char* e = getenv("GNC_CHAIN_TWO_TILES"); return !e || e[0] != '0'; }();
     return two ? launch_spec2<7>(p, st) : launch_spec<7>(p, st);
   }
+  if (p.A2) return launch_spec2n<3, true, true, 0>(p, st);
   if (p.trace && p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && p.residual && !p.res_idx && p.gamma && !p.dot_w)
     return launch_spec<8>(p, st);
   if (!p.trace) {
@@ -1369,6 +1824,10 @@ static int launch(const Params& p, cudaStream_t st) {
       return two_tiles ? launch_spec2<1>(p, st) : launch_spec<1>(p, st);
     if (p.nlayers == 3 && p.g0 && !p.i0 && !p.g1 && res && !p.res_idx && ln && !dot)
       return two_tiles ? launch_spec2<2>(p, st) : launch_spec<2>(p, st);
+    if (p.A2) return launch_spec2n<3, true, true, 0>(p, st);     // (shape validated by the caller)
+    if (two_tiles && p.nlayers == 2 && !p.g0 && !p.g1 && res && !p.res_idx && ln && !dot) return launch_spec2n<2, false, true, 0>(p, st);
+    if (two_tiles && p.nlayers == 2 && !p.g0 && !p.g1 && !res && ln && !dot) return launch_spec2n<2, false, false, 0>(p, st);
+    if (two_tiles && p.nlayers == 2 && !p.g0 && !p.g1 && !res && !ln && dot) return launch_spec2n<2, false, false, 1>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && res && ln && !dot) return launch_spec<3>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && ln && !dot) return launch_spec<4>(p, st);
     if (p.nlayers == 2 && !p.g0 && !p.g1 && !res && !ln && dot) return launch_spec<5>(p, st);
@@ -1403,6 +1862,14 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
   for (int l = 0; l < ch->nlayers; ++l) {
     GNC_REQUIRE(ch->W[l] && aligned16(ch->W[l]) && ch->ldw[l] >= chain::kD && ch->ldw[l] % 4 == 0, "tc_mlp_chain: bad weight pointer / stride");
     p.W[l] = ch->W[l]; p.ldw[l] = ch->ldw[l]; p.bias[l] = ch->bias[l];
+  }
+  if (ch->operand2) {
+    // two-operand first layer (the node processor's cat([x, agg]) @ V0^T): three layers, LayerNorm, residual by row
+    GNC_REQUIRE(A && ch->nlayers == 3 && !ch->gather0 && !ch->gather1 && ch->gamma && ch->residual && !ch->residual_idx && !ch->dot_w,
+                "tc_mlp_chain: operand2 takes the form 3 layers + LayerNorm + residual by row, without gathered addends");
+    GNC_REQUIRE(ok4(ch->operand2, ch->ld_operand2) && ch->W_operand2 && aligned16(ch->W_operand2) && ch->ldw_operand2 >= chain::kD &&
+                ch->ldw_operand2 % 4 == 0, "tc_mlp_chain: operand2 / W_operand2 must be 16-byte aligned, 128 wide");
+    p.A2 = ch->operand2; p.lda2 = ch->ld_operand2; p.W_A2 = ch->W_operand2; p.ldw_A2 = ch->ldw_operand2;
   }
   GNC_REQUIRE(ok4(ch->gather0, ch->ld_gather0) && ok4(ch->gather1, ch->ld_gather1) && ok4(ch->residual, ch->ld_residual),
               "tc_mlp_chain: addend / residual rows must be 16-byte aligned, 128 wide");

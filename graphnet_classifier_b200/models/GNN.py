@@ -234,8 +234,8 @@ class GraphNet(nn.Module):
             nm = blk.node_model.node_processor
             W0, b0 = em.model[0].weight, em.model[0].bias
             V0, c0 = nm.model[0].weight, nm.model[0].bias
-            # the three node-side products of the block read the same h: one co-scheduled launch
-            P, Q, T = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256], V0[:, 0:128]])
+            # the two node-side products of the edge processor read the same h: one launch
+            P, Q = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256]])
             if e is None:       # block 0 in table form: e @ Wc.T is a 4-row table too
                 # relu(R[class] + P[row] + Q[col] + b0) is built inside the launch as its first operand
                 R = tcl(e_tab, W0[:, 256:384])
@@ -245,9 +245,9 @@ class GraphNet(nn.Module):
                 e = chain(e, (W0[:, 256:384], b0), em, gather0=(P, graph.src), gather1=(Q, graph.dst), residual=e)
             del P, Q
             agg = ops.aggregate(e, graph)
-            # the whole node MLP in one launch: agg Vb^T + (h Va^T) + c0 -> ... -> LN + h
-            h = chain(agg, (V0[:, 128:256], c0), nm, gather0=(T, None), residual=h)
-            del agg, T
+            # the whole node MLP in one launch: cat([h, agg]) V0^T + c0 as a two-operand contraction -> ... -> LN + h
+            h = chain(agg, (V0[:, 128:256], c0), nm, operand2=(h, V0[:, 0:128]), residual=h)
+            del agg
         dec = self.node_decoder.model
         return ops.tc_mlp_chain(h, [(dec[0].weight, dec[0].bias), (dec[2].weight, dec[2].bias)],
                                 dot_w=dec[4].weight, dot_b=dec[4].bias)

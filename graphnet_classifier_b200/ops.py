@@ -599,12 +599,13 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain")
 
 def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
-                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None) -> Tensor:
+                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None, operand2=None) -> Tensor:
     """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
     all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
     ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
     layer (``idx=None``: row m); the tail is ``LayerNorm(gamma, beta) + residual`` (``residual`` a
     tensor or ``(table, idx)``) or the decoder's ``relu(.) . dot_w + dot_b``.
+    ``operand2=(A2, W_A2)`` adds ``A2 @ W_A2.T`` to the first layer (two-operand contraction, no addend tensor).
     ``A=None`` with ``pre=(table, idx int32 [M], bias)`` is the pre-stage form: the first operand is
     ``relu(table[idx] + gather0 + gather1 + bias)`` and ``layers`` are the two layers after it.
     See include/gnc.h ``gnc_tc_chain_t``."""
@@ -632,6 +633,14 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
         ch.W[l], ch.ldw[l] = W.data_ptr(), W.stride(0)
         ch.bias[l] = None if b is None else b.data_ptr()
     nbytes = 4.0 * 128 * ((M if A is not None else 0) + len(layers) * 128)
+    if operand2 is not None:
+        A2, W2 = operand2
+        A2 = _rows(A2)
+        if W2.stride(1) != 1:
+            W2 = W2.contiguous()
+        keep += [A2, W2]
+        ch.operand2, ch.ld_operand2, ch.W_operand2, ch.ldw_operand2 = A2.data_ptr(), _ld(A2), W2.data_ptr(), W2.stride(0)
+        nbytes += 4.0 * 128 * (M + 128)
 
     def rows(t):
         t = _rows(t)
@@ -670,7 +679,8 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
     if out is None:
         out = torch.empty(M, n_out, dtype=torch.float32, device=dev)
     nbytes += 4.0 * M * n_out
-    check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * len(layers), nbytes, _lib.load().gnc_tc_mlp_chain_f32,
+    check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * (len(layers) + (operand2 is not None)), nbytes,
+                _lib.load().gnc_tc_mlp_chain_f32,
                 a_ptr, a_ld, M, ctypes.byref(ch), out.data_ptr(), _ld(out), _stream()), "tc_mlp_chain")
     return out
 

@@ -291,6 +291,9 @@ typedef struct gnc_tc_chain {
    * and W[0], W[1] are the two layers after it - the block-0 edge processor when the encoded edge latents
    * are a small table indexed by edge class. */
   const float* gather2; const int32_t* gather2_idx; int64_t ld_gather2; const float* pre_bias;
+  /* two-operand first layer: z0 += operand2[m] W_operand2^T (3 layers, LayerNorm, residual by row, no gathers) -
+   * cat([x, agg]) @ V0^T of NodeProcessor.forward (models/GNN.py:100) with V0 = [W_operand2 | W[0]]. */
+  const float* operand2; int64_t ld_operand2; const float* W_operand2; int64_t ldw_operand2;
 } gnc_tc_chain_t;
 
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,

@@ -67,6 +67,10 @@ cases = {
     "edge chain 2 layers, LN+res": (lambda: ops.tc_mlp_chain(e, layers[:2], gamma=gamma, beta=beta, residual=e, out=out), E, 2, 4.0 * 128 * 2 * E),
     "node MLP per-layer (3 launches)": (per_layer_node, N, 3, 4.0 * 128 * 4 * N),
     "node MLP chained": (lambda: ops.tc_mlp_chain(agg, layers, gather0=(T, None), gamma=gamma, beta=beta, residual=h, out=outn), N, 3, 4.0 * 128 * 4 * N),
+    "node MLP chained, two-operand L0": (lambda: ops.tc_mlp_chain(agg, layers, operand2=(h, layers[0][0]), gamma=gamma, beta=beta, residual=h, out=outn), N, 4, 4.0 * 128 * 3 * N),
+    "P,Q,T products (multi, 3 sets)": (lambda: ops.tc_linear_multi(h, [layers[0][0], layers[1][0], layers[2][0]]), N, 3, 4.0 * 128 * 4 * N),
+    "P,Q products (multi, 2 sets)": (lambda: ops.tc_linear_multi(h, [layers[0][0], layers[1][0]]), N, 2, 4.0 * 128 * 3 * N),
+    "encoder tail (2 layers, LN)": (lambda: ops.tc_mlp_chain(h, layers[:2], gamma=gamma, beta=beta, out=outn), N, 2, 4.0 * 128 * 2 * N),
 }
 only = sys.argv[2] if len(sys.argv) > 2 else None
 if os.environ.get("CHAIN_NO_PREFETCH"):
@@ -86,5 +90,5 @@ for name, (fn, rows, nl, nbytes) in cases.items():
     if not res[name]:
         continue
     best = statistics.median(res[name])
-    tf = 2.0 * rows * 128 * 128 * nl * 6 / best / 1e9      # executed bf16 tensor flops (6 products)
-    print(f"{name:34s} rows={rows}  median {best:8.3f} ms  (min {min(res[name]):7.3f})   {nbytes/best/1e6:7.0f} GB/s algorithmic   {tf:7.1f} bf16-TFLOP/s executed")
+    tf = 2.0 * rows * 128 * 128 * nl * 3 / best / 1e9      # executed fp16 tensor flops (3 MMAs per product)
+    print(f"{name:34s} rows={rows}  median {best:8.3f} ms  (min {min(res[name]):7.3f})   {nbytes/best/1e6:7.0f} GB/s algorithmic   {tf:7.1f} fp16-TFLOP/s executed")

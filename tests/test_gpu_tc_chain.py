@@ -178,3 +178,23 @@ def test_chain_out_of_domain_is_loud(libgnc):
     assert not torch.isfinite(out[7]).all()
     ok = torch.ones(300, dtype=torch.bool); ok[7] = False
     assert torch.isfinite(out[ok.cuda()]).all()
+
+
+@pytest.mark.parametrize("M", [200, 256 * 74 * 4 + 256 * 11 + 3])
+def test_chain_two_operand_node_form(libgnc, M):
+    """NodeProcessor form without a T tensor: z0 = agg Vb^T + h Va^T + c0 (cat([x, agg]) @ V0^T, models/GNN.py:100),
+    two more layers, LayerNorm, + h."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + 1)
+    agg, h = torch.randn(M, 128, generator=gen) * 2, torch.randn(M, 128, generator=gen)
+    V0 = torch.randn(128, 256, generator=gen) / 16
+    c0 = torch.randn(128, generator=gen) * 0.2
+    rest = _layers(gen, 2)
+    gamma, beta = torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.2
+    z = torch.relu(torch.cat([h, agg], 1).double() @ V0.double().t() + c0.double())
+    z = torch.relu(z @ rest[0][0].double().t() + rest[0][1].double()) @ rest[1][0].double().t() + rest[1][1].double()
+    ref = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5) + h.double()
+    V0c = V0.cuda()
+    got = ops.tc_mlp_chain(agg.cuda(), [(V0c[:, 128:256], c0.cuda())] + [(W.cuda(), b.cuda()) for W, b in rest],
+                           operand2=(h.cuda(), V0c[:, 0:128]), gamma=gamma.cuda(), beta=beta.cuda(), residual=h.cuda())
+    assert _maxrel(got, ref) < RTOL
