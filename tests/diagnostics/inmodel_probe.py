@@ -1,6 +1,6 @@
 """In-model check of every tensor-core training op against torch on the SAME inputs (failing smoke config)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from graphnet_classifier_b200 import ops, build
 build.build()
