@@ -40,7 +40,8 @@ class GncTcChain(Structure):
                 ("residual", c_void_p), ("residual_idx", c_void_p), ("ld_residual", c_int64),
                 ("dot_w", c_void_p), ("dot_b", c_void_p),
                 ("gather2", c_void_p), ("gather2_idx", c_void_p), ("ld_gather2", c_int64), ("pre_bias", c_void_p),
-                ("operand2", c_void_p), ("ld_operand2", c_int64), ("W_operand2", c_void_p), ("ldw_operand2", c_int64)]
+                ("operand2", c_void_p), ("ld_operand2", c_int64), ("W_operand2", c_void_p), ("ldw_operand2", c_int64),
+                ("narrow_W", c_void_p), ("ld_narrow_W", c_int64), ("narrow_b", c_void_p), ("narrow_k", c_int32), ("_pad2", c_int32)]
 
 
 class GncError(RuntimeError):

@@ -86,6 +86,8 @@ struct Params {
   const float* g2; const int32_t* i2; long long ld_g2; const float* pre_bias;
   // second operand of the first layer: z0 += A2 W_A2^T (the node processor's cat([x, agg]) without a T tensor)
   const float* A2; long long lda2; const float* W_A2; long long ldw_A2;
+  // narrow first layer folded into the loader: the operand is relu(A[:, :syn_k] syn_W^T + syn_b), syn_k <= 8
+  const float* syn_W; long long ld_syn_W; const float* syn_b; int syn_k;
   long long num_tiles;
   unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
 };
@@ -1336,8 +1338,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 // the second operand into the same TMEM chunks once the first operand's MMAs have read them); RES: residual = the
 // tile's own rows of p.residual; TAIL 0: LayerNorm (if gamma) + residual -> Y, TAIL 1: relu . dot_w + dot_b.
 // Shared memory: (NL + K2) weight images, loader ring, two 2 KB slots per epilogue warp (residual ring / transpose).
-template <int NL, bool K2, bool RES, int TAIL>
+template <int NL, bool K2, bool RES, int TAIL, bool SYN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain2n_kernel(const Params p) {
+  static_assert(!(SYN && K2), "the synthesised operand is a single-operand form");
   constexpr int kImgs = NL + (K2 ? 1 : 0);
   static_assert(kImgs <= 4 && NL >= 2, "at most four weight images");
   constexpr int kOffLd2 = kImgs * kLayerBytes;
@@ -1402,6 +1405,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       *reinterpret_cast<uint4*>(img + 2 * kImgBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
     }
   }
+  // SYN: the narrow layer's weights live where the (unused) loader ring would be: per output column 8 weights
+  // (zero-padded) + the bias, all x kScaleA (the loader emits the scaled operand; ReLU commutes with the scaling)
+  float* s_syn = reinterpret_cast<float*>(sm + kOffLd2);
+  if (SYN) {
+    for (int i = threadIdx.x; i < kD * 12; i += kThreads) {
+      const int col = i / 12, j = i - col * 12;
+      float v = 0.f;
+      if (j < p.syn_k) v = __ldg(p.syn_W + (long long)col * p.ld_syn_W + j) * kScaleA;
+      else if (j == 8) v = p.syn_b ? __ldg(p.syn_b + col) * kScaleA : 0.f;
+      s_syn[i] = v;
+    }
+  }
   for (int i = threadIdx.x; i < kD; i += kThreads) {
     for (int l = 0; l < NL; ++l) s_const[l * kD + i] = p.bias[l] ? __ldg(p.bias[l] + i) * (l < NL - 1 ? kScaleA : 1.f) : 0.f;
     s_const[3 * kD + i] = TAIL == 1 ? __ldg(p.dot_w + i) : (p.gamma ? __ldg(p.gamma + i) : 1.f);
@@ -1462,15 +1477,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       }
       cp_async_commit();
     };
+    if (!SYN) {
 #pragma unroll
-    for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+      for (int b = 0; b < kLoadBufs; ++b) issue(b, b);
+    }
     int b = 0;
+    float xin[8];                                     // SYN: this lane's input row (thread = row)
     for (long long it = 0; it < total; ++it) {
-      asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
+      if (!SYN) asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
       __syncwarp();
       long long j; int op, c;
       decode(it, j, op, c);
       const int S = (int)(j & 1);
+      if (SYN && c == 0) {
+        const long long row = (pair + j * npairs) * kTileM + rank * 128 + q * 32 + lane;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xin[t] = (row < p.M && t < p.syn_k) ? __ldg(p.A + row * p.lda + t) : 0.f;
+      }
       const uint32_t u = (uint32_t)(j >> 1);          // tiles this slot has seen
       if (op == 0) mbar_wait(a_empty(S, c), (u & 1u) ^ 1u);   // the slot's previous tile has read chunk c
       else mbar_wait(a_mid(S, c), u & 1u);                    // this tile's first-operand MMAs have read chunk c
@@ -1480,11 +1503,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t p1[8], p2[8];
+        if (SYN) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
-          split2(x.x * kScaleA, x.y * kScaleA, p1[2 * jj], p2[2 * jj]);
-          split2(x.z * kScaleA, x.w * kScaleA, p1[2 * jj + 1], p2[2 * jj + 1]);
+          for (int jj = 0; jj < 8; ++jj) {
+            float y[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float* w = s_syn + (c * 32 + half * 16 + 2 * jj + e) * 12;
+              const float4 w0 = *reinterpret_cast<const float4*>(w), w1 = *reinterpret_cast<const float4*>(w + 4);
+              float acc = w[8];
+              acc = fmaf(xin[0], w0.x, acc); acc = fmaf(xin[1], w0.y, acc); acc = fmaf(xin[2], w0.z, acc); acc = fmaf(xin[3], w0.w, acc);
+              acc = fmaf(xin[4], w1.x, acc); acc = fmaf(xin[5], w1.y, acc); acc = fmaf(xin[6], w1.z, acc); acc = fmaf(xin[7], w1.w, acc);
+              y[e] = relu_nan(acc);
+            }
+            split2(y[0], y[1], p1[jj], p2[jj]);
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
+            split2(x.x * kScaleA, x.y * kScaleA, p1[2 * jj], p2[2 * jj]);
+            split2(x.z * kScaleA, x.w * kScaleA, p1[2 * jj + 1], p2[2 * jj + 1]);
+          }
         }
         tmem_st8(ta + half * 8, p1);
         tmem_st8(ta + 64 + half * 8, p2);
@@ -1493,7 +1533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       tc_fence_before();
       mbar_arrive_remote(a0_remote + 144u * (uint32_t)S + 8u * (uint32_t)c);
       __syncwarp();
-      issue(it + kLoadBufs, b);
+      if (!SYN) issue(it + kLoadBufs, b);
       b = (b + 1 == kLoadBufs) ? 0 : b + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1765,19 +1805,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   }
 }
 
-template <int NL, bool K2, bool RES, int TAIL>
+template <int NL, bool K2, bool RES, int TAIL, bool SYN = false>
 static int launch_spec2n(const Params& p, cudaStream_t st) {
   // (the kernel's own layout: weight images, loader ring, 2 slots per epilogue warp, constants, barriers, slack)
   constexpr int kSmem2n = (NL + (K2 ? 1 : 0)) * kLayerBytes + kLoaderWarps * kLoadBufs * kChunkBytes + kEpiWarps * 2 * kSlotBytes +
                           5 * kD * 4 + 2 * kEpiWarps * 32 * 4 + 320 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain2n_kernel<NL, K2, RES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2n);
+    cudaError_t e = cudaFuncSetAttribute(tc_chain2n_kernel<NL, K2, RES, TAIL, SYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2n);
     if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain2n: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  tc_chain2n_kernel<NL, K2, RES, TAIL><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
+  tc_chain2n_kernel<NL, K2, RES, TAIL, SYN><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
   return check_launch("tc_chain2n_kernel");
 }
 
@@ -1815,6 +1855,7 @@ static int launch(const Params& p, cudaStream_t st) {
     return two ? launch_spec2<7>(p, st) : launch_spec<7>(p, st);
   }
   if (p.A2) return launch_spec2n<3, true, true, 0>(p, st);
+  if (p.syn_W) return launch_spec2n<2, false, false, 0, true>(p, st);     // (shape validated by the caller)
   if (p.trace && p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && p.residual && !p.res_idx && p.gamma && !p.dot_w)
     return launch_spec<8>(p, st);
   if (!p.trace) {
@@ -1848,7 +1889,9 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
   chain::Params p = {};
   p.A = A; p.lda = lda; p.M = M; p.nlayers = ch->nlayers;
   auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0 && ld >= chain::kD); };
-  if (A) {
+  if (A && ch->narrow_W) {
+    /* validated with the narrow-first-layer fields below */
+  } else if (A) {
     GNC_REQUIRE(lda >= chain::kD && lda % 4 == 0 && aligned16(A), "tc_mlp_chain: A rows must be 16-byte aligned");
     GNC_REQUIRE(!ch->gather2, "tc_mlp_chain: gather2 belongs to the pre-stage form (A == NULL)");
   } else {
@@ -1862,6 +1905,14 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
   for (int l = 0; l < ch->nlayers; ++l) {
     GNC_REQUIRE(ch->W[l] && aligned16(ch->W[l]) && ch->ldw[l] >= chain::kD && ch->ldw[l] % 4 == 0, "tc_mlp_chain: bad weight pointer / stride");
     p.W[l] = ch->W[l]; p.ldw[l] = ch->ldw[l]; p.bias[l] = ch->bias[l];
+  }
+  if (ch->narrow_W) {
+    // narrow first layer folded into the launch: relu(A[:, :k] narrow_W^T + narrow_b) -> 2 layers -> LayerNorm (encoders)
+    GNC_REQUIRE(A && ch->narrow_k >= 1 && ch->narrow_k <= 8 && lda >= ch->narrow_k && ch->ld_narrow_W >= ch->narrow_k,
+                "tc_mlp_chain: narrow first layer takes 1..8 input columns");
+    GNC_REQUIRE(ch->nlayers == 2 && !ch->gather0 && !ch->gather1 && !ch->operand2 && ch->gamma && !ch->residual && !ch->dot_w,
+                "tc_mlp_chain: the narrow-first-layer form is narrow layer + 2 layers + LayerNorm");
+    p.syn_W = ch->narrow_W; p.ld_syn_W = ch->ld_narrow_W; p.syn_b = ch->narrow_b; p.syn_k = ch->narrow_k;
   }
   if (ch->operand2) {
     // two-operand first layer (the node processor's cat([x, agg]) @ V0^T): three layers, LayerNorm, residual by row

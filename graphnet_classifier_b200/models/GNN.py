@@ -217,7 +217,10 @@ class GraphNet(nn.Module):
             return ops.tc_mlp_chain(a, layers, **kw)
 
         ne, ee = self.node_encoder.model, self.edge_encoder.model
-        h = chain(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), None, self.node_encoder)
+        if ne[0].in_features <= 8:       # Linear(3, 128) + ReLU folded into the launch's loader
+            h = chain(x, None, self.node_encoder, narrow=(ne[0].weight, ne[0].bias))
+        else:
+            h = chain(ops.linear([x], ne[0].weight, ne[0].bias, relu=True), None, self.node_encoder)
         # Grid graphs from our builders: edges fall into <= 4 classes with identical geometry rows
         # (SURVEY.md 0.4), so the edge encoder runs on one row per class and the encoded edge
         # latent of block 0 is a 4-row table indexed by class - never an [E, 128] tensor.  Only

@@ -599,13 +599,15 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain")
 
 def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
-                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None, operand2=None) -> Tensor:
+                 dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None, operand2=None,
+                 narrow=None) -> Tensor:
     """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
     all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
     ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
     layer (``idx=None``: row m); the tail is ``LayerNorm(gamma, beta) + residual`` (``residual`` a
     tensor or ``(table, idx)``) or the decoder's ``relu(.) . dot_w + dot_b``.
-    ``operand2=(A2, W_A2)`` adds ``A2 @ W_A2.T`` to the first layer (two-operand contraction, no addend tensor).
+    ``narrow=(Wn [128, k<=8], bn)``: ``A`` has k columns and the first operand is ``relu(A @ Wn.T + bn)`` (the
+    encoders' first layer folded into the launch).  ``operand2=(A2, W_A2)`` adds ``A2 @ W_A2.T`` to the first layer (two-operand contraction, no addend tensor).
     ``A=None`` with ``pre=(table, idx int32 [M], bias)`` is the pre-stage form: the first operand is
     ``relu(table[idx] + gather0 + gather1 + bias)`` and ``layers`` are the two layers after it.
     See include/gnc.h ``gnc_tc_chain_t``."""
@@ -624,6 +626,13 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
         A = _rows(A)
         M = A.shape[0]
         a_ptr, a_ld, dev = A.data_ptr(), _ld(A), A.device
+        if narrow is not None:
+            Wn, bn = narrow
+            if Wn.stride(1) != 1:
+                Wn = Wn.contiguous()
+            keep.append(Wn)
+            ch.narrow_W, ch.ld_narrow_W, ch.narrow_k = Wn.data_ptr(), Wn.stride(0), Wn.shape[1]
+            ch.narrow_b = None if bn is None else bn.data_ptr()
     ch.nlayers = len(layers)
     for l, (W, b) in enumerate(layers):
         _require_cuda(W)
@@ -632,7 +641,7 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
         keep.append(W)
         ch.W[l], ch.ldw[l] = W.data_ptr(), W.stride(0)
         ch.bias[l] = None if b is None else b.data_ptr()
-    nbytes = 4.0 * 128 * ((M if A is not None else 0) + len(layers) * 128)
+    nbytes = 4.0 * ((M * (A.shape[1] if narrow is not None else 128) if A is not None else 0) + len(layers) * 128 * 128)
     if operand2 is not None:
         A2, W2 = operand2
         A2 = _rows(A2)

@@ -294,6 +294,10 @@ typedef struct gnc_tc_chain {
   /* two-operand first layer: z0 += operand2[m] W_operand2^T (3 layers, LayerNorm, residual by row, no gathers) -
    * cat([x, agg]) @ V0^T of NodeProcessor.forward (models/GNN.py:100) with V0 = [W_operand2 | W[0]]. */
   const float* operand2; int64_t ld_operand2; const float* W_operand2; int64_t ldw_operand2;
+  /* narrow first layer folded into the launch (encoders, models/GNN.py:259-287: Linear(3, 128) on pixel channels /
+   * edge geometry): A has narrow_k <= 8 columns and the chain's first operand is relu(A narrow_W^T + narrow_b),
+   * followed by nlayers = 2 layers and LayerNorm.  narrow_W is [128, narrow_k] with row stride ld_narrow_W. */
+  const float* narrow_W; int64_t ld_narrow_W; const float* narrow_b; int32_t narrow_k; int32_t _pad2;
 } gnc_tc_chain_t;
 
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,

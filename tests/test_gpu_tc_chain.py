@@ -198,3 +198,20 @@ def test_chain_two_operand_node_form(libgnc, M):
     got = ops.tc_mlp_chain(agg.cuda(), [(V0c[:, 128:256], c0.cuda())] + [(W.cuda(), b.cuda()) for W, b in rest],
                            operand2=(h.cuda(), V0c[:, 0:128]), gamma=gamma.cuda(), beta=beta.cuda(), residual=h.cuda())
     assert _maxrel(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("M,k", [(500, 3), (256 * 74 * 3 + 100, 3), (1000, 8), (700, 1)])
+def test_chain_narrow_first_layer(libgnc, M, k):
+    """Encoder form: relu(x Wn^T + bn) built by the loader from k <= 8 input columns, two layers, LayerNorm."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + k)
+    x = torch.rand(M, k, generator=gen) * 255
+    Wn, bn = (torch.rand(128, k, generator=gen) - 0.5) / k ** 0.5, torch.randn(128, generator=gen) * 0.3
+    rest = _layers(gen, 2)
+    gamma, beta = torch.rand(128, generator=gen) + 0.5, torch.randn(128, generator=gen) * 0.2
+    a1 = torch.relu(x.double() @ Wn.double().t() + bn.double())
+    z = torch.relu(a1 @ rest[0][0].double().t() + rest[0][1].double()) @ rest[1][0].double().t() + rest[1][1].double()
+    ref = torch.nn.functional.layer_norm(z, (128,), gamma.double(), beta.double(), 1e-5)
+    got = ops.tc_mlp_chain(x.cuda(), [(W.cuda(), b.cuda()) for W, b in rest], narrow=(Wn.cuda(), bn.cuda()),
+                           gamma=gamma.cuda(), beta=beta.cuda())
+    assert _maxrel(got, ref) < RTOL
