@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .. import ops
+from .. import ops, tc_train
 from ..ops import GraphIndex, scatter_sum  # noqa: F401  (re-exported: reference module-level name)
 from .MLP import MLP
 
@@ -256,7 +256,21 @@ class GraphNet(nn.Module):
                                 dot_w=dec[4].weight, dot_b=dec[4].bias)
 
     def _forward_tc_train(self, x, pos, graph: GraphIndex):
-        """Differentiable form of ``_forward_tc``: the same restructured contractions through
+        """Differentiable form of ``_forward_tc``.  The K = 3 first layers of the encoders and the decoder's
+        ``Linear(128, 1)`` are autograd operators of their own (thin streaming kernels that mask their own
+        ReLU); everything between them is one ``autograd.Function`` with a hand-scheduled backward
+        (``tc_train.GraphNetCoreFn``: gradient sums folded into GEMM epilogues, no elementwise passes)."""
+        if ops.TRAIN_PATH != "core":
+            return self._forward_tc_train_opwise(x, pos, graph)
+        ne, ee, dec = self.node_encoder.model, self.edge_encoder.model, self.node_decoder.model
+        a1n = ops.linear([x], ne[0].weight, ne[0].bias, relu=True)
+        a1e = ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True)
+        d2 = tc_train.graphnet_core(self, graph, a1n, a1e)
+        return ops.linear([d2], dec[4].weight, dec[4].bias, relu=False)
+
+    def _forward_tc_train_opwise(self, x, pos, graph: GraphIndex):
+        """Op-by-op autograd form (every layer its own ``autograd.Function``): the implementation the
+        hand-scheduled core is tested against.  The same restructured contractions through
         ``ops.tc_linear_autograd`` (tensor-core forward and data gradients), LayerNorm and the
         K=3 / N=1 end layers through the fp32 operators, which save what their backward needs."""
         tcl = ops.tc_linear_autograd

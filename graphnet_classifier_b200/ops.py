@@ -29,6 +29,9 @@ from ._lib import GncSeg, GncTcChain, GncTcEpilogue, check
 # "fp32" = CUDA-core GEMM (csrc/dense.cu).  Both meet the 1e-5 parity bar; "fp32" is the
 # implementation the tensor-core path is tested against.
 ENGINE = os.environ.get("GNC_ENGINE", "tc")
+# Training schedule of the tensor-core engine: "core" = one autograd.Function with a hand-scheduled
+# backward (tc_train.py), "opwise" = one autograd.Function per layer (what "core" is tested against).
+TRAIN_PATH = os.environ.get("GNC_TRAIN_PATH", "core")
 
 
 def _require_cuda(*ts: Tensor) -> None:

@@ -1,0 +1,248 @@
+"""Training pass of the width-128 core of GraphNet with a hand-scheduled backward.
+
+One ``torch.autograd.Function`` covers everything between the encoders' thin first layers and the
+decoder's last ``Linear(128, 1)``: encoder tails, the ``n_blocks`` edge / node processors
+(models/GNN.py:57-64, 95-104, MetaLayer order :146, 215) and the decoder's two hidden layers
+(models/GNN.py:289-295).  The forward is the same kernel sequence as the op-by-op autograd path
+(``ops.tc_linear`` 3xTF32, LayerNorm, ordered CSR aggregation); what changes is the backward:
+
+* gradients that autograd would add with separate elementwise passes (``h`` feeds three products and a
+  residual, ``e`` a product and a residual, ``e'`` the aggregation and the next block) are accumulated
+  in the data-gradient GEMM's epilogue (``addend``) or by the gather kernel (``accumulate``) -
+  one extra row read instead of a read-read-write pass each;
+* ReLU backward rides in the producing data-gradient's epilogue (``mask``) everywhere;
+* weight gradients of the split first layers are written straight into column slices of the
+  ``[128, 384]`` / ``[128, 256]`` gradient, biases come out of the same tcgen05 pass;
+* activations are released as soon as their last consumer has run.
+
+Same arithmetic, same kernels, hence the same parity figures as the op-by-op path (logits 2.7e-6,
+gradients <= 8e-6 rel-L2 against the CPU oracle).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from ._lib import check
+
+_f32 = torch.float32
+
+
+def _ln_fwd(z: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optional[Tensor]):
+    M, D = z.shape
+    y = torch.empty(M, D, dtype=_f32, device=z.device)
+    mean = torch.empty(M, dtype=_f32, device=z.device)
+    rstd = torch.empty(M, dtype=_f32, device=z.device)
+    check(ops._call("layernorm_fwd", 0.0, 4.0 * M * D * (3 if res is not None else 2),
+                    _lib.load().gnc_layernorm_fwd_f32, z.data_ptr(), ops._ld(z), M, D, gamma.data_ptr(),
+                    beta.data_ptr(), float(eps), ops._p(res), ops._ld(res) if res is not None else 0, y.data_ptr(),
+                    ops._ld(y), mean.data_ptr(), rstd.data_ptr(), ops._stream()), "layernorm_fwd")
+    return y, mean, rstd
+
+
+def _ln_bwd(dy: Tensor, z: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor):
+    lib = _lib.load()
+    M, D = z.shape
+    dev = z.device
+    dz = torch.empty(M, D, dtype=_f32, device=dev)
+    dg = torch.empty(D, dtype=_f32, device=dev)
+    db = torch.empty(D, dtype=_f32, device=dev)
+    ws_n = int(lib.gnc_layernorm_bwd_workspace(M, D))
+    ws = ops._workspace(dev, ws_n)
+    check(ops._call("layernorm_bwd", 0.0, 4.0 * M * D * 3, lib.gnc_layernorm_bwd_f32, dy.data_ptr(), ops._ld(dy),
+                    z.data_ptr(), ops._ld(z), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), M, D, dz.data_ptr(),
+                    ops._ld(dz), dg.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), ws_n, ops._stream()), "layernorm_bwd")
+    return dz, dg, db
+
+
+def _relu_bwd(dY: Tensor, Y: Tensor):
+    """dZ = dY * (Y > 0) and its column sums (bias gradient) in one pass."""
+    lib = _lib.load()
+    M, N = Y.shape
+    dev = Y.device
+    dZ = torch.empty(M, N, dtype=_f32, device=dev)
+    db = torch.empty(N, dtype=_f32, device=dev)
+    ws_n = int(lib.gnc_colsum_workspace(M, N))
+    ws = ops._workspace(dev, ws_n)
+    check(ops._call("relu_bwd_colsum", 0.0, 4.0 * M * N * 3, lib.gnc_relu_bwd_colsum_f32, dY.data_ptr(), ops._ld(dY),
+                    Y.data_ptr(), ops._ld(Y), M, N, dZ.data_ptr(), ops._ld(dZ), db.data_ptr(), 0, ws.data_ptr(), ws_n,
+                    ops._stream()), "relu_bwd_colsum")
+    return dZ, db
+
+
+def core_param_list(gn) -> List[Tensor]:
+    """Parameters the core consumes, in the order ``GraphNetCoreFn`` returns their gradients:
+    per MLP tail ``W2 b2 W4 b4 gamma beta``; blocks add their first layers ``W0 b0`` / ``V0 c0`` in front;
+    the decoder contributes ``W0 b0 W2 b2``."""
+    ps: List[Tensor] = []
+
+    def tail(m):
+        return [m[2].weight, m[2].bias, m[4].weight, m[4].bias, m[5].weight, m[5].bias]
+
+    ps += tail(gn.node_encoder.model)
+    ps += tail(gn.edge_encoder.model)
+    for blk in gn.graph_processor.blocks:
+        em, nm = blk.edge_model.edge_processor.model, blk.node_model.node_processor.model
+        ps += [em[0].weight, em[0].bias] + tail(em)
+        ps += [nm[0].weight, nm[0].bias] + tail(nm)
+    dec = gn.node_decoder.model
+    ps += [dec[0].weight, dec[0].bias, dec[2].weight, dec[2].bias]
+    return ps
+
+
+class GraphNetCoreFn(torch.autograd.Function):
+    """``(a1n [N,128], a1e [E,128]) -> d2 [N,128]``: ``a1n`` / ``a1e`` are the ReLU outputs of the encoders'
+    first layers, ``d2`` the decoder's second hidden activation.  ``eps`` = (node enc, edge enc,
+    [edge proc, node proc] per block) LayerNorm epsilons."""
+
+    @staticmethod
+    def forward(ctx, graph, eps, n_blocks, a1n, a1e, *params):
+        tcl = ops.tc_linear
+        a1n, a1e = ops._rows(a1n), ops._rows(a1e)
+        saved = []          # per MLP tail: (a1, a2, z3, mean, rstd)
+        eps_it = iter(eps)
+
+        def tail(a1, p0, residual):
+            W2, b2, W4, b4, g, bt = params[p0:p0 + 6]
+            a2 = tcl(a1, W2, bias=b2, relu=True)
+            z3 = tcl(a2, W4, bias=b4)
+            y, mean, rstd = _ln_fwd(z3, g, bt, next(eps_it), residual)
+            saved.append((a1, a2, z3, mean, rstd))
+            return y
+
+        h = tail(a1n, 0, None)
+        e = tail(a1e, 6, None)
+        blocks = []
+        for k in range(n_blocks):
+            pe = 12 + 16 * k
+            pn = pe + 8
+            W0, b0, V0, c0 = params[pe], params[pe + 1], params[pn], params[pn + 1]
+            # the two node-side products of the edge processor and the node processor's h-side product read the
+            # same rows: one launch of the chained kernel in multi mode (h read once, kept in tensor memory)
+            P, Q, T = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256], V0[:, 0:128]])
+            a1 = tcl(e, W0[:, 256:384], bias=b0, relu=True, gather0=(P, graph.src), gather1=(Q, graph.dst))
+            del P, Q
+            e_in = e
+            e = tail(a1, pe + 2, e_in)
+            agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
+            n1 = tcl(agg, V0[:, 128:256], bias=c0, relu=True, addend=T)
+            del T
+            h_in = h
+            h = tail(n1, pn + 2, h_in)
+            blocks.append((h_in, e_in, agg))
+        Wd0, bd0, Wd2, bd2 = params[12 + 16 * n_blocks:12 + 16 * n_blocks + 4]
+        d1 = tcl(h, Wd0, bias=bd0, relu=True)
+        d2 = tcl(d1, Wd2, bias=bd2, relu=True)
+        ctx.graph, ctx.n_blocks = graph, n_blocks
+        ctx.saved, ctx.blocks, ctx.dec = saved, blocks, (h, d1)
+        ctx.params = params
+        ctx.save_for_backward(d2)
+        return d2
+
+    @staticmethod
+    def backward(ctx, dd2):
+        tcl, wgrad = ops.tc_linear, ops.tc_wgrad
+        graph, n_blocks, params = ctx.graph, ctx.n_blocks, ctx.params
+        (d2,) = ctx.saved_tensors
+        saved, blocks = ctx.saved, ctx.blocks
+        dd2 = ops._rows(dd2)
+        dev = dd2.device
+        n_tail = 6
+        grads: List[Optional[Tensor]] = [None] * len(params)
+
+        def tail_bwd(dy, idx, p0, mask_a1):
+            """Backward of Linear-ReLU-Linear-LayerNorm behind ``a1``; returns the gradient with respect to ``a1``
+            (times ``a1 > 0`` when ``mask_a1``: then it is the first layer's pre-activation gradient)."""
+            a1, a2, z3, mean, rstd = saved[idx]
+            saved[idx] = None
+            W2, _, W4, _, g, _ = params[p0:p0 + n_tail]
+            dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g)
+            del z3
+            dW4, db4 = wgrad(dz3, a2, want_db=True)
+            dz2 = tcl(dz3, W4, transpose_w=True, mask=a2)
+            del dz3, a2
+            dW2, db2 = wgrad(dz2, a1, want_db=True)
+            da1 = tcl(dz2, W2, transpose_w=True, mask=a1 if mask_a1 else None)
+            grads[p0:p0 + n_tail] = [dW2, db2, dW4, db4, dg, dbt]
+            return da1, a1
+
+        # parameter offsets
+        p_node_enc, p_edge_enc = 0, n_tail
+        p_blk = [2 * n_tail + k * 2 * (2 + n_tail) for k in range(n_blocks)]
+        p_dec = 2 * n_tail + n_blocks * 2 * (2 + n_tail)
+
+        # ---- decoder ----
+        h_last, d1 = ctx.dec
+        Wd0, _, Wd2, _ = params[p_dec:p_dec + 4]
+        dz2, dbd2 = _relu_bwd(dd2, d2)
+        dWd2 = wgrad(dz2, d1)
+        dz1 = tcl(dz2, Wd2, transpose_w=True, mask=d1)
+        del dz2, d1
+        dWd0, dbd0 = wgrad(dz1, h_last, want_db=True)
+        dh = tcl(dz1, Wd0, transpose_w=True)
+        del dz1, h_last
+        grads[p_dec:p_dec + 4] = [dWd0, dbd0, dWd2, dbd2]
+        ctx.dec = None
+
+        # ---- blocks, last to first ----
+        de = None                                   # gradient with respect to the block's output e'
+        for k in range(n_blocks - 1, -1, -1):
+            h_in, e_in, agg = blocks[k]
+            blocks[k] = None
+            pe = p_blk[k]
+            pn = pe + 2 + n_tail
+            W0 = params[pe]
+            V0 = params[pn]
+            # node processor: h' = LN(MLP(cat[h, agg])) + h
+            dn1, _ = tail_bwd(dh, 2 + 2 * k + 1, pn + 2, True)
+            dV0 = torch.empty(128, 256, dtype=_f32, device=dev)
+            _, dc0 = wgrad(dn1, agg, out=dV0[:, 128:256], want_db=True)
+            del agg
+            wgrad(dn1, h_in, out=dV0[:, 0:128])
+            grads[pn], grads[pn + 1] = dV0, dc0
+            dagg = tcl(dn1, V0[:, 128:256], transpose_w=True)
+            dh = tcl(dn1, V0[:, 0:128], transpose_w=True, addend=dh)     # + the residual's gradient
+            del dn1
+            # aggregation backward: every edge receives its destination's row, on top of what later blocks sent
+            if de is None:
+                de = ops._gather_raw(dagg, graph.dst)
+            else:
+                ops._gather_raw(dagg, graph.dst, out=de, accumulate=True)
+            del dagg
+            # edge processor: e' = LN(MLP(cat[h[row], h[col], e])) + e
+            da1, _ = tail_bwd(de, 2 + 2 * k, pe + 2, True)
+            dW0 = torch.empty(128, 384, dtype=_f32, device=dev)
+            _, db0 = wgrad(da1, e_in, out=dW0[:, 256:384], want_db=True)
+            del e_in
+            dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
+            dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
+            de = tcl(da1, W0[:, 256:384], transpose_w=True, addend=de)   # + the residual's gradient
+            del da1
+            wgrad(dP, h_in, out=dW0[:, 0:128])
+            wgrad(dQ, h_in, out=dW0[:, 128:256])
+            del h_in
+            grads[pe], grads[pe + 1] = dW0, db0
+            dh = tcl(dP, W0[:, 0:128], transpose_w=True, addend=dh)
+            del dP
+            dh = tcl(dQ, W0[:, 128:256], transpose_w=True, addend=dh)
+            del dQ
+        # ---- encoder tails: the thin first layers mask their own ReLU ----
+        da1e, _ = tail_bwd(de, 1, p_edge_enc, False)
+        del de
+        da1n, _ = tail_bwd(dh, 0, p_node_enc, False)
+        ctx.saved = ctx.blocks = None
+        need = ctx.needs_input_grad
+        out_params = [g if need[5 + i] else None for i, g in enumerate(grads)]
+        return (None, None, None, da1n if need[3] else None, da1e if need[4] else None, *out_params)
+
+
+def graphnet_core(gn, graph, a1n: Tensor, a1e: Tensor) -> Tensor:
+    """Run the width-128 core of ``gn`` (a tensor-core-eligible ``GraphNet``) with the hand-scheduled backward."""
+    eps = [gn.node_encoder.model[5].eps, gn.edge_encoder.model[5].eps]
+    for blk in gn.graph_processor.blocks:
+        eps += [blk.edge_model.edge_processor.model[5].eps, blk.node_model.node_processor.model[5].eps]
+    n_blocks = len(gn.graph_processor.blocks)
+    return GraphNetCoreFn.apply(graph, tuple(eps), n_blocks, a1n, a1e, *core_param_list(gn))

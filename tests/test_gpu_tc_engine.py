@@ -127,13 +127,16 @@ def test_model_tc_engine_vs_oracle_and_fp32_engine(libgnc, monkeypatch, r, diag,
     assert _maxrel(y_tc, y_or) < RTOL          # node-level decoder outputs, not only the 2 logits
 
 
-@pytest.mark.parametrize("engine", ["tc", "fp32"])
+@pytest.mark.parametrize("engine", ["tc", "tc-opwise", "fp32"])
 @pytest.mark.parametrize("r,diag,B", [(8, True, 2), (16, False, 3)])
 def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B):
-    """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine."""
+    """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine ("tc": the
+    hand-scheduled core backward of tc_train.py, "tc-opwise": one autograd.Function per layer)."""
     from graphnet_classifier_b200 import ops
     from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
     from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    monkeypatch.setattr(ops, "TRAIN_PATH", "opwise" if engine == "tc-opwise" else "core")
+    engine = engine.split("-")[0]
     monkeypatch.setattr(ops, "ENGINE", engine)
     cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
     om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=r * r, classes=2)
@@ -187,6 +190,10 @@ def test_tc_wgrad(libgnc, M):
     assert _maxrel(acc, ref + 1.0) < RTOL
     _, db = ops.tc_wgrad(dZ.cuda() + 0.25, X.cuda(), want_db=True)          # bias gradient on the same pass
     assert _maxrel(db, (dZ.double() + 0.25).sum(0)) < RTOL
+    wide = torch.full((128, 384), 7.0, device="cuda")                      # into a column slice of a wider gradient
+    ops.tc_wgrad(dZ.cuda(), X.cuda(), out=wide[:, 128:256])
+    assert _maxrel(wide[:, 128:256], ref) < RTOL
+    assert bool((wide[:, :128] == 7).all()) and bool((wide[:, 256:] == 7).all())
 
 
 def test_dgrad_with_fused_relu_mask(libgnc):
