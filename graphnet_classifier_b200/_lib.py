@@ -64,6 +64,10 @@ SIGNATURES = {
     "gnc_slic_num_centers": (c_int, [c_int, c_int, c_int]),
     "gnc_slic_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "gnc_slic_labels_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P]),
+    "gnc_resize_bicubic_ksize": (c_int, [c_int, c_int]),
+    "gnc_resize_bicubic_coeffs": (c_int, [c_int, c_int, _P, _P]),
+    "gnc_resize_bicubic_u8": (c_int, [_P, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_int, _P, _P, c_int, _P, _P, c_int,
+                                      _P, _P, _P]),
     "gnc_csr_workspace": (c_int64, [c_int64]),
     "gnc_csr_build": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "gnc_agg_csr_sum_f32": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, _P, c_int64, c_int, _P]),

@@ -1,0 +1,245 @@
+// Pillow-exact bicubic resize of RGB uint8 images on the device (input staging of the graph builders).
+//
+// The reference turns every image into its working resolution with PIL:
+//   Image.open(path).convert('RGB').resize((r, r))         utils/image_to_graph/image_to_graph_optimized.py:65-70
+// i.e. Pillow's ImagingResample with the BICUBIC filter: a separable two-pass convolution (horizontal first),
+// an 8-bit intermediate image, per-output-pixel coefficient windows computed in double precision and
+// quantised to 22-bit fixed point, int32 accumulation from the rounding constant 1 << 21, arithmetic shift,
+// clamp to a byte.  Everything after the coefficient tables is integer arithmetic, so the device result is
+// bit-identical to Pillow's; the tables themselves are computed on the host with the same double-precision
+// expressions (gnc_resize_bicubic_coeffs).
+//
+// HBM-bound byte work: per image 3*H*W bytes in, 3*OH*OW bytes out; the intermediate [H, OW, 3] image is
+// written and re-read once (it stays in L2 for typical photo sizes).
+//   horizontal pass: one CTA per source row - the row is staged in shared memory with 16-byte loads, every
+//                    thread produces 4 consecutive output bytes (one 32-bit store);
+//   vertical pass:   one thread per 4 consecutive bytes of an output row, taps read as 32-bit words
+//                    (adjacent threads -> adjacent words), weights are warp-uniform.
+#include "common.cuh"
+
+namespace gnc {
+namespace rsz {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ uint32_t clip8(int v) {
+  v >>= kPrecisionBits;
+  return (uint32_t)min(max(v, 0), 255);
+}
+
+// src rows: [rows] x row_bytes = 3 * W, row r of image b at src + b * image_stride + y * pitch
+__global__ void __launch_bounds__(kThreads) resize_h_kernel(const uint8_t* __restrict__ src, int H, int W, long long pitch,
+                                                             long long image_stride, int OW, const int32_t* __restrict__ bounds,
+                                                             const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ dst) {
+  extern __shared__ __align__(16) uint8_t s_row[];
+  const long long row = blockIdx.x;
+  const long long b = row / H;
+  const int y = (int)(row - b * H);
+  const uint8_t* g = src + b * image_stride + (long long)y * pitch;
+  const int nbytes = 3 * W;
+  // stage the row: shared offset keeps the global address's 16-byte phase, so that the aligned middle part
+  // moves as 128-bit words
+  const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
+  uint8_t* s = s_row + phase;
+  const int head = min(nbytes, (16 - phase) & 15);
+  const int nvec = (nbytes - head) >> 4;
+  for (int i = threadIdx.x; i < head; i += kThreads) s[i] = g[i];
+  const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+  uint4* sv = reinterpret_cast<uint4*>(s + head);
+  for (int i = threadIdx.x; i < nvec; i += kThreads) sv[i] = __ldg(gv + i);
+  for (int i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += kThreads) s[i] = g[i];
+  __syncthreads();
+
+  const int obytes = 3 * OW;
+  uint8_t* out = dst + row * (long long)obytes;
+  const bool word_ok = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+  for (int o4 = threadIdx.x * 4; o4 < obytes; o4 += kThreads * 4) {
+    uint32_t packed = 0;
+    const int n_out = min(4, obytes - o4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < n_out) {
+        const int o = o4 + t;
+        const int xx = o / 3, c = o - 3 * xx;
+        const int xmin = __ldg(bounds + 2 * xx), n = __ldg(bounds + 2 * xx + 1);
+        const int32_t* k = kk + (long long)xx * ksize;
+        const uint8_t* p = s + 3 * xmin + c;
+        int acc = 1 << (kPrecisionBits - 1);
+        for (int x = 0; x < n; ++x) acc += (int)p[3 * x] * __ldg(k + x);
+        packed |= clip8(acc) << (8 * t);
+      }
+    }
+    if (n_out == 4 && word_ok) {
+      *reinterpret_cast<uint32_t*>(out + o4) = packed;
+    } else {
+      for (int t = 0; t < n_out; ++t) out[o4 + t] = (uint8_t)(packed >> (8 * t));
+    }
+  }
+}
+
+// src: [B] images of H rows x row_bytes (pitch / image_stride in bytes); dst: [B, OH, row_bytes] contiguous.
+// One thread per 32-bit word of the output (flattened over rows, so narrow rows still fill the CTAs).
+__global__ void __launch_bounds__(kThreads) resize_v_kernel(const uint8_t* __restrict__ src, int row_bytes, long long pitch,
+                                                             long long image_stride, int OH, long long n_rows,
+                                                             const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk,
+                                                             int ksize, uint8_t* __restrict__ dst) {
+  const int wpr = (row_bytes + 3) >> 2;              // words per output row
+  const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long orow = idx / wpr;                  // b * OH + yy
+  if (orow >= n_rows) return;
+  const int o4 = (int)(idx - orow * wpr) * 4;
+  const long long b = orow / OH;
+  const int yy = (int)(orow - b * OH);
+  const int ymin = __ldg(bounds + 2 * yy), n = __ldg(bounds + 2 * yy + 1);
+  const int32_t* k = kk + (long long)yy * ksize;
+  const uint8_t* p = src + b * image_stride + (long long)ymin * pitch + o4;
+  uint8_t* out = dst + orow * (long long)row_bytes + o4;
+  const int n_out = min(4, row_bytes - o4);
+  int a0, a1, a2, a3;
+  a0 = a1 = a2 = a3 = 1 << (kPrecisionBits - 1);
+  const bool word_in = n_out == 4 && ((reinterpret_cast<uintptr_t>(p) | (uintptr_t)pitch) & 3u) == 0;
+  if (word_in) {
+    for (int y = 0; y < n; ++y) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + (long long)y * pitch));
+      const int c = __ldg(k + y);
+      a0 += (int)(w & 255u) * c;
+      a1 += (int)((w >> 8) & 255u) * c;
+      a2 += (int)((w >> 16) & 255u) * c;
+      a3 += (int)(w >> 24) * c;
+    }
+  } else {
+    for (int y = 0; y < n; ++y) {
+      const uint8_t* q = p + (long long)y * pitch;
+      const int c = __ldg(k + y);
+      a0 += (int)q[0] * c;
+      if (n_out > 1) a1 += (int)q[1] * c;
+      if (n_out > 2) a2 += (int)q[2] * c;
+      if (n_out > 3) a3 += (int)q[3] * c;
+    }
+  }
+  const uint32_t packed = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16) | (clip8(a3) << 24);
+  if (n_out == 4 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+    *reinterpret_cast<uint32_t*>(out) = packed;
+  } else {
+    for (int t = 0; t < n_out; ++t) out[t] = (uint8_t)(packed >> (8 * t));
+  }
+}
+
+// ---- coefficient tables (host; Pillow's precompute_coeffs + normalize_coeffs_8bpc, full box) --------------------
+static inline double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+static int ksize_of(int in_size, int out_size) {
+  double filterscale = (double)in_size / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  return (int)ceil(support) * 2 + 1;
+}
+
+}  // namespace rsz
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" int gnc_resize_bicubic_ksize(int in_size, int out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  return rsz::ksize_of(in_size, out_size);
+}
+
+extern "C" int gnc_resize_bicubic_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk) {
+  GNC_REQUIRE(in_size > 0 && out_size > 0 && bounds && kk, "resize_bicubic_coeffs: bad arguments");
+  const double scale = (double)in_size / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    int32_t* k = kk + (long long)xx * ksize;
+    double ww = 0.0;
+    // two passes over the window: Pillow stores the raw weights, sums them, then normalises
+    for (int x = 0; x < xmax; ++x) ww += rsz::bicubic_filter((x + xmin - center + 0.5) * ss);
+    for (int x = 0; x < xmax; ++x) {
+      double v = rsz::bicubic_filter((x + xmin - center + 0.5) * ss);
+      if (ww != 0.0) v /= ww;
+      v *= (double)(1 << rsz::kPrecisionBits);
+      k[x] = v < 0 ? (int)(-0.5 + v) : (int)(0.5 + v);
+    }
+    for (int x = xmax; x < ksize; ++x) k[x] = 0;
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return GNC_OK;
+}
+
+extern "C" int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W, int64_t src_pitch, int64_t src_image_stride,
+                                     int OH, int OW, const int32_t* bounds_x, const int32_t* kk_x, int ksize_x,
+                                     const int32_t* bounds_y, const int32_t* kk_y, int ksize_y, uint8_t* tmp, uint8_t* dst,
+                                     gnc_stream_t stream) {
+  GNC_REQUIRE(src && dst && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "resize_bicubic: bad arguments");
+  GNC_REQUIRE(src_pitch >= 3LL * W && src_image_stride >= (int64_t)H * src_pitch, "resize_bicubic: pitch / image stride too small");
+  GNC_REQUIRE((W == OW) == (bounds_x == nullptr) && (W == OW || (kk_x && ksize_x > 0)), "resize_bicubic: horizontal tables must be given exactly when the width changes");
+  GNC_REQUIRE((H == OH) == (bounds_y == nullptr) && (H == OH || (kk_y && ksize_y > 0)), "resize_bicubic: vertical tables must be given exactly when the height changes");
+  GNC_REQUIRE(B * (int64_t)(H > OH ? H : OH) < (1LL << 31), "resize_bicubic: too many rows for one launch");
+  if (B == 0) return GNC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool do_h = W != OW, do_v = H != OH;
+  if (!do_h && !do_v) {
+    cudaError_t e;
+    if (src_image_stride == (int64_t)H * src_pitch) {
+      e = cudaMemcpy2DAsync(dst, 3LL * W, src, src_pitch, 3LL * W, (size_t)(B * H), cudaMemcpyDeviceToDevice, st);
+    } else {
+      e = cudaSuccess;
+      for (int64_t b = 0; b < B && e == cudaSuccess; ++b)
+        e = cudaMemcpy2DAsync(dst + b * 3LL * W * H, 3LL * W, src + b * src_image_stride, src_pitch, 3LL * W, (size_t)H,
+                              cudaMemcpyDeviceToDevice, st);
+    }
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: copy: %s", cudaGetErrorString(e));
+    return GNC_OK;
+  }
+  const uint8_t* vsrc = src;
+  int64_t vpitch = src_pitch, vstride = src_image_stride;
+  if (do_h) {
+    GNC_REQUIRE(!do_v || tmp, "resize_bicubic: tmp [B, H, OW, 3] is required when both axes change");
+    const size_t smem = (size_t)3 * W + 32;
+    GNC_REQUIRE(smem <= 200 * 1024, "resize_bicubic: source rows wider than 68 000 pixels are not supported");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(rsz::resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured = 200 * 1024;
+    }
+    uint8_t* hdst = do_v ? tmp : dst;
+    rsz::resize_h_kernel<<<(unsigned)(B * H), rsz::kThreads, smem, st>>>(src, H, W, src_pitch, src_image_stride, OW, bounds_x, kk_x,
+                                                                        ksize_x, hdst);
+    int rc = check_launch("resize_h_kernel");
+    if (rc != GNC_OK) return rc;
+    vsrc = tmp;
+    vpitch = 3LL * OW;
+    vstride = (int64_t)H * vpitch;
+  }
+  if (do_v) {
+    const int row_bytes = 3 * OW;
+    const long long rows = B * (long long)OH;
+    const long long words = rows * ((row_bytes + 3) >> 2);
+    const long long blocks = ceil_div(words, (long long)rsz::kThreads);
+    GNC_REQUIRE(blocks < (1LL << 31), "resize_bicubic: output too large for one launch");
+    rsz::resize_v_kernel<<<(unsigned)blocks, rsz::kThreads, 0, st>>>(vsrc, row_bytes, vpitch, vstride, OH, rows, bounds_y, kk_y,
+                                                                    ksize_y, dst);
+    int rc = check_launch("resize_v_kernel");
+    if (rc != GNC_OK) return rc;
+  }
+  return GNC_OK;
+}

@@ -11,6 +11,7 @@ Operators (each with its backward wired through ``torch.autograd.Function``):
   aggregate            scatter_sum(edge_attr, col)                     models/GNN.py:99
   gather_rows          x[row] / x[col]                                 PyG MetaLayer, models/GNN.py:146
   edge_geometry        [pos[col]-pos[row], L1]                         models/GNN.py:299-302
+  resize_bicubic       PIL Image.resize((r, r)) on the device, bit-exact  utils/image_to_graph/image_to_graph_optimized.py:65-70
 """
 from __future__ import annotations
 
@@ -457,6 +458,59 @@ def edge_geometry(pos: Tensor, graph: GraphIndex) -> Tensor:
                 pos.data_ptr(), P, graph.src.data_ptr(), graph.dst.data_ptr(), graph.num_edges, out.data_ptr(),
                 _stream()), "edge_geometry")
     return out
+
+
+_resize_tables: dict = {}
+
+
+def _resize_axis_tables(in_size: int, out_size: int, device):
+    """Device copies of Pillow's coefficient tables for one axis, cached per (in, out, device) - the same
+    role as the reference's ``lru_cache`` on the grid topology."""
+    key = (int(in_size), int(out_size), str(device))
+    ent = _resize_tables.get(key)
+    if ent is None:
+        import numpy as np
+        lib = _lib.load()
+        ksize = int(lib.gnc_resize_bicubic_ksize(in_size, out_size))
+        if ksize <= 0:
+            raise ValueError(f"resize_bicubic: bad sizes {in_size} -> {out_size}")
+        bounds = np.empty((out_size, 2), np.int32)
+        kk = np.empty((out_size, ksize), np.int32)
+        check(lib.gnc_resize_bicubic_coeffs(in_size, out_size, bounds.ctypes.data, kk.ctypes.data), "resize_bicubic_coeffs")
+        if len(_resize_tables) >= 512:
+            _resize_tables.clear()
+        ent = _resize_tables[key] = (torch.from_numpy(bounds).to(device), torch.from_numpy(kk).to(device), ksize)
+    return ent
+
+
+def resize_bicubic(images: Tensor, out_h: int, out_w: Optional[int] = None) -> Tensor:
+    """``PIL.Image.resize((out_w, out_h))`` (BICUBIC, Pillow's default for RGB) of ``uint8 [H, W, 3]`` or
+    ``[B, H, W, 3]`` CUDA images, bit-identical to Pillow - the resize the reference's builders apply
+    (utils/image_to_graph/image_to_graph_optimized.py:65-70).  Returns ``uint8 [(B,) out_h, out_w, 3]``."""
+    _require_cuda(images)
+    if images.dtype != torch.uint8 or images.dim() not in (3, 4) or images.shape[-1] != 3:
+        raise ValueError(f"resize_bicubic expects uint8 [.., H, W, 3], got {images.dtype} {tuple(images.shape)}")
+    out_w = out_h if out_w is None else out_w
+    single = images.dim() == 3
+    img = images.unsqueeze(0) if single else images
+    if img.stride(3) != 1 or img.stride(2) != 3:
+        img = img.contiguous()
+    B, H, W, _ = img.shape
+    dev = img.device
+    dst = torch.empty(B, out_h, out_w, 3, dtype=torch.uint8, device=dev)
+    bx = kx = by = ky = None
+    ksx = ksy = 0
+    if W != out_w:
+        bx, kx, ksx = _resize_axis_tables(W, out_w, dev)
+    if H != out_h:
+        by, ky, ksy = _resize_axis_tables(H, out_h, dev)
+    tmp = torch.empty(B, H, out_w, 3, dtype=torch.uint8, device=dev) if (bx is not None and by is not None) else None
+    pitch = img.stride(1) if H > 1 else 3 * W
+    istride = img.stride(0) if B > 1 else H * pitch
+    nbytes = 3.0 * B * (H * W + out_h * out_w)
+    check(_call("resize_bicubic", 0.0, nbytes, _lib.load().gnc_resize_bicubic_u8, img.data_ptr(), B, H, W, pitch, istride,
+                out_h, out_w, _p(bx), _p(kx), ksx, _p(by), _p(ky), ksy, _p(tmp), dst.data_ptr(), _stream()), "resize_bicubic")
+    return dst[0] if single else dst
 
 
 class _ScatterSumFn(torch.autograd.Function):

@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import ops
 from .utils.image_to_graph.batched import build_patch_graphs, build_pixel_graphs
 
 
@@ -45,11 +46,20 @@ class GraphClassifierPipeline:
 
     # -- staging ----------------------------------------------------------------
     def _to_device(self, images) -> Tensor:
+        """``uint8 [B, r, r, 3]`` on the device.  Images of another size (one ``[B, H, W, 3]`` array, or a
+        list of differently sized ``[H, W, 3]`` arrays, e.g. decoded files) are resized on the device exactly
+        as the reference's ``image.resize((r, r))`` does (``ops.resize_bicubic``)."""
+        r = self.resize_value
+        if isinstance(images, (list, tuple)):
+            parts = [self._to_device(im) for im in images]
+            return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         t = images if isinstance(images, Tensor) else torch.as_tensor(images)
         if t.dim() == 3:
             t = t.unsqueeze(0)
         if not t.is_cuda:
             t = t.to(self.device, non_blocking=True)
+        if t.shape[1] != r or t.shape[2] != r:
+            t = ops.resize_bicubic(t, r, r)
         return t
 
     def _build(self, images_dev: Tensor):

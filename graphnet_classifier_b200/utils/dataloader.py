@@ -10,6 +10,7 @@ import torch
 from torch.utils.data import Dataset
 
 from .image_to_graph.batched import build_patch_graphs, build_pixel_graphs
+from .image_to_graph.image_to_graph_optimized import load_rgb_device
 from .image_to_graph.image_to_graph_superpixel import image_to_graph_superpixel
 
 
@@ -39,9 +40,7 @@ class OptimizedDatasetLoader(Dataset):
         return len(self.dataset)
 
     def _pixels(self, image) -> torch.Tensor:
-        r = self.resize_value
-        tab = np.asarray(image.convert("RGB").resize((r, r)))          # host side: PIL (out of the hot path)
-        return torch.from_numpy(np.ascontiguousarray(tab))
+        return load_rgb_device(image, self.resize_value)               # PIL decode on the host, Pillow-exact resize on the device
 
     def __getitem__(self, idx):
         image, label = self.dataset[idx]

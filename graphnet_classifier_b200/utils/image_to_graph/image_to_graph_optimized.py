@@ -5,7 +5,8 @@
 These are the single-image, host-visible entry points: numpy in the reference's
 dtypes (uint8 ``x``, int64 ``pos``, int64 ``edge_index``), so existing callers keep
 working.  The device-resident batched form is ``build_pixel_graphs`` (batched.py).
-PIL decode / resize stay on the host (out of the hot path).
+The file decode (``Image.open`` + ``convert('RGB')``) stays on the host; the resize to the working
+resolution runs on the device, bit-identical to PIL's (``ops.resize_bicubic``).
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ import numpy as np
 import torch
 from PIL import Image
 
+from ... import ops
 from .batched import build_pixel_graphs
 
 
@@ -37,9 +39,17 @@ def get_cached_edge_index(resize_value, diagonals):
     return create_grid_edges_optimized(resize_value, resize_value, diagonals)
 
 
-def _load_rgb(image_or_path, resize_value):
+def load_rgb_device(image_or_path, resize_value) -> torch.Tensor:
+    """``image.convert('RGB').resize((r, r))`` (reference :65-70) as ``uint8 [r, r, 3]`` on the device:
+    decoded on the host, resized by the Pillow-exact device kernel."""
     image = Image.open(image_or_path) if isinstance(image_or_path, str) else image_or_path
-    return np.asarray(image.convert("RGB").resize((resize_value, resize_value)))
+    rgb = torch.from_numpy(np.array(image.convert("RGB"), dtype=np.uint8))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return ops.resize_bicubic(rgb.to(dev, non_blocking=True), int(resize_value), int(resize_value))
+
+
+def _load_rgb(image_or_path, resize_value):
+    return load_rgb_device(image_or_path, resize_value).cpu().numpy()
 
 
 def image_to_graph_pixel_optimized(image_or_path, resize_value=128, diagonals=False, use_cache=True):

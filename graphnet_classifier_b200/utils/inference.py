@@ -7,10 +7,10 @@ from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
-from PIL import Image
 
 from ..models.GNN import CombinedModel, GraphNet
 from .image_to_graph.batched import build_pixel_graphs
+from .image_to_graph.image_to_graph_optimized import load_rgb_device
 
 
 def gnn_inference(image_path, weights_path: str = "weights/GNN/best_model_epoch2.pth", resize_value: int = 64,
@@ -20,11 +20,8 @@ def gnn_inference(image_path, weights_path: str = "weights/GNN/best_model_epoch2
     state = torch.load(weights_path, map_location="cpu")
     model.load_state_dict(state)
     model = model.cuda().eval()
-    import numpy as np
-    image = Image.open(image_path) if isinstance(image_path, str) else image_path
-    tab = np.ascontiguousarray(np.asarray(image.convert("RGB").resize((resize_value, resize_value))))
     with torch.no_grad():
-        gb = build_pixel_graphs(torch.from_numpy(tab))
+        gb = build_pixel_graphs(load_rgb_device(image_path, resize_value))
         if verbose:
             print(f"Input x shape: {gb.x.shape}, x range: [{gb.x.min():.3f}, {gb.x.max():.3f}]")
             print(f"Input pos shape: {gb.pos.shape}, pos range: [{gb.pos.min():.3f}, {gb.pos.max():.3f}]")

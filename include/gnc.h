@@ -123,6 +123,26 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
 /* Debug aid: 1 = one set of centre atomics per pixel instead of per 8-pixel label run (same result). */
 int gnc_debug_slic_run_length(int run);
 
+/* Input staging: the resize the reference applies to every image before building its graph,
+ *   Image.open(path).convert('RGB').resize((r, r))     utils/image_to_graph/image_to_graph_optimized.py:65-70,
+ *                                                      image_to_graph_patch.py / _superpixel.py likewise
+ * = Pillow's two-pass BICUBIC ImagingResample (horizontal pass first, 8-bit intermediate, 22-bit fixed-point
+ * coefficients).  Bit-identical to Pillow (csrc/resize.cu, oracle/resize.py).
+ *   gnc_resize_bicubic_ksize   taps per output pixel along an axis resized in_size -> out_size (0 on bad sizes);
+ *   gnc_resize_bicubic_coeffs  HOST: fills bounds int32 [out_size, 2] (first tap, tap count) and
+ *                              kk int32 [out_size, ksize] with Pillow's tables for that axis;
+ *   gnc_resize_bicubic_u8      src uint8 [B, H, W, 3] (src_pitch bytes between rows, src_image_stride bytes between
+ *                              images) -> dst uint8 [B, OH, OW, 3] contiguous.  bounds_* / kk_* are DEVICE copies of
+ *                              the tables of the x (W -> OW) and y (H -> OH) axes; an axis whose size does not change
+ *                              is not filtered and takes NULL tables (Pillow does the same).  tmp: uint8
+ *                              [B, H, OW, 3] scratch, needed only when both axes change. */
+int gnc_resize_bicubic_ksize(int in_size, int out_size);
+int gnc_resize_bicubic_coeffs(int in_size, int out_size, int32_t* bounds /*HOST*/, int32_t* kk /*HOST*/);
+int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W, int64_t src_pitch, int64_t src_image_stride,
+                          int OH, int OW, const int32_t* bounds_x, const int32_t* kk_x, int ksize_x,
+                          const int32_t* bounds_y, const int32_t* kk_y, int ksize_y, uint8_t* tmp, uint8_t* dst,
+                          gnc_stream_t stream);
+
 /* Stable CSR of edge ids grouped by key (= edge_index row 0 or row 1): the order
  * index_add_ visits edges in (models/GNN.py:20).  key is read with an element
  * stride so that non-contiguous edge_index is accepted.

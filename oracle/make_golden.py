@@ -225,13 +225,50 @@ def gen_model(ref):
     print("model.npz:", len(out), "entries")
 
 
+def gen_resize(ref):
+    """Input staging: ``image.convert('RGB').resize((r, r))`` inside the reference's own builder
+    (image_to_graph_optimized.py:65-70; Pillow BICUBIC) on the shipped JPEGs at sizes other than the file's and on
+    random non-square images.  The builder's ``x`` IS the resized image; oracle/resize.py must reproduce it bit for bit."""
+    from oracle.resize import resize_bicubic
+    out = {}
+    cases = [("static/chihuahua/img_4_799_256.jpg", 128), ("static/chihuahua/img_4_799_256.jpg", 100),
+             ("static/muffin/img_0_187_128.jpg", 256), ("static/muffin/img_0_187_256.jpg", 64),
+             ("static/muffin/img_4_880_32.jpg", 48)]
+    srcs = {}
+    for rel, r_ in cases:
+        path = os.path.join(rl.REFERENCE_ROOT, rel)
+        x, _, _ = ref.optimized.image_to_graph_pixel_optimized(path, r_)
+        src = np.array(Image.open(path).convert("RGB"))
+        _check(x.dtype == np.uint8 and np.array_equal(resize_bicubic(src, r_, r_).reshape(-1, 3), x), f"resize {rel} -> {r_}")
+        name = os.path.basename(rel).replace(".jpg", "")
+        srcs[name] = src
+        out[f"jpeg_{name}_to{r_}_x"] = x.reshape(r_, r_, 3)
+    for name, src in srcs.items():
+        out[f"jpeg_{name}_src"] = src
+    rng = np.random.default_rng(77)
+    for i, (H, W, r_) in enumerate([(75, 100, 32), (33, 17, 24), (64, 200, 64), (200, 64, 64), (9, 9, 40), (301, 203, 50)]):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        if i % 2:                       # smooth content with saturated regions: exercises the clamp
+            yy, xx = np.mgrid[0:H, 0:W]
+            img = np.stack([(yy * 255 // max(H - 1, 1)), (xx * 255 // max(W - 1, 1)), ((yy // 3 + xx // 3) % 2) * 255], -1).astype(np.uint8)
+        x, _, _ = ref.optimized.image_to_graph_pixel_optimized(Image.fromarray(img), r_)
+        _check(np.array_equal(resize_bicubic(img, r_, r_).reshape(-1, 3), x), f"resize random {H}x{W} -> {r_}")
+        out[f"rand{i}_src"], out[f"rand{i}_to{r_}_x"] = img, x.reshape(r_, r_, 3)
+    np.savez_compressed(os.path.join(GOLDEN, "resize.npz"), **out)
+    print("resize.npz:", len(out), "entries")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rl.load_reference()
     torch.set_num_threads(4)
+    if "--only-resize" in sys.argv:
+        gen_resize(ref)
+        return
     gen_grids(ref)
     gen_builders(ref)
     gen_model(ref)
+    gen_resize(ref)
     print("all reference-vs-oracle comparisons passed; golden vectors written to", GOLDEN)
 
 

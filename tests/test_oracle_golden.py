@@ -116,3 +116,45 @@ def test_batched_equals_per_sample(golden):
     with torch.no_grad():
         out = om(ogb.to_model_inputs(bx, bp, be))
     np.testing.assert_allclose(out.numpy(), m["model_r8_d0_logits"], rtol=2e-6, atol=1e-7)
+
+
+def _resize_cases(g):
+    for k in g:
+        if k.endswith("_x"):
+            name, to = k[:-2].rsplit("_to", 1)
+            yield k, g[name + "_src"], int(to), g[k]
+
+
+def test_resize_oracle_vs_reference_golden_and_pillow(golden):
+    """oracle/resize.py == the reference builder's resized pixels (golden, produced through
+    image_to_graph_pixel_optimized) == Pillow itself on further shapes."""
+    from PIL import Image
+    from oracle.resize import precompute_coeffs, resize_bicubic
+    n = 0
+    for k, src, r, ref in _resize_cases(golden["resize"]):
+        assert np.array_equal(resize_bicubic(src, r, r), ref), k
+        n += 1
+    assert n >= 10
+    rng = np.random.default_rng(5)
+    for H, W, oh, ow in [(375, 500, 128, 128), (64, 64, 128, 128), (128, 300, 128, 128), (300, 128, 128, 128),
+                         (128, 128, 128, 128), (1, 1, 4, 4), (2, 3, 8, 8), (640, 480, 64, 32), (50, 40, 7, 9)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        assert np.array_equal(resize_bicubic(img, oh, ow), np.asarray(Image.fromarray(img).resize((ow, oh)))), (H, W, oh, ow)
+    b, kk = precompute_coeffs(500, 128)
+    assert kk.shape == (128, 17) and int(kk.sum(1).min()) > (1 << 22) - 20 and int(kk.sum(1).max()) < (1 << 22) + 20
+
+
+def test_resize_coefficient_tables_through_the_c_abi(libgnc):
+    """Host-only entry point: Pillow's per-axis tables from libgnc == the oracle's, bit for bit."""
+    from oracle.resize import precompute_coeffs
+    for i, o in [(500, 128), (375, 128), (64, 128), (37, 64), (1000, 256), (5, 64), (129, 128), (127, 128), (3, 8), (1, 4),
+                 (640, 32), (4000, 128), (128, 256), (333, 77)]:
+        ks = libgnc.gnc_resize_bicubic_ksize(i, o)
+        ob, ok = precompute_coeffs(i, o)
+        assert ks == ok.shape[1]
+        b = np.zeros((o, 2), np.int32)
+        k = np.full((o, ks), -7, np.int32)
+        assert libgnc.gnc_resize_bicubic_coeffs(i, o, b.ctypes.data, k.ctypes.data) == 0
+        assert np.array_equal(b, ob) and np.array_equal(k, ok), (i, o)
+    assert libgnc.gnc_resize_bicubic_ksize(0, 5) == 0
+    assert libgnc.gnc_resize_bicubic_coeffs(5, 5, None, None) == 1
