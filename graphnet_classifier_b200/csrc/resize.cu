@@ -78,6 +78,92 @@ __global__ void __launch_bounds__(kThreads) resize_h_kernel(const uint8_t* __res
   }
 }
 
+// Register-resident form of the horizontal pass (windows of at most KMAX taps): a CTA stages R source rows, thread
+// xx keeps its KMAX weights in registers and walks its byte window of every staged row as 32-bit shared-memory
+// words (funnel-shifted to the window's byte phase) - one LDS per 4 multiply-adds instead of one per multiply-add,
+// and the weight table is read once per R rows instead of once per row.
+template <int KMAX>
+__global__ void __launch_bounds__(kThreads) resize_h_reg_kernel(const uint8_t* __restrict__ src, int H, int W, long long pitch,
+                                                                 long long image_stride, int OW, const int32_t* __restrict__ bounds,
+                                                                 const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ dst,
+                                                                 long long total_rows, int R, int row_stride) {
+  extern __shared__ __align__(16) uint8_t s_all[];
+  int* s_phase = reinterpret_cast<int*>(s_all);          // [16]: 16-byte phase of each staged row's global address
+  uint8_t* s_rows = s_all + 64;
+  const long long row0 = (long long)blockIdx.x * R;
+  const int nrows = (int)min((long long)R, total_rows - row0);
+  const int nbytes = 3 * W;
+  for (int r = 0; r < nrows; ++r) {
+    const long long row = row0 + r;
+    const long long b = row / H;
+    const uint8_t* g = src + b * image_stride + (row - b * H) * pitch;
+    const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
+    if (threadIdx.x == 0) s_phase[r] = phase;
+    uint8_t* s = s_rows + (long long)r * row_stride + phase;
+    const int head = min(nbytes, (16 - phase) & 15);
+    const int nvec = (nbytes - head) >> 4;
+    for (int i = threadIdx.x; i < head; i += kThreads) s[i] = g[i];
+    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+    uint4* sv = reinterpret_cast<uint4*>(s + head);
+    for (int i = threadIdx.x; i < nvec; i += kThreads) sv[i] = __ldg(gv + i);
+    for (int i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += kThreads) s[i] = g[i];
+  }
+  __syncthreads();
+  const int xx = blockIdx.y * kThreads + threadIdx.x;
+  if (xx >= OW) return;
+  const int xmin = __ldg(bounds + 2 * xx), n = __ldg(bounds + 2 * xx + 1);
+  int kreg[KMAX];
+#pragma unroll
+  for (int x = 0; x < KMAX; ++x) kreg[x] = x < n ? __ldg(kk + (long long)xx * ksize + x) : 0;
+  constexpr int kWinBytes = 3 * KMAX;
+  constexpr int kWords = (kWinBytes + 3) / 4;
+  for (int r = 0; r < nrows; ++r) {
+    const long long row = row0 + r;
+    const int a = s_phase[r] + 3 * xmin;                  // first byte of the window inside the staged row
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_rows + (long long)r * row_stride) + (a >> 2);
+    const int sh = (a & 3) * 8;
+    uint32_t wd[kWords + 1];
+#pragma unroll
+    for (int j = 0; j <= kWords; ++j) wd[j] = wp[j];      // bytes past the window meet zero weights
+    int acc[3] = {1 << (kPrecisionBits - 1), 1 << (kPrecisionBits - 1), 1 << (kPrecisionBits - 1)};
+#pragma unroll
+    for (int j = 0; j < kWords; ++j) {
+      const uint32_t w = __funnelshift_r(wd[j], wd[j + 1], sh);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = 4 * j + t;
+        if (i < kWinBytes) acc[i % 3] += (int)__byte_perm(w, 0u, 0x4440u + t) * kreg[i / 3];
+      }
+    }
+    uint8_t* out = dst + row * (3LL * OW) + 3 * xx;
+    out[0] = (uint8_t)clip8(acc[0]);
+    out[1] = (uint8_t)clip8(acc[1]);
+    out[2] = (uint8_t)clip8(acc[2]);
+  }
+}
+
+template <int KMAX>
+static int launch_h_reg(const uint8_t* src, int64_t B, int H, int W, int64_t pitch, int64_t istride, int OW, const int32_t* bounds,
+                        const int32_t* kk, int ksize, uint8_t* dst, cudaStream_t st) {
+  constexpr int kSmemCap = 64 * 1024;
+  const int slack = 3 * KMAX + 16 + 64;
+  const int row_stride = (3 * W + 16 + 15) & ~15;
+  int R = (kSmemCap - slack) / row_stride;
+  if (R < 1) return -1;                                   // row too wide for this form: the caller falls back
+  if (R > 16) R = 16;
+  const size_t smem = (size_t)R * row_stride + slack;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(resize_h_reg_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long rows = B * (long long)H;
+  dim3 grid((unsigned)ceil_div(rows, (long long)R), (unsigned)ceil_div(OW, kThreads));
+  resize_h_reg_kernel<KMAX><<<grid, kThreads, smem, st>>>(src, H, W, pitch, istride, OW, bounds, kk, ksize, dst, rows, R, row_stride);
+  return check_launch("resize_h_reg_kernel");
+}
+
 // src: [B] images of H rows x row_bytes (pitch / image_stride in bytes); dst: [B, OH, row_bytes] contiguous.
 // One thread per 32-bit word of the output (flattened over rows, so narrow rows still fill the CTAs).
 __global__ void __launch_bounds__(kThreads) resize_v_kernel(const uint8_t* __restrict__ src, int row_bytes, long long pitch,
@@ -213,18 +299,29 @@ extern "C" int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W
   int64_t vpitch = src_pitch, vstride = src_image_stride;
   if (do_h) {
     GNC_REQUIRE(!do_v || tmp, "resize_bicubic: tmp [B, H, OW, 3] is required when both axes change");
-    const size_t smem = (size_t)3 * W + 32;
-    GNC_REQUIRE(smem <= 200 * 1024, "resize_bicubic: source rows wider than 68 000 pixels are not supported");
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(rsz::resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      configured = 200 * 1024;
-    }
     uint8_t* hdst = do_v ? tmp : dst;
-    rsz::resize_h_kernel<<<(unsigned)(B * H), rsz::kThreads, smem, st>>>(src, H, W, src_pitch, src_image_stride, OW, bounds_x, kk_x,
-                                                                        ksize_x, hdst);
-    int rc = check_launch("resize_h_kernel");
+    int rc = -1;                          // -1: the register-resident form does not apply
+#define GNC_RSZ_H(K) rsz::launch_h_reg<K>(src, B, H, W, src_pitch, src_image_stride, OW, bounds_x, kk_x, ksize_x, hdst, st)
+    if (ksize_x <= 5) rc = GNC_RSZ_H(5);
+    else if (ksize_x <= 9) rc = GNC_RSZ_H(9);
+    else if (ksize_x <= 13) rc = GNC_RSZ_H(13);
+    else if (ksize_x <= 17) rc = GNC_RSZ_H(17);
+    else if (ksize_x <= 25) rc = GNC_RSZ_H(25);
+    else if (ksize_x <= 33) rc = GNC_RSZ_H(33);
+#undef GNC_RSZ_H
+    if (rc < 0) {                         // long windows (downscaling by more than 8) or very wide rows: generic form
+      const size_t smem = (size_t)3 * W + 32;
+      GNC_REQUIRE(smem <= 200 * 1024, "resize_bicubic: source rows wider than 68 000 pixels are not supported");
+      static size_t configured = 48 * 1024;
+      if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(rsz::resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = 200 * 1024;
+      }
+      rsz::resize_h_kernel<<<(unsigned)(B * H), rsz::kThreads, smem, st>>>(src, H, W, src_pitch, src_image_stride, OW, bounds_x,
+                                                                          kk_x, ksize_x, hdst);
+      rc = check_launch("resize_h_kernel");
+    }
     if (rc != GNC_OK) return rc;
     vsrc = tmp;
     vpitch = 3LL * OW;
