@@ -48,8 +48,8 @@ def parse_args():
     ap.add_argument("--train-steps", type=int, default=2)
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-graphs", type=int, default=48, help="graphs in the bounded CPU sample")
-    ap.add_argument("--ref-graphs-per-step", type=int, default=4)
+    ap.add_argument("--cpu-graphs", type=int, default=256, help="graphs in the bounded CPU sample")
+    ap.add_argument("--ref-graphs-per-step", type=int, default=32)
     return ap.parse_args()
 
 
