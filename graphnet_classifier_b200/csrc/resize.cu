@@ -93,20 +93,28 @@ __global__ void __launch_bounds__(kThreads) resize_h_reg_kernel(const uint8_t* _
   const long long row0 = (long long)blockIdx.x * R;
   const int nrows = (int)min((long long)R, total_rows - row0);
   const int nbytes = 3 * W;
-  for (int r = 0; r < nrows; ++r) {
-    const long long row = row0 + r;
-    const long long b = row / H;
-    const uint8_t* g = src + b * image_stride + (row - b * H) * pitch;
-    const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
-    if (threadIdx.x == 0) s_phase[r] = phase;
-    uint8_t* s = s_rows + (long long)r * row_stride + phase;
-    const int head = min(nbytes, (16 - phase) & 15);
-    const int nvec = (nbytes - head) >> 4;
-    for (int i = threadIdx.x; i < head; i += kThreads) s[i] = g[i];
-    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
-    uint4* sv = reinterpret_cast<uint4*>(s + head);
-    for (int i = threadIdx.x; i < nvec; i += kThreads) sv[i] = __ldg(gv + i);
-    for (int i = head + (nvec << 4) + threadIdx.x; i < nbytes; i += kThreads) s[i] = g[i];
+  // staging: one warp per row (rows warp, warp + 4, ...), so the per-row address set-up is paid by 32 lanes only
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long img0 = row0 / H;                      // one division per thread, then carried
+    const int y0 = (int)(row0 - img0 * H);
+    for (int r = warp; r < nrows; r += kThreads / 32) {
+      long long img = img0;
+      int y = y0 + r;
+      while (y >= H) { y -= H; ++img; }
+      const uint8_t* g = src + img * image_stride + (long long)y * pitch;
+      const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
+      if (lane == 0) s_phase[r] = phase;
+      uint8_t* s = s_rows + (long long)r * row_stride + phase;
+      const int head = min(nbytes, (16 - phase) & 15);
+      const int nvec = (nbytes - head) >> 4;
+      if (lane < head) s[lane] = g[lane];
+      const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+      uint4* sv = reinterpret_cast<uint4*>(s + head);
+      for (int i = lane; i < nvec; i += 32) sv[i] = __ldg(gv + i);
+      const int tail0 = head + (nvec << 4);
+      if (tail0 + lane < nbytes) s[tail0 + lane] = g[tail0 + lane];
+    }
   }
   __syncthreads();
   const int xx = blockIdx.y * kThreads + threadIdx.x;
@@ -210,6 +218,40 @@ __global__ void __launch_bounds__(kThreads) resize_v_kernel(const uint8_t* __res
   } else {
     for (int t = 0; t < n_out; ++t) out[t] = (uint8_t)(packed >> (8 * t));
   }
+}
+
+// Vertical pass, 16 output bytes per thread (rows and pitches that are multiples of 16 bytes: any OW % 16 == 0):
+// one 128-bit load and one weight per tap feed 16 multiply-adds.
+__global__ void __launch_bounds__(kThreads) resize_v16_kernel(const uint8_t* __restrict__ src, int row_bytes, long long pitch,
+                                                               long long image_stride, int OH, long long n_rows,
+                                                               const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk,
+                                                               int ksize, uint8_t* __restrict__ dst) {
+  const int vpr = row_bytes >> 4;                    // 16-byte vectors per output row
+  const long long idx = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long orow = idx / vpr;
+  if (orow >= n_rows) return;
+  const int o16 = (int)(idx - orow * vpr) * 16;
+  const long long b = orow / OH;
+  const int yy = (int)(orow - b * OH);
+  const int ymin = __ldg(bounds + 2 * yy), n = __ldg(bounds + 2 * yy + 1);
+  const int32_t* k = kk + (long long)yy * ksize;
+  const uint8_t* p = src + b * image_stride + (long long)ymin * pitch + o16;
+  int acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 1 << (kPrecisionBits - 1);
+#pragma unroll 2
+  for (int y = 0; y < n; ++y, p += pitch) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    const int c = __ldg(k + y);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += (int)__byte_perm(w[i >> 2], 0u, 0x4440u + (i & 3)) * c;
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = clip8(acc[4 * j]) | (clip8(acc[4 * j + 1]) << 8) | (clip8(acc[4 * j + 2]) << 16) | (clip8(acc[4 * j + 3]) << 24);
+  *reinterpret_cast<uint4*>(dst + orow * (long long)row_bytes + o16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ---- coefficient tables (host; Pillow's precompute_coeffs + normalize_coeffs_8bpc, full box) --------------------
@@ -330,11 +372,16 @@ extern "C" int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W
   if (do_v) {
     const int row_bytes = 3 * OW;
     const long long rows = B * (long long)OH;
-    const long long words = rows * ((row_bytes + 3) >> 2);
-    const long long blocks = ceil_div(words, (long long)rsz::kThreads);
+    const bool vec16 = row_bytes % 16 == 0 && vpitch % 16 == 0 && vstride % 16 == 0 && aligned16(vsrc) && aligned16(dst);
+    const long long items = rows * (vec16 ? row_bytes >> 4 : (row_bytes + 3) >> 2);
+    const long long blocks = ceil_div(items, (long long)rsz::kThreads);
     GNC_REQUIRE(blocks < (1LL << 31), "resize_bicubic: output too large for one launch");
-    rsz::resize_v_kernel<<<(unsigned)blocks, rsz::kThreads, 0, st>>>(vsrc, row_bytes, vpitch, vstride, OH, rows, bounds_y, kk_y,
-                                                                    ksize_y, dst);
+    if (vec16)
+      rsz::resize_v16_kernel<<<(unsigned)blocks, rsz::kThreads, 0, st>>>(vsrc, row_bytes, vpitch, vstride, OH, rows, bounds_y, kk_y,
+                                                                        ksize_y, dst);
+    else
+      rsz::resize_v_kernel<<<(unsigned)blocks, rsz::kThreads, 0, st>>>(vsrc, row_bytes, vpitch, vstride, OH, rows, bounds_y, kk_y,
+                                                                      ksize_y, dst);
     int rc = check_launch("resize_v_kernel");
     if (rc != GNC_OK) return rc;
   }
