@@ -525,7 +525,9 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, long lo
 }
 
 // ---- LayerNorm ------------------------------------------------------------------
-template <int VPL>
+// RPW rows per warp and iteration: all of their loads (z and the residual) are issued before the first reduction, so a
+// warp keeps RPW x 1 KB in flight instead of 512 B (one row per iteration left the kernel latency-bound at ~60 % of HBM).
+template <int VPL, int RPW>
 __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __restrict__ z, long long ldz,
                                                                 long long M, int D, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps,
@@ -537,50 +539,64 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __r
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
   const float invD = 1.0f / (float)D;
-  for (long long r = warp_global; r < M; r += warps_total) {
-    float4 v[VPL];
-    float s = 0.f;
+  float4 g[VPL], bt[VPL];
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) {
-      const int c4 = lane + 32 * q;
-      v[q] = (c4 < D4) ? ldg_stream(reinterpret_cast<const float4*>(z + r * ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[q].x + v[q].y) + (v[q].z + v[q].w);
-    }
+  for (int q = 0; q < VPL; ++q) {
+    const int c4 = lane + 32 * q;
+    g[q] = (c4 < D4) ? __ldg(reinterpret_cast<const float4*>(gamma) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[q] = (c4 < D4) ? __ldg(reinterpret_cast<const float4*>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r0 = warp_global * RPW; r0 < M; r0 += warps_total * RPW) {
+    float4 v[RPW][VPL], p[RPW][VPL];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mu = s * invD;
-    float ss = 0.f;
+    for (int t = 0; t < RPW; ++t) {
+      const long long r = r0 + t;
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) {
-      const int c4 = lane + 32 * q;
-      if (c4 < D4) {
-        const float a = v[q].x - mu, b = v[q].y - mu, c = v[q].z - mu, d = v[q].w - mu;
-        ss += (a * a + b * b) + (c * c + d * d);
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        const bool ok = r < M && c4 < D4;
+        v[t][q] = ok ? ldg_stream(reinterpret_cast<const float4*>(z + r * ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        p[t][q] = (ok && res) ? ldg_stream(reinterpret_cast<const float4*>(res + r * ldres) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rs = 1.0f / sqrtf(ss * invD + eps);
-    if (lane == 0) {
-      if (mean) mean[r] = mu;
-      if (rstd) rstd[r] = rs;
-    }
+    for (int t = 0; t < RPW; ++t) {
+      const long long r = r0 + t;
+      if (r >= M) break;
+      float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) {
-      const int c4 = lane + 32 * q;
-      if (c4 < D4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
-        float4 o;
-        o.x = (v[q].x - mu) * rs * g.x + b.x;
-        o.y = (v[q].y - mu) * rs * g.y + b.y;
-        o.z = (v[q].z - mu) * rs * g.z + b.z;
-        o.w = (v[q].w - mu) * rs * g.w + b.w;
-        if (res) {
-          const float4 p = ldg_stream(reinterpret_cast<const float4*>(res + r * ldres) + c4);
-          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      for (int q = 0; q < VPL; ++q) s += (v[t][q].x + v[t][q].y) + (v[t][q].z + v[t][q].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * invD;
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        if (c4 < D4) {
+          const float a = v[t][q].x - mu, b = v[t][q].y - mu, c = v[t][q].z - mu, d = v[t][q].w - mu;
+          ss += (a * a + b * b) + (c * c + d * d);
         }
-        stg_stream(reinterpret_cast<float4*>(y + r * ldy) + c4, o);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rs = 1.0f / sqrtf(ss * invD + eps);
+      if (lane == 0) {
+        if (mean) mean[r] = mu;
+        if (rstd) rstd[r] = rs;
+      }
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        if (c4 < D4) {
+          float4 o;
+          o.x = (v[t][q].x - mu) * rs * g[q].x + bt[q].x;
+          o.y = (v[t][q].y - mu) * rs * g[q].y + bt[q].y;
+          o.z = (v[t][q].z - mu) * rs * g[q].z + bt[q].z;
+          o.w = (v[t][q].w - mu) * rs * g[q].w + bt[q].w;
+          if (res) { o.x += p[t][q].x; o.y += p[t][q].y; o.z += p[t][q].z; o.w += p[t][q].w; }
+          stg_stream(reinterpret_cast<float4*>(y + r * ldy) + c4, o);
+        }
       }
     }
   }
@@ -622,7 +638,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_scalar_kernel(const float* 
 
 // dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // partial[b][0][c] = sum dy * xhat, partial[b][1][c] = sum dy  over the block's rows
-template <int VPL>
+template <int VPL, int RPW>
 __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __restrict__ dy, long long lddy,
                                                                 const float* __restrict__ z, long long ldz,
                                                                 const float* __restrict__ mean,
@@ -646,43 +662,65 @@ __global__ void __launch_bounds__(256) layernorm_bwd_vec_kernel(const float* __r
     sg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     sb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (long long r = rbeg + warp; r < rend; r += 8) {
-    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float4 d[VPL], xh[VPL];
-    float c1 = 0.f, c2 = 0.f;
+  for (long long r0 = rbeg + warp; r0 < rend; r0 += 8 * RPW) {
+    // RPW rows of this warp (r0, r0 + 8, ...) with all loads issued up front; rows are retired in the same order as
+    // a one-row-per-iteration loop, so the column sums are bit-identical to it
+    float4 d[RPW][VPL], zz[RPW][VPL];
+    float mu[RPW], rs[RPW];
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) {
-      const int c4 = lane + 32 * q;
-      if (c4 < D4) {
-        d[q] = ldg_stream(reinterpret_cast<const float4*>(dy + r * lddy) + c4);
-        const float4 zz = ldg_stream(reinterpret_cast<const float4*>(z + r * ldz) + c4);
-        xh[q] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs, (zz.w - mu) * rs);
-      } else {
-        d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xh[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < RPW; ++t) {
+      const long long r = r0 + 8 * t;
+      const bool okr = r < rend;
+      mu[t] = okr ? __ldg(mean + r) : 0.f;
+      rs[t] = okr ? __ldg(rstd + r) : 0.f;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        const bool ok = okr && c4 < D4;
+        d[t][q] = ok ? ldg_stream(reinterpret_cast<const float4*>(dy + r * lddy) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zz[t][q] = ok ? ldg_stream(reinterpret_cast<const float4*>(z + r * ldz) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      sg[q].x += d[q].x * xh[q].x; sg[q].y += d[q].y * xh[q].y; sg[q].z += d[q].z * xh[q].z; sg[q].w += d[q].w * xh[q].w;
-      sb[q].x += d[q].x; sb[q].y += d[q].y; sb[q].z += d[q].z; sb[q].w += d[q].w;
-      const float gx = d[q].x * gm[q].x, gy = d[q].y * gm[q].y, gz = d[q].z * gm[q].z, gw = d[q].w * gm[q].w;
-      c1 += (gx + gy) + (gz + gw);
-      c2 += (gx * xh[q].x + gy * xh[q].y) + (gz * xh[q].z + gw * xh[q].w);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-      c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-    }
-    c1 *= invD; c2 *= invD;
+    for (int t = 0; t < RPW; ++t) {
+      const long long r = r0 + 8 * t;
+      if (r >= rend) break;
+      float4 xh[VPL];
+      float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int q = 0; q < VPL; ++q) {
-      const int c4 = lane + 32 * q;
-      if (c4 < D4) {
-        float4 o;
-        o.x = rs * (d[q].x * gm[q].x - c1 - xh[q].x * c2);
-        o.y = rs * (d[q].y * gm[q].y - c1 - xh[q].y * c2);
-        o.z = rs * (d[q].z * gm[q].z - c1 - xh[q].z * c2);
-        o.w = rs * (d[q].w * gm[q].w - c1 - xh[q].w * c2);
-        stg_stream(reinterpret_cast<float4*>(dz + r * lddz) + c4, o);
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        if (c4 < D4) {
+          xh[q] = make_float4((zz[t][q].x - mu[t]) * rs[t], (zz[t][q].y - mu[t]) * rs[t], (zz[t][q].z - mu[t]) * rs[t],
+                              (zz[t][q].w - mu[t]) * rs[t]);
+        } else {
+          xh[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 dd = d[t][q];
+        sg[q].x += dd.x * xh[q].x; sg[q].y += dd.y * xh[q].y; sg[q].z += dd.z * xh[q].z; sg[q].w += dd.w * xh[q].w;
+        sb[q].x += dd.x; sb[q].y += dd.y; sb[q].z += dd.z; sb[q].w += dd.w;
+        const float gx = dd.x * gm[q].x, gy = dd.y * gm[q].y, gz = dd.z * gm[q].z, gw = dd.w * gm[q].w;
+        c1 += (gx + gy) + (gz + gw);
+        c2 += (gx * xh[q].x + gy * xh[q].y) + (gz * xh[q].z + gw * xh[q].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+      }
+      c1 *= invD; c2 *= invD;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int c4 = lane + 32 * q;
+        if (c4 < D4) {
+          const float4 dd = d[t][q];
+          float4 o;
+          o.x = rs[t] * (dd.x * gm[q].x - c1 - xh[q].x * c2);
+          o.y = rs[t] * (dd.y * gm[q].y - c1 - xh[q].y * c2);
+          o.z = rs[t] * (dd.z * gm[q].z - c1 - xh[q].z * c2);
+          o.w = rs[t] * (dd.w * gm[q].w - c1 - xh[q].w * c2);
+          stg_stream(reinterpret_cast<float4*>(dz + r * lddz) + c4, o);
+        }
       }
     }
   }
@@ -912,9 +950,9 @@ int gnc_layernorm_fwd_f32(const float* z, int64_t ldz, int64_t M, int D, const f
                    aligned16(gamma) && aligned16(beta) && (!res || (ldres % 4 == 0 && aligned16(res)));
   if (vec) {
     const int D4 = D / 4;
-    if (D4 <= 32) layernorm_fwd_vec_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
-    else if (D4 <= 64) layernorm_fwd_vec_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
-    else layernorm_fwd_vec_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
+    if (D4 <= 32) layernorm_fwd_vec_kernel<1, 4><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
+    else if (D4 <= 64) layernorm_fwd_vec_kernel<2, 2><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
+    else layernorm_fwd_vec_kernel<4, 1><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
   } else {
     layernorm_fwd_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, ldz, M, D, gamma, beta, eps, res, ldres, y, ldy, mean, rstd);
   }
@@ -938,9 +976,9 @@ int gnc_layernorm_bwd_f32(const float* dy, int64_t lddy, const float* z, int64_t
                      aligned16(z) && aligned16(dz) && aligned16(gamma) && aligned16(work);
     if (vec) {
       const int D4 = D / 4;
-      if (D4 <= 32) layernorm_bwd_vec_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
-      else if (D4 <= 64) layernorm_bwd_vec_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
-      else layernorm_bwd_vec_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
+      if (D4 <= 32) layernorm_bwd_vec_kernel<1, 4><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
+      else if (D4 <= 64) layernorm_bwd_vec_kernel<2, 2><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
+      else layernorm_bwd_vec_kernel<4, 1><<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
     } else {
       layernorm_bwd_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, lddy, z, ldz, mean, rstd, gamma, M, D, dz, lddz, work);
     }
