@@ -7,7 +7,11 @@ Extensions that leave the single-process behaviour unchanged:
   * labels are moved to the logits' device (the reference is CPU-only);
   * ``grad_sync`` - a callable run between ``backward()`` and ``step()``; the
     data-parallel launcher passes ``GradBucket.all_reduce`` (utils/distributed.py);
-  * only rank 0 writes files when ``torch.distributed`` is initialised.
+  * only rank 0 writes files when ``torch.distributed`` is initialised;
+  * ``cuda_graph`` (default: on for CUDA models without ``grad_sync``) - the reference makes one optimizer step per
+    graph, so a step is ~350 small launches; the whole step (forward, loss, backward, Adam) is captured once per
+    sample shape as a CUDA graph and replayed with the item's tensors copied into its static inputs.  Same kernels
+    and same update rule; items whose shapes or topology differ from the captured ones run eagerly.
 """
 from __future__ import annotations
 
@@ -25,9 +29,99 @@ def _is_rank0() -> bool:
     return not (d.is_available() and d.is_initialized()) or d.get_rank() == 0
 
 
-def train(model, dataset, epochs, patience=5, output_path="weights", start_weights=None, grad_sync=None):
-    optimizer = optim.Adam(model.parameters(), lr=1e-3)
+class _GraphedStep:
+    """One training step (forward, cross entropy, backward, Adam) captured as a CUDA graph for one sample layout:
+    a tuple of CUDA tensors whose ``edge_index`` carries a prebuilt topology (``ops.attach_graph``; the cached grid
+    of the pixel / patch builders), or a single CUDA tensor."""
+
+    def __init__(self, model, optimizer, criterion, sample, label):
+        self.model, self.optimizer, self.criterion = model, optimizer, criterion
+        self.tuple_in = isinstance(sample, (tuple, list))
+        parts = tuple(sample) if self.tuple_in else (sample,)
+        self.key = self.layout(sample, label)
+        # floating-point inputs change per item and are copied in; index tensors (edge_index) are topology:
+        # the captured kernels read the attached CSR, so an item must carry the very same topology object
+        self.static = tuple(p.clone() if p.is_floating_point() else p for p in parts)
+        self.label = label.clone()
+        self.loss = None
+        self.graph = None
+
+    @staticmethod
+    def layout(sample, label):
+        parts = tuple(sample) if isinstance(sample, (tuple, list)) else (sample,)
+        if not all(isinstance(p, torch.Tensor) and p.is_cuda for p in parts) or not isinstance(label, torch.Tensor):
+            return None
+        key = []
+        for p in parts:
+            if p.is_floating_point():
+                key.append((tuple(p.shape), p.dtype))
+            else:
+                topo = getattr(p, "_gnc_graph", None)
+                if topo is None:
+                    return None
+                key.append((tuple(p.shape), id(topo)))
+        return tuple(key) + (tuple(label.shape),)
+
+    def _step(self):
+        sample = self.static if self.tuple_in else self.static[0]
+        loss = self.criterion(self.model(sample), self.label)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def capture(self):
+        dev = self.label.device
+        side = torch.cuda.Stream(device=dev)
+        # the warm-up steps (kernel attributes, workspaces, allocator pools) must not train: parameters and the
+        # optimizer state are snapshotted and put back
+        snap = [p.detach().clone() for p in self.model.parameters()]
+        opt_snap = {p: {k: v.clone() for k, v in st.items() if isinstance(v, torch.Tensor)}
+                    for p, st in self.optimizer.state.items()}
+        grads = [p.grad for p in self.model.parameters()]
+        side.wait_stream(torch.cuda.current_stream(dev))     # after the snapshots have been enqueued
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for p, s0 in zip(self.model.parameters(), snap):
+                p.copy_(s0)
+            for p, st in self.optimizer.state.items():
+                before = opt_snap.get(p, {})
+                for k, v in st.items():
+                    if isinstance(v, torch.Tensor):
+                        v.copy_(before[k]) if k in before else v.zero_()     # no state before = a fresh optimizer
+        for p, g in zip(self.model.parameters(), grads):
+            p.grad = g
+        del snap, opt_snap, grads
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+        # the capture itself does not execute: parameters and optimizer state are still at their start values
+
+    def run(self, sample, label):
+        parts = tuple(sample) if self.tuple_in else (sample,)
+        for dst, src in zip(self.static, parts):
+            if dst.is_floating_point():
+                dst.copy_(src, non_blocking=True)
+        self.label.copy_(label, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
+def train(model, dataset, epochs, patience=5, output_path="weights", start_weights=None, grad_sync=None,
+          cuda_graph=None):
+    params = list(model.parameters())
+    on_cuda = bool(params) and all(p.is_cuda for p in params)
+    if cuda_graph is None:
+        cuda_graph = on_cuda and grad_sync is None
+    # capturable: Adam keeps its step count on the device, which a replayed graph needs; the update rule is the same
+    optimizer = optim.Adam(model.parameters(), lr=1e-3, capturable=True) if (cuda_graph and on_cuda) else \
+        optim.Adam(model.parameters(), lr=1e-3)
     criterion = nn.CrossEntropyLoss()
+    graphed = {}                                         # sample layout -> _GraphedStep
     best_loss = float("inf")
     stale_epochs = 0
     rank0 = _is_rank0()
@@ -51,15 +145,29 @@ def train(model, dataset, epochs, patience=5, output_path="weights", start_weigh
         t0 = time.time()
         running, steps = 0.0, 0
         for sample, label in dataset:
-            logits = model(sample)                      # tensor for MLP, (x, pos, edge_index) for GNN
-            if isinstance(label, torch.Tensor) and label.device != logits.device:
-                label = label.to(logits.device)
-            loss = criterion(logits, label)
-            optimizer.zero_grad()
-            loss.backward()
-            if grad_sync is not None:
-                grad_sync()
-            optimizer.step()
+            key = None
+            if cuda_graph and on_cuda:
+                if isinstance(label, torch.Tensor) and not label.is_cuda:
+                    label = label.to(params[0].device)
+                key = _GraphedStep.layout(sample, label)
+            if key is not None:
+                step = graphed.get(key)
+                if step is None:
+                    if len(graphed) >= 4:                # a handful of layouts at most (pixel graphs have one)
+                        graphed.clear()
+                    step = graphed[key] = _GraphedStep(model, optimizer, criterion, sample, label)
+                    step.capture()
+                loss = step.run(sample, label)
+            else:
+                logits = model(sample)                  # tensor for MLP, (x, pos, edge_index) for GNN
+                if isinstance(label, torch.Tensor) and label.device != logits.device:
+                    label = label.to(logits.device)
+                loss = criterion(logits, label)
+                optimizer.zero_grad()
+                loss.backward()
+                if grad_sync is not None:
+                    grad_sync()
+                optimizer.step()
             running += loss.item()
             steps += 1
         avg_loss = running / max(1, steps)

@@ -186,6 +186,63 @@ def test_reference_train_loop_one_graph_per_step(libgnc, tmp_path):
     assert "Epochs: 2, Patience: 5" in text and "Epoch 2/2, avg_loss=" in text and "Best loss achieved:" in text
 
 
+def test_train_loop_cuda_graph_equals_eager(libgnc, tmp_path):
+    """utils/train_model.train replays one captured step per item (forward, CE, backward, Adam).  The replay is
+    bit-identical to eager steps with the same (capturable) Adam, also when a second sample layout shows up
+    mid-training; against torch's host-scalar Adam flavour the two update rules differ by rounding (1e-7 on the
+    first step), which a dozen sign-like early Adam steps amplify."""
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    from graphnet_classifier_b200.utils.train_model import _GraphedStep, train
+    r = 8
+    imgs = synthetic_images(6, r, seed=13)
+    labels = [0, 1, 1, 0, 1, 0]
+    data = [(build_pixel_graphs(torch.from_numpy(im), use_cache=True).as_tuple(), torch.tensor(l)) for im, l in zip(imgs, labels)]
+    # items 4 and 5 on another topology object (diagonals): a second layout, captured with a non-empty Adam state
+    for i in (4, 5):
+        data[i] = (build_pixel_graphs(torch.from_numpy(imgs[i]), diagonals=True, use_cache=True).as_tuple(), torch.tensor(labels[i]))
+    crit = torch.nn.CrossEntropyLoss()
+    finals = []
+    for graphed in (True, False):
+        _, gm = _models(r, n_blocks=1)
+        opt = torch.optim.Adam(gm.parameters(), lr=1e-3, capturable=True)
+        steps, losses = {}, []
+        for _ in range(2):
+            for sample, label in data:
+                label = label.cuda()
+                if graphed:
+                    key = _GraphedStep.layout(sample, label)
+                    assert key is not None
+                    if key not in steps:
+                        steps[key] = _GraphedStep(gm, opt, crit, sample, label)
+                        steps[key].capture()
+                    losses.append(steps[key].run(sample, label).item())
+                else:
+                    loss = crit(gm(sample), label)
+                    opt.zero_grad(), loss.backward(), opt.step()
+                    losses.append(loss.item())
+        if graphed:
+            assert len(steps) == 2
+        finals.append((losses, [p.detach().clone() for p in gm.parameters()]))
+    assert finals[0][0] == finals[1][0]                                  # every step's loss, bit for bit
+    for a, b in zip(finals[0][1], finals[1][1]):
+        assert torch.equal(a, b)
+    # the public entry point, graph on (default) vs off (host-scalar Adam)
+    results = []
+    for use_graph in (True, False):
+        _, gm = _models(r, n_blocks=1)
+        best = train(gm, data, epochs=2, patience=5, output_path=str(tmp_path / f"g{int(use_graph)}"), cuda_graph=use_graph)
+        results.append((best, [p.detach().clone() for p in gm.parameters()]))
+    (b1, p1), (b0, p0) = results
+    assert abs(b1 - b0) < 1e-5
+    for a, c in zip(p1, finals[0][1]):
+        assert torch.equal(a, c)                                         # train() == the hand-driven captured steps
+    # against the host-scalar Adam only the aggregate is compared: elements whose true gradient is zero carry
+    # rounding-noise gradients, which Adam normalises to +-lr steps of either sign in either flavour
+    num = sum(float((a - b).pow(2).sum()) for a, b in zip(p1, p0)) ** 0.5
+    den = sum(float(b.pow(2).sum()) for b in p0) ** 0.5
+    assert num / den < 1e-3, num / den
+
+
 def test_infer_graphed_equals_infer(libgnc):
     """CUDA-graph replay of the small-batch call returns the eager call's logits, for
     changing inputs and after a weight update."""
