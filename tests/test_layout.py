@@ -38,6 +38,8 @@ def test_no_cpu_fallback():
         ops.linear([torch.zeros(4, 8)], torch.zeros(3, 8), None)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.scatter_sum(torch.zeros(4, 8), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.resize_bicubic(torch.zeros(4, 4, 3, dtype=torch.uint8), 2)
     m = CombinedModel(GraphNet(n_blocks=1), num_nodes=4)
     x, pos = torch.zeros(4, 3), torch.zeros(4, 2)
     ei = torch.tensor([[0, 1], [1, 2]])
