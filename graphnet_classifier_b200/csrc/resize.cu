@@ -78,6 +78,33 @@ __global__ void __launch_bounds__(kThreads) resize_h_kernel(const uint8_t* __res
   }
 }
 
+// Stages `nrows` consecutive source rows (flattened over images) in shared memory, one warp per row (rows warp,
+// warp + 4, ...), so the per-row address set-up is paid by 32 lanes only.  Each row keeps the 16-byte phase of its
+// global address (s_phase[r]), so that its aligned middle part moves as 128-bit words.
+__device__ __forceinline__ void stage_rows(const uint8_t* __restrict__ src, int H, long long pitch, long long image_stride,
+                                           long long row0, int nrows, int nbytes, int row_stride, int* s_phase, uint8_t* s_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long img0 = row0 / H;                        // one division per thread, then carried
+  const int y0 = (int)(row0 - img0 * H);
+  for (int r = warp; r < nrows; r += kThreads / 32) {
+    long long img = img0;
+    int y = y0 + r;
+    while (y >= H) { y -= H; ++img; }
+    const uint8_t* g = src + img * image_stride + (long long)y * pitch;
+    const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
+    if (lane == 0) s_phase[r] = phase;
+    uint8_t* s = s_rows + (long long)r * row_stride + phase;
+    const int head = min(nbytes, (16 - phase) & 15);
+    const int nvec = (nbytes - head) >> 4;
+    if (lane < head) s[lane] = g[lane];
+    const uint4* gv = reinterpret_cast<const uint4*>(g + head);
+    uint4* sv = reinterpret_cast<uint4*>(s + head);
+    for (int i = lane; i < nvec; i += 32) sv[i] = __ldg(gv + i);
+    const int tail0 = head + (nvec << 4);
+    if (tail0 + lane < nbytes) s[tail0 + lane] = g[tail0 + lane];
+  }
+}
+
 // Register-resident form of the horizontal pass (windows of at most KMAX taps): a CTA stages R source rows, thread
 // xx keeps its KMAX weights in registers and walks its byte window of every staged row as 32-bit shared-memory
 // words (funnel-shifted to the window's byte phase) - one LDS per 4 multiply-adds instead of one per multiply-add,
@@ -93,29 +120,7 @@ __global__ void __launch_bounds__(kThreads) resize_h_reg_kernel(const uint8_t* _
   const long long row0 = (long long)blockIdx.x * R;
   const int nrows = (int)min((long long)R, total_rows - row0);
   const int nbytes = 3 * W;
-  // staging: one warp per row (rows warp, warp + 4, ...), so the per-row address set-up is paid by 32 lanes only
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long img0 = row0 / H;                      // one division per thread, then carried
-    const int y0 = (int)(row0 - img0 * H);
-    for (int r = warp; r < nrows; r += kThreads / 32) {
-      long long img = img0;
-      int y = y0 + r;
-      while (y >= H) { y -= H; ++img; }
-      const uint8_t* g = src + img * image_stride + (long long)y * pitch;
-      const int phase = (int)(reinterpret_cast<uintptr_t>(g) & 15u);
-      if (lane == 0) s_phase[r] = phase;
-      uint8_t* s = s_rows + (long long)r * row_stride + phase;
-      const int head = min(nbytes, (16 - phase) & 15);
-      const int nvec = (nbytes - head) >> 4;
-      if (lane < head) s[lane] = g[lane];
-      const uint4* gv = reinterpret_cast<const uint4*>(g + head);
-      uint4* sv = reinterpret_cast<uint4*>(s + head);
-      for (int i = lane; i < nvec; i += 32) sv[i] = __ldg(gv + i);
-      const int tail0 = head + (nvec << 4);
-      if (tail0 + lane < nbytes) s[tail0 + lane] = g[tail0 + lane];
-    }
-  }
+  stage_rows(src, H, pitch, image_stride, row0, nrows, nbytes, row_stride, s_phase, s_rows);
   __syncthreads();
   const int xx = blockIdx.y * kThreads + threadIdx.x;
   if (xx >= OW) return;
@@ -170,6 +175,86 @@ static int launch_h_reg(const uint8_t* src, int64_t B, int H, int W, int64_t pit
   dim3 grid((unsigned)ceil_div(rows, (long long)R), (unsigned)ceil_div(OW, kThreads));
   resize_h_reg_kernel<KMAX><<<grid, kThreads, smem, st>>>(src, H, W, pitch, istride, OW, bounds, kk, ksize, dst, rows, R, row_stride);
   return check_launch("resize_h_reg_kernel");
+}
+
+// Long windows (down-scaling by more than 8: more than 33 taps): the window is walked in chunks of KCH taps; a chunk's
+// weights are loaded once and applied to all RMAX staged rows, whose accumulators stay in registers across chunks.
+template <int KCH, int RMAX>
+__global__ void __launch_bounds__(kThreads) resize_h_long_kernel(const uint8_t* __restrict__ src, int H, int W, long long pitch,
+                                                                  long long image_stride, int OW, const int32_t* __restrict__ bounds,
+                                                                  const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ dst,
+                                                                  long long total_rows, int R, int row_stride) {
+  extern __shared__ __align__(16) uint8_t s_all[];
+  int* s_phase = reinterpret_cast<int*>(s_all);
+  uint8_t* s_rows = s_all + 64;
+  const long long row0 = (long long)blockIdx.x * R;
+  const int nrows = (int)min((long long)R, total_rows - row0);
+  stage_rows(src, H, pitch, image_stride, row0, nrows, 3 * W, row_stride, s_phase, s_rows);
+  __syncthreads();
+  const int xx = blockIdx.y * kThreads + threadIdx.x;
+  if (xx >= OW) return;
+  const int xmin = __ldg(bounds + 2 * xx), n = __ldg(bounds + 2 * xx + 1);
+  const int32_t* k = kk + (long long)xx * ksize;
+  constexpr int kWinBytes = 3 * KCH;
+  constexpr int kWords = (kWinBytes + 3) / 4;
+  int acc[RMAX][3];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
+  for (int c0 = 0; c0 < n; c0 += KCH) {
+    int kreg[KCH];
+#pragma unroll
+    for (int x = 0; x < KCH; ++x) kreg[x] = c0 + x < n ? __ldg(k + c0 + x) : 0;
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < nrows) {
+        const int a = s_phase[r] + 3 * (xmin + c0);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_rows + (long long)r * row_stride) + (a >> 2);
+        const int sh = (a & 3) * 8;
+        uint32_t wd[kWords + 1];
+#pragma unroll
+        for (int j = 0; j <= kWords; ++j) wd[j] = wp[j];
+#pragma unroll
+        for (int j = 0; j < kWords; ++j) {
+          const uint32_t w = __funnelshift_r(wd[j], wd[j + 1], sh);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int i = 4 * j + t;
+            if (i < kWinBytes) acc[r][i % 3] += (int)__byte_perm(w, 0u, 0x4440u + t) * kreg[i / 3];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) {
+    if (r < nrows) {
+      uint8_t* out = dst + (row0 + r) * (3LL * OW) + 3 * xx;
+      out[0] = (uint8_t)clip8(acc[r][0]);
+      out[1] = (uint8_t)clip8(acc[r][1]);
+      out[2] = (uint8_t)clip8(acc[r][2]);
+    }
+  }
+}
+
+static int launch_h_long(const uint8_t* src, int64_t B, int H, int W, int64_t pitch, int64_t istride, int OW, const int32_t* bounds,
+                         const int32_t* kk, int ksize, uint8_t* dst, cudaStream_t st) {
+  constexpr int KCH = 32, RMAX = 4, kSmemCap = 96 * 1024;
+  const int slack = 3 * KCH + 16 + 64;
+  const int row_stride = (3 * W + 16 + 15) & ~15;
+  int R = (kSmemCap - slack) / row_stride;
+  if (R < 1) return -1;                                   // wider than ~32 000 pixels: the generic kernel
+  if (R > RMAX) R = RMAX;
+  const size_t smem = (size_t)R * row_stride + slack;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(resize_h_long_kernel<KCH, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
+    if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long rows = B * (long long)H;
+  dim3 grid((unsigned)ceil_div(rows, (long long)R), (unsigned)ceil_div(OW, kThreads));
+  resize_h_long_kernel<KCH, RMAX><<<grid, kThreads, smem, st>>>(src, H, W, pitch, istride, OW, bounds, kk, ksize, dst, rows, R, row_stride);
+  return check_launch("resize_h_long_kernel");
 }
 
 // src: [B] images of H rows x row_bytes (pitch / image_stride in bytes); dst: [B, OH, row_bytes] contiguous.
@@ -350,8 +435,9 @@ extern "C" int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W
     else if (ksize_x <= 17) rc = GNC_RSZ_H(17);
     else if (ksize_x <= 25) rc = GNC_RSZ_H(25);
     else if (ksize_x <= 33) rc = GNC_RSZ_H(33);
+    else rc = rsz::launch_h_long(src, B, H, W, src_pitch, src_image_stride, OW, bounds_x, kk_x, ksize_x, hdst, st);
 #undef GNC_RSZ_H
-    if (rc < 0) {                         // long windows (downscaling by more than 8) or very wide rows: generic form
+    if (rc < 0) {                         // rows too wide for the staged forms: generic kernel, one row per CTA
       const size_t smem = (size_t)3 * W + 32;
       GNC_REQUIRE(smem <= 200 * 1024, "resize_bicubic: source rows wider than 68 000 pixels are not supported");
       static size_t configured = 48 * 1024;
