@@ -1,5 +1,6 @@
-"""Entry points with the reference's names (reference main.py:32-76): ``train_GNN``
-wires dataset -> loader -> GraphNet(3 blocks) -> CombinedModel -> ``train``.
+"""Entry points with the reference's names (reference main.py:13-76): ``train_GNN``
+wires dataset -> loader -> GraphNet(3 blocks) -> CombinedModel -> ``train``; ``load_data`` / ``train_MLP`` are
+the MLP baseline (main.py:13-29) on the same operators.
 
 ``train_GNN`` keeps the reference's one-graph-per-step semantics (DataLoader with
 batch_size=1).  ``train_GNN_batched`` is the data-parallel form: block-diagonal
@@ -22,6 +23,27 @@ def num_nodes_for(method: str, resize_value: int) -> int:
     if method == "patch":
         return (resize_value // 8) ** 2
     return resize_value * resize_value
+
+
+def load_data(dataset_path, resize_value=128, batch_size=8):
+    """ImageFolder -> Resize -> ToTensor batches, shuffled (reference main.py:13-18; host side, torchvision)."""
+    import torchvision.datasets as datasets
+    from torchvision import transforms
+    transform = transforms.Compose([transforms.Resize((resize_value, resize_value)), transforms.ToTensor()])
+    dataset = datasets.ImageFolder(root=dataset_path, transform=transform)
+    return DataLoader(dataset, batch_size=batch_size, shuffle=True)
+
+
+def train_MLP(epochs=30, channels=3, resize_value=128, batch_size=8, hidden_layers=2, output_path="weights/MLP",
+              dataset_path="dataset"):
+    """The MLP baseline (reference main.py:21-29): flattened pixels -> MLP(hidden 128, LayerNorm on the logits).
+    The batches come from the host loader; ``train`` moves them to the model's device."""
+    from .models.MLP import MLP
+    input_dim = channels * resize_value * resize_value
+    dataset = load_data(dataset_path, resize_value, batch_size)
+    num_classes = len(dataset.dataset.classes)
+    model = MLP(in_dim=input_dim, out_dim=num_classes, hidden_layers=hidden_layers).cuda()
+    return train(model, dataset, epochs, patience=5, output_path=output_path)
 
 
 def train_GNN(epochs=30, channels=3, resize_value=64, batch_size=8, hidden_layers=2, max_samples=None,

@@ -4,7 +4,8 @@ optimizer step per item of ``dataset``, early stopping on the *training* loss,
 ``best_model_epoch{n}.pth`` / ``final_model.pth`` and a timestamped text log.
 
 Extensions that leave the single-process behaviour unchanged:
-  * labels are moved to the logits' device (the reference is CPU-only);
+  * labels - and plain tensor samples from a host loader - are moved to the model's device (the reference is
+    CPU-only);
   * ``grad_sync`` - a callable run between ``backward()`` and ``step()``; the
     data-parallel launcher passes ``GradBucket.all_reduce`` (utils/distributed.py);
   * only rank 0 writes files when ``torch.distributed`` is initialised;
@@ -145,6 +146,8 @@ def train(model, dataset, epochs, patience=5, output_path="weights", start_weigh
         t0 = time.time()
         running, steps = 0.0, 0
         for sample, label in dataset:
+            if on_cuda and isinstance(sample, torch.Tensor) and not sample.is_cuda:
+                sample = sample.to(params[0].device, non_blocking=True)     # host loader batches (MLP baseline)
             key = None
             if cuda_graph and on_cuda:
                 if isinstance(label, torch.Tensor) and not label.is_cuda:

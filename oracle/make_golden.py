@@ -24,7 +24,7 @@ from PIL import Image
 from . import gnn as ognn
 from . import graph_build as ogb
 from . import reference_loader as rl
-from .weights import fill_deterministic, synthetic_images, voronoi_labels
+from .weights import fill_deterministic, fill_parameters, synthetic_images, voronoi_labels
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -258,6 +258,31 @@ def gen_resize(ref):
     print("resize.npz:", len(out), "entries")
 
 
+def gen_mlp(ref):
+    """The MLP baseline (reference models/MLP.py:5-47 as main.py:21-29 / utils/inference.py:16-29 use it): logits,
+    cross-entropy loss and every gradient of the UNMODIFIED reference class on a ToTensor-style batch and on a raw
+    0..255 flattened image, deterministic weights."""
+    out = {}
+    for tag, in_shape, kw in (("b4", (4, 3, 6, 6), dict(hidden_layers=2)), ("raw", (1, 3 * 8 * 8), dict(hidden_layers=3)),
+                              ("bn", (5, 3, 4, 4), dict(hidden_layers=1, norm_type="BatchNorm1d", activation="Tanh"))):
+        in_dim = int(np.prod(in_shape[1:]))
+        m = ref.MLP.MLP(in_dim=in_dim, out_dim=2, **kw)
+        fill_parameters(m, seed=31)
+        rng = np.random.default_rng(in_dim)
+        x = rng.random(in_shape, dtype=np.float32) if tag != "raw" else rng.integers(0, 256, in_shape).astype(np.float32)
+        labels = rng.integers(0, 2, in_shape[0])
+        logits = m(torch.from_numpy(x))
+        loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(labels))
+        loss.backward()
+        out[f"{tag}_x"], out[f"{tag}_labels"] = x, labels
+        out[f"{tag}_logits"], out[f"{tag}_loss"] = logits.detach().numpy(), np.float64(loss.item())
+        out[f"{tag}_keys"] = np.array(list(m.state_dict().keys()))
+        for name, p in m.named_parameters():
+            out[f"{tag}_grad_{name}"] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN, "mlp.npz"), **out)
+    print("mlp.npz:", len(out), "entries")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rl.load_reference()
@@ -265,10 +290,14 @@ def main():
     if "--only-resize" in sys.argv:
         gen_resize(ref)
         return
+    if "--only-mlp" in sys.argv:
+        gen_mlp(ref)
+        return
     gen_grids(ref)
     gen_builders(ref)
     gen_model(ref)
     gen_resize(ref)
+    gen_mlp(ref)
     print("all reference-vs-oracle comparisons passed; golden vectors written to", GOLDEN)
 
 

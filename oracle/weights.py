@@ -29,6 +29,16 @@ def fill_deterministic(model: torch.nn.Module, seed: int = 0) -> None:
             p.copy_(torch.from_numpy(v.astype(np.float32)))
 
 
+def fill_parameters(model: torch.nn.Module, seed: int = 0) -> None:
+    """Deterministic values for ``named_parameters`` only (buffers such as BatchNorm's counters stay): matrices
+    uniform in +-1/sqrt(fan_in), vectors 0.5 + 0.1 N(0, 1)."""
+    with torch.no_grad():
+        for i, (_, p) in enumerate(model.named_parameters()):
+            g = np.random.default_rng([seed, i])
+            v = g.uniform(-1.0, 1.0, tuple(p.shape)) / np.sqrt(p.shape[-1]) if p.dim() == 2 else 0.5 + 0.1 * g.standard_normal(tuple(p.shape))
+            p.copy_(torch.from_numpy(v.astype(np.float32)))
+
+
 def synthetic_images(batch: int, resize: int, seed: int = 0) -> np.ndarray:
     """BASELINE.md section 4 inputs: uint8 [B, r, r, 3], i.i.d. uniform 0..255."""
     return np.random.default_rng(seed).integers(0, 256, size=(batch, resize, resize, 3), dtype=np.uint8)

@@ -32,7 +32,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("grid_edges", "builders", "model", "resize"):
+    for name in ("grid_edges", "builders", "model", "resize", "mlp"):
         with np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False) as z:
             out[name] = {k: z[k] for k in z.files}
     return out
