@@ -73,3 +73,31 @@ def test_gnn_inference_helper(libgnc, tmp_path):
     with torch.no_grad():
         exp = om(ogb.to_model_inputs(*ogb.pixel_graph(img)))
     np.testing.assert_allclose(logits[0].cpu().numpy(), exp.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_train_gnn_batched_one_step_matches_oracle(libgnc, tmp_path):
+    """main.train_GNN_batched, single process: a dataset of B unresized PIL images with batch_size = B is one Adam step
+    on the mean cross entropy of the B graphs - compared with the oracle doing exactly that on PIL-resized pixels."""
+    import numpy as np
+    from PIL import Image
+    from graphnet_classifier_b200.main import train_GNN_batched
+    from oracle import gnn as ognn
+    from oracle import graph_build as ogb
+    r, B = 8, 4
+    rng = np.random.default_rng(17)
+    photos = [rng.integers(0, 256, (20 + 3 * i, 31 - 2 * i, 3), dtype=np.uint8) for i in range(B)]
+    labels = [0, 1, 1, 0]
+    data = [(Image.fromarray(p), l) for p, l in zip(photos, labels)]
+    torch.manual_seed(0)
+    best, gm = train_GNN_batched(epochs=1, resize_value=r, batch_size=B, output_path=str(tmp_path), dataset=data, shuffle=False)
+    # oracle: same init (seed 0, same construction order), PIL resize, one graph per forward, mean loss, one Adam step
+    om = ognn.build_reference_config_model(r, seed=0)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    loss = sum(torch.nn.functional.cross_entropy(
+        om(ogb.to_model_inputs(*ogb.pixel_graph(np.asarray(Image.fromarray(p).resize((r, r)))))), torch.tensor(l))
+        for p, l in zip(photos, labels)) / B
+    opt.zero_grad(), loss.backward(), opt.step()
+    assert abs(best - loss.item()) < 1e-5 * max(1.0, loss.item())
+    for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
+        assert float((p.detach().cpu() - po.detach()).abs().max()) < 2e-3 * 1.01, name     # first Adam step: |update| <= lr
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".pth")) == ["best_model_epoch1.pth", "final_model.pth"]

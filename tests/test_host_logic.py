@@ -141,3 +141,31 @@ def test_core_param_list_layout_and_graphed_step_layout():
     x, pos, ei = torch.zeros(4, 3), torch.zeros(4, 2), torch.zeros(2, 3, dtype=torch.long)
     assert _GraphedStep.layout((x, pos, ei), torch.tensor(1)) is None
     assert _GraphedStep.layout(x, 1) is None
+
+
+def test_batched_shard_loader_plan():
+    """main.BatchedShardLoader: all ranks shuffle alike, shards of a global batch are disjoint, equal-sized and cover it
+    (truncated to a multiple of the world size), epochs reshuffle."""
+    import pytest
+    from graphnet_classifier_b200.main import BatchedShardLoader
+    data = list(range(23))
+    world = 4
+    loaders = [BatchedShardLoader(data, batch_size=10, resize_value=8, rank=r, world_size=world, seed=5) for r in range(world)]
+    for epoch in (0, 1):
+        plans = [ld.plan(epoch) for ld in loaders]
+        assert all(len(p) == 2 for p in plans)                 # batches of 10, 10, (3 -> truncated to 0)
+        seen = []
+        for b in range(2):
+            shards = [p[b] for p in plans]
+            assert [len(s) for s in shards] == [2, 2, 2, 2]   # 10 -> 8 graphs, 2 per rank
+            flat = [i for s in shards for i in s]
+            assert len(set(flat)) == len(flat)
+            seen += flat
+        assert len(set(seen)) == 16
+    assert loaders[0].plan(0) != loaders[0].plan(1)
+    one = BatchedShardLoader(data, batch_size=10, resize_value=8, shuffle=False)
+    assert one.plan(0) == [list(range(0, 10)), list(range(10, 20)), [20, 21, 22]] and len(one) == 3
+    with pytest.raises(ValueError):
+        BatchedShardLoader(data, 10, 8, method="superpixel")
+    with pytest.raises(ValueError):
+        BatchedShardLoader(data, 2, 8, world_size=4)
