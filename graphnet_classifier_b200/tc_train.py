@@ -3,8 +3,10 @@
 One ``torch.autograd.Function`` covers everything between the encoders' thin first layers and the
 decoder's last ``Linear(128, 1)``: encoder tails, the ``n_blocks`` edge / node processors
 (models/GNN.py:57-64, 95-104, MetaLayer order :146, 215) and the decoder's two hidden layers
-(models/GNN.py:289-295).  The forward is the same kernel sequence as the op-by-op autograd path
-(``ops.tc_linear`` 3xTF32, LayerNorm, ordered CSR aggregation); what changes is the backward:
+(models/GNN.py:289-295).  The forward is the kernel sequence of the op-by-op autograd path (``ops.tc_linear``
+3xTF32, LayerNorm, ordered CSR aggregation), except that the three node-side products of a block (``P``, ``Q`` of the
+edge processor's split first layer and the node processor's ``h``-side product) are ONE multi-mode launch of the
+chained kernel (``h`` read once; fp16 two-piece operands, 4.7e-7 per product); what changes is the backward:
 
 * gradients that autograd would add with separate elementwise passes (``h`` feeds three products and a
   residual, ``e`` a product and a residual, ``e'`` the aggregation and the next block) are accumulated
@@ -15,8 +17,9 @@ decoder's last ``Linear(128, 1)``: encoder tails, the ``n_blocks`` edge / node p
   ``[128, 384]`` / ``[128, 256]`` gradient, biases come out of the same tcgen05 pass;
 * activations are released as soon as their last consumer has run.
 
-Same arithmetic, same kernels, hence the same parity figures as the op-by-op path (logits 2.7e-6,
-gradients <= 8e-6 rel-L2 against the CPU oracle).
+Same arithmetic as the op-by-op path, hence the same parity figures (logits 2.7e-6, gradients <= 8e-6 rel-L2 against
+the CPU oracle; tests/test_gpu_tc_engine.py runs both).  ``backward`` releases the saved activations as it goes, so a
+second backward through the same graph (``retain_graph=True``) is not supported.
 """
 from __future__ import annotations
 
