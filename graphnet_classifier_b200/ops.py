@@ -128,7 +128,7 @@ class GraphIndex:
     reference's summation order) and by source."""
 
     __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid",
-                 "edge_class", "class_geom", "pos_ref")
+                 "edge_class", "class_geom", "pos_ref", "class_sum_plan")
 
     def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
         self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
@@ -142,6 +142,7 @@ class GraphIndex:
         self.edge_class = None
         self.class_geom = None
         self.pos_ref = None
+        self.class_sum_plan = None      # lazily built CSRs for per-class gradient sums (tc_train.class_sum_plan)
 
     @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, validate: bool = True) -> "GraphIndex":

@@ -102,22 +102,25 @@ class GraphNetCoreFn(torch.autograd.Function):
     [edge proc, node proc] per block) LayerNorm epsilons."""
 
     @staticmethod
-    def forward(ctx, graph, eps, n_blocks, a1n, a1e, *params):
+    def forward(ctx, graph, eps, n_blocks, edge_ready, a1n, a1e, *params):
         tcl = ops.tc_linear
         a1n, a1e = ops._rows(a1n), ops._rows(a1e)
         saved = []          # per MLP tail: (a1, a2, z3, mean, rstd)
-        eps_it = iter(eps)
 
-        def tail(a1, p0, residual):
+        def tail(a1, p0, residual, eps_l):
             W2, b2, W4, b4, g, bt = params[p0:p0 + 6]
             a2 = tcl(a1, W2, bias=b2, relu=True)
             z3 = tcl(a2, W4, bias=b4)
-            y, mean, rstd = _ln_fwd(z3, g, bt, next(eps_it), residual)
+            y, mean, rstd = _ln_fwd(z3, g, bt, eps_l, residual)
             saved.append((a1, a2, z3, mean, rstd))
             return y
 
-        h = tail(a1n, 0, None)
-        e = tail(a1e, 6, None)
+        h = tail(a1n, 0, None, eps[0])
+        if edge_ready:      # ``a1e`` already is the encoded edge latent (class-table form, see GraphNet._forward_tc_train)
+            e = a1e
+            saved.append(None)
+        else:
+            e = tail(a1e, 6, None, eps[1])
         blocks = []
         for k in range(n_blocks):
             pe = 12 + 16 * k
@@ -129,17 +132,17 @@ class GraphNetCoreFn(torch.autograd.Function):
             a1 = tcl(e, W0[:, 256:384], bias=b0, relu=True, gather0=(P, graph.src), gather1=(Q, graph.dst))
             del P, Q
             e_in = e
-            e = tail(a1, pe + 2, e_in)
+            e = tail(a1, pe + 2, e_in, eps[2 + 2 * k])
             agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
             n1 = tcl(agg, V0[:, 128:256], bias=c0, relu=True, addend=T)
             del T
             h_in = h
-            h = tail(n1, pn + 2, h_in)
+            h = tail(n1, pn + 2, h_in, eps[3 + 2 * k])
             blocks.append((h_in, e_in, agg))
         Wd0, bd0, Wd2, bd2 = params[12 + 16 * n_blocks:12 + 16 * n_blocks + 4]
         d1 = tcl(h, Wd0, bias=bd0, relu=True)
         d2 = tcl(d1, Wd2, bias=bd2, relu=True)
-        ctx.graph, ctx.n_blocks = graph, n_blocks
+        ctx.graph, ctx.n_blocks, ctx.edge_ready = graph, n_blocks, edge_ready
         ctx.saved, ctx.blocks, ctx.dec = saved, blocks, (h, d1)
         ctx.params = params
         ctx.save_for_backward(d2)
@@ -233,19 +236,63 @@ class GraphNetCoreFn(torch.autograd.Function):
             dh = tcl(dQ, W0[:, 128:256], transpose_w=True, addend=dh)
             del dQ
         # ---- encoder tails: the thin first layers mask their own ReLU ----
-        da1e, _ = tail_bwd(de, 1, p_edge_enc, False)
+        if ctx.edge_ready:
+            da1e = de                               # gradient of the encoded edge latent itself
+        else:
+            da1e, _ = tail_bwd(de, 1, p_edge_enc, False)
         del de
         da1n, _ = tail_bwd(dh, 0, p_node_enc, False)
         ctx.saved = ctx.blocks = None
         need = ctx.needs_input_grad
-        out_params = [g if need[5 + i] else None for i, g in enumerate(grads)]
-        return (None, None, None, da1n if need[3] else None, da1e if need[4] else None, *out_params)
+        out_params = [g if need[6 + i] else None for i, g in enumerate(grads)]
+        return (None, None, None, None, da1n if need[4] else None, da1e if need[5] else None, *out_params)
 
 
-def graphnet_core(gn, graph, a1n: Tensor, a1e: Tensor) -> Tensor:
-    """Run the width-128 core of ``gn`` (a tensor-core-eligible ``GraphNet``) with the hand-scheduled backward."""
+class ExpandClassRowsFn(torch.autograd.Function):
+    """``table[idx]`` for a table of a few rows (edge classes of a grid) expanded to every edge; the backward is the
+    per-class column sum of the incoming gradient, as two ordered CSR segmented sums (chunks of 512 edges, then the
+    chunks of a class) - deterministic, no atomics."""
+
+    @staticmethod
+    def forward(ctx, table, idx, plan):
+        ctx.plan, ctx.n_rows = plan, table.shape[0]
+        return ops._gather_raw(ops._rows(table), idx)
+
+    @staticmethod
+    def backward(ctx, dout):
+        rowptr1, eid1, rowptr2, eid2 = ctx.plan
+        partial = ops._agg_raw(rowptr1, eid1, ops._rows(dout), int(rowptr1.shape[0]) - 1)
+        return ops._agg_raw(rowptr2, eid2, partial, ctx.n_rows), None, None
+
+
+def class_sum_plan(edge_class: Tensor, n_classes: int, chunk: int = 512):
+    """CSRs for ``ExpandClassRowsFn.backward``: level 1 groups the edges of a class (ascending edge id) into chunks of
+    ``chunk`` rows, level 2 groups the chunks of each class."""
+    cls = edge_class.long()
+    order = torch.argsort(cls, stable=True)
+    counts = torch.bincount(cls, minlength=n_classes).cpu().tolist()
+    bounds, seg_class, off = [0], [], 0
+    for c, n in enumerate(counts):
+        for lo in range(0, n, chunk):
+            bounds.append(off + min(lo + chunk, n))
+            seg_class.append(c)
+        off += n
+    dev = edge_class.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr1 = torch.tensor(bounds, **i32)
+    n_seg = len(seg_class)
+    per_class = [seg_class.count(c) for c in range(n_classes)]
+    rp2 = [0]
+    for n in per_class:
+        rp2.append(rp2[-1] + n)
+    return rowptr1, order.to(torch.int32), torch.tensor(rp2, **i32), torch.arange(max(n_seg, 1), **i32)[:n_seg]
+
+
+def graphnet_core(gn, graph, a1n: Tensor, a1e: Tensor, edge_ready: bool = False) -> Tensor:
+    """Run the width-128 core of ``gn`` (a tensor-core-eligible ``GraphNet``) with the hand-scheduled backward.
+    ``edge_ready``: ``a1e`` is the encoded edge latent itself (the edge encoder ran elsewhere)."""
     eps = [gn.node_encoder.model[5].eps, gn.edge_encoder.model[5].eps]
     for blk in gn.graph_processor.blocks:
         eps += [blk.edge_model.edge_processor.model[5].eps, blk.node_model.node_processor.model[5].eps]
     n_blocks = len(gn.graph_processor.blocks)
-    return GraphNetCoreFn.apply(graph, tuple(eps), n_blocks, a1n, a1e, *core_param_list(gn))
+    return GraphNetCoreFn.apply(graph, tuple(eps), n_blocks, bool(edge_ready), a1n, a1e, *core_param_list(gn))

@@ -41,11 +41,19 @@ class _GraphedStep:
         parts = tuple(sample) if self.tuple_in else (sample,)
         self.key = self.layout(sample, label)
         # floating-point inputs change per item and are copied in; index tensors (edge_index) are topology:
-        # the captured kernels read the attached CSR, so an item must carry the very same topology object
-        self.static = tuple(p.clone() if p.is_floating_point() else p for p in parts)
+        # the captured kernels read the attached CSR, so an item must carry the very same topology object.  The
+        # positions the builder emitted with that topology are part of it (same tensor for every item; the model's
+        # edge-class shortcut recognises it by identity), so they are kept, not cloned
+        self.fixed = self._topology_bound(parts)
+        self.static = tuple(p if fx else p.clone() for p, fx in zip(parts, self.fixed))
         self.label = label.clone()
         self.loss = None
         self.graph = None
+
+    @staticmethod
+    def _topology_bound(parts):
+        topos = [getattr(p, "_gnc_graph", None) for p in parts if not p.is_floating_point()]
+        return tuple((not p.is_floating_point()) or any(t is not None and t.pos_ref is p for t in topos) for p in parts)
 
     @staticmethod
     def layout(sample, label):
@@ -53,9 +61,10 @@ class _GraphedStep:
         if not all(isinstance(p, torch.Tensor) and p.is_cuda for p in parts) or not isinstance(label, torch.Tensor):
             return None
         key = []
-        for p in parts:
+        fixed = _GraphedStep._topology_bound(parts)
+        for p, fx in zip(parts, fixed):
             if p.is_floating_point():
-                key.append((tuple(p.shape), p.dtype))
+                key.append((tuple(p.shape), p.dtype, id(p) if fx else None))
             else:
                 topo = getattr(p, "_gnc_graph", None)
                 if topo is None:
@@ -104,8 +113,8 @@ class _GraphedStep:
 
     def run(self, sample, label):
         parts = tuple(sample) if self.tuple_in else (sample,)
-        for dst, src in zip(self.static, parts):
-            if dst.is_floating_point():
+        for dst, src, fx in zip(self.static, parts, self.fixed):
+            if not fx:
                 dst.copy_(src, non_blocking=True)
         self.label.copy_(label, non_blocking=True)
         self.graph.replay()
