@@ -27,7 +27,8 @@ class GncTcEpilogue(Structure):
                 ("residual", c_void_p), ("ld_residual", c_int64),
                 ("dot_w", c_void_p), ("dot_b", c_void_p),
                 ("mask", c_void_p), ("ld_mask", c_int64),
-                ("residual_idx", c_void_p)]
+                ("residual_idx", c_void_p),
+                ("ln_z", c_void_p), ("ld_ln_z", c_int64), ("ln_mean", c_void_p), ("ln_rstd", c_void_p)]
 
 
 class GncTcChain(Structure):

@@ -83,6 +83,7 @@ struct Params {
   const float* mask; long long ld_mask;
   const float* dot_w; const float* dot_b;
   float* Y; long long ldy;
+  float* ln_z; long long ld_ln_z; float* ln_mean; float* ln_rstd;   // LayerNorm epilogue: what its backward needs
   long long num_tiles;
   // co-scheduled weight sets (plain epilogue): CTA b uses set b % nsets and walks the tiles of
   // group b / nsets, so the nsets CTAs of a group read the same A tiles at the same time (L2 reuse)
@@ -522,6 +523,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
         const float mu = shift + m1;
         const float var = fmaxf(s2 * (1.0f / kD) - m1 * m1, 0.f);
         const float rs = 1.0f / sqrtf(var + p.eps);
+        if (p.ln_mean && wrow0 + lane < p.M) {          // thread = row: the statistics the backward reuses
+          p.ln_mean[wrow0 + lane] = mu;
+          p.ln_rstd[wrow0 + lane] = rs;
+        }
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           {
@@ -529,6 +534,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
             tmem_ld32(taddr + ch * 32, r);
             tmem_ld_wait();
             if (ch == 3) { tc_fence_before(); mbar_arrive(d_empty(eg)); }
+            if (p.ln_z) {
+              // training: the pre-LayerNorm activation goes out too (same transpose through the staging tile), so
+              // that no separate LayerNorm pass has to re-read it
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int cb = ch * 32 + 4 * j;
+                *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) =
+                    make_float4(r[4 * j] + s_bias[cb], r[4 * j + 1] + s_bias[cb + 1], r[4 * j + 2] + s_bias[cb + 2], r[4 * j + 3] + s_bias[cb + 3]);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 zz = *reinterpret_cast<const float4*>(stg + (j * 4 + rl) * kStagePitch + 4 * c4);
+                if (wrow0 + j * 4 + rl < p.M) stg_stream(reinterpret_cast<float4*>(p.ln_z + grow[j] * p.ld_ln_z + ch * 32 + c4 * 4), zz);
+              }
+              __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int cb = ch * 32 + 4 * j;
@@ -613,6 +635,7 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
   p.mask = epi->mask; p.ld_mask = epi->ld_mask;
   p.dot_w = epi->dot_w; p.dot_b = epi->dot_b;
   p.Y = Y; p.ldy = ldy;
+  p.ln_z = epi->ln_z; p.ld_ln_z = epi->ld_ln_z; p.ln_mean = epi->ln_mean; p.ln_rstd = epi->ln_rstd;
   p.nsets = 1;
   p.W_alt[0] = p.W_alt[1] = nullptr; p.ldw_alt[0] = p.ldw_alt[1] = 0; p.Y_alt[0] = p.Y_alt[1] = nullptr;
   p.num_tiles = (M + tc::kTileM - 1) / tc::kTileM;
@@ -632,8 +655,11 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
   GNC_REQUIRE(!epi->residual_idx || (epi->gamma && epi->residual), "tc_linear: residual_idx is supported by the LayerNorm epilogue only");
   if (epi->gamma) {
     GNC_REQUIRE(epi->beta && !p.addend && !p.g0 && !p.g1 && !epi->relu, "tc_linear: LayerNorm epilogue takes bias + residual only");
+    GNC_REQUIRE(!p.ln_z || (aligned16(p.ln_z) && p.ld_ln_z >= tc::kD && p.ld_ln_z % 4 == 0), "tc_linear: ln_z rows must be 16-byte aligned");
+    GNC_REQUIRE((p.ln_mean == nullptr) == (p.ln_rstd == nullptr), "tc_linear: ln_mean and ln_rstd come together");
     return tc::launch<tc::MODE_LAYERNORM>(p, st);
   }
+  GNC_REQUIRE(!p.ln_z && !p.ln_mean && !p.ln_rstd, "tc_linear: ln_z / ln_mean / ln_rstd belong to the LayerNorm epilogue");
   return tc::launch<tc::MODE_ELEMENTWISE>(p, st);
 }
 

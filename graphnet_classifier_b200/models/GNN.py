@@ -268,10 +268,9 @@ class GraphNet(nn.Module):
             # Grid graphs from our builders (same condition as the inference shortcut): the edges fall into <= 4
             # classes with identical geometry rows, so the edge ENCODER - forward and backward - runs on one row per
             # class; its output is expanded to the edges by a gather and its gradient comes back as per-class sums.
-            tcl = ops.tc_linear_autograd
             a1t = ops.linear([graph.class_geom], ee[0].weight, ee[0].bias, relu=True)
-            a2t = tcl(a1t, ee[2].weight, ee[2].bias, relu=True)
-            e_tab = ops.layer_norm(tcl(a2t, ee[4].weight, ee[4].bias), ee[5].weight, ee[5].bias, ee[5].eps)
+            e_tab = tc_train.MlpTailFn.apply(ee[5].eps, a1t, ee[2].weight, ee[2].bias, ee[4].weight, ee[4].bias,
+                                             ee[5].weight, ee[5].bias)
             if graph.class_sum_plan is None:
                 graph.class_sum_plan = tc_train.class_sum_plan(graph.edge_class, e_tab.shape[0])
             e0 = tc_train.ExpandClassRowsFn.apply(e_tab, graph.edge_class, graph.class_sum_plan)

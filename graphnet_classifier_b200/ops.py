@@ -564,7 +564,7 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
               gamma: Optional[Tensor] = None, beta: Optional[Tensor] = None, eps: float = 1e-5,
               residual: Optional[Tensor] = None, dot_w: Optional[Tensor] = None,
               dot_b: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-              out: Optional[Tensor] = None) -> Tensor:
+              out: Optional[Tensor] = None, ln_save=None) -> Tensor:
     """``epilogue(A @ W.T)`` on the tcgen05 3xTF32 engine (``A @ W`` with transpose_w).
     ``gather0`` / ``gather1`` are ``(rows [R, 128], idx int32 [M])`` pairs added row-wise as
     ``rows[idx[m]]``.  See include/gnc.h ``gnc_tc_epilogue_t`` for the epilogue algebra."""
@@ -609,6 +609,12 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     if mask is not None:
         t = rows(mask)
         epi.mask, epi.ld_mask = t.data_ptr(), _ld(t)
+    if ln_save is not None:                       # (z [M, 128], mean [M], rstd [M]) outputs of the LayerNorm epilogue
+        if gamma is None:
+            raise ValueError("ln_save belongs to the LayerNorm epilogue (gamma / beta)")
+        z_out, mean_out, rstd_out = ln_save
+        epi.ln_z, epi.ld_ln_z = z_out.data_ptr(), _ld(z_out)
+        epi.ln_mean, epi.ln_rstd = mean_out.data_ptr(), rstd_out.data_ptr()
     if dot_w is not None:
         dw = dot_w.reshape(-1)
         if dw.stride(0) != 1:
@@ -622,7 +628,7 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     # algorithmic HBM bytes: every operand row once (gathered tables count their own rows, not
     # one row per reference - re-references are expected to hit L2)
     nbytes = 4.0 * (M * K + M * n_out + N * K
-                    + M * 128 * ((addend is not None) + (mask is not None)) + res_rows * 128
+                    + M * 128 * ((addend is not None) + (mask is not None) + (ln_save is not None)) + res_rows * 128
                     + (gather0[0].shape[0] * 128 + M if gather0 is not None else 0)
                     + (gather1[0].shape[0] * 128 + M if gather1 is not None else 0))
     check(_call("tc_linear", 2.0 * M * N * K, nbytes, _lib.load().gnc_tc_linear_f32, A.data_ptr(), _ld(A), M, K,

@@ -76,6 +76,55 @@ def _relu_bwd(dY: Tensor, Y: Tensor):
     return dZ, db
 
 
+def _tail_fwd(a1: Tensor, tail_params, eps_l: float, residual: Optional[Tensor]):
+    """``LayerNorm(Linear(ReLU(Linear(a1)))) + residual`` behind a first layer's ReLU output ``a1``; returns the output and
+    what ``_tail_bwd`` needs.  ``tail_params`` = (W2, b2, W4, b4, gamma, beta)."""
+    W2, b2, W4, b4, g, bt = tail_params
+    a2 = ops.tc_linear(a1, W2, bias=b2, relu=True)
+    # last layer + LayerNorm + residual in one launch; the LayerNorm input and its row statistics are written out for
+    # the backward by the same epilogue (no separate LayerNorm pass over z3)
+    M = a2.shape[0]
+    z3 = torch.empty(M, 128, dtype=_f32, device=a2.device)
+    mean = torch.empty(M, dtype=_f32, device=a2.device)
+    rstd = torch.empty(M, dtype=_f32, device=a2.device)
+    y = ops.tc_linear(a2, W4, bias=b4, gamma=g, beta=bt, eps=eps_l, residual=residual, ln_save=(z3, mean, rstd))
+    return y, (a1, a2, z3, mean, rstd)
+
+
+def _tail_bwd(dy: Tensor, saved, tail_params, mask_a1: bool):
+    """Backward of ``_tail_fwd``: returns the gradient with respect to ``a1`` (times ``a1 > 0`` when ``mask_a1``: then
+    it is the first layer's pre-activation gradient) and ``[dW2, db2, dW4, db4, dgamma, dbeta]``.  The residual's
+    gradient is ``dy`` itself."""
+    a1, a2, z3, mean, rstd = saved
+    W2, _, W4, _, g, _ = tail_params
+    dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g)
+    del z3
+    dW4, db4 = ops.tc_wgrad(dz3, a2, want_db=True)
+    dz2 = ops.tc_linear(dz3, W4, transpose_w=True, mask=a2)
+    del dz3, a2
+    dW2, db2 = ops.tc_wgrad(dz2, a1, want_db=True)
+    da1 = ops.tc_linear(dz2, W2, transpose_w=True, mask=a1 if mask_a1 else None)
+    return da1, [dW2, db2, dW4, db4, dg, dbt]
+
+
+class MlpTailFn(torch.autograd.Function):
+    """``_tail_fwd`` / ``_tail_bwd`` as an operator of its own (no residual): the edge encoder on the class table runs
+    through exactly the kernels the per-edge encoder runs through inside ``GraphNetCoreFn``, so both give the same bits."""
+
+    @staticmethod
+    def forward(ctx, eps_l, a1, *tail_params):
+        y, saved = _tail_fwd(ops._rows(a1), tail_params, eps_l, None)
+        ctx.saved, ctx.tail_params = saved, tail_params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        da1, grads = _tail_bwd(ops._rows(dy), ctx.saved, ctx.tail_params, False)
+        ctx.saved = None
+        need = ctx.needs_input_grad
+        return (None, da1 if need[1] else None, *[g if need[2 + i] else None for i, g in enumerate(grads)])
+
+
 def core_param_list(gn) -> List[Tensor]:
     """Parameters the core consumes, in the order ``GraphNetCoreFn`` returns their gradients:
     per MLP tail ``W2 b2 W4 b4 gamma beta``; blocks add their first layers ``W0 b0`` / ``V0 c0`` in front;
@@ -108,11 +157,8 @@ class GraphNetCoreFn(torch.autograd.Function):
         saved = []          # per MLP tail: (a1, a2, z3, mean, rstd)
 
         def tail(a1, p0, residual, eps_l):
-            W2, b2, W4, b4, g, bt = params[p0:p0 + 6]
-            a2 = tcl(a1, W2, bias=b2, relu=True)
-            z3 = tcl(a2, W4, bias=b4)
-            y, mean, rstd = _ln_fwd(z3, g, bt, eps_l, residual)
-            saved.append((a1, a2, z3, mean, rstd))
+            y, sv = _tail_fwd(a1, params[p0:p0 + 6], eps_l, residual)
+            saved.append(sv)
             return y
 
         h = tail(a1n, 0, None, eps[0])
@@ -160,20 +206,11 @@ class GraphNetCoreFn(torch.autograd.Function):
         grads: List[Optional[Tensor]] = [None] * len(params)
 
         def tail_bwd(dy, idx, p0, mask_a1):
-            """Backward of Linear-ReLU-Linear-LayerNorm behind ``a1``; returns the gradient with respect to ``a1``
-            (times ``a1 > 0`` when ``mask_a1``: then it is the first layer's pre-activation gradient)."""
-            a1, a2, z3, mean, rstd = saved[idx]
+            sv = saved[idx]
             saved[idx] = None
-            W2, _, W4, _, g, _ = params[p0:p0 + n_tail]
-            dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g)
-            del z3
-            dW4, db4 = wgrad(dz3, a2, want_db=True)
-            dz2 = tcl(dz3, W4, transpose_w=True, mask=a2)
-            del dz3, a2
-            dW2, db2 = wgrad(dz2, a1, want_db=True)
-            da1 = tcl(dz2, W2, transpose_w=True, mask=a1 if mask_a1 else None)
-            grads[p0:p0 + n_tail] = [dW2, db2, dW4, db4, dg, dbt]
-            return da1, a1
+            da1, g6 = _tail_bwd(dy, sv, params[p0:p0 + n_tail], mask_a1)
+            grads[p0:p0 + n_tail] = g6
+            return da1, sv[0]
 
         # parameter offsets
         p_node_enc, p_edge_enc = 0, n_tail

@@ -272,6 +272,9 @@ typedef struct gnc_tc_epilogue {
   const float* dot_w; const float* dot_b;
   const float* mask; int64_t ld_mask;   /* elementwise only: Y *= (mask[m] > 0) - ReLU backward fused into the data gradient */
   const int32_t* residual_idx;          /* LayerNorm epilogue only: residual row = residual[residual_idx[m]] (table lookup) */
+  /* LayerNorm epilogue only, all optional (training): ln_z [M, 128] receives acc + bias (the LayerNorm input), ln_mean /
+   * ln_rstd [M] the row statistics - what gnc_layernorm_bwd_f32 consumes, without a separate forward pass over z */
+  float* ln_z; int64_t ld_ln_z; float* ln_mean; float* ln_rstd;
 } gnc_tc_epilogue_t;
 
 /* Y[M, N] = epilogue( A[M, K] * B^T ), B = W[N, K] (transpose_w = 0) or B = W^T with W[K, N]

@@ -73,6 +73,18 @@ def test_layernorm_epilogue(libgnc, M, res):
     if res:
         ref = ref + r.double()
     assert _maxrel(got, ref) < RTOL
+    # training form: the same launch also writes the LayerNorm input and its row statistics for the backward
+    z = torch.full((M, 128), 7.0, device="cuda")
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    got2 = ops.tc_linear(A.cuda(), W.cuda(), bias=b.cuda(), gamma=g.cuda(), beta=be.cuda(), eps=1e-5,
+                         residual=r.cuda() if res else None, ln_save=(z, mean, rstd))
+    assert torch.equal(got2, got)
+    z64 = A.double() @ W.double().t() + b.double()
+    assert _maxrel(z, z64) < RTOL
+    assert _maxrel(mean, z64.mean(1)) < RTOL or float((mean.double().cpu() - z64.mean(1)).abs().max()) < 1e-5
+    assert _maxrel(rstd, 1.0 / torch.sqrt(z64.var(1, unbiased=False) + 1e-5)) < RTOL
+    with pytest.raises(Exception):
+        ops.tc_linear(A.cuda(), W.cuda(), bias=b.cuda(), ln_save=(z, mean, rstd))      # LayerNorm epilogue only
 
 
 def test_relu_dot_epilogue(libgnc):
