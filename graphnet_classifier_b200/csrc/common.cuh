@@ -32,6 +32,26 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute: remembered per (call site, device
+// ordinal) so that a second GPU used by the same process is configured too; safe to call from several threads.
+struct SmemAttrOnce {
+  std::atomic<unsigned long long> done{0};
+  template <typename Kernel>
+  int ensure(Kernel kernel, int bytes, const char* what) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return GNC_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+      return GNC_ECUDA;
+    }
+    done.fetch_or(bit, std::memory_order_release);
+    return GNC_OK;
+  }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>

@@ -165,12 +165,8 @@ static int launch_h_reg(const uint8_t* src, int64_t B, int H, int W, int64_t pit
   if (R < 1) return -1;                                   // row too wide for this form: the caller falls back
   if (R > 16) R = 16;
   const size_t smem = (size_t)R * row_stride + slack;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(resize_h_reg_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(resize_h_reg_kernel<KMAX>, kSmemCap, "resize_bicubic")) return rc_attr;
   const long long rows = B * (long long)H;
   dim3 grid((unsigned)ceil_div(rows, (long long)R), (unsigned)ceil_div(OW, kThreads));
   resize_h_reg_kernel<KMAX><<<grid, kThreads, smem, st>>>(src, H, W, pitch, istride, OW, bounds, kk, ksize, dst, rows, R, row_stride);
@@ -245,12 +241,8 @@ static int launch_h_long(const uint8_t* src, int64_t B, int H, int W, int64_t pi
   if (R < 1) return -1;                                   // wider than ~32 000 pixels: the generic kernel
   if (R > RMAX) R = RMAX;
   const size_t smem = (size_t)R * row_stride + slack;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(resize_h_long_kernel<KCH, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(resize_h_long_kernel<KCH, RMAX>, kSmemCap, "resize_bicubic")) return rc_attr;
   const long long rows = B * (long long)H;
   dim3 grid((unsigned)ceil_div(rows, (long long)R), (unsigned)ceil_div(OW, kThreads));
   resize_h_long_kernel<KCH, RMAX><<<grid, kThreads, smem, st>>>(src, H, W, pitch, istride, OW, bounds, kk, ksize, dst, rows, R, row_stride);

@@ -1810,12 +1810,8 @@ static int launch_spec2n(const Params& p, cudaStream_t st) {
   // (the kernel's own layout: weight images, loader ring, 2 slots per epilogue warp, constants, barriers, slack)
   constexpr int kSmem2n = (NL + (K2 ? 1 : 0)) * kLayerBytes + kLoaderWarps * kLoadBufs * kChunkBytes + kEpiWarps * 2 * kSlotBytes +
                           5 * kD * 4 + 2 * kEpiWarps * 32 * 4 + 320 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain2n_kernel<NL, K2, RES, TAIL, SYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2n);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain2n: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(tc_chain2n_kernel<NL, K2, RES, TAIL, SYN>, kSmem2n, "tc_chain2n")) return rc_attr;
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
   tc_chain2n_kernel<NL, K2, RES, TAIL, SYN><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
   return check_launch("tc_chain2n_kernel");
@@ -1823,12 +1819,8 @@ static int launch_spec2n(const Params& p, cudaStream_t st) {
 
 template <int SPEC>
 static int launch_spec2(const Params& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain2_kernel<SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(tc_chain2_kernel<SPEC>, kSmemBytes, "tc_chain2")) return rc_attr;
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
   tc_chain2_kernel<SPEC><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
   return check_launch("tc_chain2_kernel");
@@ -1836,12 +1828,8 @@ static int launch_spec2(const Params& p, cudaStream_t st) {
 
 template <int SPEC>
 static int launch_spec(const Params& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_chain_kernel<SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(tc_chain_kernel<SPEC>, kSmemBytes, "tc_chain")) return rc_attr;
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
   tc_chain_kernel<SPEC><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
   return check_launch("tc_chain_kernel");

@@ -595,12 +595,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const Params p) 
 
 template <int MODE>
 static int launch(const Params& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(tc_linear_kernel<MODE>, kSmemBytes, "tc_linear")) return rc_attr;
   long long grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   if (p.nsets > 1) {
     long long groups = kNumSMs / p.nsets;

@@ -385,12 +385,8 @@ int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx,
   GNC_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && aligned16(dZ) && aligned16(X), "tc_wgrad: rows must be 16-byte aligned");
   if (!work || work_elems < gnc_tc_wgrad_workspace(M)) return fail(GNC_EWORKSPACE, "%s", "tc_wgrad: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tcw::tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcw::kSmemBytes);
-    if (e != cudaSuccess) return fail(GNC_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemAttrOnce smem_attr;
+  if (int rc_attr = smem_attr.ensure(tcw::tc_wgrad_kernel, tcw::kSmemBytes, "tc_wgrad")) return rc_attr;
   const long long nblocks = (M + tcw::kRows - 1) / tcw::kRows;
   long long grid = nblocks < kNumSMs ? nblocks : kNumSMs;
   if (grid < 1) grid = 1;

@@ -170,9 +170,8 @@ class GraphNet(nn.Module):
         with LayerNorm (none on the decoder), i.e. the configuration main.py builds."""
         if ops.ENGINE != "tc":
             return False
-        cached = getattr(self, "_tc_ok", None)
-        if cached is not None:
-            return cached
+        # recomputed on every forward (a few isinstance / shape checks): a module edited after construction - swapped
+        # norm or activation, resized or re-typed layers, a half()/double() cast - must not keep dispatching here
 
         def mlp_ok(mlp, in_dim, out_dim, norm):
             m = list(mlp.model)
@@ -182,7 +181,7 @@ class GraphNet(nn.Module):
                 return False
             if [tuple(m[i].weight.shape) for i in (0, 2, 4)] != [(128, in_dim), (128, 128), (out_dim, 128)]:
                 return False
-            if any(m[i].bias is None for i in (0, 2, 4)):
+            if any(m[i].bias is None or m[i].weight.dtype != torch.float32 for i in (0, 2, 4)):
                 return False
             if norm:
                 ln = m[5]
@@ -196,8 +195,7 @@ class GraphNet(nn.Module):
             ok = ok and isinstance(blk.edge_model, EdgeProcessor) and isinstance(blk.node_model, NodeProcessor)
             ok = ok and mlp_ok(blk.edge_model.edge_processor, 384, 128, True)
             ok = ok and mlp_ok(blk.node_model.node_processor, 256, 128, True)
-        self._tc_ok = bool(ok)
-        return self._tc_ok
+        return bool(ok)
 
     def _forward_tc(self, x, pos, graph: GraphIndex):
         """Same function as ``forward`` on the 3xTF32 tensor-core engine.  The first Linear of
@@ -226,7 +224,7 @@ class GraphNet(nn.Module):
         # latent of block 0 is a 4-row table indexed by class - never an [E, 128] tensor.  Only
         # taken when `pos` is the very tensor the builder emitted with that topology.
         e_tab = None
-        if graph.edge_class is not None and graph.pos_ref is pos and graph.class_geom.shape[1] == ee[0].in_features:
+        if graph.classes_valid_for(pos) and graph.class_geom.shape[1] == ee[0].in_features:
             e_tab = chain(ops.linear([graph.class_geom], ee[0].weight, ee[0].bias, relu=True), None, self.edge_encoder)
             e = None
         else:
@@ -264,7 +262,7 @@ class GraphNet(nn.Module):
             return self._forward_tc_train_opwise(x, pos, graph)
         ne, ee, dec = self.node_encoder.model, self.edge_encoder.model, self.node_decoder.model
         a1n = ops.linear([x], ne[0].weight, ne[0].bias, relu=True)
-        if graph.edge_class is not None and graph.pos_ref is pos and graph.class_geom.shape[1] == ee[0].in_features:
+        if graph.classes_valid_for(pos) and graph.class_geom.shape[1] == ee[0].in_features:
             # Grid graphs from our builders (same condition as the inference shortcut): the edges fall into <= 4
             # classes with identical geometry rows, so the edge ENCODER - forward and backward - runs on one row per
             # class; its output is expanded to the edges by a gather and its gradient comes back as per-class sums.

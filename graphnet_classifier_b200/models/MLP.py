@@ -33,12 +33,12 @@ class MLP(nn.Module):
         self.activation = getattr(nn, activation)()
         if initializer is not None:
             self.initializer = getattr(nn.init, initializer)
-        stack = []
-        width = in_dim
-        for _ in range(hidden_layers):
-            stack += [nn.Linear(width, hidden_dim), self.activation]
-            width = hidden_dim
-        stack.append(nn.Linear(width, out_dim))
+        # the first Linear + activation exist for every hidden_layers (0 included), as in the reference's layer list
+        # (models/MLP.py:24-27): module indices, state_dict keys and parameter-creation order stay the same
+        stack = [nn.Linear(in_dim, hidden_dim), self.activation]
+        for _ in range(hidden_layers - 1):
+            stack += [nn.Linear(hidden_dim, hidden_dim), self.activation]
+        stack.append(nn.Linear(hidden_dim, out_dim))
         if norm_type is not None:
             assert norm_type in ["LayerNorm", "BatchNorm1d"]
             stack.append(getattr(nn, norm_type)(out_dim))

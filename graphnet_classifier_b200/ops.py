@@ -128,7 +128,7 @@ class GraphIndex:
     reference's summation order) and by source."""
 
     __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid",
-                 "edge_class", "class_geom", "pos_ref", "class_sum_plan")
+                 "edge_class", "class_geom", "pos_ref", "pos_version", "class_sum_plan")
 
     def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
         self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
@@ -142,7 +142,18 @@ class GraphIndex:
         self.edge_class = None
         self.class_geom = None
         self.pos_ref = None
+        self.pos_version = -1           # pos_ref._version when the classes were derived from it
         self.class_sum_plan = None      # lazily built CSRs for per-class gradient sums (tc_train.class_sum_plan)
+
+    def bind_positions(self, pos: Tensor) -> None:
+        """Remember the ``pos`` tensor (and its in-place version) the edge classes were derived from."""
+        self.pos_ref, self.pos_version = pos, pos._version
+
+    def classes_valid_for(self, pos: Tensor) -> bool:
+        """True when ``pos`` is the very tensor the builder emitted with this topology AND it has not been edited in
+        place since (jitter / normalisation bump ``_version``): only then does the per-class geometry table describe
+        the edges, otherwise the model takes the generic per-edge path."""
+        return (self.edge_class is not None and self.pos_ref is pos and pos._version == self.pos_version)
 
     @staticmethod
     def from_edge_index(edge_index: Tensor, num_nodes: int, validate: bool = True) -> "GraphIndex":
@@ -218,6 +229,26 @@ def _gather_raw(src: Tensor, idx: Tensor, out: Optional[Tensor] = None, accumula
     check(_call("gather_rows", 0.0, nbytes, _lib.load().gnc_gather_rows_f32, src.data_ptr(), _ld(src),
                 idx.data_ptr(), M, D, out.data_ptr(), _ld(out), int(accumulate), _stream()), "gather_rows")
     return out
+
+
+def _check_linear_operands(srcs: Sequence[Tensor], W: Tensor, b: Optional[Tensor], what: str) -> None:
+    """The reference's ``nn.Linear`` raises on a width mismatch (models/MLP.py:24-27 via F.linear); the kernels derive K
+    from the segments and read raw fp32 pointers, so the same conditions are checked here instead of computing on a
+    prefix of ``W`` or on reinterpreted bytes."""
+    if W.dim() != 2:
+        raise RuntimeError(f"{what}: weight must be 2-D, got {tuple(W.shape)}")
+    if W.dtype != torch.float32 or (b is not None and b.dtype != torch.float32):
+        raise RuntimeError(f"{what}: float32 parameters only (got weight {W.dtype}"
+                           f"{', bias ' + str(b.dtype) if b is not None else ''}); MLP.forward computes in float "
+                           "(reference models/MLP.py:46)")
+    k = sum(int(s.shape[1]) if s.dim() == 2 else int(s.numel() // max(s.shape[0], 1)) for s in srcs)
+    if k != W.shape[1]:
+        raise RuntimeError(f"{what}: mat1 and mat2 shapes cannot be multiplied (input width {k}, weight {tuple(W.shape)})")
+    if b is not None and b.numel() != W.shape[0]:
+        raise RuntimeError(f"{what}: bias has {b.numel()} elements, weight has {W.shape[0]} rows")
+    for t in list(srcs) + ([b] if b is not None else []):
+        if t.device != W.device:
+            raise RuntimeError(f"{what}: operands on different devices ({t.device} vs {W.device})")
 
 
 def _make_segs(srcs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]]):
@@ -344,6 +375,7 @@ def linear(srcs: Sequence[Tensor], W: Tensor, b: Optional[Tensor], relu: bool = 
            gathers: Optional[Sequence] = None) -> Tensor:
     """``gathers[i]`` is None (rows used as is) or (idx32, (rowptr, eid), n_src_rows)."""
     _require_cuda(W, *srcs)
+    _check_linear_operands(srcs, W, b, "linear")
     if gathers is None:
         gathers = [None] * len(srcs)
     meta = tuple((None, None, 0) if g is None else g for g in gathers)
@@ -572,6 +604,10 @@ def tc_linear(A: Tensor, W: Tensor, *, transpose_w: bool = False, bias: Optional
     A = _rows(A)
     M, K = A.shape
     N = W.shape[1] if transpose_w else W.shape[0]
+    if W.dtype != torch.float32 or W.device != A.device or K != (W.shape[0] if transpose_w else W.shape[1]):
+        raise RuntimeError(f"tc_linear: input width {K} / weight {tuple(W.shape)} {W.dtype} on {W.device} do not match")
+    if bias is not None and (bias.numel() != N or bias.dtype != torch.float32 or bias.device != A.device):
+        raise RuntimeError(f"tc_linear: bias must be a float32 vector of {N} elements on {A.device}")
     if W.stride(1) != 1:
         W = W.contiguous()
     epi = GncTcEpilogue()
@@ -700,6 +736,9 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
     ch.nlayers = len(layers)
     for l, (W, b) in enumerate(layers):
         _require_cuda(W)
+        if tuple(W.shape) != (128, 128) or W.dtype != torch.float32 or (b is not None and (b.numel() != 128 or b.dtype != torch.float32)):
+            raise RuntimeError(f"tc_mlp_chain: layer {l} must be a float32 [128, 128] weight with a 128-element bias, "
+                               f"got {tuple(W.shape)} {W.dtype}")
         if W.stride(1) != 1:
             W = W.contiguous()
         keep.append(W)
@@ -857,3 +896,52 @@ def tc_wgrad(dZ: Tensor, X: Tensor, out: Optional[Tensor] = None, accumulate: bo
                 lib.gnc_tc_wgrad_f32, dZ.data_ptr(), _ld(dZ), X.data_ptr(), _ld(X), M, dZ.shape[1], X.shape[1],
                 out.data_ptr(), _ld(out), int(accumulate), _p(db), ws.data_ptr(), ws_n, _stream()), "tc_wgrad")
     return (out, db) if want_db else out
+
+
+def tc_bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend: Optional[Tensor] = None,
+                 dW_out: Optional[Tensor] = None, accumulate: bool = False, want_db: bool = False,
+                 db_out: Optional[Tensor] = None, want_dW: bool = True):
+    """Backward of ``y = x @ W.T (+ b)`` for ``[M, 128]`` operands in ONE pass over ``dZ`` and ``X`` (csrc/tc_bwd.cu):
+    returns ``(dX, dW, db)`` with ``dX = dZ @ W`` (``* (X > 0)`` with ``mask``, ``+ addend``), ``dW = dZ.T @ X``
+    (written into ``dW_out`` when given, added to it with ``accumulate``; ``accumulate`` also applies to ``db_out``)
+    and ``db`` = column sums of ``dZ`` (``None`` unless asked for)."""
+    _require_cuda(dZ, X, W)
+    dZ, X = _rows(dZ), _rows(X)
+    M = dZ.shape[0]
+    if dZ.shape[1] != 128 or X.shape != dZ.shape or tuple(W.shape) != (128, 128):
+        raise ValueError(f"tc_bwd_layer: width-128 operands only, got dZ {tuple(dZ.shape)}, X {tuple(X.shape)}, W {tuple(W.shape)}")
+    if W.dtype != torch.float32 or W.device != dZ.device or X.device != dZ.device:
+        raise ValueError("tc_bwd_layer: W / X must be float32 tensors on dZ's device")
+    if W.stride(1) != 1:
+        W = W.contiguous()
+    lib = _lib.load()
+    dev = dZ.device
+    dX = torch.empty(M, 128, dtype=torch.float32, device=dev)
+    ad = None
+    if addend is not None:
+        ad = _rows(addend)
+        if ad.shape != dZ.shape:
+            raise ValueError("tc_bwd_layer: addend must have dZ's shape")
+    dW = None
+    if want_dW:
+        if dW_out is None:
+            if accumulate:
+                raise ValueError("tc_bwd_layer: accumulate needs dW_out")
+            dW = torch.empty(128, 128, dtype=torch.float32, device=dev)
+        else:
+            dW = dW_out
+            if tuple(dW.shape) != (128, 128) or dW.stride(1) != 1 or dW.dtype != torch.float32:
+                raise ValueError("tc_bwd_layer: dW_out must be a float32 [128, 128] view with unit column stride")
+    db = None
+    if want_db:
+        if db_out is None and accumulate:
+            raise ValueError("tc_bwd_layer: accumulate with want_db needs db_out")
+        db = db_out if db_out is not None else torch.empty(128, dtype=torch.float32, device=dev)
+    ws_n = int(lib.gnc_tc_bwd_layer_workspace())
+    ws = _workspace(dev, ws_n)
+    check(_call("tc_bwd_layer", 4.0 * M * 128 * 128, 4.0 * 128 * M * (3 + (ad is not None)),
+                lib.gnc_tc_bwd_layer_f32, dZ.data_ptr(), _ld(dZ), X.data_ptr(), _ld(X), M, W.data_ptr(), W.stride(0),
+                int(bool(mask)), _p(ad), _ld(ad) if ad is not None else 0, dX.data_ptr(), _ld(dX),
+                _p(dW), dW.stride(0) if dW is not None else 0, _p(db), int(bool(accumulate)), ws.data_ptr(), ws_n,
+                _stream()), "tc_bwd_layer")
+    return dX, dW, db

@@ -23,6 +23,7 @@ second backward through the same graph (``retain_graph=True``) is not supported.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -32,6 +33,23 @@ from . import _lib, ops
 from ._lib import check
 
 _f32 = torch.float32
+# Backward of a width-128 layer: "fused" = data + weight + bias gradient from one pass over (dZ, X)
+# (csrc/tc_bwd.cu); "pair" = the round-1 schedule (tc_linear data gradient + tc_wgrad), kept as the implementation
+# the fused kernel is tested against.
+BWD = os.environ.get("GNC_BWD", "fused")
+
+
+def _bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend: Optional[Tensor] = None,
+               dW_out: Optional[Tensor] = None, want_db: bool = False):
+    """``(dX, dW, db)`` of ``y = x @ W.T + b`` given ``dZ = dL/dy`` and the layer input ``X``; ``mask``: ``dX *= (X > 0)``
+    (``X`` is a ReLU output, ``dX`` its pre-activation gradient); ``addend`` is added to ``dX``; ``dW_out``: a
+    ``[128, 128]`` column slice the weight gradient is written to."""
+    if BWD == "fused":
+        return ops.tc_bwd_layer(dZ, X, W, mask=mask, addend=addend, dW_out=dW_out, want_db=want_db)
+    r = ops.tc_wgrad(dZ, X, out=dW_out, want_db=want_db)
+    dW, db = r if want_db else (r, None)
+    dX = ops.tc_linear(dZ, W, transpose_w=True, mask=X if mask else None, addend=addend)
+    return dX, dW, db
 
 
 def _ln_fwd(z: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optional[Tensor]):
@@ -99,11 +117,9 @@ def _tail_bwd(dy: Tensor, saved, tail_params, mask_a1: bool):
     W2, _, W4, _, g, _ = tail_params
     dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g)
     del z3
-    dW4, db4 = ops.tc_wgrad(dz3, a2, want_db=True)
-    dz2 = ops.tc_linear(dz3, W4, transpose_w=True, mask=a2)
+    dz2, dW4, db4 = _bwd_layer(dz3, a2, W4, mask=True, want_db=True)
     del dz3, a2
-    dW2, db2 = ops.tc_wgrad(dz2, a1, want_db=True)
-    da1 = ops.tc_linear(dz2, W2, transpose_w=True, mask=a1 if mask_a1 else None)
+    da1, dW2, db2 = _bwd_layer(dz2, a1, W2, mask=mask_a1, want_db=True)
     return da1, [dW2, db2, dW4, db4, dg, dbt]
 
 
@@ -196,7 +212,6 @@ class GraphNetCoreFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dd2):
-        tcl, wgrad = ops.tc_linear, ops.tc_wgrad
         graph, n_blocks, params = ctx.graph, ctx.n_blocks, ctx.params
         (d2,) = ctx.saved_tensors
         saved, blocks = ctx.saved, ctx.blocks
@@ -221,11 +236,9 @@ class GraphNetCoreFn(torch.autograd.Function):
         h_last, d1 = ctx.dec
         Wd0, _, Wd2, _ = params[p_dec:p_dec + 4]
         dz2, dbd2 = _relu_bwd(dd2, d2)
-        dWd2 = wgrad(dz2, d1)
-        dz1 = tcl(dz2, Wd2, transpose_w=True, mask=d1)
+        dz1, dWd2, _ = _bwd_layer(dz2, d1, Wd2, mask=True)
         del dz2, d1
-        dWd0, dbd0 = wgrad(dz1, h_last, want_db=True)
-        dh = tcl(dz1, Wd0, transpose_w=True)
+        dh, dWd0, dbd0 = _bwd_layer(dz1, h_last, Wd0, want_db=True)
         del dz1, h_last
         grads[p_dec:p_dec + 4] = [dWd0, dbd0, dWd2, dbd2]
         ctx.dec = None
@@ -242,12 +255,10 @@ class GraphNetCoreFn(torch.autograd.Function):
             # node processor: h' = LN(MLP(cat[h, agg])) + h
             dn1, _ = tail_bwd(dh, 2 + 2 * k + 1, pn + 2, True)
             dV0 = torch.empty(128, 256, dtype=_f32, device=dev)
-            _, dc0 = wgrad(dn1, agg, out=dV0[:, 128:256], want_db=True)
+            dagg, _, dc0 = _bwd_layer(dn1, agg, V0[:, 128:256], dW_out=dV0[:, 128:256], want_db=True)
             del agg
-            wgrad(dn1, h_in, out=dV0[:, 0:128])
+            dh, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], addend=dh, dW_out=dV0[:, 0:128])   # + the residual's gradient
             grads[pn], grads[pn + 1] = dV0, dc0
-            dagg = tcl(dn1, V0[:, 128:256], transpose_w=True)
-            dh = tcl(dn1, V0[:, 0:128], transpose_w=True, addend=dh)     # + the residual's gradient
             del dn1
             # aggregation backward: every edge receives its destination's row, on top of what later blocks sent
             if de is None:
@@ -258,20 +269,15 @@ class GraphNetCoreFn(torch.autograd.Function):
             # edge processor: e' = LN(MLP(cat[h[row], h[col], e])) + e
             da1, _ = tail_bwd(de, 2 + 2 * k, pe + 2, True)
             dW0 = torch.empty(128, 384, dtype=_f32, device=dev)
-            _, db0 = wgrad(da1, e_in, out=dW0[:, 256:384], want_db=True)
-            del e_in
             dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
             dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
-            de = tcl(da1, W0[:, 256:384], transpose_w=True, addend=de)   # + the residual's gradient
-            del da1
-            wgrad(dP, h_in, out=dW0[:, 0:128])
-            wgrad(dQ, h_in, out=dW0[:, 128:256])
-            del h_in
-            grads[pe], grads[pe + 1] = dW0, db0
-            dh = tcl(dP, W0[:, 0:128], transpose_w=True, addend=dh)
+            de, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], addend=de, dW_out=dW0[:, 256:384], want_db=True)   # + residual
+            del da1, e_in
+            dh, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], addend=dh, dW_out=dW0[:, 0:128])
             del dP
-            dh = tcl(dQ, W0[:, 128:256], transpose_w=True, addend=dh)
-            del dQ
+            dh, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], addend=dh, dW_out=dW0[:, 128:256])
+            del dQ, h_in
+            grads[pe], grads[pe + 1] = dW0, db0
         # ---- encoder tails: the thin first layers mask their own ReLU ----
         if ctx.edge_ready:
             da1e = de                               # gradient of the encoded edge latent itself

@@ -125,7 +125,8 @@ def _build_grid(images, patch: int, diagonals: bool, device, use_cache: bool) ->
                     rel = pos[dst[firsts[c]].long()] - pos[src[firsts[c]].long()]
                     geom[c, :2] = rel
                     geom[c, 2] = rel.abs().sum()
-            graph.edge_class, graph.class_geom, graph.pos_ref = cls, geom, pos
+            graph.edge_class, graph.class_geom = cls, geom
+            graph.bind_positions(pos)
         attach_graph(ei, graph)
         if use_cache:
             _topology_cache.put(key, (pos, ei, graph))

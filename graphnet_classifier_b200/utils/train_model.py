@@ -8,7 +8,8 @@ Extensions that leave the single-process behaviour unchanged:
     CPU-only);
   * ``grad_sync`` - a callable run between ``backward()`` and ``step()``; the
     data-parallel launcher passes ``GradBucket.all_reduce`` (utils/distributed.py);
-  * only rank 0 writes files when ``torch.distributed`` is initialised;
+  * only rank 0 writes files when ``torch.distributed`` is initialised; the epoch loss that drives the best-model /
+    early-stopping decisions is averaged over all ranks, so every rank leaves the loop in the same epoch;
   * ``cuda_graph`` (default: on for CUDA models without ``grad_sync``) - the reference makes one optimizer step per
     graph, so a step is ~350 small launches; the whole step (forward, loss, backward, Adam) is captured once per
     sample shape as a CUDA graph and replayed with the item's tensors copied into its static inputs.  Same kernels
@@ -28,6 +29,19 @@ import torch.optim as optim
 def _is_rank0() -> bool:
     d = torch.distributed
     return not (d.is_available() and d.is_initialized()) or d.get_rank() == 0
+
+
+def _global_mean_loss(running: float, steps: int, device) -> float:
+    """Epoch loss over ALL ranks' shards.  Every rank must take the same best-model / early-stopping decision
+    (reference utils/train_model.py:57-69): a rank that left the loop on its own shard's loss would leave the others
+    blocked in the next gradient all-reduce."""
+    d = torch.distributed
+    if not (d.is_available() and d.is_initialized()) or d.get_world_size() == 1:
+        return running / max(1, steps)
+    on_gpu = d.get_backend() == "nccl"
+    t = torch.tensor([running, float(steps)], dtype=torch.float64, device=device if on_gpu else "cpu")
+    d.all_reduce(t)
+    return float(t[0]) / max(1.0, float(t[1]))
 
 
 class _GraphedStep:
@@ -53,7 +67,7 @@ class _GraphedStep:
     @staticmethod
     def _topology_bound(parts):
         topos = [getattr(p, "_gnc_graph", None) for p in parts if not p.is_floating_point()]
-        return tuple((not p.is_floating_point()) or any(t is not None and t.pos_ref is p for t in topos) for p in parts)
+        return tuple((not p.is_floating_point()) or any(t is not None and t.classes_valid_for(p) for t in topos) for p in parts)
 
     @staticmethod
     def layout(sample, label):
@@ -182,7 +196,7 @@ def train(model, dataset, epochs, patience=5, output_path="weights", start_weigh
                 optimizer.step()
             running += loss.item()
             steps += 1
-        avg_loss = running / max(1, steps)
+        avg_loss = _global_mean_loss(running, steps, params[0].device if params else "cpu")
         t1 = time.time()
         if rank0:
             print(f"Epoch {epoch+1}/{epochs}, avg_loss={avg_loss:.4f}")

@@ -347,6 +347,18 @@ int gnc_tc_wgrad_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx,
                      float* dW, int64_t lddw, int accumulate, float* db,
                      float* work, int64_t work_elems, gnc_stream_t stream);
 
+/* Fused backward of one width-128 Linear layer (models/MLP.py:24-27 under autograd), both gradients from ONE read
+ * of dZ and X:  dX[M,128] = dZ * W  (* (X > 0) when mask_by_x: ReLU backward of the layer that produced X;
+ * + addend, e.g. the gradient arriving through a residual; addend may be NULL),  dW[128,128] (+)= dZ^T * X,
+ * db[128] (+)= column sums of dZ (dW / db may be NULL).  W is [128 out, 128 in] with row pitch ldw, as torch stores it.
+ * fp16 two-piece operands with a per-32-row-block power-of-two scale (csrc/tc_bwd.cu); deterministic.
+ * work: float [gnc_tc_bwd_layer_workspace()]. */
+int64_t gnc_tc_bwd_layer_workspace(void);
+int gnc_tc_bwd_layer_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M,
+                         const float* W, int64_t ldw, int mask_by_x, const float* addend, int64_t ld_addend,
+                         float* dX, int64_t lddx, float* dW, int64_t lddw, float* db, int accumulate,
+                         float* work, int64_t work_elems, gnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,20 +139,19 @@ def test_model_tc_engine_vs_oracle_and_fp32_engine(libgnc, monkeypatch, r, diag,
     assert _maxrel(y_tc, y_or) < RTOL          # node-level decoder outputs, not only the 2 logits
 
 
-@pytest.mark.parametrize("engine", ["tc", "tc-opwise", "fp32"])
-@pytest.mark.parametrize("r,diag,B", [(8, True, 2), (16, False, 3)])
-def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B):
-    """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine ("tc": the
-    hand-scheduled core backward of tc_train.py, "tc-opwise": one autograd.Function per layer)."""
-    from graphnet_classifier_b200 import ops
+def _gradient_parity(monkeypatch, engine, r, diag, B, fixture_seed=11):
+    """Loss and every parameter gradient of a batched step against the oracle (float32 and float64).  Returns
+    (worst per-tensor rel-L2, number of tensors that needed the relaxed bar, worst noise of the oracle itself)."""
+    from graphnet_classifier_b200 import ops, tc_train
     from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
     from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
     monkeypatch.setattr(ops, "TRAIN_PATH", "opwise" if engine == "tc-opwise" else "core")
+    monkeypatch.setattr(tc_train, "BWD", "pair" if engine == "tc-pair" else "fused")
     engine = engine.split("-")[0]
     monkeypatch.setattr(ops, "ENGINE", engine)
     cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
     om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=r * r, classes=2)
-    fill_deterministic(om, seed=11)
+    fill_deterministic(om, seed=fixture_seed)
     gm = CombinedModel(GraphNet(**cfg), num_nodes=r * r, classes=2)
     gm.load_state_dict(om.state_dict())
     gm = gm.cuda()
@@ -161,7 +160,7 @@ def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B
     gb = build_pixel_graphs(torch.from_numpy(imgs), diagonals=diag)
     logits = gm(gb.as_tuple())
     assert gm.graph_net._tc_eligible() == (engine == "tc")
-    loss = torch.nn.functional.cross_entropy(logits, labels.cuda())
+    loss = torch.nn.functional.cross_entropy(logits.reshape(B, -1), labels.cuda())
     loss.backward()
     lo = sum(torch.nn.functional.cross_entropy(om(ogb.to_model_inputs(*ogb.pixel_graph(im, diag))), l) for im, l in
              zip(imgs, labels)) / B
@@ -179,13 +178,36 @@ def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B
         om64(tuple(t.double() if t.is_floating_point() else t for t in ogb.to_model_inputs(*ogb.pixel_graph(im, diag)))), l)
         for im, l in zip(imgs, labels)) / B
     l64.backward()
-    worst = 0.0
+    worst, relaxed, worst_noise = 0.0, 0, 0.0
     for (name, p), (_, po), (_, p64) in zip(gm.named_parameters(), om.named_parameters(), om64.named_parameters()):
         noise = _rel(po.grad, p64.grad)
         rel = min(_rel(p.grad, po.grad), _rel(p.grad, p64.grad))
-        worst = max(worst, rel)
+        worst, worst_noise = max(worst, rel), max(worst_noise, noise)
+        relaxed += int(rel >= RTOL)
         assert rel < max(RTOL, 3 * noise), (engine, name, rel, noise)
-    print(f"engine={engine} r={r}: worst per-tensor gradient rel-L2 error {worst:.2e}")
+    # the record shows how often the relaxed bar (3 x the oracle's own fp32-vs-fp64 difference) was needed
+    print(f"GRADIENT-PARITY engine={engine} r={r} B={B} diag={diag}: worst per-tensor rel-L2 {worst:.2e}, "
+          f"{relaxed} of 76 tensors above {RTOL:g} (accepted under the relaxed bar), oracle fp32-vs-fp64 worst {worst_noise:.2e}")
+    return worst, relaxed, worst_noise
+
+
+@pytest.mark.parametrize("engine", ["tc", "tc-pair", "tc-opwise", "fp32"])
+@pytest.mark.parametrize("r,diag,B", [(8, True, 2), (16, False, 3)])
+def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B):
+    """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine ("tc": the
+    hand-scheduled core backward of tc_train.py on the fused backward-layer kernel, "tc-pair": the same schedule on the
+    round-1 kernel pair, "tc-opwise": one autograd.Function per layer)."""
+    _gradient_parity(monkeypatch, engine, r, diag, B)
+
+
+@pytest.mark.parametrize("engine", ["tc", "fp32"])
+@pytest.mark.parametrize("r,B", [(32, 2), (64, 4), (128, 1)])
+def test_training_gradients_at_baseline_shapes(libgnc, monkeypatch, engine, r, B):
+    """gradient parity at the BASELINE shapes - configs[0] (resize 64, 4 graphs of the batch) and one
+    resize-128 graph - where the tile tails and the per-block scaling of the backward kernels see real row counts
+    (16 384 nodes / 32 512 edges per graph).  No tensor may need the relaxed bar here."""
+    worst, relaxed, _ = _gradient_parity(monkeypatch, engine, r, False, B)
+    assert relaxed == 0 and worst < RTOL, (worst, relaxed)
 
 
 @pytest.mark.parametrize("M", [1, 31, 32, 100, 4096, 32 * 148 * 2 + 5, 200000])
