@@ -109,6 +109,9 @@ SIGNATURES = {
     "gnc_tc_wgrad_workspace": (c_int64, [c_int64]),
     "gnc_tc_wgrad_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int, _P, _P, c_int64,
                                  _P]),
+    "gnc_dot_tail_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, _P]),
+    "gnc_dot_tail_bwd_workspace": (c_int64, [c_int64, c_int]),
+    "gnc_dot_tail_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, _P, c_int, _P, c_int64, _P]),
     "gnc_tc_bwd_layer_workspace": (c_int64, []),
     "gnc_tc_bwd_layer_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64, _P, c_int64,
                                      _P, c_int64, _P, c_int, _P, c_int64, _P]),

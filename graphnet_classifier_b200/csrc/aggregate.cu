@@ -173,9 +173,9 @@ __global__ void edge_geometry_kernel(const float* __restrict__ pos, int P, const
 // graphs): the product with the weights is taken once per table row, and the layer becomes this
 // streaming gather-add (see GraphNet._forward_tc).
 struct GatherAddArgs {
-  const float* tab[3];
-  const int32_t* idx[3];
-  long long ld[3];
+  const float* tab[4];
+  const int32_t* idx[4];
+  long long ld[4];
   int nsrc;
   const float* bias;
   int relu;
@@ -196,14 +196,15 @@ __global__ void __launch_bounds__(256) gather_add_rows_kernel(const GatherAddArg
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = b;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
+      for (int s = 0; s < 4; ++s) {
         if (s < a.nsrc) {
           float4 t[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const long long m = m0 + u < a.M ? m0 + u : a.M - 1;
             const long long r = a.idx[s] ? (long long)__ldg(a.idx[s] + m) : m;
-            t[u] = __ldg(reinterpret_cast<const float4*>(a.tab[s] + r * a.ld[s]) + c4);
+            t[u] = a.idx[s] ? __ldg(reinterpret_cast<const float4*>(a.tab[s] + r * a.ld[s]) + c4)
+                            : ldg_stream(reinterpret_cast<const float4*>(a.tab[s] + r * a.ld[s]) + c4);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) { v[u].x += t[u].x; v[u].y += t[u].y; v[u].z += t[u].z; v[u].w += t[u].w; }
@@ -309,11 +310,11 @@ int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, in
 int gnc_gather_add_rows_f32(const float* const* tables, const int32_t* const* idx, const int64_t* ld, int nsrc,
                             const float* bias, int relu, int64_t M, int D, float* out, int64_t ld_out,
                             gnc_stream_t stream) {
-  GNC_REQUIRE(nsrc >= 1 && nsrc <= 3 && tables && idx && ld && out && M >= 0 && D > 0 && D % 4 == 0 && ld_out >= D,
-              "gather_add_rows: need 1..3 sources, D % 4 == 0");
+  GNC_REQUIRE(nsrc >= 1 && nsrc <= 4 && tables && idx && ld && out && M >= 0 && D > 0 && D % 4 == 0 && ld_out >= D,
+              "gather_add_rows: need 1..4 sources, D % 4 == 0");
   if (M == 0) return GNC_OK;
   GatherAddArgs a;
-  for (int s = 0; s < 3; ++s) {
+  for (int s = 0; s < 4; ++s) {
     a.tab[s] = s < nsrc ? tables[s] : nullptr;
     a.idx[s] = s < nsrc ? idx[s] : nullptr;
     a.ld[s] = s < nsrc ? ld[s] : 0;

@@ -524,6 +524,96 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, long lo
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// ---- Linear(D, 1) tail (the decoder's last layer, models/GNN.py:289-295 with out_channels = 1) ----------------------
+// A [M, D] x [D, 1] product is a row dot product: as a GEMM it fills one column of a 128-wide tile.  Forward: one warp
+// per row, 128-bit loads.  Backward (one pass over X): dX[m, :] = dy[m] * w (* (X[m, :] > 0) when X is a ReLU output
+// and dX is wanted as its pre-activation gradient), dw = sum_m dy[m] X[m, :], db = sum_m dy[m].
+template <int VPL>
+__global__ void __launch_bounds__(256) dot_tail_fwd_kernel(const float* __restrict__ X, long long ldx, long long M, int D4,
+                                                           const float* __restrict__ w, const float* __restrict__ b,
+                                                           float* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wv[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int c4 = lane + 32 * q;
+    wv[q] = c4 < D4 ? __ldg(reinterpret_cast<const float4*>(w) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float bias = b ? __ldg(b) : 0.f;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < M; r += (long long)gridDim.x * 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int c4 = lane + 32 * q;
+      if (c4 < D4) {
+        const float4 x = ldg_stream(reinterpret_cast<const float4*>(X + r * ldx) + c4);
+        s = fmaf(x.x, wv[q].x, s); s = fmaf(x.y, wv[q].y, s); s = fmaf(x.z, wv[q].z, s); s = fmaf(x.w, wv[q].w, s);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[r] = s + bias;
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) dot_tail_bwd_kernel(const float* __restrict__ X, long long ldx, long long M, int D4,
+                                                           const float* __restrict__ w, const float* __restrict__ dy,
+                                                           int relu_mask, float* __restrict__ dX, long long lddx,
+                                                           float* __restrict__ partial) {
+  __shared__ float4 red[8][32 * VPL];
+  __shared__ float redb[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rows_per_block = ceil_div<long long>(M, gridDim.x);
+  const long long rbeg = (long long)blockIdx.x * rows_per_block;
+  long long rend = rbeg + rows_per_block;
+  if (rend > M) rend = M;
+  float4 wv[VPL], s[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int c4 = lane + 32 * q;
+    wv[q] = c4 < D4 ? __ldg(reinterpret_cast<const float4*>(w) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float sb = 0.f;
+  for (long long r = rbeg + warp; r < rend; r += 8) {
+    const float g = __ldg(dy + r);
+    sb += g;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int c4 = lane + 32 * q;
+      if (c4 < D4) {
+        const float4 x = ldg_stream(reinterpret_cast<const float4*>(X + r * ldx) + c4);
+        s[q].x = fmaf(g, x.x, s[q].x); s[q].y = fmaf(g, x.y, s[q].y); s[q].z = fmaf(g, x.z, s[q].z); s[q].w = fmaf(g, x.w, s[q].w);
+        if (dX) {
+          float4 d = make_float4(g * wv[q].x, g * wv[q].y, g * wv[q].z, g * wv[q].w);
+          if (relu_mask) {
+            d.x = x.x > 0.f ? d.x : 0.f; d.y = x.y > 0.f ? d.y : 0.f; d.z = x.z > 0.f ? d.z : 0.f; d.w = x.w > 0.f ? d.w : 0.f;
+          }
+          stg_stream(reinterpret_cast<float4*>(dX + r * lddx) + c4, d);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) red[warp][lane + 32 * q] = s[q];
+  if (lane == 0) redb[warp] = sb;
+  __syncthreads();
+  const int D = D4 * 4;
+  for (int c4 = threadIdx.x; c4 < D4; c4 += blockDim.x) {
+    float4 t = red[0][c4];
+#pragma unroll
+    for (int wi = 1; wi < 8; ++wi) { t.x += red[wi][c4].x; t.y += red[wi][c4].y; t.z += red[wi][c4].z; t.w += red[wi][c4].w; }
+    reinterpret_cast<float4*>(partial + (long long)blockIdx.x * D)[c4] = t;
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) t += redb[wi];
+    partial[(long long)gridDim.x * D + blockIdx.x] = t;
+  }
+}
+
 // ---- LayerNorm ------------------------------------------------------------------
 // RPW rows per warp and iteration: all of their loads (z and the residual) are issued before the first reduction, so a
 // warp keeps RPW x 1 KB in flight instead of 512 B (one row per iteration left the kernel latency-bound at ~60 % of HBM).
@@ -901,6 +991,50 @@ int gnc_linear_wgrad_f32(const float* dZ, int64_t lddz, int64_t M, int N, const 
   wgrad_reduce_kernel<<<(unsigned)ceil_div<long long>(NK, 256), 256, 0, st>>>(work, splits, NK, (int)K, dW, lddw,
                                                                              accumulate);
   return check_launch("wgrad_reduce_kernel");
+}
+
+int gnc_dot_tail_fwd_f32(const float* X, int64_t ldx, int64_t M, int D, const float* w, const float* b, float* y,
+                         gnc_stream_t stream) {
+  GNC_REQUIRE(X && w && y && M >= 0 && D > 0 && D % 4 == 0 && D <= 512 && ldx >= D && ldx % 4 == 0 && aligned16(X) && aligned16(w),
+              "dot_tail_fwd: D % 4 == 0, D <= 512, 16-byte aligned rows");
+  if (M == 0) return GNC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blocks = ceil_div<long long>(M, 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  const int D4 = D / 4;
+  if (D4 <= 32) dot_tail_fwd_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, b, y);
+  else if (D4 <= 64) dot_tail_fwd_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, b, y);
+  else dot_tail_fwd_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, b, y);
+  return check_launch("dot_tail_fwd_kernel");
+}
+
+int64_t gnc_dot_tail_bwd_workspace(int64_t M, int D) { return col_blocks(M) * (int64_t)(D + 1); }
+
+int gnc_dot_tail_bwd_f32(const float* X, int64_t ldx, int64_t M, int D, const float* w, const float* dy, int relu_mask,
+                         float* dX, int64_t lddx, float* dw, float* db, int accumulate, float* work, int64_t work_elems,
+                         gnc_stream_t stream) {
+  GNC_REQUIRE(X && w && dy && M >= 0 && D > 0 && D % 4 == 0 && D <= 512 && ldx >= D && ldx % 4 == 0 && aligned16(X) && aligned16(w),
+              "dot_tail_bwd: D % 4 == 0, D <= 512, 16-byte aligned rows");
+  GNC_REQUIRE(!dX || (lddx >= D && lddx % 4 == 0 && aligned16(dX)), "dot_tail_bwd: dX rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long blocks = col_blocks(M);
+  if (!work || work_elems < blocks * (long long)(D + 1)) return fail(GNC_EWORKSPACE, "%s", "dot_tail_bwd: workspace too small");
+  const int D4 = D / 4;
+  if (D4 <= 32) dot_tail_bwd_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, dy, relu_mask, dX, lddx, work);
+  else if (D4 <= 64) dot_tail_bwd_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, dy, relu_mask, dX, lddx, work);
+  else dot_tail_bwd_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, M, D4, w, dy, relu_mask, dX, lddx, work);
+  int rc = check_launch("dot_tail_bwd_kernel");
+  if (rc) return rc;
+  if (dw) {
+    partial_reduce_kernel<<<(unsigned)ceil_div<int>(D, 256), 256, 0, st>>>(work, blocks, D, dw, accumulate);
+    if ((rc = check_launch("partial_reduce_kernel"))) return rc;
+  }
+  if (db) {
+    // the per-block scalars are a [blocks][1] stack: same fixed-order reduction with N = 1
+    partial_reduce_kernel<<<1, 32, 0, st>>>(work + blocks * (long long)D, blocks, 1, db, accumulate);
+    if ((rc = check_launch("partial_reduce_kernel"))) return rc;
+  }
+  return GNC_OK;
 }
 
 int64_t gnc_colsum_workspace(int64_t M, int N) { return col_blocks(M) * (int64_t)N; }

@@ -58,8 +58,8 @@ constexpr int kXStage = 2 * kXPiece;               // hi | lo
 constexpr int kMetaRing = 16;                      // per-block scales / flags / ReLU bitmaps, consumed up to ~8 blocks later
 constexpr int kConvWarps = 8, kConvThreads = kConvWarps * 32;
 constexpr int kThreads = 640;
-constexpr int kRegsMma = 40, kRegsEpi = 72, kRegsDrain = 176;    // converters keep the launch budget (96)
-static_assert(kConvWarps * 96 + 4 * kRegsMma + 4 * kRegsEpi + 4 * kRegsDrain <= (kThreads / 32) * 96,
+constexpr int kRegsConv = 88, kRegsMma = 40, kRegsEpi = 88, kRegsDrain = 176;    // launch budget: 96
+static_assert(kConvWarps * kRegsConv + 4 * kRegsMma + 4 * kRegsEpi + 4 * kRegsDrain <= (kThreads / 32) * 96,
               "setmaxnreg budget exceeds the CTA's register pool");
 constexpr int kGroupMax = 4;                       // blocks accumulated in the tensor core before a drain
 
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
 
   if (warp < kConvWarps) {
     // ======================= converters =======================
+    reg_dec<kRegsConv>();
     const int w = warp;
     float cs[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};   // Kahan column sums of dZ (columns 4 lane .. + 3)
     float* s_max = reinterpret_cast<float*>(sm + kOffMax);
@@ -508,7 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
         if (ADDEND) {
           // the epilogue reads this block's addend rows ~3 blocks from now with 4-byte loads per thread: have them
           // in L2 by then (a shared-memory ring for them does not fit next to the operand stages)
-          if (p.ld_addend == kD) {
+          if (p.dbg & 64) {
+          } else if (p.ld_addend == kD && !(p.dbg & 32)) {
             if (lane == 0) bulk_prefetch_l2(p.addend + row0 * kD, (uint32_t)nvalid * 512u);
           } else if (lane < nvalid) {
             bulk_prefetch_l2(p.addend + (row0 + lane) * p.ld_addend, 512u);
@@ -524,6 +526,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int bw = lane & 3, bb = 8 * q + (lane >> 2);           // bitmap word / bit of column k
     const long long npairs = (nblk + 1) >> 1;
+    float ad[32];
+    if (ADDEND) {                                                // the first block's addend rows
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const long long row = block_row0(0) + j;
+        ad[j] = (nblk > 0 && row < p.M) ? __ldg(p.addend + row * p.ld_addend + k) : 0.f;
+      }
+    }
 #pragma unroll 1
     for (long long pi = 0; pi < npairs; ++pi) {
       const int da = (int)(pi & 1);
@@ -533,36 +543,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
       mbar_wait(dacc_full(da), (uint32_t)((pi >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + kTmemDacc + (uint32_t)da * 64 + lane_off;
-      const int nch = 4 * nb;
-      float ad[8];                                               // addend values of the chunk being processed
-      auto load_addend = [&](int ch, float* dst) {
-        const long long r0 = block_row0(2 * pi + (ch >> 2)) + (ch & 3) * 8;
+      // Addend rows are read with 4-byte loads per thread (a warp covers 128 contiguous bytes of a row): latency-bound
+      // unless many are in flight.  A rotating window of 32 registers holds the values of the next four 8-row chunks;
+      // a chunk's slot is refilled with the chunk four steps ahead right after it has been consumed.
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = (r0 + j < p.M) ? __ldg(p.addend + (r0 + j) * p.ld_addend + k) : 0.f;
-      };
-      if (ADDEND) load_addend(0, ad);
-#pragma unroll 1
-      for (int ch = 0; ch < nch; ++ch) {                         // 8 rows per step
+      for (int ch = 0; ch < 8; ++ch) {                           // 8 rows per step; rows of an absent block are >= M
         float r[8];
         tmem_ld8(taddr + ch * 8, r);
         const long long it = 2 * pi + (ch >> 2);
         const int ring = (int)(it & (kMetaRing - 1));
         const long long row0 = block_row0(it) + (ch & 3) * 8;
-        float ad_next[8];
-        if (ADDEND && ch + 1 < nch) load_addend(ch + 1, ad_next);   // one chunk ahead (L2 hits: the producer prefetched)
         const float us = reinterpret_cast<const float4*>(sm + kOffMeta)[ring].x;
         const uint32_t* bits = reinterpret_cast<const uint32_t*>(sm + kOffBits + ring * kRows * 16) + (ch & 3) * 32 + bw;
         tmem_ld_wait();
+        if (ch < 4 * nb) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = r[j] * us;
-          if (MASK) v = ((bits[j * 4] >> bb) & 1u) ? v : 0.f;
-          if (ADDEND) v += ad[j];
-          if (row0 + j < p.M && !(p.dbg & 8)) p.dX[(row0 + j) * p.lddx + k] = v;
+          for (int j = 0; j < 8; ++j) {
+            float v = r[j] * us;
+            if (MASK) v = ((bits[j * 4] >> bb) & 1u) ? v : 0.f;
+            if (ADDEND) v += ad[(ch & 3) * 8 + j];
+            if (row0 + j < p.M && !(p.dbg & 8)) p.dX[(row0 + j) * p.lddx + k] = v;
+          }
         }
         if (ADDEND) {
+          const long long nit = ch < 4 ? 2 * pi + 1 : 2 * pi + 2;          // block of the chunk four steps ahead
+          const long long nr0 = block_row0(nit) + (ch & 3) * 8;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ad[j] = ad_next[j];
+          for (int j = 0; j < 8; ++j)
+            ad[(ch & 3) * 8 + j] = (nr0 + j < p.M) ? __ldg(p.addend + (nr0 + j) * p.ld_addend + k) : 0.f;
         }
       }
       tc_fence_before();

@@ -254,9 +254,9 @@ class GraphNet(nn.Module):
                                 dot_w=dec[4].weight, dot_b=dec[4].bias)
 
     def _forward_tc_train(self, x, pos, graph: GraphIndex):
-        """Differentiable form of ``_forward_tc``.  The K = 3 first layers of the encoders and the decoder's
-        ``Linear(128, 1)`` are autograd operators of their own (thin streaming kernels that mask their own
-        ReLU); everything between them is one ``autograd.Function`` with a hand-scheduled backward
+        """Differentiable form of ``_forward_tc``.  The K = 3 first layers of the encoders are autograd operators of
+        their own (thin streaming kernels that mask their own ReLU); everything behind them, down to the decoder's
+        ``Linear(128, 1)`` row dot product, is one ``autograd.Function`` with a hand-scheduled backward
         (``tc_train.GraphNetCoreFn``: gradient sums folded into GEMM epilogues, no elementwise passes)."""
         if ops.TRAIN_PATH != "core":
             return self._forward_tc_train_opwise(x, pos, graph)
@@ -272,11 +272,9 @@ class GraphNet(nn.Module):
             if graph.class_sum_plan is None:
                 graph.class_sum_plan = tc_train.class_sum_plan(graph.edge_class, e_tab.shape[0])
             e0 = tc_train.ExpandClassRowsFn.apply(e_tab, graph.edge_class, graph.class_sum_plan)
-            d2 = tc_train.graphnet_core(self, graph, a1n, e0, edge_ready=True)
-        else:
-            a1e = ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True)
-            d2 = tc_train.graphnet_core(self, graph, a1n, a1e)
-        return ops.linear([d2], dec[4].weight, dec[4].bias, relu=False)
+            return tc_train.graphnet_core(self, graph, a1n, e0, edge_ready=True)
+        a1e = ops.linear([ops.edge_geometry(pos, graph)], ee[0].weight, ee[0].bias, relu=True)
+        return tc_train.graphnet_core(self, graph, a1n, a1e)
 
     def _forward_tc_train_opwise(self, x, pos, graph: GraphIndex):
         """Op-by-op autograd form (every layer its own ``autograd.Function``): the implementation the

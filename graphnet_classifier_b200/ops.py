@@ -463,8 +463,8 @@ def gather_rows(x: Tensor, idx: Tensor, rowptr: Tensor, eid: Tensor) -> Tensor:
 
 def gather_add_rows(tables: Sequence[Tensor], idxs: Sequence[Optional[Tensor]], bias: Optional[Tensor] = None,
                     relu: bool = False) -> Tensor:
-    """``act(sum_s tables[s][idxs[s]] + bias)`` - up to three row-gathered tables summed in one
-    streaming pass (no autograd; inference path)."""
+    """``act(sum_s tables[s][idxs[s]] + bias)`` - up to four tables (row-gathered, or taken row by row when their
+    index is None) summed in one streaming pass (no autograd)."""
     _require_cuda(*tables)
     tabs = [_rows(t) for t in tables]
     M = int(next(i.shape[0] for i in idxs if i is not None)) if any(i is not None for i in idxs) else tabs[0].shape[0]
@@ -945,3 +945,46 @@ def tc_bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend
                 _p(dW), dW.stride(0) if dW is not None else 0, _p(db), int(bool(accumulate)), ws.data_ptr(), ws_n,
                 _stream()), "tc_bwd_layer")
     return dX, dW, db
+
+
+def dot_tail_fwd(X: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    """``X @ w.T + b`` for a one-row weight ``w [1, D]`` (the decoder's ``Linear(128, 1)``) as a row dot product: ``[M, 1]``."""
+    _require_cuda(X, w)
+    X = _rows(X)
+    M, D = X.shape
+    wv = w.reshape(-1)
+    if wv.numel() != D or wv.dtype != torch.float32 or (b is not None and b.numel() != 1):
+        raise RuntimeError(f"dot_tail: weight {tuple(w.shape)} does not match input width {D}")
+    if wv.stride(0) != 1:
+        wv = wv.contiguous()
+    y = torch.empty(M, 1, dtype=torch.float32, device=X.device)
+    check(_call("dot_tail_fwd", 2.0 * M * D, 4.0 * M * (D + 1), _lib.load().gnc_dot_tail_fwd_f32, X.data_ptr(), _ld(X), M, D,
+                wv.data_ptr(), _p(b), y.data_ptr(), _stream()), "dot_tail_fwd")
+    return y
+
+
+def dot_tail_bwd(X: Tensor, w: Tensor, dy: Tensor, relu_mask: bool = False, want_dX: bool = True):
+    """Backward of ``dot_tail_fwd`` in one pass over ``X``: ``(dX, dw [1, D], db [1])`` with ``dX = dy * w``
+    (``* (X > 0)`` with ``relu_mask``: then it is the pre-activation gradient of the ReLU that produced ``X``)."""
+    _require_cuda(X, w, dy)
+    X = _rows(X)
+    M, D = X.shape
+    wv = w.reshape(-1)
+    if wv.stride(0) != 1:
+        wv = wv.contiguous()
+    g = dy.reshape(-1)
+    if g.dtype != torch.float32 or g.stride(0) != 1:
+        g = g.float().contiguous()
+    if g.numel() != M or wv.numel() != D:
+        raise RuntimeError("dot_tail_bwd: shapes do not match")
+    lib = _lib.load()
+    dev = X.device
+    dX = torch.empty(M, D, dtype=torch.float32, device=dev) if want_dX else None
+    dw = torch.empty(1, D, dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    ws_n = int(lib.gnc_dot_tail_bwd_workspace(M, D))
+    ws = _workspace(dev, ws_n)
+    check(_call("dot_tail_bwd", 4.0 * M * D, 4.0 * M * D * (2 if want_dX else 1), lib.gnc_dot_tail_bwd_f32, X.data_ptr(),
+                _ld(X), M, D, wv.data_ptr(), g.data_ptr(), int(bool(relu_mask)), _p(dX), _ld(dX) if dX is not None else 0,
+                dw.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), ws_n, _stream()), "dot_tail_bwd")
+    return dX, dw, db

@@ -37,6 +37,15 @@ _f32 = torch.float32
 # (csrc/tc_bwd.cu); "pair" = the round-1 schedule (tc_linear data gradient + tc_wgrad), kept as the implementation
 # the fused kernel is tested against.
 BWD = os.environ.get("GNC_BWD", "fused")
+# Test hook (tests/test_gpu_tc_engine.py): when set to a dict, the forward records the sign pattern ``activation > 0``
+# of every ReLU of the core under the reference's module path, e.g. ``("graph_processor.blocks.0.edge_model.
+# edge_processor", 1)`` for ``model[1]`` - what a mask-conditioned gradient comparison against the oracle needs.
+CAPTURE: Optional[dict] = None
+
+
+def _capture(path: str, index: int, act: Tensor) -> None:
+    if CAPTURE is not None:
+        CAPTURE[(path, index)] = (act > 0)
 
 
 def _bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend: Optional[Tensor] = None,
@@ -144,7 +153,7 @@ class MlpTailFn(torch.autograd.Function):
 def core_param_list(gn) -> List[Tensor]:
     """Parameters the core consumes, in the order ``GraphNetCoreFn`` returns their gradients:
     per MLP tail ``W2 b2 W4 b4 gamma beta``; blocks add their first layers ``W0 b0`` / ``V0 c0`` in front;
-    the decoder contributes ``W0 b0 W2 b2``."""
+    the decoder contributes ``W0 b0 W2 b2 W4 b4`` (``W4`` is its ``[1, 128]`` output layer)."""
     ps: List[Tensor] = []
 
     def tail(m):
@@ -157,14 +166,15 @@ def core_param_list(gn) -> List[Tensor]:
         ps += [em[0].weight, em[0].bias] + tail(em)
         ps += [nm[0].weight, nm[0].bias] + tail(nm)
     dec = gn.node_decoder.model
-    ps += [dec[0].weight, dec[0].bias, dec[2].weight, dec[2].bias]
+    ps += [dec[0].weight, dec[0].bias, dec[2].weight, dec[2].bias, dec[4].weight, dec[4].bias]
     return ps
 
 
 class GraphNetCoreFn(torch.autograd.Function):
-    """``(a1n [N,128], a1e [E,128]) -> d2 [N,128]``: ``a1n`` / ``a1e`` are the ReLU outputs of the encoders'
-    first layers, ``d2`` the decoder's second hidden activation.  ``eps`` = (node enc, edge enc,
-    [edge proc, node proc] per block) LayerNorm epsilons."""
+    """``(a1n [N,128], a1e [E,128]) -> y [N,1]``: ``a1n`` / ``a1e`` are the ReLU outputs of the encoders'
+    first layers, ``y`` the decoder's output (its ``Linear(128, 1)`` is a row dot product whose backward also applies
+    the ReLU mask of the layer below and yields that layer's pre-activation gradient in one pass).  ``eps`` = (node
+    enc, edge enc, [edge proc, node proc] per block) LayerNorm epsilons."""
 
     @staticmethod
     def forward(ctx, graph, eps, n_blocks, edge_ready, a1n, a1e, *params):
@@ -172,17 +182,19 @@ class GraphNetCoreFn(torch.autograd.Function):
         a1n, a1e = ops._rows(a1n), ops._rows(a1e)
         saved = []          # per MLP tail: (a1, a2, z3, mean, rstd)
 
-        def tail(a1, p0, residual, eps_l):
+        def tail(a1, p0, residual, eps_l, path):
             y, sv = _tail_fwd(a1, params[p0:p0 + 6], eps_l, residual)
             saved.append(sv)
+            _capture(path, 1, sv[0])
+            _capture(path, 3, sv[1])
             return y
 
-        h = tail(a1n, 0, None, eps[0])
+        h = tail(a1n, 0, None, eps[0], "node_encoder")
         if edge_ready:      # ``a1e`` already is the encoded edge latent (class-table form, see GraphNet._forward_tc_train)
             e = a1e
             saved.append(None)
         else:
-            e = tail(a1e, 6, None, eps[1])
+            e = tail(a1e, 6, None, eps[1], "edge_encoder")
         blocks = []
         for k in range(n_blocks):
             pe = 12 + 16 * k
@@ -194,29 +206,29 @@ class GraphNetCoreFn(torch.autograd.Function):
             a1 = tcl(e, W0[:, 256:384], bias=b0, relu=True, gather0=(P, graph.src), gather1=(Q, graph.dst))
             del P, Q
             e_in = e
-            e = tail(a1, pe + 2, e_in, eps[2 + 2 * k])
+            e = tail(a1, pe + 2, e_in, eps[2 + 2 * k], f"graph_processor.blocks.{k}.edge_model.edge_processor")
             agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
             n1 = tcl(agg, V0[:, 128:256], bias=c0, relu=True, addend=T)
             del T
             h_in = h
-            h = tail(n1, pn + 2, h_in, eps[3 + 2 * k])
+            h = tail(n1, pn + 2, h_in, eps[3 + 2 * k], f"graph_processor.blocks.{k}.node_model.node_processor")
             blocks.append((h_in, e_in, agg))
-        Wd0, bd0, Wd2, bd2 = params[12 + 16 * n_blocks:12 + 16 * n_blocks + 4]
+        Wd0, bd0, Wd2, bd2, Wd4, bd4 = params[12 + 16 * n_blocks:12 + 16 * n_blocks + 6]
         d1 = tcl(h, Wd0, bias=bd0, relu=True)
         d2 = tcl(d1, Wd2, bias=bd2, relu=True)
+        y = ops.dot_tail_fwd(d2, Wd4, bd4)
+        _capture("node_decoder", 1, d1)
+        _capture("node_decoder", 3, d2)
         ctx.graph, ctx.n_blocks, ctx.edge_ready = graph, n_blocks, edge_ready
-        ctx.saved, ctx.blocks, ctx.dec = saved, blocks, (h, d1)
+        ctx.saved, ctx.blocks, ctx.dec = saved, blocks, (h, d1, d2)
         ctx.params = params
-        ctx.save_for_backward(d2)
-        return d2
+        return y
 
     @staticmethod
-    def backward(ctx, dd2):
+    def backward(ctx, dy):
         graph, n_blocks, params = ctx.graph, ctx.n_blocks, ctx.params
-        (d2,) = ctx.saved_tensors
         saved, blocks = ctx.saved, ctx.blocks
-        dd2 = ops._rows(dd2)
-        dev = dd2.device
+        dev = dy.device
         n_tail = 6
         grads: List[Optional[Tensor]] = [None] * len(params)
 
@@ -233,18 +245,27 @@ class GraphNetCoreFn(torch.autograd.Function):
         p_dec = 2 * n_tail + n_blocks * 2 * (2 + n_tail)
 
         # ---- decoder ----
-        h_last, d1 = ctx.dec
-        Wd0, _, Wd2, _ = params[p_dec:p_dec + 4]
-        dz2, dbd2 = _relu_bwd(dd2, d2)
-        dz1, dWd2, _ = _bwd_layer(dz2, d1, Wd2, mask=True)
+        h_last, d1, d2 = ctx.dec
+        Wd0, _, Wd2, _, Wd4, _ = params[p_dec:p_dec + 6]
+        # Linear(128, 1) backward + the ReLU mask of d2 in one pass: dz2 = (dy * w4) * (d2 > 0), dW4 = dy^T d2, db4 = sum dy
+        dz2, dWd4, dbd4 = ops.dot_tail_bwd(d2, Wd4, dy, relu_mask=True)
+        del d2
+        dz1, dWd2, dbd2 = _bwd_layer(dz2, d1, Wd2, mask=True, want_db=True)
         del dz2, d1
         dh, dWd0, dbd0 = _bwd_layer(dz1, h_last, Wd0, want_db=True)
         del dz1, h_last
-        grads[p_dec:p_dec + 4] = [dWd0, dbd0, dWd2, dbd2]
+        grads[p_dec:p_dec + 6] = [dWd0, dbd0, dWd2, dbd2, dWd4.reshape(Wd4.shape), dbd4.reshape(params[p_dec + 5].shape)]
         ctx.dec = None
 
         # ---- blocks, last to first ----
-        de = None                                   # gradient with respect to the block's output e'
+        # Gradient sums.  The round-1 kernels add an incoming gradient in the data-gradient epilogue (``addend``).  The
+        # fused kernel's epilogue owns one input feature per thread (32 rows each), so an addend would be read with
+        # 4-byte loads queued behind the operand stream; there the partial products are written as they are and summed
+        # by ONE streaming pass (gather_add_rows: up to four row sources) - the same number of row reads as an addend for
+        # the edge latents (whose sum also takes the aggregation's gathered rows), two more [N, 128] rows for the nodes.
+        in_kernel = BWD != "fused"
+        de = None                                   # gradient with respect to the block's output e' (complete)
+        de_part = None                              # its part that arrived through the NEXT block's edge MLP input
         for k in range(n_blocks - 1, -1, -1):
             h_in, e_in, agg = blocks[k]
             blocks[k] = None
@@ -257,27 +278,47 @@ class GraphNetCoreFn(torch.autograd.Function):
             dV0 = torch.empty(128, 256, dtype=_f32, device=dev)
             dagg, _, dc0 = _bwd_layer(dn1, agg, V0[:, 128:256], dW_out=dV0[:, 128:256], want_db=True)
             del agg
-            dh, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], addend=dh, dW_out=dV0[:, 0:128])   # + the residual's gradient
+            if in_kernel:
+                dh, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], addend=dh, dW_out=dV0[:, 0:128])   # + the residual's gradient
+            else:
+                t1, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], dW_out=dV0[:, 0:128])
             grads[pn], grads[pn + 1] = dV0, dc0
             del dn1
             # aggregation backward: every edge receives its destination's row, on top of what later blocks sent
             if de is None:
                 de = ops._gather_raw(dagg, graph.dst)
-            else:
+            elif in_kernel:
                 ops._gather_raw(dagg, graph.dst, out=de, accumulate=True)
+            else:
+                de = ops.gather_add_rows([de_part, de, dagg], [None, None, graph.dst])
+                de_part = None
             del dagg
             # edge processor: e' = LN(MLP(cat[h[row], h[col], e])) + e
             da1, _ = tail_bwd(de, 2 + 2 * k, pe + 2, True)
             dW0 = torch.empty(128, 384, dtype=_f32, device=dev)
             dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
             dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
-            de, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], addend=de, dW_out=dW0[:, 256:384], want_db=True)   # + residual
+            if in_kernel:
+                de, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], addend=de, dW_out=dW0[:, 256:384], want_db=True)   # + residual
+            else:
+                de_part, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], dW_out=dW0[:, 256:384], want_db=True)
             del da1, e_in
-            dh, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], addend=dh, dW_out=dW0[:, 0:128])
-            del dP
-            dh, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], addend=dh, dW_out=dW0[:, 128:256])
-            del dQ, h_in
+            if in_kernel:
+                dh, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], addend=dh, dW_out=dW0[:, 0:128])
+                del dP
+                dh, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], addend=dh, dW_out=dW0[:, 128:256])
+                del dQ, h_in
+            else:
+                t2, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], dW_out=dW0[:, 0:128])
+                del dP
+                t3, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], dW_out=dW0[:, 128:256])
+                del dQ, h_in
+                dh = ops.gather_add_rows([t1, t2, t3, dh], [None, None, None, None])
+                del t1, t2, t3
             grads[pe], grads[pe + 1] = dW0, db0
+        if de_part is not None:                     # gradient of the encoded edge latent: through block 0's MLP + its residual
+            de = ops.gather_add_rows([de_part, de], [None, None])
+            de_part = None
         # ---- encoder tails: the thin first layers mask their own ReLU ----
         if ctx.edge_ready:
             da1e = de                               # gradient of the encoded edge latent itself

@@ -170,7 +170,7 @@ int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid,
 int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D,
                         float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);
 
-/* out[m, :] = act( sum_s tables[s][idx[s][m], :] + bias ), 1 <= nsrc <= 3 (idx[s] NULL = identity).
+/* out[m, :] = act( sum_s tables[s][idx[s][m], :] + bias ), 1 <= nsrc <= 4 (idx[s] NULL = identity).
  * tables / idx / ld are HOST arrays of device pointers / strides.  D % 4 == 0. */
 int gnc_gather_add_rows_f32(const float* const* tables /*HOST*/, const int32_t* const* idx /*HOST*/,
                             const int64_t* ld /*HOST*/, int nsrc, const float* bias, int relu,
@@ -357,6 +357,17 @@ int64_t gnc_tc_bwd_layer_workspace(void);
 int gnc_tc_bwd_layer_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M,
                          const float* W, int64_t ldw, int mask_by_x, const float* addend, int64_t ld_addend,
                          float* dX, int64_t lddx, float* dW, int64_t lddw, float* db, int accumulate,
+                         float* work, int64_t work_elems, gnc_stream_t stream);
+
+/* Linear(D, 1) as a row dot product (the decoder's last layer, models/GNN.py:289-295):  y[m] = X[m, :] . w + b.
+ * Backward in one pass over X:  dX[m, :] = dy[m] * w  (* (X[m, :] > 0) with relu_mask: X is a ReLU output and dX its
+ * pre-activation gradient; dX may be NULL),  dw[D] (+)= sum_m dy[m] X[m, :],  db[1] (+)= sum_m dy[m].
+ * D % 4 == 0, D <= 512.  work: float [gnc_dot_tail_bwd_workspace(M, D)]; fixed-order reductions (deterministic). */
+int gnc_dot_tail_fwd_f32(const float* X, int64_t ldx, int64_t M, int D, const float* w, const float* b /*may be NULL*/,
+                         float* y, gnc_stream_t stream);
+int64_t gnc_dot_tail_bwd_workspace(int64_t M, int D);
+int gnc_dot_tail_bwd_f32(const float* X, int64_t ldx, int64_t M, int D, const float* w, const float* dy, int relu_mask,
+                         float* dX, int64_t lddx, float* dw, float* db, int accumulate,
                          float* work, int64_t work_elems, gnc_stream_t stream);
 
 #ifdef __cplusplus

@@ -37,12 +37,11 @@ def _mlp_stack(in_dim, out_dim, hidden_dim, hidden_layers, activation, norm_type
     5 norm - which is where the checkpoint keys ``model.{0,2,4,5}`` come from.
     """
     act = getattr(nn, activation)()
-    seq = []
-    d = in_dim
-    for _ in range(hidden_layers):
-        seq += [nn.Linear(d, hidden_dim), act]
-        d = hidden_dim
-    seq.append(nn.Linear(d, out_dim))
+    # the first Linear + activation exist for every hidden_layers, 0 included (models/MLP.py:24-25)
+    seq = [nn.Linear(in_dim, hidden_dim), act]
+    for _ in range(hidden_layers - 1):
+        seq += [nn.Linear(hidden_dim, hidden_dim), act]
+    seq.append(nn.Linear(hidden_dim, out_dim))
     if norm_type is not None:
         assert norm_type in ("LayerNorm", "BatchNorm1d")
         seq.append(getattr(nn, norm_type)(out_dim))

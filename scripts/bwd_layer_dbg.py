@@ -14,13 +14,15 @@ dZ = torch.randn(M, 128, device=dev, generator=g) * 1e-4
 X = torch.relu(torch.randn(M, 128, device=dev, generator=g))
 W = torch.randn(128, 128, device=dev, generator=g) / 11
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-masks = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 8, 16, 7, 15, 31]
+addend_mode = "addend" in sys.argv
+ad = torch.randn(M, 128, device=dev, generator=g) * 1e-4 if addend_mode else None
+masks = [int(a) for a in sys.argv[1:] if a != "addend"] or [0, 1, 2, 3, 4, 8, 16, 7, 15, 31]
 for mask in masks:
     os.environ["GNC_BWD_DBG"] = str(mask)
     ts = []
     for rep in range(5):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); ops.tc_bwd_layer(dZ, X, W, mask=True, want_db=True); e.record(); torch.cuda.synchronize()
+        s.record(); ops.tc_bwd_layer(dZ, X, W, mask=not addend_mode, addend=ad, want_db=True); e.record(); torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
     print(f"dbg mask {mask:2d}: {sorted(ts)[2]:.3f} ms")

@@ -94,3 +94,23 @@ def test_bwd_layer_accumulate_and_equals_separate_kernels():
     # deterministic
     dX2, dW2, _ = ops.tc_bwd_layer(dZ, X, W, mask=True)
     assert torch.equal(dX, dX2) and torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("M,D", [(1, 128), (77, 128), (100003, 128), (5000, 64), (3000, 512)])
+def test_dot_tail_forward_backward(M, D):
+    """Linear(D, 1) as a row dot product (the decoder's last layer, reference models/GNN.py:289-295) and its one-pass
+    backward with the ReLU mask of the layer below, against float64."""
+    from graphnet_classifier_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    X = torch.relu(torch.randn(M, D, generator=g, device="cuda"))
+    w = torch.randn(1, D, generator=g, device="cuda") / 7
+    b = torch.randn(1, generator=g, device="cuda")
+    dy = torch.randn(M, 1, generator=g, device="cuda") * 1e-3
+    y = ops.dot_tail_fwd(X, w, b)
+    assert y.shape == (M, 1) and _rel(y, X.double() @ w.double().t() + b.double()) < 1e-6
+    dX, dw, db = ops.dot_tail_bwd(X, w, dy, relu_mask=True)
+    ref = (dy.double() @ w.double()) * (X > 0)
+    assert _rel(dX, ref) < 1e-6 and bool((dX[X <= 0] == 0).all())
+    assert _rel(dw, dy.double().t() @ X.double()) < 2e-6 and _rel(db, dy.double().sum().reshape(1)) < 2e-6
+    dX2, _, _ = ops.dot_tail_bwd(X, w, dy, relu_mask=False)
+    assert _rel(dX2, dy.double() @ w.double()) < 1e-6

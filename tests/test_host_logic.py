@@ -119,24 +119,25 @@ def test_grad_bucket_views_and_rebind():
 
 def test_core_param_list_layout_and_graphed_step_layout():
     """Host logic of the training schedule: the parameter order the hand-scheduled backward indexes into
-    (tc_train.GraphNetCoreFn: 12 + 16 * n_blocks + 4 tensors) and the eligibility rule of the captured step."""
+    (tc_train.GraphNetCoreFn: 12 + 16 * n_blocks + 6 tensors) and the eligibility rule of the captured step."""
     from graphnet_classifier_b200 import tc_train
     from graphnet_classifier_b200.models.GNN import GraphNet
     from graphnet_classifier_b200.utils.train_model import _GraphedStep
     for nb in (1, 3):
         gn = GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=nb)
         ps = tc_train.core_param_list(gn)
-        assert len(ps) == 12 + 16 * nb + 4
+        assert len(ps) == 12 + 16 * nb + 6
         for k in range(nb):
             pe = 12 + 16 * k
             assert tuple(ps[pe].shape) == (128, 384) and ps[pe] is gn.graph_processor.blocks[k].edge_model.edge_processor.model[0].weight
             assert tuple(ps[pe + 8].shape) == (128, 256) and ps[pe + 8] is gn.graph_processor.blocks[k].node_model.node_processor.model[0].weight
             assert ps[pe + 6] is gn.graph_processor.blocks[k].edge_model.edge_processor.model[5].weight      # LayerNorm gamma
-        assert ps[-4] is gn.node_decoder.model[0].weight and ps[-1] is gn.node_decoder.model[2].bias
+        assert ps[-6] is gn.node_decoder.model[0].weight and ps[-3] is gn.node_decoder.model[2].bias
+        assert ps[-2] is gn.node_decoder.model[4].weight and ps[-1] is gn.node_decoder.model[4].bias
         assert len({id(p) for p in ps}) == len(ps)
-        # everything except the encoders' first layers and the decoder's last one
+        # everything except the encoders' first layers (the decoder's Linear(128, 1) is part of the core)
         rest = {id(p) for p in gn.parameters()} - {id(p) for p in ps}
-        assert len(rest) == 6
+        assert len(rest) == 4
     # host tensors, or index tensors without an attached topology, never take the captured path
     x, pos, ei = torch.zeros(4, 3), torch.zeros(4, 2), torch.zeros(2, 3, dtype=torch.long)
     assert _GraphedStep.layout((x, pos, ei), torch.tensor(1)) is None
