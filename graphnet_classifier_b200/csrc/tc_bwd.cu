@@ -61,6 +61,7 @@ constexpr int kThreads = 640;
 constexpr int kRegsConv = 88, kRegsMma = 40, kRegsEpi = 88, kRegsDrain = 176;    // launch budget: 96
 static_assert(kConvWarps * kRegsConv + 4 * kRegsMma + 4 * kRegsEpi + 4 * kRegsDrain <= (kThreads / 32) * 96,
               "setmaxnreg budget exceeds the CTA's register pool");
+constexpr int kPrefetchAhead = 6;                  // L2 prefetch distance of the producer, in blocks
 constexpr int kGroupMax = 4;                       // blocks accumulated in the tensor core before a drain
 
 constexpr float kScaleW = 256.f;                   // weights x 2^8 (|w| < 255), as in csrc/tc_chain.cu
@@ -495,6 +496,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
         const long long row0 = block_row0(it);
         const int nvalid = (int)((p.M - row0) < kRows ? (p.M - row0) : kRows);
         const uint32_t dst = base + kOffRaw + (uint32_t)rs * kRawStage;
+        {
+          // the shared-memory ring holds 3 blocks; rows further ahead are pulled into L2 so that the bulk copies that
+          // fill the ring later hit there (distance in blocks: bits 8..15 of the debug word, default kPrefetchAhead)
+          const int ahead = (p.dbg >> 8) & 0xff ? ((p.dbg >> 8) & 0xff) - 1 : kPrefetchAhead;
+          const long long pit = it + ahead;
+          if (ahead > 0 && pit < nblk) {
+            const long long prow0 = block_row0(pit);
+            const int pvalid = (int)((p.M - prow0) < kRows ? (p.M - prow0) : kRows);
+            if (contiguous) {
+              if (lane == 0) bulk_prefetch_l2(p.dZ + prow0 * kD, (uint32_t)pvalid * 512u);
+              if (lane == 1) bulk_prefetch_l2(p.X + prow0 * kD, (uint32_t)pvalid * 512u);
+            } else if (lane < pvalid) {
+              bulk_prefetch_l2(p.dZ + (prow0 + lane) * p.lddz, 512u);
+              bulk_prefetch_l2(p.X + (prow0 + lane) * p.ldx, 512u);
+            }
+          }
+        }
         if (lane == 0) mbar_arrive_expect_tx(raw_full(rs), (uint32_t)nvalid * 1024u);
         __syncwarp();
         if (contiguous) {
@@ -543,6 +561,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bwd_layer_kernel(const Params 
       mbar_wait(dacc_full(da), (uint32_t)((pi >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + kTmemDacc + (uint32_t)da * 64 + lane_off;
+      if constexpr (!ADDEND) {
+        // The accumulator is copied to registers and handed back to the MMA thread at once: the 64 row stores of this
+        // thread then overlap the next pair's products instead of holding the buffer for their whole duration.
+        float r[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(taddr + c * 16, r + c * 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dacc_empty(da));
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (b < nb) {
+            const long long it = 2 * pi + b;
+            const int ring = (int)(it & (kMetaRing - 1));
+            const long long row0 = block_row0(it);
+            const float us = reinterpret_cast<const float4*>(sm + kOffMeta)[ring].x;
+            const uint32_t* bits = reinterpret_cast<const uint32_t*>(sm + kOffBits + ring * kRows * 16) + bw;
+            float* out = p.dX + row0 * p.lddx + k;
+            const bool full = row0 + kRows <= p.M;
+            if (!(p.dbg & 8)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float v = r[b * 32 + j] * us;
+                if (MASK) v = ((bits[j * 4] >> bb) & 1u) ? v : 0.f;
+                if (full || row0 + j < p.M) *out = v;
+                out += p.lddx;
+              }
+            }
+          }
+        }
+        continue;
+      }
       // Addend rows are read with 4-byte loads per thread (a warp covers 128 contiguous bytes of a row): latency-bound
       // unless many are in flight.  A rotating window of 32 registers holds the values of the next four 8-row chunks;
       // a chunk's slot is refilled with the chunk four steps ahead right after it has been consumed.

@@ -963,9 +963,11 @@ def dot_tail_fwd(X: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
     return y
 
 
-def dot_tail_bwd(X: Tensor, w: Tensor, dy: Tensor, relu_mask: bool = False, want_dX: bool = True):
+def dot_tail_bwd(X: Tensor, w: Tensor, dy: Tensor, relu_mask: bool = False, want_dX: bool = True,
+                 dw_out: Optional[Tensor] = None, db_out: Optional[Tensor] = None):
     """Backward of ``dot_tail_fwd`` in one pass over ``X``: ``(dX, dw [1, D], db [1])`` with ``dX = dy * w``
-    (``* (X > 0)`` with ``relu_mask``: then it is the pre-activation gradient of the ReLU that produced ``X``)."""
+    (``* (X > 0)`` with ``relu_mask``: then it is the pre-activation gradient of the ReLU that produced ``X``).
+    With ``dw_out`` / ``db_out`` (both or neither) the parameter gradients are ADDED to those tensors."""
     _require_cuda(X, w, dy)
     X = _rows(X)
     M, D = X.shape
@@ -980,11 +982,14 @@ def dot_tail_bwd(X: Tensor, w: Tensor, dy: Tensor, relu_mask: bool = False, want
     lib = _lib.load()
     dev = X.device
     dX = torch.empty(M, D, dtype=torch.float32, device=dev) if want_dX else None
-    dw = torch.empty(1, D, dtype=torch.float32, device=dev)
-    db = torch.empty(1, dtype=torch.float32, device=dev)
+    acc = dw_out is not None
+    if acc and (db_out is None or dw_out.numel() != D or not dw_out.is_contiguous() or db_out.numel() != 1):
+        raise ValueError("dot_tail_bwd: dw_out [1, D] and db_out [1] come together, contiguous")
+    dw = dw_out if acc else torch.empty(1, D, dtype=torch.float32, device=dev)
+    db = db_out if acc else torch.empty(1, dtype=torch.float32, device=dev)
     ws_n = int(lib.gnc_dot_tail_bwd_workspace(M, D))
     ws = _workspace(dev, ws_n)
     check(_call("dot_tail_bwd", 4.0 * M * D, 4.0 * M * D * (2 if want_dX else 1), lib.gnc_dot_tail_bwd_f32, X.data_ptr(),
                 _ld(X), M, D, wv.data_ptr(), g.data_ptr(), int(bool(relu_mask)), _p(dX), _ld(dX) if dX is not None else 0,
-                dw.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), ws_n, _stream()), "dot_tail_bwd")
+                dw.data_ptr(), db.data_ptr(), int(acc), ws.data_ptr(), ws_n, _stream()), "dot_tail_bwd")
     return dX, dw, db

@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-from . import ops
+from . import ops, tc_train
 from .utils.image_to_graph.batched import build_patch_graphs, build_pixel_graphs
 
 
@@ -39,9 +39,10 @@ class GraphClassifierPipeline:
             raise RuntimeError("GraphClassifierPipeline needs the model on a CUDA device (no CPU fallback)")
         n = self.resize_value * self.resize_value if method == "pixel" else (self.resize_value // self.patch_size) ** 2
         # live fp32 activations: ~8 KB per node in inference (5 edge tensors + node tensors of
-        # width 128, E ~ 2N), ~40 KB per node kept for the backward over 3 blocks; budget 64 GB
+        # width 128, E ~ 2N); training peaks at ~24 KB per node (activations kept for the backward over 3 blocks plus
+        # the backward's transients: 63.6 GiB measured for 171 resize-128 graphs); budget 64 GiB of the 180 GB
         self.micro_batch = micro_batch or max(1, min(512, (64 << 30) // (n * 8192)))
-        self.train_micro_batch = train_micro_batch or max(1, min(256, (64 << 30) // (n * 40_000)))
+        self.train_micro_batch = train_micro_batch or max(1, min(256, (64 << 30) // (n * 24_000)))
         self._graphs = {}            # image batch shape -> (CUDAGraph, static input, static logits)
 
     # -- staging ----------------------------------------------------------------
@@ -135,14 +136,20 @@ class GraphClassifierPipeline:
         B = img.shape[0]
         total = torch.zeros((), dtype=torch.float32, device=self.device)
         mb = self._even_chunk(B, self.train_micro_batch)
-        for lo in range(0, B, mb):
-            gb = self._build(img[lo:lo + mb])
-            logits = self.model(gb.as_tuple())
-            if logits.dim() == 1:
-                logits = logits.reshape(1, -1)
-            loss = F.cross_entropy(logits, lab[lo:lo + mb], reduction="sum") / B
-            loss.backward()
-            total += loss.detach()
+        # gradients that already have storage (the flat bucket, or zero_grad(set_to_none=False)) are accumulated in place
+        # by the kernels that produce them (tc_train.ACCUMULATE)
+        prev, tc_train.ACCUMULATE = tc_train.ACCUMULATE, True
+        try:
+            for lo in range(0, B, mb):
+                gb = self._build(img[lo:lo + mb])
+                logits = self.model(gb.as_tuple())
+                if logits.dim() == 1:
+                    logits = logits.reshape(1, -1)
+                loss = F.cross_entropy(logits, lab[lo:lo + mb], reduction="sum") / B
+                loss.backward()
+                total += loss.detach()
+        finally:
+            tc_train.ACCUMULATE = prev
         return total
 
     def train_step(self, images, labels, optimizer, grad_bucket=None) -> Tensor:

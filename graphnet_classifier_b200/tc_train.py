@@ -41,6 +41,11 @@ BWD = os.environ.get("GNC_BWD", "fused")
 # of every ReLU of the core under the reference's module path, e.g. ``("graph_processor.blocks.0.edge_model.
 # edge_processor", 1)`` for ``model[1]`` - what a mask-conditioned gradient comparison against the oracle needs.
 CAPTURE: Optional[dict] = None
+# Set by GraphClassifierPipeline.forward_backward while it accumulates a step over micro-batches: the kernels that
+# produce a parameter gradient then ADD it into the parameter's existing ``.grad`` (a view of the flat gradient bucket)
+# and autograd receives None for it - no per-micro-batch ``grad += new`` passes (reference: ``loss.backward()`` on one
+# graph per step, utils/train_model.py:41; the accumulation over micro-batches is ours).
+ACCUMULATE = False
 
 
 def _capture(path: str, index: int, act: Tensor) -> None:
@@ -49,12 +54,15 @@ def _capture(path: str, index: int, act: Tensor) -> None:
 
 
 def _bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend: Optional[Tensor] = None,
-               dW_out: Optional[Tensor] = None, want_db: bool = False):
+               dW_out: Optional[Tensor] = None, want_db: bool = False, db_out: Optional[Tensor] = None,
+               accumulate: bool = False):
     """``(dX, dW, db)`` of ``y = x @ W.T + b`` given ``dZ = dL/dy`` and the layer input ``X``; ``mask``: ``dX *= (X > 0)``
     (``X`` is a ReLU output, ``dX`` its pre-activation gradient); ``addend`` is added to ``dX``; ``dW_out``: a
     ``[128, 128]`` column slice the weight gradient is written to."""
     if BWD == "fused":
-        return ops.tc_bwd_layer(dZ, X, W, mask=mask, addend=addend, dW_out=dW_out, want_db=want_db)
+        return ops.tc_bwd_layer(dZ, X, W, mask=mask, addend=addend, dW_out=dW_out, want_db=want_db, db_out=db_out,
+                                accumulate=accumulate)
+    assert not accumulate and db_out is None, "in-place accumulation is a feature of the fused backward kernel"
     r = ops.tc_wgrad(dZ, X, out=dW_out, want_db=want_db)
     dW, db = r if want_db else (r, None)
     dX = ops.tc_linear(dZ, W, transpose_w=True, mask=X if mask else None, addend=addend)
@@ -73,18 +81,21 @@ def _ln_fwd(z: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optional[Te
     return y, mean, rstd
 
 
-def _ln_bwd(dy: Tensor, z: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor):
+def _ln_bwd(dy: Tensor, z: Tensor, mean: Tensor, rstd: Tensor, gamma: Tensor, dg_out: Optional[Tensor] = None,
+            db_out: Optional[Tensor] = None):
+    """LayerNorm backward; with ``dg_out`` / ``db_out`` the affine gradients are ADDED to those tensors."""
     lib = _lib.load()
     M, D = z.shape
     dev = z.device
     dz = torch.empty(M, D, dtype=_f32, device=dev)
-    dg = torch.empty(D, dtype=_f32, device=dev)
-    db = torch.empty(D, dtype=_f32, device=dev)
+    acc = dg_out is not None
+    dg = dg_out if acc else torch.empty(D, dtype=_f32, device=dev)
+    db = db_out if acc else torch.empty(D, dtype=_f32, device=dev)
     ws_n = int(lib.gnc_layernorm_bwd_workspace(M, D))
     ws = ops._workspace(dev, ws_n)
     check(ops._call("layernorm_bwd", 0.0, 4.0 * M * D * 3, lib.gnc_layernorm_bwd_f32, dy.data_ptr(), ops._ld(dy),
                     z.data_ptr(), ops._ld(z), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), M, D, dz.data_ptr(),
-                    ops._ld(dz), dg.data_ptr(), db.data_ptr(), 0, ws.data_ptr(), ws_n, ops._stream()), "layernorm_bwd")
+                    ops._ld(dz), dg.data_ptr(), db.data_ptr(), int(acc), ws.data_ptr(), ws_n, ops._stream()), "layernorm_bwd")
     return dz, dg, db
 
 
@@ -118,18 +129,34 @@ def _tail_fwd(a1: Tensor, tail_params, eps_l: float, residual: Optional[Tensor])
     return y, (a1, a2, z3, mean, rstd)
 
 
-def _tail_bwd(dy: Tensor, saved, tail_params, mask_a1: bool):
+def _grad_sinks(params) -> Optional[list]:
+    """``[p.grad for p in params]`` when the step accumulates in place (``ACCUMULATE``, fused backward, every gradient
+    already allocated as a contiguous fp32 tensor), else None: gradients are then returned to autograd."""
+    if not ACCUMULATE or BWD != "fused":
+        return None
+    out = []
+    for p in params:
+        g = getattr(p, "grad", None)
+        if g is None or g.dtype != _f32 or not g.is_contiguous() or not p.requires_grad:
+            return None
+        out.append(g)
+    return out
+
+
+def _tail_bwd(dy: Tensor, saved, tail_params, mask_a1: bool, sinks: Optional[list] = None):
     """Backward of ``_tail_fwd``: returns the gradient with respect to ``a1`` (times ``a1 > 0`` when ``mask_a1``: then
-    it is the first layer's pre-activation gradient) and ``[dW2, db2, dW4, db4, dgamma, dbeta]``.  The residual's
-    gradient is ``dy`` itself."""
+    it is the first layer's pre-activation gradient) and ``[dW2, db2, dW4, db4, dgamma, dbeta]`` (all None when the
+    gradients were added into ``sinks``, the parameters' ``.grad`` tensors).  The residual's gradient is ``dy`` itself."""
     a1, a2, z3, mean, rstd = saved
     W2, _, W4, _, g, _ = tail_params
-    dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g)
+    acc = sinks is not None
+    sk = sinks if acc else [None] * 6
+    dz3, dg, dbt = _ln_bwd(dy, z3, mean, rstd, g, sk[4], sk[5])
     del z3
-    dz2, dW4, db4 = _bwd_layer(dz3, a2, W4, mask=True, want_db=True)
+    dz2, dW4, db4 = _bwd_layer(dz3, a2, W4, mask=True, want_db=True, dW_out=sk[2], db_out=sk[3], accumulate=acc)
     del dz3, a2
-    da1, dW2, db2 = _bwd_layer(dz2, a1, W2, mask=mask_a1, want_db=True)
-    return da1, [dW2, db2, dW4, db4, dg, dbt]
+    da1, dW2, db2 = _bwd_layer(dz2, a1, W2, mask=mask_a1, want_db=True, dW_out=sk[0], db_out=sk[1], accumulate=acc)
+    return da1, ([None] * 6 if acc else [dW2, db2, dW4, db4, dg, dbt])
 
 
 class MlpTailFn(torch.autograd.Function):
@@ -144,7 +171,7 @@ class MlpTailFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        da1, grads = _tail_bwd(ops._rows(dy), ctx.saved, ctx.tail_params, False)
+        da1, grads = _tail_bwd(ops._rows(dy), ctx.saved, ctx.tail_params, False, _grad_sinks(ctx.tail_params))
         ctx.saved = None
         need = ctx.needs_input_grad
         return (None, da1 if need[1] else None, *[g if need[2 + i] else None for i, g in enumerate(grads)])
@@ -232,10 +259,18 @@ class GraphNetCoreFn(torch.autograd.Function):
         n_tail = 6
         grads: List[Optional[Tensor]] = [None] * len(params)
 
+        sinks = _grad_sinks(params)                 # the parameters' .grad tensors when accumulating in place
+        acc = sinks is not None
+
+        def sink(i, lo=None, hi=None):
+            if not acc:
+                return None
+            return sinks[i] if lo is None else sinks[i][:, lo:hi]
+
         def tail_bwd(dy, idx, p0, mask_a1):
             sv = saved[idx]
             saved[idx] = None
-            da1, g6 = _tail_bwd(dy, sv, params[p0:p0 + n_tail], mask_a1)
+            da1, g6 = _tail_bwd(dy, sv, params[p0:p0 + n_tail], mask_a1, sinks[p0:p0 + n_tail] if acc else None)
             grads[p0:p0 + n_tail] = g6
             return da1, sv[0]
 
@@ -248,13 +283,15 @@ class GraphNetCoreFn(torch.autograd.Function):
         h_last, d1, d2 = ctx.dec
         Wd0, _, Wd2, _, Wd4, _ = params[p_dec:p_dec + 6]
         # Linear(128, 1) backward + the ReLU mask of d2 in one pass: dz2 = (dy * w4) * (d2 > 0), dW4 = dy^T d2, db4 = sum dy
-        dz2, dWd4, dbd4 = ops.dot_tail_bwd(d2, Wd4, dy, relu_mask=True)
+        dz2, dWd4, dbd4 = ops.dot_tail_bwd(d2, Wd4, dy, relu_mask=True, dw_out=sink(p_dec + 4), db_out=sink(p_dec + 5))
         del d2
-        dz1, dWd2, dbd2 = _bwd_layer(dz2, d1, Wd2, mask=True, want_db=True)
+        dz1, dWd2, dbd2 = _bwd_layer(dz2, d1, Wd2, mask=True, want_db=True, dW_out=sink(p_dec + 2), db_out=sink(p_dec + 3),
+                                     accumulate=acc)
         del dz2, d1
-        dh, dWd0, dbd0 = _bwd_layer(dz1, h_last, Wd0, want_db=True)
+        dh, dWd0, dbd0 = _bwd_layer(dz1, h_last, Wd0, want_db=True, dW_out=sink(p_dec), db_out=sink(p_dec + 1), accumulate=acc)
         del dz1, h_last
-        grads[p_dec:p_dec + 6] = [dWd0, dbd0, dWd2, dbd2, dWd4.reshape(Wd4.shape), dbd4.reshape(params[p_dec + 5].shape)]
+        if not acc:
+            grads[p_dec:p_dec + 6] = [dWd0, dbd0, dWd2, dbd2, dWd4.reshape(Wd4.shape), dbd4.reshape(params[p_dec + 5].shape)]
         ctx.dec = None
 
         # ---- blocks, last to first ----
@@ -275,14 +312,16 @@ class GraphNetCoreFn(torch.autograd.Function):
             V0 = params[pn]
             # node processor: h' = LN(MLP(cat[h, agg])) + h
             dn1, _ = tail_bwd(dh, 2 + 2 * k + 1, pn + 2, True)
-            dV0 = torch.empty(128, 256, dtype=_f32, device=dev)
-            dagg, _, dc0 = _bwd_layer(dn1, agg, V0[:, 128:256], dW_out=dV0[:, 128:256], want_db=True)
+            dV0 = sinks[pn] if acc else torch.empty(128, 256, dtype=_f32, device=dev)
+            dagg, _, dc0 = _bwd_layer(dn1, agg, V0[:, 128:256], dW_out=dV0[:, 128:256], want_db=True, db_out=sink(pn + 1),
+                                      accumulate=acc)
             del agg
             if in_kernel:
                 dh, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], addend=dh, dW_out=dV0[:, 0:128])   # + the residual's gradient
             else:
-                t1, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], dW_out=dV0[:, 0:128])
-            grads[pn], grads[pn + 1] = dV0, dc0
+                t1, _, _ = _bwd_layer(dn1, h_in, V0[:, 0:128], dW_out=dV0[:, 0:128], accumulate=acc)
+            if not acc:
+                grads[pn], grads[pn + 1] = dV0, dc0
             del dn1
             # aggregation backward: every edge receives its destination's row, on top of what later blocks sent
             if de is None:
@@ -295,13 +334,14 @@ class GraphNetCoreFn(torch.autograd.Function):
             del dagg
             # edge processor: e' = LN(MLP(cat[h[row], h[col], e])) + e
             da1, _ = tail_bwd(de, 2 + 2 * k, pe + 2, True)
-            dW0 = torch.empty(128, 384, dtype=_f32, device=dev)
+            dW0 = sinks[pe] if acc else torch.empty(128, 384, dtype=_f32, device=dev)
             dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
             dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
             if in_kernel:
                 de, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], addend=de, dW_out=dW0[:, 256:384], want_db=True)   # + residual
             else:
-                de_part, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], dW_out=dW0[:, 256:384], want_db=True)
+                de_part, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], dW_out=dW0[:, 256:384], want_db=True,
+                                             db_out=sink(pe + 1), accumulate=acc)
             del da1, e_in
             if in_kernel:
                 dh, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], addend=dh, dW_out=dW0[:, 0:128])
@@ -309,13 +349,14 @@ class GraphNetCoreFn(torch.autograd.Function):
                 dh, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], addend=dh, dW_out=dW0[:, 128:256])
                 del dQ, h_in
             else:
-                t2, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], dW_out=dW0[:, 0:128])
+                t2, _, _ = _bwd_layer(dP, h_in, W0[:, 0:128], dW_out=dW0[:, 0:128], accumulate=acc)
                 del dP
-                t3, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], dW_out=dW0[:, 128:256])
+                t3, _, _ = _bwd_layer(dQ, h_in, W0[:, 128:256], dW_out=dW0[:, 128:256], accumulate=acc)
                 del dQ, h_in
                 dh = ops.gather_add_rows([t1, t2, t3, dh], [None, None, None, None])
                 del t1, t2, t3
-            grads[pe], grads[pe + 1] = dW0, db0
+            if not acc:
+                grads[pe], grads[pe + 1] = dW0, db0
         if de_part is not None:                     # gradient of the encoded edge latent: through block 0's MLP + its residual
             de = ops.gather_add_rows([de_part, de], [None, None])
             de_part = None

@@ -25,4 +25,4 @@ for mask in masks:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); ops.tc_bwd_layer(dZ, X, W, mask=not addend_mode, addend=ad, want_db=True); e.record(); torch.cuda.synchronize()
         ts.append(s.elapsed_time(e))
-    print(f"dbg mask {mask:2d}: {sorted(ts)[2]:.3f} ms")
+    print(f"dbg mask {mask & 255:2d} prefetch-ahead {(mask >> 8) - 1 if mask >> 8 else 'default'}: {sorted(ts)[2]:.3f} ms")

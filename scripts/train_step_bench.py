@@ -16,7 +16,7 @@ modes = sys.argv[2:] or ["fused", "pair"]
 r = 128
 torch.manual_seed(0)
 model = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=r * r, classes=2).cuda()
-pipe = GraphClassifierPipeline(model, resize_value=r)
+pipe = GraphClassifierPipeline(model, resize_value=r, train_micro_batch=int(os.environ.get("TRAIN_MB", "0")) or None)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 rng = np.random.default_rng(0)
 img = torch.from_numpy(rng.integers(0, 256, (B, r, r, 3), dtype=np.uint8)).cuda()
