@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnc.so")
 
@@ -112,6 +112,9 @@ SIGNATURES = {
     "gnc_dot_tail_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, _P]),
     "gnc_dot_tail_bwd_workspace": (c_int64, [c_int64, c_int]),
     "gnc_dot_tail_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, _P, c_int, _P, c_int64, _P]),
+    "gnc_cross_entropy_f32": (c_int, [_P, c_int64, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P]),
+    "gnc_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P]),
+    "gnc_zero_f32": (c_int, [_P, c_int64, _P]),
     "gnc_tc_bwd_layer_workspace": (c_int64, []),
     "gnc_tc_bwd_layer_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64, _P, c_int64,
                                      _P, c_int64, _P, c_int, _P, c_int64, _P]),

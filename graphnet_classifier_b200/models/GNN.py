@@ -319,7 +319,14 @@ class GraphNet(nn.Module):
         if x.is_cuda and self._tc_eligible():
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
                 return self._forward_tc_train(x, pos, graph)
-            return self._forward_tc(x, pos, graph)
+            y = self._forward_tc(x, pos, graph)
+            if ops.CHAIN_GUARD and not torch.cuda.is_current_stream_capturing() and not bool(torch.isfinite(y).all()):
+                # an activation left the fp16 two-piece domain of the chained kernels (|a| >= 4094): same function on
+                # the 3xTF32 per-layer engine, which has fp32's exponent range
+                ops.CHAIN_GUARD_EVENTS += 1
+                with torch.no_grad():
+                    y = self._forward_tc_train_opwise(x, pos, graph)
+            return y
         edge_attr = ops.edge_geometry(pos, graph)          # [pos[col]-pos[row], L1]  (reference :299-302)
         out = self.node_encoder(x)
         edge_attr = self.edge_encoder(edge_attr)

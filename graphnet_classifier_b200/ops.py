@@ -33,6 +33,29 @@ ENGINE = os.environ.get("GNC_ENGINE", "tc")
 # Training schedule of the tensor-core engine: "core" = one autograd.Function with a hand-scheduled
 # backward (tc_train.py), "opwise" = one autograd.Function per layer (what "core" is tested against).
 TRAIN_PATH = os.environ.get("GNC_TRAIN_PATH", "core")
+# The chained inference kernels split operands into two fp16 pieces after a FIXED power-of-two scaling: hidden activations
+# of magnitude >= 4094 leave their domain and come out as inf / NaN (csrc/tc_chain.cu).  With the guard on, an inference
+# forward whose node outputs are not all finite is evaluated again on the 3xTF32 per-layer engine (no such limit); the
+# check costs one reduction over [N, 1] and a device->host sync, and is skipped while a CUDA graph is being captured.
+# Set by GraphClassifierPipeline.forward_backward while it accumulates a step over micro-batches: the kernels that
+# produce a parameter gradient then ADD it into the parameter's existing ``.grad`` (a view of the flat gradient bucket)
+# and autograd receives None for it - no per-micro-batch ``grad += new`` passes (reference: ``loss.backward()`` on one
+# graph per step, utils/train_model.py:41; the accumulation over micro-batches is ours).
+ACCUMULATE_GRADS = False
+
+
+def grad_sink(p):
+    """``p.grad`` when gradients are accumulated in place and ``p`` has contiguous fp32 gradient storage, else None."""
+    if not ACCUMULATE_GRADS or p is None:
+        return None
+    g = getattr(p, "grad", None)
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or not p.requires_grad:
+        return None
+    return g
+
+
+CHAIN_GUARD = os.environ.get("GNC_CHAIN_GUARD", "1") != "0"
+CHAIN_GUARD_EVENTS = 0          # how many forwards took the fallback (tests, diagnostics)
 
 
 def _require_cuda(*ts: Tensor) -> None:
@@ -304,6 +327,7 @@ class _LinearFn(torch.autograd.Function):
         Y = _linear_fwd_raw(srcs, idxs, M, Wc, b, relu)
         ctx.relu, ctx.meta, ctx.M = bool(relu), meta, M
         ctx.has_bias = b is not None
+        ctx.W_param, ctx.b_param = W, b            # for in-place gradient accumulation (grad_sink)
         ctx.save_for_backward(Wc, Y if relu else None, *srcs)
         return Y
 
@@ -315,39 +339,45 @@ class _LinearFn(torch.autograd.Function):
         M, N, K = ctx.M, Wc.shape[0], Wc.shape[1]
         dY = _rows(dY)
         need_W, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and ctx.has_bias
+        # in-place accumulation into existing .grad storage (both or neither, so one flag serves the kernels)
+        gW, gb = grad_sink(ctx.W_param) if need_W else None, grad_sink(ctx.b_param) if need_b else None
+        acc = (gW is not None or not need_W) and (gb is not None or not need_b) and (need_W or need_b) \
+            and (gW is None or (gW.dim() == 2 and gW.shape == Wc.shape))
+        if not acc:
+            gW = gb = None
         if (_is_narrowk(srcs, [m[0] for m in ctx.meta], Wc) and N <= 128 and not ctx.needs_input_grad[4]
                 and dY.stride(0) % 4 == 0):
             # thin first layer: ReLU mask + bias gradient + weight gradient in one pass, no data gradient
-            dW = torch.empty(N, K, dtype=torch.float32, device=dev) if need_W else None
-            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+            dW = (gW if acc else torch.empty(N, K, dtype=torch.float32, device=dev)) if need_W else None
+            db = (gb if acc else torch.empty(N, dtype=torch.float32, device=dev)) if need_b else None
             ws_n = int(lib.gnc_linear_narrowk_wgrad_workspace(M, N, K))
             ws = _workspace(dev, ws_n)
             X = srcs[0]
             check(_call("linear_narrowk_wgrad", 2.0 * M * N * K, 4.0 * M * (N * (2 if ctx.relu else 1) + K),
                         lib.gnc_linear_narrowk_wgrad_f32, dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None,
-                        _ld(Y) if ctx.relu else 0, X.data_ptr(), _ld(X), M, N, K, _p(dW), K, _p(db), 0,
+                        _ld(Y) if ctx.relu else 0, X.data_ptr(), _ld(X), M, N, K, _p(dW), K, _p(db), int(acc),
                         ws.data_ptr(), ws_n, _stream()), "linear_narrowk_wgrad")
-            return (dW, db, None, None, None)
+            return (None, None, None, None, None) if acc else (dW, db, None, None, None)
         # bias + ReLU backward: dZ = dY * (Y > 0), db = column sums
         dZ, db = dY, None
         if ctx.relu or need_b:
             if ctx.relu:
                 dZ = torch.empty(M, N, dtype=torch.float32, device=dev)
-            db = torch.empty(N, dtype=torch.float32, device=dev) if need_b else None
+            db = (gb if acc else torch.empty(N, dtype=torch.float32, device=dev)) if need_b else None
             ws_n = int(lib.gnc_colsum_workspace(M, N))
             ws = _workspace(dev, ws_n)
             check(_call("relu_bwd_colsum", 0.0, 4.0 * M * N * (3 if ctx.relu else 1), lib.gnc_relu_bwd_colsum_f32,
                         dY.data_ptr(), _ld(dY), _p(Y) if ctx.relu else None, _ld(Y) if ctx.relu else 0, M, N,
-                        dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), 0, ws.data_ptr(), ws_n, _stream()),
+                        dZ.data_ptr() if ctx.relu else None, _ld(dZ), _p(db), int(acc), ws.data_ptr(), ws_n, _stream()),
                   "relu_bwd_colsum")
         dW = None
         if need_W:
-            dW = torch.empty(N, K, dtype=torch.float32, device=dev)
+            dW = gW if acc else torch.empty(N, K, dtype=torch.float32, device=dev)
             segs = _make_segs(srcs, [m[0] for m in ctx.meta])
             ws_n = int(lib.gnc_linear_wgrad_workspace(M, N, K))
             ws = _workspace(dev, ws_n)
             check(_call("linear_wgrad", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K), lib.gnc_linear_wgrad_f32,
-                        dZ.data_ptr(), _ld(dZ), M, N, segs, len(srcs), dW.data_ptr(), K, 0, ws.data_ptr(), ws_n,
+                        dZ.data_ptr(), _ld(dZ), M, N, segs, len(srcs), dW.data_ptr(), K, int(acc), ws.data_ptr(), ws_n,
                         _stream()), "linear_wgrad")
         dsrcs = []
         k0 = 0
@@ -368,6 +398,8 @@ class _LinearFn(torch.autograd.Function):
                     g = _agg_raw(csr[0], csr[1], dX, n_src)
             dsrcs.append(g)
             k0 += w
+        if acc:
+            dW = db = None
         return (dW, db, None, None, *dsrcs)
 
 
@@ -993,3 +1025,63 @@ def dot_tail_bwd(X: Tensor, w: Tensor, dy: Tensor, relu_mask: bool = False, want
                 _ld(X), M, D, wv.data_ptr(), g.data_ptr(), int(bool(relu_mask)), _p(dX), _ld(dX) if dX is not None else 0,
                 dw.data_ptr(), db.data_ptr(), int(acc), ws.data_ptr(), ws_n, _stream()), "dot_tail_bwd")
     return dX, dw, db
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    """``scale * sum_b CE(logits[b], labels[b])`` (reference: nn.CrossEntropyLoss, utils/train_model.py:10, 38) with its
+    gradient computed by the same launch."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, scale, total):
+        lg = _rows(logits)
+        B, C = lg.shape
+        lab = labels.reshape(-1)
+        if lab.dtype != torch.int64 or lab.device != lg.device or lab.numel() != B:
+            raise RuntimeError(f"cross_entropy: labels must be {B} int64 values on {lg.device}")
+        if not lab.is_contiguous():
+            lab = lab.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+        need = ctx.needs_input_grad[0]
+        dl = torch.empty(B, C, dtype=torch.float32, device=lg.device) if need else None
+        lib = _lib.load()
+        check(_call("cross_entropy", 0.0, 8.0 * B * C, lib.gnc_cross_entropy_f32, lg.data_ptr(), _ld(lg), lab.data_ptr(), B, C,
+                    float(scale), loss.data_ptr(), _p(total), _p(dl), C, None, _stream()), "cross_entropy")
+        ctx.dl, ctx.shape = dl, logits.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dl = ctx.dl
+        ctx.dl = None
+        # the upstream gradient of a loss is the scalar 1 in every use here; a different one scales the stored gradient
+        return dl.reshape(ctx.shape) * g if dl is not None else None, None, None, None
+
+
+def cross_entropy(logits: Tensor, labels: Tensor, scale: float = 1.0, total: Optional[Tensor] = None) -> Tensor:
+    """``scale * sum_b CE(logits[b], labels[b])`` for ``[B, C]`` logits (``[C]`` = one graph) and int64 labels; with
+    ``total`` (a 1-element fp32 device tensor) the value is also added to it."""
+    _require_cuda(logits, labels)
+    if logits.dim() == 1:
+        logits = logits.reshape(1, -1)
+    return _CrossEntropyFn.apply(logits, labels, float(scale), total)
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int, lr: float = 1e-3,
+              betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """In-place Adam update of flat fp32 buffers (torch.optim.Adam's rule; ``step`` is the 1-based step count)."""
+    _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+            raise RuntimeError("adam_step: flat contiguous fp32 buffers of equal length")
+    check(_call("adam_step", 0.0, 28.0 * n, _lib.load().gnc_adam_step_f32, param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                exp_avg_sq.data_ptr(), n, float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), float(grad_scale),
+                _stream()), "adam_step")
+
+
+def zero_(buf: Tensor) -> None:
+    """``buf[:] = 0`` for a contiguous fp32 device tensor (cudaMemsetAsync on the current stream)."""
+    _require_cuda(buf)
+    if buf.dtype != torch.float32 or not buf.is_contiguous():
+        raise RuntimeError("zero_: contiguous fp32 tensor")
+    check(_lib.load().gnc_zero_f32(buf.data_ptr(), buf.numel(), _stream()), "zero")

@@ -18,10 +18,9 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 from torch import Tensor
 
-from . import ops, tc_train
+from . import ops
 from .utils.image_to_graph.batched import build_patch_graphs, build_pixel_graphs
 
 
@@ -134,25 +133,27 @@ class GraphClassifierPipeline:
         lab = labels if isinstance(labels, Tensor) else torch.as_tensor(labels)
         lab = lab.to(self.device, non_blocking=True).long()
         B = img.shape[0]
-        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        total = torch.zeros(1, dtype=torch.float32, device=self.device)
         mb = self._even_chunk(B, self.train_micro_batch)
         # gradients that already have storage (the flat bucket, or zero_grad(set_to_none=False)) are accumulated in place
-        # by the kernels that produce them (tc_train.ACCUMULATE)
-        prev, tc_train.ACCUMULATE = tc_train.ACCUMULATE, True
+        # by the kernels that produce them (ops.ACCUMULATE_GRADS); loss, its gradient and the running total are one launch
+        prev, ops.ACCUMULATE_GRADS = ops.ACCUMULATE_GRADS, True
         try:
             for lo in range(0, B, mb):
                 gb = self._build(img[lo:lo + mb])
                 logits = self.model(gb.as_tuple())
-                if logits.dim() == 1:
-                    logits = logits.reshape(1, -1)
-                loss = F.cross_entropy(logits, lab[lo:lo + mb], reduction="sum") / B
+                loss = ops.cross_entropy(logits, lab[lo:lo + mb], scale=1.0 / B, total=total)
                 loss.backward()
-                total += loss.detach()
         finally:
-            tc_train.ACCUMULATE = prev
-        return total
+            ops.ACCUMULATE_GRADS = prev
+        return total.reshape(())
 
     def train_step(self, images, labels, optimizer, grad_bucket=None) -> Tensor:
+        """One optimizer step on this rank's graphs.  ``optimizer``: ``utils.distributed.FlatAdam`` (flat parameters and
+        gradients, one-launch update, doubles as the gradient bucket) or any torch optimizer, optionally with a
+        ``GradBucket`` for the data-parallel all-reduce."""
+        if grad_bucket is None and hasattr(optimizer, "all_reduce"):
+            grad_bucket = optimizer                       # FlatAdam
         if grad_bucket is not None:
             grad_bucket.zero()
         else:

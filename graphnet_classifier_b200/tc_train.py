@@ -41,11 +41,6 @@ BWD = os.environ.get("GNC_BWD", "fused")
 # of every ReLU of the core under the reference's module path, e.g. ``("graph_processor.blocks.0.edge_model.
 # edge_processor", 1)`` for ``model[1]`` - what a mask-conditioned gradient comparison against the oracle needs.
 CAPTURE: Optional[dict] = None
-# Set by GraphClassifierPipeline.forward_backward while it accumulates a step over micro-batches: the kernels that
-# produce a parameter gradient then ADD it into the parameter's existing ``.grad`` (a view of the flat gradient bucket)
-# and autograd receives None for it - no per-micro-batch ``grad += new`` passes (reference: ``loss.backward()`` on one
-# graph per step, utils/train_model.py:41; the accumulation over micro-batches is ours).
-ACCUMULATE = False
 
 
 def _capture(path: str, index: int, act: Tensor) -> None:
@@ -130,17 +125,12 @@ def _tail_fwd(a1: Tensor, tail_params, eps_l: float, residual: Optional[Tensor])
 
 
 def _grad_sinks(params) -> Optional[list]:
-    """``[p.grad for p in params]`` when the step accumulates in place (``ACCUMULATE``, fused backward, every gradient
+    """``[p.grad for p in params]`` when the step accumulates in place (``ops.ACCUMULATE_GRADS``, fused backward, every gradient
     already allocated as a contiguous fp32 tensor), else None: gradients are then returned to autograd."""
-    if not ACCUMULATE or BWD != "fused":
+    if not ops.ACCUMULATE_GRADS or BWD != "fused":
         return None
-    out = []
-    for p in params:
-        g = getattr(p, "grad", None)
-        if g is None or g.dtype != _f32 or not g.is_contiguous() or not p.requires_grad:
-            return None
-        out.append(g)
-    return out
+    out = [ops.grad_sink(p) for p in params]
+    return None if any(g is None for g in out) else out
 
 
 def _tail_bwd(dy: Tensor, saved, tail_params, mask_a1: bool, sinks: Optional[list] = None):

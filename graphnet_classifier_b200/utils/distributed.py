@@ -71,6 +71,86 @@ class GradBucket:
             self.flat.mul_(1.0 / dist.get_world_size())
 
 
+class FlatAdam:
+    """``torch.optim.Adam(params, lr)``'s update rule (no weight decay, no amsgrad: what the reference's ``train`` uses,
+    utils/train_model.py:9) over ONE flat buffer: the parameters and their gradients become views of two flat fp32
+    tensors (every slot 256-byte aligned, so the views keep the 16-byte alignment the kernels require) and a step is
+    one kernel launch (csrc/train_ops.cu) after at most one all-reduce.  Also serves as the gradient bucket of the
+    data-parallel step (``flat``, ``zero``, ``all_reduce``): the 1 / world_size of the average is folded into the
+    update's gradient read instead of a separate pass over the bucket."""
+
+    _ALIGN = 64          # elements
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        from .. import ops
+        self._ops = ops
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatAdam needs at least one trainable parameter")
+        dev = self.params[0].device
+        if dev.type != "cuda" or any(p.dtype != torch.float32 or p.device != dev for p in self.params):
+            raise ValueError("FlatAdam: float32 parameters on one CUDA device")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self._ALIGN) * self._ALIGN
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)          # gradients
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self._grad_scale = 1.0
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                slot = self.flat_p[o:o + p.numel()].view_as(p)
+                slot.copy_(p.data)
+                p.data = slot
+                p.grad = self.flat[o:o + p.numel()].view_as(p)
+
+    def rebind(self) -> None:
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+    def zero(self) -> None:
+        self._ops.zero_(self.flat)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.rebind()
+        self.zero()
+
+    def all_reduce(self, average: bool = True) -> None:
+        self._grad_scale = 1.0
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        self.rebind()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        if average:
+            self._grad_scale = 1.0 / dist.get_world_size()     # applied by the update's gradient read
+
+    def step(self) -> None:
+        self.rebind()
+        self.step_count += 1
+        self._ops.adam_step(self.flat_p, self.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
+                            self.eps, self._grad_scale)
+        self._grad_scale = 1.0
+
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
     """Make every rank start from rank ``src``'s weights."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

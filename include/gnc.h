@@ -370,6 +370,20 @@ int gnc_dot_tail_bwd_f32(const float* X, int64_t ldx, int64_t M, int D, const fl
                          float* dX, int64_t lddx, float* dw, float* db, int accumulate,
                          float* work, int64_t work_elems, gnc_stream_t stream);
 
+/* Loss and optimizer of the training step (reference utils/train_model.py:9-10, 38-42: nn.CrossEntropyLoss, Adam).
+ * cross_entropy: loss[0] = scale * sum_b CE(logits[b, :], labels[b]), the same value added to total[0] (either pointer
+ * may be NULL, not both) and, when dlogits is given,
+ * dlogits[b, c] = scale * (softmax(logits[b])[c] - [c == labels[b]]); labels are int64; *bad_label_flag (device int, may
+ * be NULL) is set to 1 when a label is outside [0, C).  One launch, fixed summation order.
+ * adam_step: torch.optim.Adam's update (no weight decay, no amsgrad) over flat fp32 buffers of n elements, step >= 1 the
+ * 1-based step count, gradients read as grad * grad_scale (the data-parallel average).  zero: cudaMemsetAsync. */
+int gnc_cross_entropy_f32(const float* logits, int64_t ld, const int64_t* labels, int B, int C, float scale,
+                          float* loss, float* total, float* dlogits, int64_t ldd, int* bad_label_flag,
+                          gnc_stream_t stream);
+int gnc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                      double beta1, double beta2, double eps, int64_t step, float grad_scale, gnc_stream_t stream);
+int gnc_zero_f32(float* buf, int64_t n, gnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,58 @@ def gen_mlp(ref):
     print("mlp.npz:", len(out), "entries")
 
 
+def gen_checkpoint(ref):
+    """The shipped checkpoint (weights/GNN/dim32_3block/best_model_epoch5.pth, resize 32) through the UNMODIFIED reference
+    on two shipped JPEGs: logits, the GraphNet node outputs and the largest hidden activation (386-427 with raw 0..255
+    pixels: the fp16 two-piece kernels' domain is 4094).  The 76 tensors travel with the fixture so that the GPU tests can
+    load them without /root/reference.  Second case: deterministic weights whose first node-encoder layer is scaled by
+    60 - hidden activations beyond that domain, where the product path must fall back to its 3xTF32 engine."""
+    out = {}
+    ck = torch.load(os.path.join(rl.REFERENCE_ROOT, "weights/GNN/dim32_3block/best_model_epoch5.pth"), map_location="cpu")
+    rm = _ref_model(ref, 32)
+    rm.load_state_dict(ck)
+    rm.eval()
+    out["keys"] = np.array(list(ck.keys()))
+    for i, (k, v) in enumerate(ck.items()):
+        out[f"w{i:02d}"] = v.numpy()
+    acts = []
+    hook = rm.graph_net.node_encoder.model[1].register_forward_hook(lambda m, a, o: acts.append(float(o.abs().max())))
+    for tag, rel in (("chihuahua", "static/chihuahua/img_4_799_32.jpg"), ("muffin", "static/muffin/img_4_880_32.jpg")):
+        path = os.path.join(rl.REFERENCE_ROOT, rel)
+        x, pos, ei = ref.optimized.image_to_graph_pixel_optimized(path, 32)
+        tx, tpos, tei = ogb.to_model_inputs(x, pos, ei)
+        with torch.no_grad():
+            out[f"{tag}_logits"] = rm((tx, tpos, tei)).numpy()
+            out[f"{tag}_nodes"] = rm.graph_net(tx, tpos, tei).numpy()
+        out[f"{tag}_pixels"] = x.reshape(32, 32, 3)
+    hook.remove()
+    out["max_hidden_activation"] = np.array(max(acts))
+    print("shipped checkpoint: largest node-encoder hidden activation", max(acts))
+    # activations outside the fp16 two-piece domain
+    r_ = 16
+    rm = _ref_model(ref, r_)
+    fill_deterministic(rm, seed=13)
+    with torch.no_grad():
+        rm.graph_net.node_encoder.model[0].weight.mul_(60.0)
+    acts = []
+    hook = rm.graph_net.node_encoder.model[1].register_forward_hook(lambda m, a, o: acts.append(float(o.abs().max())))
+    imgs = synthetic_images(2, r_, seed=5)
+    logits, nodes = [], []
+    for b in range(2):
+        x, pos, ei = ref.optimized.image_to_graph_pixel_optimized(Image.fromarray(imgs[b]), r_)
+        tx, tpos, tei = ogb.to_model_inputs(x, pos, ei)
+        with torch.no_grad():
+            logits.append(rm((tx, tpos, tei)).numpy())
+            nodes.append(rm.graph_net(tx, tpos, tei).numpy())
+    hook.remove()
+    _check(max(acts) > 4094, f"the large-activation case must leave the fp16 domain (max {max(acts)})")
+    out["big_imgs"], out["big_logits"], out["big_nodes"] = imgs, np.stack(logits), np.stack(nodes)
+    out["big_max_hidden_activation"] = np.array(max(acts))
+    out["big_scale"], out["big_seed"] = np.array(60.0), np.array(13)
+    np.savez_compressed(os.path.join(GOLDEN, "checkpoint.npz"), **out)
+    print("checkpoint.npz:", len(out), "entries; large-activation case max", max(acts))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rl.load_reference()
@@ -293,11 +345,15 @@ def main():
     if "--only-mlp" in sys.argv:
         gen_mlp(ref)
         return
+    if "--only-checkpoint" in sys.argv:
+        gen_checkpoint(ref)
+        return
     gen_grids(ref)
     gen_builders(ref)
     gen_model(ref)
     gen_resize(ref)
     gen_mlp(ref)
+    gen_checkpoint(ref)
     print("all reference-vs-oracle comparisons passed; golden vectors written to", GOLDEN)
 
 

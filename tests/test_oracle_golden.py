@@ -158,3 +158,32 @@ def test_resize_coefficient_tables_through_the_c_abi(libgnc):
         assert np.array_equal(b, ob) and np.array_equal(k, ok), (i, o)
     assert libgnc.gnc_resize_bicubic_ksize(0, 5) == 0
     assert libgnc.gnc_resize_bicubic_coeffs(5, 5, None, None) == 1
+
+
+def test_oracle_reproduces_reference_on_shipped_checkpoint():
+    """tests/golden/checkpoint.npz holds the shipped checkpoint's tensors and what the UNMODIFIED reference computes
+    with them on two shipped JPEGs (oracle/make_golden.py:gen_checkpoint); the oracle must reproduce both, and the
+    large-activation case (hidden activations beyond the fp16 two-piece domain of the chained kernels)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import gnn as ognn
+    from oracle.weights import fill_deterministic
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "checkpoint.npz"))
+    om = ognn.build_reference_config_model(32, seed=0)
+    om.load_state_dict({str(k): torch.from_numpy(g[f"w{i:02d}"]) for i, k in enumerate(g["keys"])}, strict=True)
+    om.eval()
+    from oracle import graph_build as ogb
+    for tag in ("chihuahua", "muffin"):
+        x, pos, ei = ogb.pixel_graph(g[f"{tag}_pixels"])
+        with torch.no_grad():
+            logits = om(ogb.to_model_inputs(x, pos, ei))
+        np.testing.assert_allclose(logits.numpy(), g[f"{tag}_logits"], rtol=2e-6, atol=1e-7)
+    cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
+    om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=256, classes=2)
+    fill_deterministic(om, seed=int(g["big_seed"]))
+    with torch.no_grad():
+        om.graph_net.node_encoder.model[0].weight.mul_(float(g["big_scale"]))
+        for b in range(2):
+            out = om(ogb.to_model_inputs(*ogb.pixel_graph(g["big_imgs"][b])))
+            np.testing.assert_allclose(out.numpy(), g["big_logits"][b], rtol=2e-6, atol=1e-7)
