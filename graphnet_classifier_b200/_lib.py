@@ -112,6 +112,10 @@ SIGNATURES = {
     "gnc_dot_tail_fwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, _P, _P]),
     "gnc_dot_tail_bwd_workspace": (c_int64, [c_int64, c_int]),
     "gnc_dot_tail_bwd_f32": (c_int, [_P, c_int64, c_int64, c_int, _P, _P, c_int, _P, c_int64, _P, _P, c_int, _P, c_int64, _P]),
+    "gnc_slic_connectivity_workspace": (c_int64, [c_int, c_int, c_int]),
+    "gnc_slic_enforce_connectivity": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
+    "gnc_segment_readout_f32": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "gnc_segment_readout_bwd_f32": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "gnc_cross_entropy_f32": (c_int, [_P, c_int64, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P]),
     "gnc_adam_step_f32": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_float, _P]),
     "gnc_zero_f32": (c_int, [_P, c_int64, _P]),

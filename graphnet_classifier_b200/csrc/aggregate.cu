@@ -221,6 +221,27 @@ __global__ void __launch_bounds__(256) gather_add_rows_kernel(const GatherAddArg
   }
 }
 
+// Readout of a batch of graphs with DIFFERENT node counts into the dense [B, num_nodes] input of the classifier head
+// (reference models/GNN.py:331, 339-340 flattens [N, 1] and needs N == num_nodes exactly; main.py:65-66 sizes the head
+// by resize_value // 2 for superpixel graphs whose node count varies).  Graph b contributes its first
+// min(n_b, num_nodes) node outputs; missing entries are zero.  Equal to the reference's flatten when n_b == num_nodes.
+__global__ void segment_readout_kernel(const float* __restrict__ y, const int32_t* __restrict__ node_ptr, int B, int num_nodes,
+                                       float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * num_nodes) return;
+  const int b = (int)(i / num_nodes), j = (int)(i - (long long)b * num_nodes);
+  const int lo = node_ptr[b], n = node_ptr[b + 1] - lo;
+  out[i] = j < n ? y[lo + j] : 0.f;
+}
+__global__ void segment_readout_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ node_ptr, int B,
+                                           int num_nodes, float* __restrict__ dy) {
+  // one thread per (graph, local node): nodes past num_nodes were truncated and receive zero
+  const int b = blockIdx.y;
+  const int lo = node_ptr[b], n = node_ptr[b + 1] - lo;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+    dy[lo + j] = j < num_nodes ? dout[(long long)b * num_nodes + j] : 0.f;
+}
+
 static inline unsigned row_grid(int64_t rows, int rows_per_block) {
   int64_t blocks = ceil_div<int64_t>(rows, rows_per_block);
   const int64_t cap = (int64_t)kNumSMs * 8;     // 8 resident 256-thread CTAs per SM
@@ -324,6 +345,22 @@ int gnc_gather_add_rows_f32(const float* const* tables, const int32_t* const* id
   a.nsrc = nsrc; a.bias = bias; a.relu = relu; a.out = out; a.ld_out = ld_out; a.M = M; a.D4 = D / 4;
   gather_add_rows_kernel<<<row_grid(M, 32), 256, 0, (cudaStream_t)stream>>>(a);
   return check_launch("gather_add_rows_kernel");
+}
+
+int gnc_segment_readout_f32(const float* y, const int32_t* node_ptr, int B, int num_nodes, float* out, gnc_stream_t stream) {
+  GNC_REQUIRE(y && node_ptr && out && B >= 0 && num_nodes >= 1, "segment_readout: bad arguments");
+  if (B == 0) return GNC_OK;
+  const long long total = (long long)B * num_nodes;
+  segment_readout_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, (cudaStream_t)stream>>>(y, node_ptr, B, num_nodes, out);
+  return check_launch("segment_readout_kernel");
+}
+
+int gnc_segment_readout_bwd_f32(const float* dout, const int32_t* node_ptr, int B, int num_nodes, float* dy, gnc_stream_t stream) {
+  GNC_REQUIRE(dout && node_ptr && dy && B >= 0 && num_nodes >= 1, "segment_readout_bwd: bad arguments");
+  if (B == 0) return GNC_OK;
+  GNC_REQUIRE(B <= 65535, "segment_readout_bwd: at most 65535 graphs per call");
+  segment_readout_bwd_kernel<<<dim3(4, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(dout, node_ptr, B, num_nodes, dy);
+  return check_launch("segment_readout_bwd_kernel");
 }
 
 int gnc_edge_geometry_f32(const float* pos, int P, const int32_t* src, const int32_t* dst, int64_t E, float* out,

@@ -1,0 +1,166 @@
+// Connectivity enforcement for SLIC label maps: the post-pass scikit-image applies by default
+// (slic(..., enforce_connectivity=True, min_size_factor=0.5), reference image_to_graph_superpixel.py:31 with library
+// defaults).  k-means assignment gives labels whose pixels need not be connected; the post-pass relabels 4-connected
+// components and dissolves the small ones into a neighbour, which is what makes a superpixel graph have one node per
+// REGION (without it the round-1 graphs had 928 edges per image where the survey's scikit-image-like maps have ~540).
+//
+// PARITY UNPINNED (scikit-image is neither vendored nor installed).  The rule implemented here, stated
+// step by step so that tests/test_gpu_slic.py can restate it on the CPU:
+//   1. components: maximal 4-connected sets of pixels with the same input label;
+//   2. components are ordered by their first pixel in row-major scan order (= their smallest pixel index);
+//   3. a component with fewer than min_size pixels is dissolved into the component that owns the pixel to the LEFT of
+//      its first pixel (the pixel ABOVE when the first pixel is in column 0; kept when it is pixel 0) - that pixel
+//      belongs to an earlier component, as the `adjacent` segment of scikit-image's scan-order pass does; the rule is
+//      applied transitively when that component is dissolved itself;
+//   4. the surviving components are numbered 0, 1, ... in the order of step 2.
+// Deviation from scikit-image's sequential pass: components larger than max_size (3 x the nominal superpixel) are not
+// split (its breadth-first search stops there), and `adjacent` is the left / upper neighbour of the first pixel rather
+// than the last labelled neighbour the search happened to meet.
+//
+// Parallel form: lock-free union-find over all pixels of the batch (roots = smallest pixel index of a component, by
+// always hooking the larger root under the smaller), warp-aggregated component sizes, pointer jumping for step 3, a
+// block scan per image for step 4.  Seven streaming passes over int32 maps.
+#include "common.cuh"
+
+namespace gnc {
+namespace cc {
+
+__device__ __forceinline__ int find_root(const int* __restrict__ parent, int x) {
+  int p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  return x;
+}
+__device__ __forceinline__ void unite(int* parent, int a, int b) {
+  while (true) {
+    a = find_root(parent, a);
+    b = find_root(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }             // a > b: hook a under b
+    const int old = atomicMin(parent + a, b);
+    if (old == a) return;
+    a = old;                                                   // somebody hooked a first: continue from there
+  }
+}
+
+__global__ void init_kernel(int* __restrict__ parent, int* __restrict__ size, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) { parent[g] = (int)g; size[g] = 0; }
+}
+__global__ void merge_kernel(const int32_t* __restrict__ labels, int* __restrict__ parent, int H, int W, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int hw = H * W;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+    const int p = (int)(g % hw), y = p / W, x = p - y * W;
+    const int l = labels[g];
+    if (x > 0 && labels[g - 1] == l) unite(parent, (int)g, (int)g - 1);
+    if (y > 0 && labels[g - W] == l) unite(parent, (int)g, (int)g - W);
+  }
+}
+// parent[g] = root; size[root] += 1 (one atomic per run of equal roots inside a warp)
+__global__ void flatten_count_kernel(int* __restrict__ parent, int* __restrict__ size, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += stride) {
+    const long long g = base + threadIdx.x;
+    const bool active = g < n;
+    int r = -1;
+    if (active) { r = find_root(parent, (int)g); parent[g] = r; }
+    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    if (active && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(size + r, __popc(peers));
+  }
+}
+// roots only: tgt[root] = root (kept) or the root of the left / upper neighbour of the root pixel (dissolved)
+__global__ void decide_kernel(const int* __restrict__ parent, const int* __restrict__ size, int* __restrict__ tgt, int H, int W,
+                              int min_size, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int hw = H * W;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+    if (parent[g] != (int)g) continue;
+    const int p = (int)(g % hw), y = p / W, x = p - y * W;
+    int t = (int)g;
+    if (size[g] < min_size) {
+      if (x > 0) t = parent[g - 1];
+      else if (y > 0) t = parent[g - W];
+    }
+    tgt[g] = t;
+  }
+}
+// pointer jumping: tgt[root] = the surviving root it ends in (targets are strictly smaller indices: terminates)
+__global__ void resolve_kernel(const int* __restrict__ parent, int* __restrict__ tgt, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+    if (parent[g] != (int)g) continue;
+    int r = tgt[g];
+    while (true) { const int t = tgt[r]; if (t == r) break; r = t; }
+    tgt[g] = r;                                                // a shortcut: other chains through g stay valid
+  }
+}
+// one CTA per image: new ids of the surviving roots in scan order (written over size[root]); n_out[b] = their number
+__global__ void __launch_bounds__(1024) number_kernel(const int* __restrict__ parent, const int* __restrict__ tgt,
+                                                      int* __restrict__ size, int hw, int* __restrict__ n_out) {
+  __shared__ int part[1024];
+  const long long base = (long long)blockIdx.x * hw;
+  const int per = (hw + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(hw, lo + per);
+  int cnt = 0;
+  for (int p = lo; p < hi; ++p) { const long long g = base + p; cnt += (parent[g] == (int)g && tgt[g] == (int)g) ? 1 : 0; }
+  part[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {                   // inclusive Hillis-Steele scan
+    const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int id = part[threadIdx.x] - cnt;
+  for (int p = lo; p < hi; ++p) {
+    const long long g = base + p;
+    if (parent[g] == (int)g && tgt[g] == (int)g) size[g] = id++;
+  }
+  if (threadIdx.x == 1023 && n_out) n_out[blockIdx.x] = part[1023];
+}
+__global__ void relabel_kernel(const int* __restrict__ parent, const int* __restrict__ tgt, const int* __restrict__ newid,
+                               int32_t* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) out[g] = newid[tgt[parent[g]]];
+}
+
+}  // namespace cc
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" {
+
+// work: int32 [gnc_slic_connectivity_workspace(B, H, W)]
+int64_t gnc_slic_connectivity_workspace(int B, int H, int W) { return 3 * (int64_t)B * H * W; }
+
+int gnc_slic_enforce_connectivity(const int32_t* labels, int B, int H, int W, int min_size, int32_t* out, int32_t* n_labels,
+                                  int32_t* work, int64_t work_elems, gnc_stream_t stream) {
+  GNC_REQUIRE(labels && out && B > 0 && H > 0 && W > 0 && min_size >= 0, "slic_enforce_connectivity: bad arguments");
+  const long long n = (long long)B * H * W;
+  GNC_REQUIRE(n < 2147483647LL, "slic_enforce_connectivity: at most 2^31 - 1 pixels per call");
+  if (!work || work_elems < 3 * n) return fail(GNC_EWORKSPACE, "%s", "slic_enforce_connectivity: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* parent = work;
+  int* size = work + n;
+  int* tgt = work + 2 * n;
+  long long blocks = ceil_div<long long>(n, 256);
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  int rc;
+  cc::init_kernel<<<(unsigned)blocks, 256, 0, st>>>(parent, size, n);
+  if ((rc = check_launch("cc_init_kernel"))) return rc;
+  cc::merge_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels, parent, H, W, n);
+  if ((rc = check_launch("cc_merge_kernel"))) return rc;
+  cc::flatten_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(parent, size, n);
+  if ((rc = check_launch("cc_flatten_count_kernel"))) return rc;
+  cc::decide_kernel<<<(unsigned)blocks, 256, 0, st>>>(parent, size, tgt, H, W, min_size, n);
+  if ((rc = check_launch("cc_decide_kernel"))) return rc;
+  cc::resolve_kernel<<<(unsigned)blocks, 256, 0, st>>>(parent, tgt, n);
+  if ((rc = check_launch("cc_resolve_kernel"))) return rc;
+  cc::number_kernel<<<(unsigned)B, 1024, 0, st>>>(parent, tgt, size, H * W, n_labels);
+  if ((rc = check_launch("cc_number_kernel"))) return rc;
+  cc::relabel_kernel<<<(unsigned)blocks, 256, 0, st>>>(parent, tgt, size, out, n);
+  return check_launch("cc_relabel_kernel");
+}
+
+}  // extern "C"

@@ -367,6 +367,15 @@ class CombinedModel(nn.Module):
         if pos is None and edge_index is None and isinstance(x, tuple):
             x, pos, edge_index = x
         y = self.graph_net(x, pos, edge_index)
+        topo = edge_index if isinstance(edge_index, GraphIndex) else getattr(edge_index, "_gnc_graph", None)
+        if topo is not None and topo.node_ptr is not None:
+            # graphs with different node counts (superpixel graphs): pad / truncate each graph's node
+            # outputs to num_nodes - the reference's flatten when the count matches, defined where it would crash
+            if self.graph_net.out_dim != 1:
+                raise NotImplementedError("the variable-size readout is defined for out_channels = 1")
+            dense = ops.segment_readout(y, topo.node_ptr, self.num_nodes)
+            out = self.classifier(dense)
+            return out.reshape(-1) if dense.shape[0] == 1 else out
         n_graphs = y.shape[0] // self.num_nodes if y.shape[0] > self.num_nodes else 1
         if n_graphs <= 1:
             return self.classifier(y.flatten())            # [classes], as the reference

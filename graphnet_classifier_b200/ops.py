@@ -151,7 +151,7 @@ class GraphIndex:
     reference's summation order) and by source."""
 
     __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid",
-                 "edge_class", "class_geom", "pos_ref", "pos_version", "class_sum_plan")
+                 "edge_class", "class_geom", "pos_ref", "pos_version", "class_sum_plan", "node_ptr")
 
     def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
         self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
@@ -167,6 +167,9 @@ class GraphIndex:
         self.pos_ref = None
         self.pos_version = -1           # pos_ref._version when the classes were derived from it
         self.class_sum_plan = None      # lazily built CSRs for per-class gradient sums (tc_train.class_sum_plan)
+        # int32 [B + 1] node offsets of a batch whose graphs have DIFFERENT node counts (superpixel graphs); None for
+        # fixed-size batches, where graph b owns rows b * num_nodes .. (b + 1) * num_nodes - 1
+        self.node_ptr = None
 
     def bind_positions(self, pos: Tensor) -> None:
         """Remember the ``pos`` tensor (and its in-place version) the edge classes were derived from."""
@@ -1085,3 +1088,43 @@ def zero_(buf: Tensor) -> None:
     if buf.dtype != torch.float32 or not buf.is_contiguous():
         raise RuntimeError("zero_: contiguous fp32 tensor")
     check(_lib.load().gnc_zero_f32(buf.data_ptr(), buf.numel(), _stream()), "zero")
+
+
+class _SegmentReadoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, node_ptr, num_nodes):
+        yv = y.reshape(-1)
+        if yv.dtype != torch.float32 or not yv.is_contiguous():
+            yv = yv.float().contiguous()
+        B = int(node_ptr.shape[0]) - 1
+        out = torch.empty(B, num_nodes, dtype=torch.float32, device=y.device)
+        check(_call("segment_readout", 0.0, 4.0 * (yv.numel() + B * num_nodes), _lib.load().gnc_segment_readout_f32,
+                    yv.data_ptr(), node_ptr.data_ptr(), B, int(num_nodes), out.data_ptr(), _stream()), "segment_readout")
+        ctx.node_ptr, ctx.num_nodes, ctx.shape = node_ptr, int(num_nodes), y.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _rows(dout)
+        if _ld(dout) != ctx.num_nodes:
+            dout = dout.contiguous()
+        n_total = 1
+        for d in ctx.shape:
+            n_total *= d
+        dy = torch.empty(n_total, dtype=torch.float32, device=dout.device)
+        B = int(ctx.node_ptr.shape[0]) - 1
+        check(_call("segment_readout_bwd", 0.0, 4.0 * (n_total + B * ctx.num_nodes), _lib.load().gnc_segment_readout_bwd_f32,
+                    dout.data_ptr(), ctx.node_ptr.data_ptr(), B, ctx.num_nodes, dy.data_ptr(), _stream()), "segment_readout_bwd")
+        return dy.reshape(ctx.shape), None, None
+
+
+def segment_readout(y: Tensor, node_ptr: Tensor, num_nodes: int) -> Tensor:
+    """Node outputs ``y [sum n_b, 1]`` of a batch of graphs with different node counts -> the dense ``[B, num_nodes]``
+    input of the classifier head: graph ``b`` contributes its first ``min(n_b, num_nodes)`` outputs, missing entries are
+    zero (the reference's flatten, models/GNN.py:339, needs ``n_b == num_nodes`` and crashes otherwise)."""
+    _require_cuda(y, node_ptr)
+    if node_ptr.dtype != torch.int32 or node_ptr.dim() != 1 or node_ptr.shape[0] < 1:
+        raise ValueError("segment_readout: node_ptr must be int32 [B + 1]")
+    if y.numel() % max(int(y.shape[0]), 1) != 0 or y.numel() != y.shape[0]:
+        raise ValueError("segment_readout: one output channel per node (out_channels = 1)")
+    return _SegmentReadoutFn.apply(y, node_ptr.contiguous(), int(num_nodes))

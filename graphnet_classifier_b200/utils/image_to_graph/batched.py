@@ -186,3 +186,29 @@ def build_superpixel_graphs(images, labels, max_nodes: Optional[int] = None, dev
                                          n_edges.data_ptr(), edges.data_ptr(), work.data_ptr(), _stream()),
           "build_superpixel_graph")
     return n_nodes, x, pos, n_edges, edges
+
+
+def build_superpixel_batch(images, labels=None, n_segments: int = 100, compactness: float = 10.0,
+                           max_nodes: Optional[int] = None, device=None) -> GraphBatch:
+    """Superpixel graphs of a batch of images as ONE block-diagonal ``GraphBatch`` whose graphs have different node
+    counts (reference image_to_graph_superpixel.py:8-73 per image): SLIC labels (``slic_labels`` unless ``labels`` is
+    supplied) -> per-image graph kernel -> compaction -> CSR.  ``graph.node_ptr`` (int32 ``[B + 1]``) tells the model's
+    readout where each graph's nodes are; ``nodes_per_graph`` is 0 (not constant)."""
+    from .slic import slic_labels
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    img = _as_device_u8(images, dev)
+    if labels is None:
+        labels = slic_labels(img, n_segments=n_segments, compactness=compactness)
+    n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(img, labels, max_nodes=max_nodes, device=dev)
+    B, S_max = x.shape[0], x.shape[1]
+    node_ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    torch.cumsum(n_nodes, 0, out=node_ptr[1:])
+    nmask = torch.arange(S_max, device=dev)[None, :] < n_nodes[:, None]
+    xb, pb = x[nmask], pos[nmask]
+    E_max = edges.shape[2]
+    emask = torch.arange(E_max, device=dev)[None, :] < n_edges[:, None]
+    eb = (edges + node_ptr[:-1, None, None].long()).permute(1, 0, 2)[:, emask].contiguous()
+    graph = GraphIndex.from_edge_index(eb, xb.shape[0])
+    graph.node_ptr = node_ptr
+    attach_graph(eb, graph)
+    return GraphBatch(xb, pb, eb, graph, B, 0)

@@ -384,6 +384,22 @@ int gnc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* ex
                       double beta1, double beta2, double eps, int64_t step, float grad_scale, gnc_stream_t stream);
 int gnc_zero_f32(float* buf, int64_t n, gnc_stream_t stream);
 
+/* Readout of a batch of graphs with different node counts (node_ptr int32 [B + 1], offsets into y [sum n_b]) into the
+ * dense classifier input:  out[b, j] = j < n_b ? y[node_ptr[b] + j] : 0  for j < num_nodes  (pad / truncate to
+ * num_nodes; equal to the reference's flatten, models/GNN.py:339, when n_b == num_nodes).  Backward: dy gets dout's
+ * entries of the kept nodes and zero for truncated ones. */
+int gnc_segment_readout_f32(const float* y, const int32_t* node_ptr, int B, int num_nodes, float* out, gnc_stream_t stream);
+int gnc_segment_readout_bwd_f32(const float* dout, const int32_t* node_ptr, int B, int num_nodes, float* dy,
+                                gnc_stream_t stream);
+
+/* Connectivity enforcement of SLIC label maps (scikit-image's default post-pass; parity unpinned, the rule is stated in
+ * csrc/slic_connect.cu): 4-connected components of equal labels, components smaller than min_size dissolved into the
+ * component left of / above their first pixel, survivors numbered 0.. in scan order of their first pixel.
+ * labels / out: int32 [B, H, W] (may alias); n_labels: int32 [B] (may be NULL); work: int32 [3 * B * H * W]. */
+int64_t gnc_slic_connectivity_workspace(int B, int H, int W);
+int gnc_slic_enforce_connectivity(const int32_t* labels, int B, int H, int W, int min_size, int32_t* out, int32_t* n_labels,
+                                  int32_t* work, int64_t work_elems, gnc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

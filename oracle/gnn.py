@@ -199,6 +199,22 @@ class OracleCombinedModel(nn.Module):
         return self.classifier(y.reshape(B, -1))
 
 
+def padded_readout_logits(model: "OracleCombinedModel", graphs) -> Tensor:
+    """Logits of graphs whose node count differs from ``model.num_nodes`` - OUR definition where the reference is
+    undefined (models/GNN.py:339-340 flattens the ``[N, 1]`` node outputs into a head sized for exactly
+    ``num_nodes`` values, main.py:65-66, and raises otherwise).  Per graph: GraphNet exactly as the reference runs it,
+    then the first ``min(N, num_nodes)`` outputs, zero-padded to ``num_nodes``, through the reference's head.  Equal to
+    ``model(graph)`` whenever ``N == num_nodes``."""
+    rows = []
+    for (x, pos, ei) in graphs:
+        y = model.graph_net(x, pos, ei).flatten()
+        v = torch.zeros(model.num_nodes, dtype=y.dtype)
+        k = min(y.numel(), model.num_nodes)
+        v[:k] = y[:k]
+        rows.append(model.classifier(v))
+    return torch.stack(rows)
+
+
 def build_reference_config_model(resize_value: int, classes: int = 2, seed: int | None = 0,
                                  n_blocks: int = 3, num_nodes: int | None = None):
     """The model main.py:72-73 builds, seeded like BASELINE.md section 4."""

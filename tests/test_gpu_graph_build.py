@@ -192,11 +192,12 @@ def test_device_slic_properties_and_superpixel_pipeline(libgnc):
     blocks = rng.integers(0, 256, (B, 4, 4, 3), dtype=np.uint8)
     imgs = np.repeat(np.repeat(blocks, 16, axis=1), 16, axis=2)
     imgs = np.clip(imgs.astype(np.int16) + rng.integers(-3, 4, imgs.shape), 0, 255).astype(np.uint8)
-    labs = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0)
+    # the k-means stage on its own (the connectivity post-pass has its own tests: tests/test_gpu_slic.py)
+    labs = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0, enforce_connectivity_=False)
     assert labs.shape == (B, r, r) and labs.dtype == torch.int32
     K = libgnc.gnc_slic_num_centers(r, r, 16)
     assert K == 16 and int(labs.min()) >= 0 and int(labs.max()) < K
-    labs2 = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0)
+    labs2 = slic_labels(torch.from_numpy(imgs).cuda(), n_segments=16, compactness=10.0, enforce_connectivity_=False)
     assert torch.equal(labs, labs2)                                   # deterministic
     ln = labs.cpu().numpy()
     for b in range(B):
@@ -228,7 +229,7 @@ def test_slic_run_aggregation_equals_per_pixel_atomics(libgnc):
         img = np.clip(img * 255 + rng.integers(-6, 7, (B, H, W, 3)), 0, 255).astype(np.uint8)
         t = torch.from_numpy(img).cuda()
         libgnc.gnc_debug_slic_run_length(1)
-        ref = slic_labels(t, n_segments=S, compactness=10.0)
+        ref = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
         libgnc.gnc_debug_slic_run_length(8)
-        got = slic_labels(t, n_segments=S, compactness=10.0)
+        got = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
         assert torch.equal(ref, got)

@@ -1,0 +1,90 @@
+"""SLIC connectivity enforcement (csrc/slic_connect.cu) against a CPU restatement of the rule stated in that file's
+header (scipy.ndimage.label for the components, a sequential pass in scan order for the rest).  Label parity with
+scikit-image itself is unpinned (not installed) - what is pinned here is the stated rule and the
+properties the post-pass exists for: every label is ONE 4-connected region, no region is smaller than min_size."""
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage
+
+pytestmark = pytest.mark.gpu
+
+
+def enforce_connectivity_ref(labels: np.ndarray, min_size: int) -> np.ndarray:
+    H, W = labels.shape
+    comp = np.full((H, W), -1, dtype=np.int64)
+    ncomp = 0
+    for l in np.unique(labels):
+        cl, n = ndimage.label(labels == l)                 # default structure: 4-connectivity
+        comp[cl > 0] = cl[cl > 0] - 1 + ncomp
+        ncomp += n
+    flat = comp.ravel()
+    first = np.full(ncomp, H * W, dtype=np.int64)
+    np.minimum.at(first, flat, np.arange(H * W))
+    size = np.bincount(flat, minlength=ncomp)
+    order = np.argsort(first)
+    final = np.arange(ncomp)
+    for c in order:                                        # scan order of the first pixel: neighbours are resolved already
+        p = int(first[c]); y, x = divmod(p, W)
+        if size[c] < min_size:
+            if x > 0:
+                final[c] = final[flat[p - 1]]
+            elif y > 0:
+                final[c] = final[flat[p - W]]
+    newid = {int(c): i for i, c in enumerate(c for c in order if final[c] == c)}
+    return np.array([newid[int(final[c])] for c in flat], dtype=np.int32).reshape(H, W)
+
+
+def _check_properties(out: np.ndarray, min_size: int):
+    for l in np.unique(out):
+        cl, n = ndimage.label(out == l)
+        assert n == 1, f"label {l} has {n} components"
+    sizes = np.bincount(out.ravel())
+    # only the region of pixel 0 may stay below min_size (it has no earlier neighbour to dissolve into)
+    small = [l for l, s in enumerate(sizes) if s < min_size]
+    assert small in ([], [int(out[0, 0])]), small
+    assert out.min() == 0 and len(np.unique(out)) == out.max() + 1
+
+
+@pytest.mark.parametrize("H,W,K,min_size", [(32, 32, 6, 8), (50, 61, 12, 20), (64, 64, 4, 0), (40, 40, 30, 10_000), (1, 97, 5, 3),
+                                             (97, 1, 5, 3), (256, 256, 100, 327)])
+def test_connectivity_equals_cpu_restatement(H, W, K, min_size):
+    from graphnet_classifier_b200.utils.image_to_graph.slic import enforce_connectivity
+    rng = np.random.default_rng(H * 1000 + W)
+    # smooth label maps (Voronoi cells) with salt noise: large regions plus many tiny components
+    seeds = rng.random((K, 2)) * [H, W]
+    yy, xx = np.mgrid[0:H, 0:W]
+    lab = ((yy[..., None] - seeds[:, 0]) ** 2 + (xx[..., None] - seeds[:, 1]) ** 2).argmin(-1).astype(np.int32)
+    noise = rng.random((H, W)) < 0.08
+    lab[noise] = rng.integers(0, K, int(noise.sum()))
+    labs = np.stack([lab, np.roll(lab, 3, axis=1), (lab * 7 + 1) % K])          # a batch: images are independent
+    got = enforce_connectivity(torch.from_numpy(labs).cuda(), min_size).cpu().numpy()
+    for b in range(labs.shape[0]):
+        assert np.array_equal(got[b], enforce_connectivity_ref(labs[b], min_size)), b
+        if min_size <= H * W:
+            _check_properties(got[b], min_size)
+
+
+def test_slic_with_connectivity_gives_one_region_per_label():
+    from graphnet_classifier_b200 import _lib
+    from graphnet_classifier_b200.utils.image_to_graph.slic import slic_labels
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_superpixel_graphs
+    rng = np.random.default_rng(1)
+    r, B, S = 128, 4, 100
+    low = rng.random((B, 9, 9, 3))
+    img = np.kron(low, np.ones((1, r // 9 + 1, r // 9 + 1, 1)))[:, :r, :r]
+    img = np.clip(img * 255 + rng.integers(-20, 21, (B, r, r, 3)), 0, 255).astype(np.uint8)
+    t = torch.from_numpy(img).cuda()
+    raw = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
+    lab = slic_labels(t, n_segments=S, compactness=10.0)
+    K = int(_lib.load().gnc_slic_num_centers(r, r, S))
+    min_size = int(0.5 * r * r / K)
+    assert torch.equal(lab, slic_labels(t, n_segments=S, compactness=10.0))      # deterministic
+    n_nodes, _, _, n_edges, _ = build_superpixel_graphs(t, lab)
+    n_raw, _, _, e_raw, _ = build_superpixel_graphs(t, raw)
+    for b in range(B):
+        out = lab[b].cpu().numpy()
+        assert np.array_equal(out, enforce_connectivity_ref(raw[b].cpu().numpy(), min_size))
+        _check_properties(out, min_size)
+        assert int(n_nodes[b]) == out.max() + 1
+    print("nodes / edges per image with the post-pass:", n_nodes.tolist(), n_edges.tolist(), " without:", n_raw.tolist(), e_raw.tolist())
