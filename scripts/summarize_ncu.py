@@ -64,5 +64,33 @@ def full(path):
             print(f"traffic_GB (dram read + write) = {gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum'):.4f}")
 
 
+def traffic(path, key, *sources):
+    """Record the DRAM bytes of the LAST captured launch in profiles/kernel_traffic.json under `key`, tagged with the
+    hash of the kernel's sources (bench.py reports the figure only while the sources are unchanged).
+        python scripts/summarize_ncu.py traffic gpurun_out/x.ncu-rep tc_chain2_edge_b512_r128 tc_chain.cu common.cuh"""
+    import hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, r = rows[0], rows[1], rows[-1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def nbytes(k):
+        return float(r[idx[k]].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[idx[k]]]
+
+    h = hashlib.sha256()
+    for n in sources:
+        with open(os.path.join(root, "graphnet_classifier_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    out = os.path.join(root, "profiles", "kernel_traffic.json")
+    table = json.load(open(out)) if os.path.exists(out) else {}
+    table[key] = {"kernel": r[idx["Kernel Name"]][:80], "source_sha": h.hexdigest()[:16], "sources": list(sources),
+                  "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+                  "gpu_time_ms": r[idx["gpu__time_duration.sum"]] + " " + units[idx["gpu__time_duration.sum"]],
+                  "from": os.path.relpath(path, root)}
+    json.dump(table, open(out, "w"), indent=1)
+    print(json.dumps(table[key]))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
