@@ -45,6 +45,12 @@ class GncTcChain(Structure):
                 ("narrow_W", c_void_p), ("ld_narrow_W", c_int64), ("narrow_b", c_void_p), ("narrow_k", c_int32), ("_pad2", c_int32)]
 
 
+class GncBwdReduceItem(Structure):
+    """struct gnc_bwd_reduce_item (include/gnc.h)."""
+    _fields_ = [("work", c_void_p), ("dW", c_void_p), ("db", c_void_p), ("lddw", c_int64), ("parts", c_int32),
+                ("accumulate", c_int32)]
+
+
 class GncError(RuntimeError):
     pass
 
@@ -122,6 +128,8 @@ SIGNATURES = {
     "gnc_tc_bwd_layer_workspace": (c_int64, []),
     "gnc_tc_bwd_layer_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64, _P, c_int64,
                                      _P, c_int64, _P, c_int, _P, c_int64, _P]),
+    "gnc_tc_bwd_layer_parts": (c_int32, [c_int64]),
+    "gnc_tc_bwd_reduce_batch_f32": (c_int, [POINTER(GncBwdReduceItem), c_int32, _P]),
 }
 
 _lib = None

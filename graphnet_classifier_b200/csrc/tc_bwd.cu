@@ -704,6 +704,29 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ ws, int parts, fl
   }
 }
 
+// the same reduction for the layers of a whole backward pass in ONE launch (blockIdx.y = layer): every layer of the
+// pass wrote its per-CTA partials to its own workspace slice (dW = db = NULL in gnc_tc_bwd_layer_f32)
+constexpr int kBatchMax = 48;
+struct ReduceBatch { gnc_bwd_reduce_item_t item[kBatchMax]; };
+__global__ void tc_bwd_reduce_batch_kernel(const ReduceBatch b) {
+  const gnc_bwd_reduce_item_t it = b.item[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kD * kD) return;
+  const int parts = it.parts;
+  if (it.db && i < kD) {
+    const float* wdb = it.work + (long long)parts * kD * kD;
+    float sb = 0.f;
+    for (int c = 0; c < parts; ++c) sb += wdb[c * kD + i];
+    it.db[i] = it.accumulate ? it.db[i] + sb : sb;
+  }
+  if (it.dW) {
+    float s = 0.f;
+    for (int c = 0; c < parts; ++c) s += it.work[(long long)c * kD * kD + i];
+    float* d = it.dW + (long long)(i >> 7) * it.lddw + (i & 127);
+    *d = it.accumulate ? (*d + s) : s;
+  }
+}
+
 template <bool MASK, bool ADDEND>
 static int launch(const Params& p, long long grid, cudaStream_t st) {
   static SmemAttrOnce smem_attr;
@@ -721,6 +744,28 @@ extern "C" {
 
 int64_t gnc_tc_bwd_layer_workspace(void) { return (int64_t)kNumSMs * (bwd::kD * bwd::kD + bwd::kD); }
 
+int32_t gnc_tc_bwd_layer_parts(int64_t M) {
+  const long long nblocks = (M + bwd::kRows - 1) / bwd::kRows;
+  return (int32_t)(nblocks < kNumSMs ? (nblocks < 1 ? 1 : nblocks) : kNumSMs);
+}
+
+int gnc_tc_bwd_reduce_batch_f32(const gnc_bwd_reduce_item_t* items, int32_t n_items, gnc_stream_t stream) {
+  GNC_REQUIRE(n_items >= 0 && (items || n_items == 0), "tc_bwd_reduce_batch: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int lo = 0; lo < n_items; lo += bwd::kBatchMax) {
+    const int n = n_items - lo < bwd::kBatchMax ? n_items - lo : bwd::kBatchMax;
+    bwd::ReduceBatch b;
+    for (int i = 0; i < n; ++i) {
+      b.item[i] = items[lo + i];
+      GNC_REQUIRE(b.item[i].work && b.item[i].parts >= 1 && b.item[i].parts <= kNumSMs && (!b.item[i].dW || b.item[i].lddw >= bwd::kD),
+                  "tc_bwd_reduce_batch: bad item");
+    }
+    bwd::tc_bwd_reduce_batch_kernel<<<dim3(bwd::kD * bwd::kD / 256, n), 256, 0, st>>>(b);
+    if (int rc = check_launch("tc_bwd_reduce_batch_kernel")) return rc;
+  }
+  return GNC_OK;
+}
+
 int gnc_tc_bwd_layer_f32(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int64_t M, const float* W, int64_t ldw,
                          int mask_by_x, const float* addend, int64_t ld_addend, float* dX, int64_t lddx, float* dW,
                          int64_t lddw, float* db, int accumulate, float* work, int64_t work_elems, gnc_stream_t stream) {
@@ -729,7 +774,8 @@ int gnc_tc_bwd_layer_f32(const float* dZ, int64_t lddz, const float* X, int64_t 
   GNC_REQUIRE(!dW || lddw >= bwd::kD, "tc_bwd_layer: bad dW pitch");
   GNC_REQUIRE(lddz % 4 == 0 && ldx % 4 == 0 && aligned16(dZ) && aligned16(X), "tc_bwd_layer: dZ / X rows must be 16-byte aligned");
   GNC_REQUIRE(!addend || ld_addend >= bwd::kD, "tc_bwd_layer: bad addend pitch");
-  if (!work || work_elems < gnc_tc_bwd_layer_workspace()) return fail(GNC_EWORKSPACE, "%s", "tc_bwd_layer: workspace too small");
+  if (!work || work_elems < (int64_t)gnc_tc_bwd_layer_parts(M) * (bwd::kD * bwd::kD + bwd::kD))
+    return fail(GNC_EWORKSPACE, "%s", "tc_bwd_layer: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   bwd::Params p;
   p.dZ = dZ; p.lddz = lddz; p.X = X; p.ldx = ldx; p.M = M; p.W = W; p.ldw = ldw;

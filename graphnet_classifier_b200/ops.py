@@ -933,6 +933,41 @@ def tc_wgrad(dZ: Tensor, X: Tensor, out: Optional[Tensor] = None, accumulate: bo
     return (out, db) if want_db else out
 
 
+class DeferredBwdReduce:
+    """Collects the weight / bias gradient reductions of the fused backward-layer launches of one backward pass and
+    finishes them with ONE launch (``gnc_tc_bwd_reduce_batch_f32``) instead of one small launch per layer.  While
+    active (``with ops.DeferredBwdReduce():``), ``tc_bwd_layer`` leaves every layer's per-CTA partial sums in a
+    workspace of its own; ``dW`` / ``db`` tensors it returns are valid after the ``with`` block (or ``flush()``)."""
+
+    active: Optional["DeferredBwdReduce"] = None
+
+    def __init__(self):
+        self.items = []          # (workspace, parts, dW, db, accumulate)
+
+    def __enter__(self):
+        self._prev, DeferredBwdReduce.active = DeferredBwdReduce.active, self
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        DeferredBwdReduce.active = self._prev
+        if exc_type is None:
+            self.flush()
+        self.items = []
+        return False
+
+    def flush(self) -> None:
+        if not self.items:
+            return
+        arr = (_lib.GncBwdReduceItem * len(self.items))()
+        for a, (ws, parts, dW, db, acc) in zip(arr, self.items):
+            a.work, a.dW, a.db = ws.data_ptr(), _p(dW), _p(db)
+            a.lddw, a.parts, a.accumulate = (dW.stride(0) if dW is not None else 0), parts, int(acc)
+        n = len(self.items)
+        check(_call("tc_bwd_reduce_batch", 0.0, sum(4.0 * it[1] * (128 * 128 + 128) for it in self.items),
+                    _lib.load().gnc_tc_bwd_reduce_batch_f32, arr, n, _stream()), "tc_bwd_reduce_batch")
+        self.items = []
+
+
 def tc_bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend: Optional[Tensor] = None,
                  dW_out: Optional[Tensor] = None, accumulate: bool = False, want_db: bool = False,
                  db_out: Optional[Tensor] = None, want_dW: bool = True):
@@ -973,12 +1008,21 @@ def tc_bwd_layer(dZ: Tensor, X: Tensor, W: Tensor, *, mask: bool = False, addend
             raise ValueError("tc_bwd_layer: accumulate with want_db needs db_out")
         db = db_out if db_out is not None else torch.empty(128, dtype=torch.float32, device=dev)
     ws_n = int(lib.gnc_tc_bwd_layer_workspace())
-    ws = _workspace(dev, ws_n)
+    defer = DeferredBwdReduce.active if (dW is not None or db is not None) else None
+    if defer is not None:
+        # the partial sums stay in a workspace of this layer's own until the pass's single reduction launch
+        parts = int(lib.gnc_tc_bwd_layer_parts(M))
+        ws = torch.empty(parts * (128 * 128 + 128), dtype=torch.float32, device=dev)
+        defer.items.append((ws, parts, dW, db, bool(accumulate)))
+        k_dW, k_db = None, None
+    else:
+        ws = _workspace(dev, ws_n)
+        k_dW, k_db = dW, db
     check(_call("tc_bwd_layer", 4.0 * M * 128 * 128, 4.0 * 128 * M * (3 + (ad is not None)),
                 lib.gnc_tc_bwd_layer_f32, dZ.data_ptr(), _ld(dZ), X.data_ptr(), _ld(X), M, W.data_ptr(), W.stride(0),
                 int(bool(mask)), _p(ad), _ld(ad) if ad is not None else 0, dX.data_ptr(), _ld(dX),
-                _p(dW), dW.stride(0) if dW is not None else 0, _p(db), int(bool(accumulate)), ws.data_ptr(), ws_n,
-                _stream()), "tc_bwd_layer")
+                _p(k_dW), dW.stride(0) if dW is not None else 0, _p(k_db), int(bool(accumulate)), ws.data_ptr(),
+                ws.numel(), _stream()), "tc_bwd_layer")
     return dX, dW, db
 
 

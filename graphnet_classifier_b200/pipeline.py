@@ -39,9 +39,10 @@ class GraphClassifierPipeline:
         n = self.resize_value * self.resize_value if method == "pixel" else (self.resize_value // self.patch_size) ** 2
         # live fp32 activations: ~8 KB per node in inference (5 edge tensors + node tensors of
         # width 128, E ~ 2N); training peaks at ~24 KB per node (activations kept for the backward over 3 blocks plus
-        # the backward's transients: 63.6 GiB measured for 171 resize-128 graphs); budget 64 GiB of the 180 GB
+        # the backward's transients: 63.6 GiB measured for 171 resize-128 graphs); budget 64 GiB of the 180 GB for
+        # inference and 100 GiB for training (256 resize-128 graphs per micro-batch: two per 512-graph step)
         self.micro_batch = micro_batch or max(1, min(512, (64 << 30) // (n * 8192)))
-        self.train_micro_batch = train_micro_batch or max(1, min(256, (64 << 30) // (n * 24_000)))
+        self.train_micro_batch = train_micro_batch or max(1, min(256, (100 << 30) // (n * 24_000)))
         self._graphs = {}            # image batch shape -> (CUDAGraph, static input, static logits)
 
     # -- staging ----------------------------------------------------------------

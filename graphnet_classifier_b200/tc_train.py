@@ -243,6 +243,13 @@ class GraphNetCoreFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        # the ~33 fused backward-layer launches of the pass leave their per-CTA partial weight / bias gradients in
+        # workspaces of their own; ONE launch reduces all of them when the pass is over (same order, same bits)
+        with ops.DeferredBwdReduce():
+            return GraphNetCoreFn._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy):
         graph, n_blocks, params = ctx.graph, ctx.n_blocks, ctx.params
         saved, blocks = ctx.saved, ctx.blocks
         dev = dy.device

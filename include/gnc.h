@@ -359,6 +359,20 @@ int gnc_tc_bwd_layer_f32(const float* dZ, int64_t lddz, const float* X, int64_t 
                          float* dX, int64_t lddx, float* dW, int64_t lddw, float* db, int accumulate,
                          float* work, int64_t work_elems, gnc_stream_t stream);
 
+/* Deferred form for a whole backward pass: with dW = db = NULL the launch above leaves its per-CTA partial sums in
+ * `work` (gnc_tc_bwd_layer_parts(M) slices); every layer of the pass uses its own `work`, and ONE launch of the batch
+ * reduction then finishes all of them in the same fixed order (same bits as the immediate form). */
+typedef struct gnc_bwd_reduce_item {
+  const float* work;   /* the layer's workspace */
+  float* dW;           /* [128, 128], row pitch lddw; may be NULL */
+  float* db;           /* [128]; may be NULL */
+  int64_t lddw;
+  int32_t parts;       /* gnc_tc_bwd_layer_parts(M) of that layer */
+  int32_t accumulate;  /* add to dW / db instead of overwriting */
+} gnc_bwd_reduce_item_t;
+int32_t gnc_tc_bwd_layer_parts(int64_t M);
+int gnc_tc_bwd_reduce_batch_f32(const gnc_bwd_reduce_item_t* items, int32_t n_items, gnc_stream_t stream);
+
 /* Linear(D, 1) as a row dot product (the decoder's last layer, models/GNN.py:289-295):  y[m] = X[m, :] . w + b.
  * Backward in one pass over X:  dX[m, :] = dy[m] * w  (* (X[m, :] > 0) with relu_mask: X is a ReLU output and dX its
  * pre-activation gradient; dX may be NULL),  dw[D] (+)= sum_m dy[m] X[m, :],  db[1] (+)= sum_m dy[m].

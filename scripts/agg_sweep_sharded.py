@@ -56,8 +56,8 @@ def shard_graph(kind, E):
 
 
 if rank == 0:
-    print(f"| topology | GPUs | E total | E per GPU | D | ms (max over ranks) | aggregate GB/s | frac of {world} x measured HBM peak | mass conservation |")
-    print("|---|---|---|---|---|---|---|---|---|")
+    print(f"| topology | GPUs | E total | E per GPU | D | ms (max over ranks) | aggregate GB/s | frac of {world} x measured HBM peak | torch index_add_ ms (max over ranks) | speed-up | mass conservation |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|")
 for kind in ("grid", "random"):
     g = shard_graph(kind, E_total // world)
     E, N = g.num_edges, g.num_nodes
@@ -82,9 +82,12 @@ for kind in ("grid", "random"):
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         nbytes = 4.0 * (E * D + E + (N + 1) + N * D)
+        idx = g.dst.long()
+        ms_t = timeit(lambda: out.zero_().index_add_(0, idx, src), n=3)      # the baseline the sweep is quoted against
+        del idx
         if rank == 0:
             gbs = world * nbytes / ms / 1e6
-            print(f"| {kind} | {world} | {E * world} | {E} | {D} | {ms:.3f} | {gbs:.0f} | {gbs / (world * PEAK):.3f} | {bool(ok.item())} |", flush=True)
+            print(f"| {kind} | {world} | {E * world} | {E} | {D} | {ms:.3f} | {gbs:.0f} | {gbs / (world * PEAK):.3f} | {ms_t:.3f} | {ms_t / ms:.1f}x | {bool(ok.item())} |", flush=True)
         del src, out
         torch.cuda.empty_cache()
     del g

@@ -114,3 +114,28 @@ def test_dot_tail_forward_backward(M, D):
     assert _rel(dw, dy.double().t() @ X.double()) < 2e-6 and _rel(db, dy.double().sum().reshape(1)) < 2e-6
     dX2, _, _ = ops.dot_tail_bwd(X, w, dy, relu_mask=False)
     assert _rel(dX2, dy.double() @ w.double()) < 1e-6
+
+
+def test_deferred_reduction_equals_immediate():
+    """One reduction launch for the layers of a whole pass (ops.DeferredBwdReduce) gives the bits of the per-layer form,
+    in overwrite and in accumulate mode, for layers of different row counts (different numbers of partial slices)."""
+    from graphnet_classifier_b200 import _lib, ops
+    cases = [_case(M, seed=M) for M in (5, 1000, 148 * 32 + 7, 70001)]
+    imm = [ops.tc_bwd_layer(dZ, X, W, mask=True, want_db=True) for dZ, X, W, _ in cases]
+    base = torch.full((128, 384), 0.25, device="cuda")
+    acc_i = [(base.clone(), torch.ones(128, device="cuda")) for _ in cases]
+    for (dZ, X, W, _), (dWo, dbo) in zip(cases, acc_i):
+        ops.tc_bwd_layer(dZ, X, W, dW_out=dWo[:, 128:256], want_db=True, db_out=dbo, accumulate=True)
+    _lib.reset_launch_count()
+    acc_d = [(base.clone(), torch.ones(128, device="cuda")) for _ in cases]
+    with ops.DeferredBwdReduce():
+        dfr = [ops.tc_bwd_layer(dZ, X, W, mask=True, want_db=True) for dZ, X, W, _ in cases]
+        for (dZ, X, W, _), (dWo, dbo) in zip(cases, acc_d):
+            ops.tc_bwd_layer(dZ, X, W, dW_out=dWo[:, 128:256], want_db=True, db_out=dbo, accumulate=True)
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == 2 * len(cases) + 1          # one launch per layer + ONE reduction
+    for (dX0, dW0, db0), (dX1, dW1, db1) in zip(imm, dfr):
+        assert torch.equal(dX0, dX1) and torch.equal(dW0, dW1) and torch.equal(db0, db1)
+    for (w0, b0), (w1, b1) in zip(acc_i, acc_d):
+        assert torch.equal(w0, w1) and torch.equal(b0, b1)
+        assert bool((w1[:, :128] == 0.25).all()) and bool((w1[:, 256:] == 0.25).all())
