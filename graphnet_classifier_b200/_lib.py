@@ -128,6 +128,7 @@ SIGNATURES = {
     "gnc_tc_bwd_layer_workspace": (c_int64, []),
     "gnc_tc_bwd_layer_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64, _P, c_int64,
                                      _P, c_int64, _P, c_int, _P, c_int64, _P]),
+    "gnc_debug_slic_connect_streaming": (c_int, [c_int]),
     "gnc_tc_bwd_layer_parts": (c_int32, [c_int64]),
     "gnc_tc_bwd_reduce_batch_f32": (c_int, [POINTER(GncBwdReduceItem), c_int32, _P]),
 }

@@ -14,12 +14,14 @@
 // Connectivity enforcement (scikit-image's post-pass) is NOT applied; the label-map ->
 // graph stage (gnc_build_superpixel_graph) treats labels that vanish correctly
 // (node id = rank among the labels present).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gnc {
 
 struct SlicDims {
-  int B, H, W, ny, nx, K;
+  int B, H, W, ny, nx, K, dbg;
   float step, inv_compactness;
 };
 
@@ -30,6 +32,21 @@ __device__ __forceinline__ float lab_f(float t) {
   return t > 0.008856f ? cbrtf(t) : 7.787f * t + 16.0f / 116.0f;
 }
 
+// squared distance in the scaled (Lab / compactness, yx / step) space; the FMA chain is spelled out so that every kernel
+// that evaluates it rounds the same way
+__device__ __forceinline__ float slic_dist(float dl, float da, float db, float sy, float sx) {
+  return __fmaf_rn(sx, sx, __fmaf_rn(sy, sy, __fmaf_rn(db, db, __fmaf_rn(da, da, dl * dl))));
+}
+__device__ __forceinline__ void rgb_to_lab(float r, float g, float b, float inv_c, float& L, float& A, float& Bc) {
+  const float X = (0.412453f * r + 0.357580f * g + 0.180423f * b) / 0.95047f;
+  const float Y = (0.212671f * r + 0.715160f * g + 0.072169f * b);
+  const float Z = (0.019334f * r + 0.119193f * g + 0.950227f * b) / 1.08883f;
+  const float fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
+  L = (116.0f * fy - 16.0f) * inv_c;
+  A = 500.0f * (fx - fy) * inv_c;
+  Bc = 200.0f * (fy - fz) * inv_c;
+}
+
 // rgb uint8 -> (L, a, b) / compactness
 __global__ void slic_lab_kernel(const uint8_t* __restrict__ img, long long npix, float inv_c, float* __restrict__ lab) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -37,13 +54,7 @@ __global__ void slic_lab_kernel(const uint8_t* __restrict__ img, long long npix,
     const float r = srgb_to_linear(img[p * 3 + 0] * (1.0f / 255.0f));
     const float g = srgb_to_linear(img[p * 3 + 1] * (1.0f / 255.0f));
     const float b = srgb_to_linear(img[p * 3 + 2] * (1.0f / 255.0f));
-    const float X = (0.412453f * r + 0.357580f * g + 0.180423f * b) / 0.95047f;
-    const float Y = (0.212671f * r + 0.715160f * g + 0.072169f * b);
-    const float Z = (0.019334f * r + 0.119193f * g + 0.950227f * b) / 1.08883f;
-    const float fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
-    lab[p * 3 + 0] = (116.0f * fy - 16.0f) * inv_c;
-    lab[p * 3 + 1] = 500.0f * (fx - fy) * inv_c;
-    lab[p * 3 + 2] = 200.0f * (fy - fz) * inv_c;
+    rgb_to_lab(r, g, b, inv_c, lab[p * 3 + 0], lab[p * 3 + 1], lab[p * 3 + 2]);
   }
 }
 
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) slic_assign_kernel(const float* __rest
             const float* c = cb + (long long)k * 5;
             const float dl = L - __ldg(c), da = A - __ldg(c + 1), db = Bc - __ldg(c + 2);
             const float sy = ((y + 0.5f) - __ldg(c + 3)) * inv_step, sxx = ((x + 0.5f) - __ldg(c + 4)) * inv_step;
-            const float dist = dl * dl + da * da + db * db + sy * sy + sxx * sxx;
+            const float dist = slic_dist(dl, da, db, sy, sxx);
             if (dist < best) { best = dist; best_k = k; }     // ties: lowest centre index (scan order)
           }
         }
@@ -210,6 +221,218 @@ __global__ void slic_update_kernel(SlicDims d, long long* __restrict__ acc, floa
   for (int j = 0; j < 6; ++j) a[j] = 0;
 }
 
+
+// ---- one CTA per image: colour conversion, every Lloyd iteration and the final assignment in ONE launch --------------
+// The streaming form above is one launch per iteration over the whole batch: every pixel re-reads its 9 candidate
+// centres from global memory, writes a label map nobody reads until the last iteration and sends its sums to global
+// 64-bit atomics (~2 ms per iteration for 1024 images of 256 x 256: 12 x the HBM time of its 16 bytes per pixel).
+// An image's centres (K x 5 floats) and accumulators (K x 6 fixed-point sums) fit in shared memory, and images are
+// independent, so a CTA can keep both there and run the whole loop for its image without leaving the SM:
+//   * sRGB -> linear through a 256-entry table built with the streaming form's expression (same Lab bits);
+//   * a thread owns runs of 8 pixels: the 3 candidate grid rows (and their scaled y distances) are found once per run,
+//     the 3 candidate columns once per pixel, centres come from shared memory, the distance is the same FMA chain;
+//   * sums leave the registers once per label run, are merged across the warp by the same segmented reduction and land
+//     in shared-memory atomics; the centre update is a __syncthreads() away instead of a launch away;
+//   * labels are written once, after the last iteration.
+// Same integer sums, same update arithmetic, same tie rule: the labels are those of the streaming form bit for bit
+// (tests/test_gpu_graph_build.py compares them).
+constexpr int kImgThreads = 512;
+constexpr int kImgMaxK = 1024;
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(const uint8_t* __restrict__ img, SlicDims d, int iters,
+                                                                   float* __restrict__ lab_ws, int32_t* __restrict__ labels) {
+  extern __shared__ unsigned char slic_smem[];
+  long long* acc = reinterpret_cast<long long*>(slic_smem);                 // [K][6]
+  float* cen = reinterpret_cast<float*>(acc + (size_t)d.K * 6);            // [K][8]: L, a, b, x, y, - (32-byte records)
+  float* lut = cen + (size_t)d.K * 8;                                      // [256]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int K = d.K, gpr = d.W >> 3, G = d.H * gpr;
+  const int Gs = ((d.H + 31) >> 5) * 32 * gpr;                             // strip form: 32-row bands
+  const long long pix0 = (long long)b * d.H * d.W;
+  float* lab = lab_ws + pix0 * 3;
+  const float inv_step = 1.0f / d.step;
+
+  for (int i = tid; i < 256; i += kImgThreads) lut[i] = srgb_to_linear(i * (1.0f / 255.0f));
+  for (int i = tid; i < K * 6; i += kImgThreads) acc[i] = 0;
+  __syncthreads();
+  // Lab of the image's pixels (kept in global memory: 12 bytes per pixel, re-read from L2 by every iteration)
+  for (int g = tid; g < G; g += kImgThreads) {
+    const long long p0 = (long long)g * 8;
+    const uint2* src = reinterpret_cast<const uint2*>(img + (pix0 + p0) * 3);
+    uint32_t w[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const uint2 v = __ldg(src + j); w[2 * j] = v.x; w[2 * j + 1] = v.y; }
+    float o[24];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int b0 = 3 * i, b1 = 3 * i + 1, b2 = 3 * i + 2;
+      const float r = lut[(w[b0 >> 2] >> (8 * (b0 & 3))) & 255u], gg = lut[(w[b1 >> 2] >> (8 * (b1 & 3))) & 255u];
+      const float bb = lut[(w[b2 >> 2] >> (8 * (b2 & 3))) & 255u];
+      rgb_to_lab(r, gg, bb, d.inv_compactness, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    }
+    float4* dst = reinterpret_cast<float4*>(lab + p0 * 3);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += kImgThreads) {                             // regular-grid initial centres
+    const int gy = k / d.nx, gx = k - gy * d.nx;
+    const float cy = (gy + 0.5f) * d.H / d.ny, cx = (gx + 0.5f) * d.W / d.nx;
+    int py = (int)cy, px = (int)cx;
+    py = py < d.H ? py : d.H - 1; px = px < d.W ? px : d.W - 1;
+    const float* l = lab + ((long long)py * d.W + px) * 3;
+    cen[8 * k] = l[0]; cen[8 * k + 1] = l[1]; cen[8 * k + 2] = l[2]; cen[8 * k + 3] = cx; cen[8 * k + 4] = cy;
+  }
+  __syncthreads();
+
+  for (int it = 0; it <= iters; ++it) {
+    const bool last = it == iters;
+    // a warp owns an 8-pixel-wide strip of 32 rows: its lanes share the candidate grid columns (uniform control flow
+    // in the candidate loop) and meet only a few labels (few label groups in the warp-level merge of the sums)
+    for (int base = 0; base < Gs; base += kImgThreads) {                   // warp-uniform trip count
+      const int gi = base + tid;
+      const int band = gi / (gpr * 32), rem = gi - band * gpr * 32;
+      const int y0 = band * 32 + (rem & 31), x0 = (rem >> 5) << 3;
+      const bool active = y0 < d.H;
+      const int y = active ? y0 : d.H - 1;
+      const int gy = (int)((long long)y * d.ny / d.H);
+      float px[24];
+      {
+        const float4* src = reinterpret_cast<const float4*>(lab + ((long long)y * d.W + x0) * 3);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const float4 v = src[j];
+          px[4 * j] = v.x; px[4 * j + 1] = v.y; px[4 * j + 2] = v.z; px[4 * j + 3] = v.w;
+        }
+      }
+      // candidate grid columns of the run: its pixels lie in cell gx_lo or, past x_b, in gx_lo + 1 (the launcher
+      // takes this kernel only for grid cells at least 8 pixels wide)
+      const int gx_lo = (int)((long long)x0 * d.nx / d.W), gx_hi = (int)((long long)(x0 + 7) * d.nx / d.W);
+      int out[8];
+      {
+        const int x_b = (int)(((long long)(gx_lo + 1) * d.W + d.nx - 1) / d.nx);      // first x of cell gx_lo + 1
+        const int ib = x_b - x0;                                           // pixels i >= ib lie in cell gx_lo + 1
+        const unsigned m_hi = ib >= 8 ? 0u : (0xffu << (ib < 0 ? 0 : ib)) & 0xffu;
+        const float xf0 = x0 + 0.5f, yf = y + 0.5f;
+        float best[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = 3.4e38f; out[i] = gy * d.nx + gx_lo + (int)((m_hi >> i) & 1u); }
+        // candidates outermost (ascending centre index, as the per-pixel scan visits them): a centre's five values
+        // are read from shared memory once per run instead of once per pixel
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = gy + dy;
+          if (yy < 0 || yy >= d.ny) continue;
+#pragma unroll 1
+          for (int xx = gx_lo - 1; xx <= gx_hi + 1; ++xx) {
+            if (xx < 0 || xx >= d.nx) continue;
+            const int k = yy * d.nx + xx;
+            const float4 c4 = *reinterpret_cast<const float4*>(cen + 8 * k);      // L, a, b, x
+            const float sy = (yf - cen[8 * k + 4]) * inv_step;
+            // pixels this centre is a candidate of: the column left of the run's first cell serves the pixels of that
+            // cell only, the column right of its second cell the pixels of the second cell only
+            const unsigned cand = xx == gx_lo - 1 ? (~m_hi & 0xffu) : (xx == gx_lo + 2 ? m_hi : 0xffu);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float dl = px[3 * i] - c4.x, da = px[3 * i + 1] - c4.y, db = px[3 * i + 2] - c4.z;
+              const float sxx = ((xf0 + (float)i) - c4.w) * inv_step;      // xf0 + i is exact: same value as (x + 0.5f)
+              const float dist = slic_dist(dl, da, db, sy, sxx);
+              if (((cand >> i) & 1u) && dist < best[i]) { best[i] = dist; out[i] = k; }
+            }
+          }
+        }
+      }
+      if (last) {
+        if (active) {
+          int4* dst = reinterpret_cast<int4*>(labels + pix0 + (long long)y * d.W + x0);
+          dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+          dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+        }
+        continue;
+      }
+      // Sums of the run's pixels per label, in 32-bit fixed point (|v| <= 108 / compactness, compactness >= 1: eight
+      // pixels stay below 2^31).  A label run that closes inside the thread goes to the accumulators directly; the
+      // open run is first merged with the equal-label runs of the other lanes (match.any + redux.sync on 16-bit
+      // halves), so one lane per label and warp issues the atomics.  64-bit adds are two native 32-bit shared-memory
+      // atomics with the carry passed on (integer sums: any order gives the same total).
+      auto add64 = [&](int k, int j, long long v) {
+        unsigned* a = reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j);
+        const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
+        if (d.dbg & 2) return;
+        const unsigned old = atomicAdd(a, lo);
+        const unsigned h2 = hi + (((old + lo) < old) ? 1u : 0u);
+        if (h2) atomicAdd(a + 1, h2);
+      };
+      if (d.dbg & 1) continue;
+      // position and count sums stay below 2^32 per image for every shape this kernel is launched for: one 32-bit atomic
+      auto add32 = [&](int k, int j, int v) {
+        if (d.dbg & 2) return;
+        atomicAdd(reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j), (unsigned)v);
+      };
+      auto merge_and_add = [&](int key, int sL, int sA, int sB, int vy, int sx, int cnt) {
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int tL = __reduce_add_sync(peers, sL & 0xffff), hL = __reduce_add_sync(peers, sL >> 16);
+        const int tA = __reduce_add_sync(peers, sA & 0xffff), hA = __reduce_add_sync(peers, sA >> 16);
+        const int tB = __reduce_add_sync(peers, sB & 0xffff), hB = __reduce_add_sync(peers, sB >> 16);
+        const int ty = __reduce_add_sync(peers, vy), tx = __reduce_add_sync(peers, sx), tn = __reduce_add_sync(peers, cnt);
+        if (key >= 0 && lane == __ffs(peers) - 1) {
+          add64(key, 0, ((long long)hL << 16) + tL); add64(key, 1, ((long long)hA << 16) + tA);
+          add64(key, 2, ((long long)hB << 16) + tB);
+          add32(key, 3, ty); add32(key, 4, tx); add32(key, 5, tn);
+        }
+      };
+      int fx[24];
+#pragma unroll
+      for (int j = 0; j < 24; ++j) fx[j] = __float2int_rn(px[j] * (float)kFix);
+      const bool uniform = out[0] == out[1] && out[0] == out[2] && out[0] == out[3] && out[0] == out[4] &&
+                           out[0] == out[5] && out[0] == out[6] && out[0] == out[7];
+      if (__all_sync(0xffffffffu, uniform)) {
+        // the strip holds no vertical label boundary (3 strips of 4): one label per thread, straight sums
+        int sL = 0, sA = 0, sB = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sL += fx[3 * i]; sA += fx[3 * i + 1]; sB += fx[3 * i + 2]; }
+        merge_and_add(active ? out[0] : -1, sL, sA, sB, 8 * (2 * y + 1), 16 * x0 + 64, 8);
+      } else {
+        int run_k = -1, sL = 0, sA = 0, sB = 0, sx = 0, cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (active) {
+            if (out[i] != run_k) {
+              if (cnt > 0) {
+                add64(run_k, 0, sL); add64(run_k, 1, sA); add64(run_k, 2, sB);
+                add32(run_k, 3, cnt * (2 * y + 1)); add32(run_k, 4, sx); add32(run_k, 5, cnt);
+              }
+              run_k = out[i]; sL = sA = sB = sx = cnt = 0;
+            }
+            sL += fx[3 * i]; sA += fx[3 * i + 1]; sB += fx[3 * i + 2];
+            sx += 2 * (x0 + i) + 1;
+            cnt += 1;
+          }
+        }
+        merge_and_add(cnt > 0 ? run_k : -1, sL, sA, sB, cnt * (2 * y + 1), sx, cnt);
+      }
+    }
+    if (last) break;
+    __syncthreads();
+    for (int k = tid; k < K; k += kImgThreads) {                           // centre update (slic_update_kernel's arithmetic)
+      long long* a = acc + (size_t)k * 6;
+      const long long n = a[5];
+      if (n > 0) {
+        const double inv = 1.0 / (double)n;
+        cen[8 * k] = (float)((double)a[0] / kFix * inv);
+        cen[8 * k + 1] = (float)((double)a[1] / kFix * inv);
+        cen[8 * k + 2] = (float)((double)a[2] / kFix * inv);
+        cen[8 * k + 4] = (float)((double)a[3] * 0.5 * inv);
+        cen[8 * k + 3] = (float)((double)a[4] * 0.5 * inv);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a[j] = 0;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace gnc
 
 using namespace gnc;
@@ -226,14 +449,16 @@ static SlicDims slic_dims(int B, int H, int W, int n_segments, float compactness
   const double sy = (double)H / d.ny, sx = (double)W / d.nx;
   d.step = (float)(sy > sx ? sy : sx);
   d.inv_compactness = 1.0f / compactness;
+  d.dbg = getenv("GNC_SLIC_DBG") ? atoi(getenv("GNC_SLIC_DBG")) : 0;      // timing experiments (results invalid)
   return d;
 }
 
 extern "C" {
 
-// Debug: 1 = per-pixel form of the assignment kernel, anything else = runs of 8 pixels (same labels).
+// Debug: 1 = per-pixel form of the streaming assignment kernel, -8 = streaming form with runs of 8 pixels (one launch per
+// iteration), anything else = default (one CTA per image where the shape allows it, else the streaming form).  Same labels.
 int gnc_debug_slic_run_length(int run) {
-  g_slic_run = run == 1 ? 1 : 8;
+  g_slic_run = run == 1 ? 1 : (run == -8 ? -8 : 8);
   return GNC_OK;
 }
 
@@ -257,13 +482,28 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
   const SlicDims d = slic_dims(B, H, W, n_segments, compactness);
   const long long npix = (long long)B * H * W;
   float* lab = reinterpret_cast<float*>(work);
+  if (g_slic_run == 8 && d.K <= kImgMaxK && W % 8 == 0 && d.nx * 8 <= W && (double)H * W * (2.0 * (H > W ? H : W) + 1.0) < 4.0e9 && compactness >= 1.f && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(labels) |
+                                                         reinterpret_cast<uintptr_t>(lab)) & 15u) == 0) {
+    // one CTA per image, the whole loop in one launch
+    const int smem = d.K * (6 * 8 + 8 * 4) + 256 * 4;
+    static SmemAttrOnce smem_attr1, smem_attr2;
+    static const int min_blocks = getenv("GNC_SLIC_MINB") ? atoi(getenv("GNC_SLIC_MINB")) : 2;
+    if (min_blocks == 1) {
+      if (int rc_attr = smem_attr1.ensure(slic_image_kernel<1>, 227 * 1024, "slic_image")) return rc_attr;
+      slic_image_kernel<1><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
+    } else {
+      if (int rc_attr = smem_attr2.ensure(slic_image_kernel<2>, 227 * 1024, "slic_image")) return rc_attr;
+      slic_image_kernel<2><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
+    }
+    return check_launch("slic_image_kernel");
+  }
   float* centers = lab + npix * 3;
   long long* acc = reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(centers + (long long)B * d.K * 5 + 1) & ~(uintptr_t)7);
   cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)B * d.K * 6 * 8, st);
   if (e != cudaSuccess) return fail(GNC_ECUDA, "slic memset: %s", cudaGetErrorString(e));
   long long blocks = ceil_div<long long>(npix, 256);
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
-  const int run = g_slic_run;
+  const int run = g_slic_run == 1 ? 1 : 8;
   long long ablocks = ceil_div<long long>((long long)B * H * ceil_div<int>(W, run), 256);   // one thread per pixel run
   if (ablocks > (long long)kNumSMs * 32) ablocks = (long long)kNumSMs * 32;
   int rc;

@@ -124,12 +124,153 @@ __global__ void relabel_kernel(const int* __restrict__ parent, const int* __rest
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) out[g] = newid[tgt[parent[g]]];
 }
 
+
+// ---- one CTA per image, the union-find forest in shared memory (images of at most 65 536 pixels) -----------------------
+// The streaming form above hooks pixel to pixel through global memory: chains as long as a row, every hop an L2 round
+// trip (8 ms for 1024 label maps of 256 x 256).  A pixel index of a 256 x 256 image fits 16 bits, so a whole image's
+// parent array is 128 KB of shared memory and one CTA can run every step of the rule for its image on chip:
+//   1. parents start at the head of their horizontal run inside a 16-pixel span (no atomics), spans and rows are then
+//      joined with the same smaller-root-wins hooking (a run that continues to the left AND above with its left
+//      neighbour needs no vertical hook of its own);
+//   2. flatten; component sizes by run-length aggregated atomics on a per-image scratch row in global memory;
+//   3. small components point at the component of the pixel left of / above their first pixel (written over the
+//      root's own parent entry: "root" now means kept), chains are followed at read time;
+//   4. kept roots are numbered in scan order by a block scan; 5. every pixel looks up the number of the root it ends in.
+// Same rule, same result as the streaming form (tests/test_gpu_slic.py runs both against the CPU restatement).
+constexpr int kImgThreads = 1024;
+constexpr int kSpan = 16;
+
+__device__ __forceinline__ unsigned find_root16(const unsigned short* parent, unsigned x) {
+  unsigned p = parent[x];
+  while (p != x) { x = p; p = parent[x]; }
+  return x;
+}
+// atomicMin on a 16-bit shared-memory entry through a CAS on its 32-bit word; returns the previous value
+__device__ __forceinline__ unsigned atomic_min16(unsigned short* addr, unsigned val) {
+  unsigned* word = reinterpret_cast<unsigned*>(reinterpret_cast<uintptr_t>(addr) & ~(uintptr_t)3);
+  const bool hi = (reinterpret_cast<uintptr_t>(addr) & 2) != 0;
+  unsigned old = *word;
+  while (true) {
+    const unsigned cur = hi ? (old >> 16) : (old & 0xffffu);
+    if (cur <= val) return cur;
+    const unsigned nw = hi ? ((old & 0xffffu) | (val << 16)) : ((old & 0xffff0000u) | val);
+    const unsigned seen = atomicCAS(word, old, nw);
+    if (seen == old) return cur;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void unite16(unsigned short* parent, unsigned a, unsigned b) {
+  while (true) {
+    a = find_root16(parent, a);
+    b = find_root16(parent, b);
+    if (a == b) return;
+    if (a < b) { const unsigned t = a; a = b; b = t; }
+    const unsigned old = atomic_min16(parent + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void __launch_bounds__(kImgThreads, 1) image_kernel(const int32_t* __restrict__ labels, int H, int W, int min_size,
+                                                               int32_t* __restrict__ out, int32_t* __restrict__ n_out,
+                                                               int* __restrict__ scratch) {
+  extern __shared__ unsigned short parent[];                              // [H * W] (+ 1024 ints of scan space behind it)
+  const int hw = H * W, tid = threadIdx.x;
+  int* part = reinterpret_cast<int*>(parent + ((hw + 1) & ~1));
+  const int32_t* lab = labels + (long long)blockIdx.x * hw;
+  int* aux = scratch + (long long)blockIdx.x * hw;                        // sizes, later the new ids (roots only)
+  int32_t* dst = out + (long long)blockIdx.x * hw;
+  // 1a. horizontal runs inside spans of kSpan pixels
+  for (int s0 = tid * kSpan; s0 < hw; s0 += kImgThreads * kSpan) {
+    const int e = min(hw, s0 + kSpan);
+    int start = s0, prev = lab[s0];
+    parent[s0] = (unsigned short)s0;
+    aux[s0] = 0;
+    int x = s0 % W;
+    for (int p = s0 + 1; p < e; ++p) {
+      ++x;
+      if (x == W) x = 0;
+      const int l = lab[p];
+      if (x == 0 || l != prev) start = p;
+      parent[p] = (unsigned short)start;
+      aux[p] = 0;
+      prev = l;
+    }
+  }
+  __syncthreads();
+  // 1b. join spans along the row and runs across rows
+  for (int p = tid; p < hw; p += kImgThreads) {
+    const int y = p / W, x = p - y * W;
+    const int l = lab[p];
+    const bool left = x > 0 && lab[p - 1] == l;
+    if (left && (p % kSpan) == 0) unite16(parent, p, p - 1);
+    if (y > 0 && lab[p - W] == l && !(left && lab[p - W - 1] == l)) unite16(parent, p, p - W);
+  }
+  __syncthreads();
+  // 2. flatten, then sizes (one atomic per run of equal roots in a span)
+  for (int p = tid; p < hw; p += kImgThreads) parent[p] = (unsigned short)find_root16(parent, p);
+  __syncthreads();
+  for (int s0 = tid * kSpan; s0 < hw; s0 += kImgThreads * kSpan) {
+    const int e = min(hw, s0 + kSpan);
+    unsigned r = parent[s0];
+    int n = 1;
+    for (int p = s0 + 1; p < e; ++p) {
+      const unsigned q = parent[p];
+      if (q == r) { ++n; continue; }
+      atomicAdd(aux + r, n);
+      r = q; n = 1;
+    }
+    atomicAdd(aux + r, n);
+  }
+  __syncthreads();
+  // 3. small components dissolve into the component left of / above their first pixel
+  for (int p = tid; p < hw; p += kImgThreads) {
+    if (parent[p] != p || aux[p] >= min_size) continue;
+    const int y = p / W, x = p - y * W;
+    if (x > 0) parent[p] = parent[p - 1];
+    else if (y > 0) parent[p] = parent[p - W];
+  }
+  __syncthreads();
+  // 4. kept roots in scan order: contiguous chunk per thread, block scan of the counts
+  const int per = (hw + kImgThreads - 1) / kImgThreads;
+  const int lo = min(hw, tid * per), hi = min(hw, lo + per);
+  int cnt = 0;
+  for (int p = lo; p < hi; ++p) cnt += parent[p] == p ? 1 : 0;
+  part[tid] = cnt;
+  __syncthreads();
+  for (int off = 1; off < kImgThreads; off <<= 1) {
+    const int v = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int id = part[tid] - cnt;
+  for (int p = lo; p < hi; ++p)
+    if (parent[p] == p) aux[p] = id++;
+  if (tid == kImgThreads - 1 && n_out) n_out[blockIdx.x] = part[kImgThreads - 1];
+  __syncthreads();
+  // 5. relabel
+  for (int p = tid; p < hw; p += kImgThreads) {
+    unsigned r = parent[p];
+    while (true) { const unsigned t = parent[r]; if (t == r) break; r = t; }
+    dst[p] = aux[r];
+  }
+}
+
 }  // namespace cc
 }  // namespace gnc
 
 using namespace gnc;
 
+static int g_cc_streaming = 0;
+
 extern "C" {
+
+// Debug: 1 = always the streaming (global-memory union-find) form, 0 = one CTA per image where the image fits.
+int gnc_debug_slic_connect_streaming(int on) {
+  g_cc_streaming = on ? 1 : 0;
+  return GNC_OK;
+}
 
 // work: int32 [gnc_slic_connectivity_workspace(B, H, W)]
 int64_t gnc_slic_connectivity_workspace(int B, int H, int W) { return 3 * (int64_t)B * H * W; }
@@ -141,6 +282,13 @@ int gnc_slic_enforce_connectivity(const int32_t* labels, int B, int H, int W, in
   GNC_REQUIRE(n < 2147483647LL, "slic_enforce_connectivity: at most 2^31 - 1 pixels per call");
   if (!work || work_elems < 3 * n) return fail(GNC_EWORKSPACE, "%s", "slic_enforce_connectivity: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (H * (long long)W <= 65536 && g_cc_streaming == 0) {
+    const int smem = (int)(((H * W + 1) & ~1) * 2 + cc::kImgThreads * 4);
+    static SmemAttrOnce smem_attr;
+    if (int rc_attr = smem_attr.ensure(cc::image_kernel, 227 * 1024, "slic_connect_image")) return rc_attr;
+    cc::image_kernel<<<(unsigned)B, cc::kImgThreads, smem, st>>>(labels, H, W, min_size, out, n_labels, work);
+    return check_launch("cc_image_kernel");
+  }
   int* parent = work;
   int* size = work + n;
   int* tgt = work + 2 * n;

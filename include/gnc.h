@@ -120,8 +120,13 @@ int gnc_slic_num_centers(int H, int W, int n_segments);
 int64_t gnc_slic_workspace_bytes(int B, int H, int W, int n_segments);
 int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, float compactness, int iters,
                        int32_t* labels, void* work, gnc_stream_t stream);
-/* Debug aid: 1 = one set of centre atomics per pixel instead of per 8-pixel label run (same result). */
+/* Debug aid: 1 = streaming form (one launch per iteration) with one set of centre atomics per pixel, -8 = streaming form
+ * with one set per 8-pixel label run, anything else = default (one CTA per image runs the whole loop in one launch
+ * when W % 8 == 0 and there are at most 1024 centres; the streaming form otherwise).  Same labels in every form. */
 int gnc_debug_slic_run_length(int run);
+/* Debug aid: 1 = gnc_slic_enforce_connectivity always uses the streaming (global-memory union-find) form, 0 = default
+ * (one CTA per image with the forest in shared memory when H * W <= 65536).  Same result. */
+int gnc_debug_slic_connect_streaming(int on);
 
 /* Input staging: the resize the reference applies to every image before building its graph,
  *   Image.open(path).convert('RGB').resize((r, r))     utils/image_to_graph/image_to_graph_optimized.py:65-70,

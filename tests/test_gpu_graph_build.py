@@ -219,17 +219,25 @@ def test_device_slic_properties_and_superpixel_pipeline(libgnc):
 
 
 def test_slic_run_aggregation_equals_per_pixel_atomics(libgnc):
-    """The assignment kernel accumulates centre sums per 8-pixel label run; the per-pixel form (debug switch)
-    must give the same labels, also for widths that are not a multiple of 8."""
+    """Three forms of the same algorithm must give the same labels: the streaming assignment kernel with one set of
+    centre atomics per pixel (debug switch 1), the streaming kernel with sums per 8-pixel label run (-8), and the default
+    (one CTA per image runs colour conversion, all iterations and the final assignment in one launch when the width is
+    a multiple of 8; the streaming form otherwise) - also for widths that are not a multiple of 8 and for more images
+    than SMs."""
     from graphnet_classifier_b200.utils.image_to_graph.slic import slic_labels
     rng = np.random.default_rng(3)
-    for (B, H, W, S) in ((2, 64, 64, 16), (3, 50, 61, 12), (1, 256, 256, 100)):
+    for (B, H, W, S) in ((2, 64, 64, 16), (3, 50, 61, 12), (1, 256, 256, 100), (5, 40, 72, 30), (160, 32, 32, 9)):
         low = rng.random((B, 6, 6, 3))
         img = np.kron(low, np.ones((1, H // 6 + 1, W // 6 + 1, 1)))[:, :H, :W]
         img = np.clip(img * 255 + rng.integers(-6, 7, (B, H, W, 3)), 0, 255).astype(np.uint8)
         t = torch.from_numpy(img).cuda()
-        libgnc.gnc_debug_slic_run_length(1)
-        ref = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
-        libgnc.gnc_debug_slic_run_length(8)
+        try:
+            libgnc.gnc_debug_slic_run_length(1)
+            ref = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
+            libgnc.gnc_debug_slic_run_length(-8)
+            run8 = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
+        finally:
+            libgnc.gnc_debug_slic_run_length(8)
         got = slic_labels(t, n_segments=S, compactness=10.0, enforce_connectivity_=False)
-        assert torch.equal(ref, got)
+        assert torch.equal(ref, run8), (B, H, W, S)
+        assert torch.equal(ref, got), (B, H, W, S, int((ref != got).sum()))

@@ -46,9 +46,12 @@ def _check_properties(out: np.ndarray, min_size: int):
     assert out.min() == 0 and len(np.unique(out)) == out.max() + 1
 
 
+@pytest.mark.parametrize("streaming", [0, 1])
 @pytest.mark.parametrize("H,W,K,min_size", [(32, 32, 6, 8), (50, 61, 12, 20), (64, 64, 4, 0), (40, 40, 30, 10_000), (1, 97, 5, 3),
-                                             (97, 1, 5, 3), (256, 256, 100, 327)])
-def test_connectivity_equals_cpu_restatement(H, W, K, min_size):
+                                             (97, 1, 5, 3), (256, 256, 100, 327), (31, 17, 3, 5)])
+def test_connectivity_equals_cpu_restatement(H, W, K, min_size, streaming, libgnc):
+    """Both device forms - one CTA per image with the forest in shared memory (default for images of at most 65 536
+    pixels) and the streaming global-memory union-find - against the CPU restatement of the stated rule."""
     from graphnet_classifier_b200.utils.image_to_graph.slic import enforce_connectivity
     rng = np.random.default_rng(H * 1000 + W)
     # smooth label maps (Voronoi cells) with salt noise: large regions plus many tiny components
@@ -58,7 +61,11 @@ def test_connectivity_equals_cpu_restatement(H, W, K, min_size):
     noise = rng.random((H, W)) < 0.08
     lab[noise] = rng.integers(0, K, int(noise.sum()))
     labs = np.stack([lab, np.roll(lab, 3, axis=1), (lab * 7 + 1) % K])          # a batch: images are independent
-    got = enforce_connectivity(torch.from_numpy(labs).cuda(), min_size).cpu().numpy()
+    libgnc.gnc_debug_slic_connect_streaming(streaming)
+    try:
+        got = enforce_connectivity(torch.from_numpy(labs).cuda(), min_size).cpu().numpy()
+    finally:
+        libgnc.gnc_debug_slic_connect_streaming(0)
     for b in range(labs.shape[0]):
         assert np.array_equal(got[b], enforce_connectivity_ref(labs[b], min_size)), b
         if min_size <= H * W:
