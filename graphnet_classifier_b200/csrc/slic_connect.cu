@@ -129,16 +129,17 @@ __global__ void relabel_kernel(const int* __restrict__ parent, const int* __rest
 // The streaming form above hooks pixel to pixel through global memory: chains as long as a row, every hop an L2 round
 // trip (8 ms for 1024 label maps of 256 x 256).  A pixel index of a 256 x 256 image fits 16 bits, so a whole image's
 // parent array is 128 KB of shared memory and one CTA can run every step of the rule for its image on chip:
-//   1. parents start at the head of their horizontal run inside a 16-pixel span (no atomics), spans and rows are then
-//      joined with the same smaller-root-wins hooking (a run that continues to the left AND above with its left
-//      neighbour needs no vertical hook of its own);
+//   0. one coalesced pass turns the labels into two bitmaps (same label as the left / upper neighbour);
+//   1. parents start at the head of their horizontal run inside a 32-pixel word (bit tricks, no atomics), words and
+//      rows are then joined with the same smaller-root-wins hooking (a pixel whose left neighbour continues its run
+//      and hangs under the same upper run needs no vertical hook of its own);
 //   2. flatten; component sizes by run-length aggregated atomics on a per-image scratch row in global memory;
 //   3. small components point at the component of the pixel left of / above their first pixel (written over the
 //      root's own parent entry: "root" now means kept), chains are followed at read time;
-//   4. kept roots are numbered in scan order by a block scan; 5. every pixel looks up the number of the root it ends in.
+//   4. kept roots are numbered in scan order (ballot per word, scan of the word counts); 5. every pixel looks up the
+//      number of the root it ends in.
 // Same rule, same result as the streaming form (tests/test_gpu_slic.py runs both against the CPU restatement).
 constexpr int kImgThreads = 1024;
-constexpr int kSpan = 16;
 
 __device__ __forceinline__ unsigned find_root16(const unsigned short* parent, unsigned x) {
   unsigned p = parent[x];
@@ -174,53 +175,65 @@ __device__ __forceinline__ void unite16(unsigned short* parent, unsigned a, unsi
 __global__ void __launch_bounds__(kImgThreads, 1) image_kernel(const int32_t* __restrict__ labels, int H, int W, int min_size,
                                                                int32_t* __restrict__ out, int32_t* __restrict__ n_out,
                                                                int* __restrict__ scratch) {
-  extern __shared__ unsigned short parent[];                              // [H * W] (+ 1024 ints of scan space behind it)
-  const int hw = H * W, tid = threadIdx.x;
-  int* part = reinterpret_cast<int*>(parent + ((hw + 1) & ~1));
+  extern __shared__ unsigned short parent[];                              // [H * W], then the words below
+  const int hw = H * W, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwords = (hw + 31) >> 5;
+  unsigned* same_left = reinterpret_cast<unsigned*>(parent + ((hw + 1) & ~1));   // bit p: pixel p continues the run of p - 1
+  unsigned* same_up = same_left + nwords;                                 // bit p: same label as the pixel above
+  int* part = reinterpret_cast<int*>(same_up + nwords);                   // [nwords + 1]: kept roots per 32 pixels, scanned
+  __shared__ int warp_tot[kImgThreads / 32];
   const int32_t* lab = labels + (long long)blockIdx.x * hw;
   int* aux = scratch + (long long)blockIdx.x * hw;                        // sizes, later the new ids (roots only)
   int32_t* dst = out + (long long)blockIdx.x * hw;
-  // 1a. horizontal runs inside spans of kSpan pixels
-  for (int s0 = tid * kSpan; s0 < hw; s0 += kImgThreads * kSpan) {
-    const int e = min(hw, s0 + kSpan);
-    int start = s0, prev = lab[s0];
-    parent[s0] = (unsigned short)s0;
-    aux[s0] = 0;
-    int x = s0 % W;
-    for (int p = s0 + 1; p < e; ++p) {
-      ++x;
-      if (x == W) x = 0;
+  const int hw32 = nwords << 5;
+  // 0. neighbour-equality bitmaps (coalesced label reads, one ballot per 32 pixels); everything below reads these
+  for (int p = tid; p < hw32; p += kImgThreads) {
+    bool sl = false, su = false;
+    if (p < hw) {
+      const int y = p / W, x = p - y * W;
       const int l = lab[p];
-      if (x == 0 || l != prev) start = p;
-      parent[p] = (unsigned short)start;
+      sl = x > 0 && lab[p - 1] == l;
+      su = y > 0 && lab[p - W] == l;
       aux[p] = 0;
-      prev = l;
+    }
+    const unsigned bl = __ballot_sync(0xffffffffu, sl), bu = __ballot_sync(0xffffffffu, su);
+    if (lane == 0) { same_left[p >> 5] = bl; same_up[p >> 5] = bu; }
+  }
+  __syncthreads();
+  // 1a. every pixel starts at the head of its horizontal run inside its 32-pixel word (bit tricks, no atomics)
+  for (int p = tid; p < hw; p += kImgThreads) {
+    const unsigned w = same_left[p >> 5];
+    const int j = p & 31;
+    const int run = __clz(~(w << (31 - j)));                              // set bits ending at bit j (0 .. j + 1)
+    parent[p] = (unsigned short)(p - (run > j ? j : run));
+  }
+  __syncthreads();
+  // 1b. join words along the row and runs across rows.  A pixel whose left neighbour continues the run and hangs
+  // under the same upper run (same_left(p) and same_up(p - 1)) needs no vertical hook of its own.
+  for (int p = tid; p < hw; p += kImgThreads) {
+    const int j = p & 31, wi = p >> 5;
+    const unsigned wl = same_left[wi], wu = same_up[wi];
+    const bool sl = (wl >> j) & 1u, su = (wu >> j) & 1u;
+    if (sl && j == 0) unite16(parent, p, p - 1);
+    if (su) {
+      const bool su_prev = j > 0 ? ((wu >> (j - 1)) & 1u) : (wi > 0 ? (same_up[wi - 1] >> 31) & 1u : 0u);
+      if (!(sl && su_prev)) unite16(parent, p, p - W);
     }
   }
   __syncthreads();
-  // 1b. join spans along the row and runs across rows
-  for (int p = tid; p < hw; p += kImgThreads) {
-    const int y = p / W, x = p - y * W;
-    const int l = lab[p];
-    const bool left = x > 0 && lab[p - 1] == l;
-    if (left && (p % kSpan) == 0) unite16(parent, p, p - 1);
-    if (y > 0 && lab[p - W] == l && !(left && lab[p - W - 1] == l)) unite16(parent, p, p - W);
-  }
-  __syncthreads();
-  // 2. flatten, then sizes (one atomic per run of equal roots in a span)
+  // 2. flatten, then sizes: one atomic per run of equal roots inside a warp's 32 consecutive pixels
   for (int p = tid; p < hw; p += kImgThreads) parent[p] = (unsigned short)find_root16(parent, p);
   __syncthreads();
-  for (int s0 = tid * kSpan; s0 < hw; s0 += kImgThreads * kSpan) {
-    const int e = min(hw, s0 + kSpan);
-    unsigned r = parent[s0];
-    int n = 1;
-    for (int p = s0 + 1; p < e; ++p) {
-      const unsigned q = parent[p];
-      if (q == r) { ++n; continue; }
-      atomicAdd(aux + r, n);
-      r = q; n = 1;
+  for (int p = tid; p < hw32; p += kImgThreads) {
+    const int r = p < hw ? (int)parent[p] : -1;
+    const int prev = __shfl_up_sync(0xffffffffu, r, 1);
+    const bool head = lane == 0 || prev != r;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (head && r >= 0) {
+      const unsigned higher = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+      const int end = higher ? __ffs(higher) - 1 : 32;                    // first lane of the next run
+      atomicAdd(aux + r, end - lane);
     }
-    atomicAdd(aux + r, n);
   }
   __syncthreads();
   // 3. small components dissolve into the component left of / above their first pixel
@@ -231,23 +244,41 @@ __global__ void __launch_bounds__(kImgThreads, 1) image_kernel(const int32_t* __
     else if (y > 0) parent[p] = parent[p - W];
   }
   __syncthreads();
-  // 4. kept roots in scan order: contiguous chunk per thread, block scan of the counts
-  const int per = (hw + kImgThreads - 1) / kImgThreads;
-  const int lo = min(hw, tid * per), hi = min(hw, lo + per);
-  int cnt = 0;
-  for (int p = lo; p < hi; ++p) cnt += parent[p] == p ? 1 : 0;
-  part[tid] = cnt;
-  __syncthreads();
-  for (int off = 1; off < kImgThreads; off <<= 1) {
-    const int v = tid >= off ? part[tid - off] : 0;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
+  // 4. kept roots in scan order: count per 32-pixel word, scan the counts, rank inside the word by the ballot
+  for (int p = tid; p < hw32; p += kImgThreads) {
+    const bool root = p < hw && parent[p] == p;
+    const unsigned b = __ballot_sync(0xffffffffu, root);
+    if (lane == 0) { part[p >> 5] = __popc(b); same_left[p >> 5] = b; }   // the bitmap is free again: root flags
   }
-  int id = part[tid] - cnt;
-  for (int p = lo; p < hi; ++p)
-    if (parent[p] == p) aux[p] = id++;
-  if (tid == kImgThreads - 1 && n_out) n_out[blockIdx.x] = part[kImgThreads - 1];
+  __syncthreads();
+  {
+    // exclusive scan of part[0 .. nwords): contiguous chunk per thread, warp scan of the chunk totals, warp totals
+    const int per = (nwords + kImgThreads - 1) / kImgThreads;
+    const int lo = min(nwords, tid * per), hi = min(nwords, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += part[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+      int ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += v; }
+      warp_tot[lane] = ti - t;
+      if (lane == 31 && n_out) n_out[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    int run = warp_tot[warp] + incl - sum;
+    for (int i = lo; i < hi; ++i) { const int c = part[i]; part[i] = run; run += c; }
+  }
+  __syncthreads();
+  for (int p = tid; p < hw; p += kImgThreads) {
+    if (parent[p] != p) continue;
+    aux[p] = part[p >> 5] + __popc(same_left[p >> 5] & ((1u << (p & 31)) - 1u));
+  }
   __syncthreads();
   // 5. relabel
   for (int p = tid; p < hw; p += kImgThreads) {
@@ -283,9 +314,9 @@ int gnc_slic_enforce_connectivity(const int32_t* labels, int B, int H, int W, in
   if (!work || work_elems < 3 * n) return fail(GNC_EWORKSPACE, "%s", "slic_enforce_connectivity: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (H * (long long)W <= 65536 && g_cc_streaming == 0) {
-    const int smem = (int)(((H * W + 1) & ~1) * 2 + cc::kImgThreads * 4);
+    const int smem = (int)(((H * W + 1) & ~1) * 2 + (3 * ((H * W + 31) / 32) + 2) * 4);
     static SmemAttrOnce smem_attr;
-    if (int rc_attr = smem_attr.ensure(cc::image_kernel, 227 * 1024, "slic_connect_image")) return rc_attr;
+    if (int rc_attr = smem_attr.ensure(cc::image_kernel, 226 * 1024, "slic_connect_image")) return rc_attr;
     cc::image_kernel<<<(unsigned)B, cc::kImgThreads, smem, st>>>(labels, H, W, min_size, out, n_labels, work);
     return check_launch("cc_image_kernel");
   }
