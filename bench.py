@@ -671,6 +671,78 @@ def run_ours(args):
                                 "api": "GraphClassifierPipeline.infer(pinned uint8 host photos) -> logits.cpu()"},
         }
         del photos_dev, photos_host
+        # ---- from image FILES: threaded host decode (utils/staging.DecodePool) -> pinned double-buffered copies -> the
+        # same device path.  The files are synthetic JPEGs written to a temporary directory (no dataset on the box).
+        if world == 1:      # the host cores are shared by the ranks of a box: measured where one rank has them all
+            import shutil
+            import tempfile
+            from PIL import Image
+            from graphnet_classifier_b200.utils.staging import DecodePool, infer_files
+            n_files = B
+            tmpd = tempfile.mkdtemp(prefix="gnc_bench_")
+            try:
+                paths = []
+                for i in range(n_files):
+                    low = rng.integers(0, 256, (ph // 16 + 2, pw // 16 + 2, 3), dtype=np.uint8)
+                    im = Image.fromarray(low).resize((pw, ph), Image.BICUBIC)
+                    pth = os.path.join(tmpd, f"{i}.jpg")
+                    im.save(pth, quality=90)
+                    paths.append(pth)
+                file_bytes = sum(os.path.getsize(pth) for pth in paths)
+                t0 = time.perf_counter()
+                for pth in paths[:32]:
+                    np.asarray(Image.open(pth).convert("RGB"))
+                one_core = 32 / (time.perf_counter() - t0)
+                with DecodePool(device=dev) as pool:
+                    infer_files(pipe, paths, pool=pool).cpu()                # warm-up: staging buffers, resize tables
+                    torch.cuda.synchronize()
+                    reps = 3
+                    t0 = time.perf_counter()
+                    for _ in range(reps):
+                        infer_files(pipe, paths, pool=pool).cpu()
+                    torch.cuda.synchronize()
+                    dt = (time.perf_counter() - t0) / reps
+                    workers = pool.workers
+                staging["e2e_from_files"] = {
+                    "value": n_files / dt, "unit": UNIT, "files_per_step": n_files, "ms_per_step": dt * 1e3,
+                    "decode_threads": workers, "host_cpu_count": os.cpu_count(),
+                    "one_thread_pil_decode_images_per_s": one_core, "file_bytes_per_step": file_bytes,
+                    "h2d_bytes_per_step": n_files * ph * pw * 3, "d2h_bytes_per_step": n_files * 8,
+                    "timing": "wall clock around the whole call (host decode is part of it), this rank only",
+                    "api": "utils.staging.infer_files(pipeline, jpeg paths): threaded PIL decode -> pinned double-buffered H2D "
+                           "-> device resize -> graph build -> GraphNet -> logits.cpu()"}
+                # nvJPEG (library: torchvision.io.decode_jpeg on the device) on the same files, measured as the
+                # alternative to the host decode.  NOT on the default path: its IDCT / chroma upsampling differ from
+                # libjpeg's, so the pixels are not the reference's - the difference against PIL is stated here.
+                try:
+                    from torchvision.io import decode_jpeg, read_file
+                    datas = [read_file(pth) for pth in paths]
+                    for _ in range(2):
+                        dec = decode_jpeg(datas, device=dev)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        dec = decode_jpeg(datas, device=dev)
+                    torch.cuda.synchronize()
+                    nv_dt = (time.perf_counter() - t0) / 3
+                    worst, mean, same = 0, 0.0, 0
+                    for pth, dimg in list(zip(paths, dec))[:64]:
+                        ref_px = torch.from_numpy(np.asarray(Image.open(pth).convert("RGB"))).to(dev)
+                        diff = (dimg.permute(1, 2, 0).int() - ref_px.int()).abs()
+                        worst = max(worst, int(diff.max()))
+                        mean += float(diff.float().mean()) / 64
+                        same += int(diff.max() == 0)
+                    staging["nvjpeg_alternative"] = {
+                        "images_per_s": n_files / nv_dt, "ms_per_step": nv_dt * 1e3, "files_per_step": n_files,
+                        "max_abs_pixel_diff_vs_pil": worst, "mean_abs_pixel_diff_vs_pil": mean,
+                        "bit_identical_images_of_64": same,
+                        "what": "torchvision.io.decode_jpeg(list of file bytes, device=cuda) = nvJPEG batched decode (file "
+                                "bytes already in host memory); library call, reported for comparison only"}
+                    del dec, datas
+                except Exception as exc:            # torchvision built without nvJPEG, or absent
+                    staging["nvjpeg_alternative"] = {"unavailable": str(exc)[:200]}
+            finally:
+                shutil.rmtree(tmpd, ignore_errors=True)
 
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:

@@ -88,6 +88,7 @@ class BatchedShardLoader:
         self.method, self.diagonals, self.patch_size = method, bool(diagonals), int(patch_size)
         self.rank, self.world_size, self.seed, self.shuffle = int(rank), int(world_size), int(seed), bool(shuffle)
         self.epoch = 0
+        self._pool = None               # utils.staging.DecodePool, created on first iteration (needs the CUDA device)
 
     def plan(self, epoch):
         """Index lists of this rank's shards for ``epoch`` (pure host logic)."""
@@ -111,12 +112,15 @@ class BatchedShardLoader:
 
     def __iter__(self):
         from .utils.image_to_graph.batched import build_patch_graphs, build_pixel_graphs
-        from .utils.image_to_graph.image_to_graph_optimized import load_rgb_device
+        from .utils.staging import DecodePool
         shards = self.plan(self.epoch)
         self.epoch += 1
+        if self._pool is None:
+            self._pool = DecodePool()
         for idxs in shards:
-            items = [self.dataset[i] for i in idxs]
-            pixels = torch.stack([load_rgb_device(img, self.resize_value) for img, _ in items])
+            # dataset[i] opens and decodes the file (ImageFolder's loader): on the pool's threads, not one by one here
+            items = list(self._pool.pool.map(self.dataset.__getitem__, idxs))
+            pixels = self._pool.stage([img for img, _ in items], self.resize_value)
             if self.method == "pixel":
                 gb = build_pixel_graphs(pixels, diagonals=self.diagonals)
             else:

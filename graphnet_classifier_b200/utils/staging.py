@@ -1,0 +1,236 @@
+"""Input staging from image FILES: the reference opens one file at a time on the training thread,
+``Image.open(path).convert('RGB').resize((r, r))`` (utils/dataloader.py:34 through torchvision's ImageFolder,
+utils/image_to_graph/image_to_graph_optimized.py:65-70, utils/inference.py:47).  Here
+
+* the decode (``Image.open`` + ``convert('RGB')``: libjpeg inside Pillow) runs on a pool of host PROCESSES (Pillow's
+  Python-level file handling holds the GIL for about half of a small file's decode time: 8 threads give 2 x one
+  thread, processes scale with the cores), each image decoded straight into its slot of a shared-memory staging
+  buffer that is registered with CUDA as pinned memory; PIL images that are already open (no path to hand to another
+  process) are decoded on a thread pool instead;
+* images of one shape travel as ONE host->device copy on a copy stream; two staging buffers alternate, so the pool
+  decodes chunk ``i + 1`` while chunk ``i`` is copied and consumed;
+* the resize is the Pillow-exact device kernel (``ops.resize_bicubic``), so the pixels that reach the graph builder are
+  bit for bit the reference's.
+
+The entropy decode stays on the host: it is sequential per image (no restart markers in Pillow-written files), and one
+GPU thread per image runs it at a few hundred MIPS - not worth a kernel while the box's cores are idle.
+"""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from PIL import Image
+from torch import Tensor
+
+from .. import ops
+
+
+def _decode(path_or_image) -> np.ndarray:
+    image = Image.open(path_or_image) if isinstance(path_or_image, (str, os.PathLike)) else path_or_image
+    return np.asarray(image.convert("RGB"), dtype=np.uint8)
+
+
+class _SharedPinned:
+    """A shared-memory segment (visible to the worker processes by name) registered with CUDA as pinned host memory."""
+
+    def __init__(self, nbytes: int):
+        from multiprocessing import shared_memory
+        self.seg = shared_memory.SharedMemory(create=True, size=int(nbytes))
+        self.tensor = torch.frombuffer(self.seg.buf, dtype=torch.uint8, count=int(nbytes))
+        rt = torch.cuda.cudart()
+        err = rt.cudaHostRegister(self.tensor.data_ptr(), int(nbytes), 0)
+        self.registered = int(err) == 0
+        self.nbytes = int(nbytes)
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
+        self.tensor = None
+        try:
+            self.seg.close()
+            self.seg.unlink()
+        except (BufferError, FileNotFoundError):
+            pass
+
+
+class DecodePool:
+    """``stage(items, resize_value)`` -> ``uint8 [n, r, r, 3]`` on the device for ``items`` = file paths or PIL images.
+    ``batches(items, resize_value, chunk)`` yields the same in chunks with decode / copy / compute overlapped.
+    ``processes=True`` (default) decodes file paths on worker processes into shared pinned memory; PIL images and
+    ``processes=False`` use the thread pool."""
+
+    def __init__(self, workers: Optional[int] = None, device=None, processes: bool = True, slot_bytes: int = 1 << 20):
+        self.workers = int(workers) if workers else max(1, (os.cpu_count() or 2) - 1)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("DecodePool stages onto a CUDA device (no CPU fallback)")
+        self.pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="gnc-decode")
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._pinned = [None, None]             # two staging buffers (bytes), grown on demand
+        self._events = [None, None]             # "buffer's last copy has finished"
+        self.processes = bool(processes)
+        self.slot_bytes = int(slot_bytes)       # one decoded image per slot (1 MiB holds 512 x 682 RGB; larger images come back through the pipe)
+        self._procs = None
+        self._shared = [None, None]
+
+    def _process_pool(self):
+        if self._procs is None:
+            import multiprocessing as mp
+            from concurrent.futures import ProcessPoolExecutor
+            from . import _decode_worker
+            self._procs = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("spawn"))
+            list(self._procs.map(_decode_worker.warm, range(2 * self.workers)))      # start the interpreters now
+        return self._procs
+
+    def close(self) -> None:
+        self.pool.shutdown(wait=True)
+        if self._procs is not None:
+            self._procs.shutdown(wait=True)
+            self._procs = None
+        torch.cuda.synchronize(self.device)
+        for i, sh in enumerate(self._shared):
+            if sh is not None:
+                sh.close()
+                self._shared[i] = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    # -- one chunk ---------------------------------------------------------------------
+    def _staging(self, slot: int, nbytes: int) -> Tensor:
+        buf = self._pinned[slot]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+            self._pinned[slot] = buf
+        return buf
+
+    def _decode_chunk_processes(self, paths: Sequence, slot: int):
+        """File paths decoded by the worker processes into slots of the shared pinned buffer; returns
+        ``[(shape, indices, [pinned views [H, W, 3]])]`` grouped by shape."""
+        from . import _decode_worker
+        procs = self._process_pool()
+        need = len(paths) * self.slot_bytes
+        sh = self._shared[slot]
+        if sh is None or sh.nbytes < need:
+            if sh is not None:
+                torch.cuda.synchronize(self.device)
+                sh.close()
+            try:
+                sh = self._shared[slot] = _SharedPinned(max(need, 64 * self.slot_bytes))
+            except OSError:                     # /dev/shm too small for the staging buffers: decode on the thread pool
+                self._shared[slot] = None
+                self.processes = False
+                return self._decode_chunk(paths, slot)
+        work = [(str(p), sh.seg.name, i * self.slot_bytes, self.slot_bytes) for i, p in enumerate(paths)]
+        results = list(procs.map(_decode_worker.decode_into, work, chunksize=max(1, len(work) // (4 * self.workers))))
+        groups = {}
+        for i, (h, w, spill) in enumerate(results):
+            n = h * w * 3
+            if spill is not None:               # larger than a slot: came back through the pipe
+                view = torch.from_numpy(np.ascontiguousarray(spill))
+            else:
+                view = sh.tensor[i * self.slot_bytes:i * self.slot_bytes + n].view(h, w, 3)
+            groups.setdefault((h, w, 3), ([], []))
+            groups[(h, w, 3)][0].append(i)
+            groups[(h, w, 3)][1].append(view)
+        return [(shape, idxs, views) for shape, (idxs, views) in groups.items()]
+
+    def _decode_chunk(self, items: Sequence, slot: int):
+        """Decodes ``items`` on the pool; returns ``[(shape, indices, pinned view [k, H, W, 3])]`` grouped by shape."""
+        if self._events[slot] is not None:
+            self._events[slot].synchronize()            # the previous copy out of this buffer is done
+        if self.processes and items and all(isinstance(it, (str, os.PathLike)) for it in items):
+            return self._decode_chunk_processes(items, slot)
+        arrays: List[np.ndarray] = list(self.pool.map(_decode, items))
+        groups = {}
+        for i, a in enumerate(arrays):
+            groups.setdefault(a.shape, []).append(i)
+        total = sum(a.nbytes for a in arrays)
+        buf = self._staging(slot, total)
+        out, off = [], 0
+        for shape, idxs in groups.items():
+            n = len(idxs) * int(np.prod(shape))
+            view = buf[off:off + n].view(len(idxs), *shape)
+            dst = view.numpy()
+
+            def put(j_i, dst=dst):
+                j, i = j_i
+                dst[j] = arrays[i]
+
+            list(self.pool.map(put, enumerate(idxs)))   # the copies into pinned memory are spread over the pool too
+            out.append((shape, idxs, view))
+            off += n
+        return out
+
+    def _upload(self, groups, slot: int, resize_value: int) -> Tensor:
+        """Host->device copies on the copy stream, Pillow-exact resize on the device; returns ``[n, r, r, 3]`` in item
+        order.  The caller's stream waits for the copies only."""
+        r = int(resize_value)
+        n = sum(len(idxs) for _, idxs, _ in groups)
+        cur = torch.cuda.current_stream(self.device)
+        parts = []
+        with torch.cuda.stream(self.copy_stream):
+            for shape, idxs, view in groups:
+                if isinstance(view, list):      # one pinned slot per image: gathered into a device batch by async copies
+                    dev_batch = torch.empty(len(idxs), *shape, dtype=torch.uint8, device=self.device)
+                    for j, v in enumerate(view):
+                        dev_batch[j].copy_(v, non_blocking=True)
+                    parts.append((idxs, dev_batch))
+                else:
+                    parts.append((idxs, view.to(self.device, non_blocking=True)))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self._events[slot] = ev
+        cur.wait_event(ev)
+        out = torch.empty(n, r, r, 3, dtype=torch.uint8, device=self.device)
+        for idxs, dev_imgs in parts:
+            dev_imgs.record_stream(cur)
+            px = dev_imgs if (dev_imgs.shape[1] == r and dev_imgs.shape[2] == r) else ops.resize_bicubic(dev_imgs, r, r)
+            if len(parts) == 1:
+                return px
+            out[torch.as_tensor(idxs, device=self.device)] = px
+        return out
+
+    # -- public ------------------------------------------------------------------------
+    def stage(self, items: Sequence, resize_value: int) -> Tensor:
+        return self._upload(self._decode_chunk(list(items), 0), 0, resize_value)
+
+    def batches(self, items: Sequence, resize_value: int, chunk: int = 128) -> Iterator[Tensor]:
+        """Chunks of ``chunk`` items as device tensors; chunk ``i + 1`` is decoded (pool threads) while the caller
+        consumes chunk ``i``."""
+        items = list(items)
+        chunks = [items[lo:lo + chunk] for lo in range(0, len(items), chunk)]
+        if not chunks:
+            return
+        feeder = ThreadPoolExecutor(max_workers=1, thread_name_prefix="gnc-stage")
+        try:
+            pending = feeder.submit(self._decode_chunk, chunks[0], 0)
+            for i in range(len(chunks)):
+                groups = pending.result()
+                if i + 1 < len(chunks):
+                    pending = feeder.submit(self._decode_chunk, chunks[i + 1], (i + 1) & 1)
+                yield self._upload(groups, i & 1, resize_value)
+        finally:
+            feeder.shutdown(wait=True)
+
+
+def infer_files(pipeline, paths: Iterable, pool: Optional[DecodePool] = None, chunk: int = 128) -> Tensor:
+    """File paths (or PIL images) -> logits ``[n, classes]`` through ``GraphClassifierPipeline.infer``: threaded decode,
+    double-buffered pinned copies, device resize, graph build and GraphNet on the stream."""
+    own = pool is None
+    pool = pool or DecodePool(device=pipeline.device)
+    try:
+        outs = [pipeline.infer(px) for px in pool.batches(list(paths), pipeline.resize_value, chunk)]
+    finally:
+        if own:
+            pool.close()
+    return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

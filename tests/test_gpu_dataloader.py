@@ -101,3 +101,52 @@ def test_train_gnn_batched_one_step_matches_oracle(libgnc, tmp_path):
     for (name, p), (_, po) in zip(gm.named_parameters(), om.named_parameters()):
         assert float((p.detach().cpu() - po.detach()).abs().max()) < 2e-3 * 1.01, name     # first Adam step: |update| <= lr
     assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".pth")) == ["best_model_epoch1.pth", "final_model.pth"]
+
+
+def test_decode_pool_equals_reference_pixels(libgnc, tmp_path):
+    """utils/staging.DecodePool (threaded decode into pinned buffers, double-buffered copies, device resize) hands the
+    graph builder the very pixels the reference's ``Image.open(path).convert('RGB').resize((r, r))`` produces - JPEG and
+    PNG files of several sizes (one of them already r x r, one greyscale), in file order, chunked or not."""
+    from graphnet_classifier_b200.utils.staging import DecodePool
+    rng = np.random.default_rng(4)
+    r = 24
+    paths = []
+    shapes = [(40, 52), (24, 24), (40, 52), (64, 30), (24, 24), (375, 500), (40, 52), (33, 47), (64, 30)]
+    for i, (h, w) in enumerate(shapes):
+        low = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, 3), dtype=np.uint8)
+        img = Image.fromarray(low).resize((w, h), Image.BILINEAR)
+        if i == 7:
+            img = img.convert("L")
+        path = tmp_path / (f"f{i}.jpg" if i % 3 else f"f{i}.png")
+        img.save(path, quality=90) if path.suffix == ".jpg" else img.save(path)
+        paths.append(str(path))
+    want = np.stack([np.array(Image.open(p).convert("RGB").resize((r, r))) for p in paths])
+    with DecodePool(workers=3) as pool:
+        got = pool.stage(paths, r)
+        assert got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (len(paths), r, r, 3)
+        assert np.array_equal(got.cpu().numpy(), want)
+        chunks = list(pool.batches(paths, r, chunk=4))
+        assert [c.shape[0] for c in chunks] == [4, 4, 1]
+        assert np.array_equal(torch.cat(chunks).cpu().numpy(), want)
+        again = torch.cat(list(pool.batches(paths, r, chunk=2))).cpu().numpy()     # staging buffers reused many times
+        assert np.array_equal(again, want)
+
+
+def test_infer_files_equals_infer(libgnc, tmp_path):
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.pipeline import GraphClassifierPipeline
+    from graphnet_classifier_b200.utils.staging import infer_files
+    rng = np.random.default_rng(5)
+    r = 16
+    paths = []
+    for i in range(7):
+        p = tmp_path / f"g{i}.jpg"
+        Image.fromarray(rng.integers(0, 256, (30 + 3 * (i % 2), 41, 3), dtype=np.uint8)).save(p, quality=85)
+        paths.append(str(p))
+    torch.manual_seed(0)
+    model = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=r * r).cuda()
+    pipe = GraphClassifierPipeline(model, resize_value=r)
+    got = infer_files(pipe, paths, chunk=3)
+    px = np.stack([np.array(Image.open(p).convert("RGB").resize((r, r))) for p in paths])
+    want = pipe.infer(torch.from_numpy(px))
+    assert torch.equal(got, want)
