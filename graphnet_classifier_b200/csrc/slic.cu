@@ -3,17 +3,25 @@
 // scikit-image (reference utils/image_to_graph/image_to_graph_superpixel.py:31:
 // slic(img, n_segments=100, compactness=10, start_label=0)).
 //
-// PARITY UNPINNED: scikit-image is neither vendored nor version-pinned by the reference
-// (requirements.txt:12) and is not installed here, so there is nothing to compare labels with.
-// This kernel follows the published algorithm with scikit-image's documented conventions:
-// RGB -> CIELAB (D65), colour scaled by 1/compactness, spatial distance scaled by 1/step,
-// regular-grid initial centres, `iters` Lloyd iterations (10 in scikit-image), each pixel
-// searching the 3x3 grid cells around it (centres move by less than one step), labels
-// 0..K-1.  Centre updates use 64-bit fixed-point atomics (one set per label run of a thread's 8 pixels, merged across the lanes of a warp), so
-// the result is deterministic.
-// Connectivity enforcement (scikit-image's post-pass) is NOT applied; the label-map ->
-// graph stage (gnc_build_superpixel_graph) treats labels that vanish correctly
-// (node id = rank among the labels present).
+// PARITY UNPINNED against the reference: scikit-image is neither vendored nor version-pinned by the reference
+// (requirements.txt:12) and is not installed here, so there are no reference labels to compare with.  What is pinned
+// is the algorithm itself: oracle/slic.py restates it step by step on the CPU and tests/test_gpu_slic.py compares
+// (>= 99.5 % identical labels, every difference a near-tie of the fp32 distance).  The steps, with scikit-image's
+// documented conventions:
+//   1. step = sqrt(H W / n_segments); ny = round(H / step) x nx = round(W / step) grid cells, K = ny nx centres;
+//      spatial scale S = max(H / ny, W / nx);
+//   2. sRGB -> CIELAB (D65), divided by `compactness`;
+//   3. centre k = gy nx + gx starts at the middle of its cell with the colour of the pixel under it;
+//   4. `iters` Lloyd iterations (10 in scikit-image): every pixel (at (y + 0.5, x + 0.5)) takes the nearest of the
+//      centres of the 3 x 3 grid cells around its own cell (centres move by less than one step) under
+//      d = |dLab|^2 + |dyx|^2 / S^2 - one fp32 FMA chain (slic_dist), ties to the lowest centre index; a centre moves
+//      to the mean of its pixels; the sums are 2^-20 fixed-point integers, so the result does not depend on the order
+//      the atomics arrive in (deterministic); a centre without pixels stays;
+//   5. one more assignment gives the labels 0..K-1.
+// Connectivity enforcement (scikit-image's post-pass) is the separate pass in csrc/slic_connect.cu, applied by
+// utils/image_to_graph/slic.py by default as scikit-image does.
+// Two device forms with identical labels: the streaming form (one launch per iteration over the whole batch) and, where
+// the shape allows it, one CTA per image running the whole loop in one launch (slic_image_kernel below).
 #include <stdlib.h>
 
 #include "common.cuh"
