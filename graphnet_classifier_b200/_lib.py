@@ -4,11 +4,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint64,
+                    c_void_p)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnc.so")
 
-GNC_OK, GNC_EINVAL, GNC_ECUDA, GNC_EWORKSPACE = 0, 1, 2, 3
+GNC_OK, GNC_EINVAL, GNC_ECUDA, GNC_EWORKSPACE, GNC_JPEG_UNSUPPORTED = 0, 1, 2, 3, 4
 
 
 class GncSeg(Structure):
@@ -49,6 +50,22 @@ class GncBwdReduceItem(Structure):
     """struct gnc_bwd_reduce_item (include/gnc.h)."""
     _fields_ = [("work", c_void_p), ("dW", c_void_p), ("db", c_void_p), ("lddw", c_int64), ("parts", c_int32),
                 ("accumulate", c_int32)]
+
+
+class GncJpegHuff(Structure):
+    """struct gnc_jpeg_huff (include/gnc.h)."""
+    _fields_ = [("look", c_uint16 * 512), ("maxcode", c_int32 * 18), ("valoff", c_int32 * 17), ("vals", c_uint8 * 256)]
+
+
+class GncJpegImage(Structure):
+    """struct gnc_jpeg_image (include/gnc.h)."""
+    _fields_ = [("width", c_int32), ("height", c_int32), ("ncomp", c_int32),
+                ("hsamp", c_int32 * 3), ("vsamp", c_int32 * 3), ("qtab", c_int32 * 3), ("dc_tab", c_int32 * 3),
+                ("ac_tab", c_int32 * 3),
+                ("restart_interval", c_int32), ("mcu_x", c_int32), ("mcu_y", c_int32), ("_pad", c_int32),
+                ("scan_offset", c_int64), ("scan_bytes", c_int64), ("n_blocks", c_int64), ("plane_bytes", c_int64),
+                ("block_offset", c_int64), ("coef_offset", c_int64), ("plane_offset", c_int64), ("pixel_offset", c_int64),
+                ("quant", (c_uint16 * 64) * 4), ("huff", GncJpegHuff * 8)]
 
 
 class GncError(RuntimeError):
@@ -129,6 +146,8 @@ SIGNATURES = {
     "gnc_tc_bwd_layer_f32": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64, _P, c_int64,
                                      _P, c_int64, _P, c_int, _P, c_int64, _P]),
     "gnc_debug_slic_connect_streaming": (c_int, [c_int]),
+    "gnc_jpeg_parse": (c_int, [_P, c_int64, POINTER(GncJpegImage)]),
+    "gnc_jpeg_decode_rgb_u8": (c_int, [_P, _P, c_int, c_int64, c_int64, _P, _P, _P, _P]),
     "gnc_tc_bwd_layer_parts": (c_int32, [c_int64]),
     "gnc_tc_bwd_reduce_batch_f32": (c_int, [POINTER(GncBwdReduceItem), c_int32, _P]),
 }

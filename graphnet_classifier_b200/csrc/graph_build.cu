@@ -8,6 +8,8 @@
 //   utils/image_to_graph/image_to_graph_patch.py:25-54
 //   utils/image_to_graph/image_to_graph_superpixel.py:34-71
 //   utils/dataloader.py:49-51 (casts to float32 / float32 / int64)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "grid_topology.h"
 
@@ -446,6 +448,156 @@ __global__ void __launch_bounds__(256) superpixel_graph_kernel(
   }
 }
 
+
+// The same stage for widths that are a multiple of 8 (every resize the reference uses): 1024 threads per image, a thread
+// owns 8 consecutive pixels of a row (labels as two 128-bit loads, pixels as three 64-bit loads) and a warp an
+// 8-pixel-wide strip of 32 rows, so its lanes meet only a few labels.  The integer statistics of a thread's label run
+// are merged per label across the warp (match.any + redux.sync) before they go to the shared-memory atomics: a few
+// atomics per warp and row strip instead of six contended atomics per pixel.  Same sums, same outputs as the kernel
+// above (tests/test_gpu_graph_build.py runs both against the oracle).
+__global__ void __launch_bounds__(1024) superpixel_graph_run8_kernel(
+    const uint8_t* __restrict__ img, const int32_t* __restrict__ labels, int H, int W, int max_label,
+    int S_max, int64_t E_max, int32_t* __restrict__ n_nodes, float* __restrict__ x, float* __restrict__ pos,
+    uint8_t* __restrict__ adj, int32_t* __restrict__ n_edges, int64_t* __restrict__ edges,
+    int32_t* __restrict__ work, int64_t work_per_image, int use_smem, int32_t* __restrict__ bad) {
+  extern __shared__ int32_t sp_smem[];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int64_t HW = (int64_t)H * W;
+  const uint8_t* im = img + (int64_t)b * HW * 3;
+  const int32_t* lab = labels + (int64_t)b * HW;
+  int32_t* rank = use_smem ? sp_smem : work + (int64_t)b * work_per_image;
+  uint32_t* stat = reinterpret_cast<uint32_t*>(rank + (max_label + 1));
+  int32_t* rowoff = reinterpret_cast<int32_t*>(stat + 6 * (int64_t)S_max);
+  uint8_t* A = adj + (int64_t)b * S_max * S_max;
+  __shared__ int s_S;
+
+  for (int l = tid; l <= max_label; l += blockDim.x) rank[l] = 0;
+  for (int i = tid; i < 6 * S_max; i += blockDim.x) stat[i] = 0;
+  __syncthreads();
+  for (int64_t q = tid; q < HW / 4; q += blockDim.x) {                  // labels present (coalesced 128-bit reads)
+    const int4 v = __ldg(reinterpret_cast<const int4*>(lab) + q);
+    const int l4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (l4[j] < 0 || l4[j] > max_label) { if (bad) atomicExch(bad, 1); continue; }
+      if (rank[l4[j]] == 0) rank[l4[j]] = 1;                            // benign race: all writers store 1
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {                                                       // rank among present labels (np.unique order)
+    int r = 0;
+    for (int l = 0; l <= max_label; ++l) {
+      const int present = rank[l];
+      rank[l] = present ? r : -1;
+      r += present;
+    }
+    s_S = r;
+    n_nodes[b] = r;
+    if (r > S_max && bad) atomicExch(bad, 2);
+  }
+  __syncthreads();
+  const int S = s_S < S_max ? s_S : S_max;
+  auto node_of = [&](int32_t l) { return (l < 0 || l > max_label) ? -1 : rank[l]; };
+  auto link = [&](int s, int32_t l2) {                                  // 4-connected adjacency (superpixel.py:62-64)
+    const int t = node_of(l2);
+    if (t >= 0 && t != s && t < S_max) { A[(int64_t)s * S_max + t] = 1; A[(int64_t)t * S_max + s] = 1; }
+  };
+  auto add_stats = [&](int s, unsigned n, unsigned r, unsigned g, unsigned bl, unsigned row, unsigned col) {
+    atomicAdd(stat + 0 * S_max + s, n); atomicAdd(stat + 1 * S_max + s, r); atomicAdd(stat + 2 * S_max + s, g);
+    atomicAdd(stat + 3 * S_max + s, bl); atomicAdd(stat + 4 * S_max + s, row); atomicAdd(stat + 5 * S_max + s, col);
+  };
+  const int gpr = W >> 3;
+  const int G = ((H + 31) >> 5) * 32 * gpr;
+  for (int base = 0; base < G; base += blockDim.x) {                    // warp-uniform trip count
+    const int gi = base + tid;
+    const int band = gi / (gpr * 32), rem = gi - band * gpr * 32;
+    const int y = band * 32 + (rem & 31), x0 = (rem >> 5) << 3;
+    const bool active = y < H;
+    int run_s = -1;
+    unsigned cn = 0, cr = 0, cg = 0, cb = 0, ccol = 0;
+    if (active) {
+      const int64_t p0 = (int64_t)y * W + x0;
+      const int4 la = __ldg(reinterpret_cast<const int4*>(lab + p0)), lb = __ldg(reinterpret_cast<const int4*>(lab + p0) + 1);
+      const int32_t l8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+      uint32_t w[6];
+      {
+        const uint2* src = reinterpret_cast<const uint2*>(im + p0 * 3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const uint2 v = __ldg(src + j); w[2 * j] = v.x; w[2 * j + 1] = v.y; }
+      }
+      int32_t d8[8];
+      const bool down = y + 1 < H;
+      if (down) {
+        const int4 da = __ldg(reinterpret_cast<const int4*>(lab + p0 + W)), db = __ldg(reinterpret_cast<const int4*>(lab + p0 + W) + 1);
+        d8[0] = da.x; d8[1] = da.y; d8[2] = da.z; d8[3] = da.w; d8[4] = db.x; d8[5] = db.y; d8[6] = db.z; d8[7] = db.w;
+      }
+      const int32_t l_next = x0 + 8 < W ? __ldg(lab + p0 + 8) : l8[7];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int s = node_of(l8[i]);
+        if (s < 0 || s >= S_max) continue;
+        if (s != run_s) {
+          if (cn) add_stats(run_s, cn, cr, cg, cb, cn * (unsigned)y, ccol);
+          run_s = s; cn = cr = cg = cb = ccol = 0;
+        }
+        const int b0 = 3 * i, b1 = 3 * i + 1, b2 = 3 * i + 2;
+        cn += 1;
+        cr += (w[b0 >> 2] >> (8 * (b0 & 3))) & 255u;
+        cg += (w[b1 >> 2] >> (8 * (b1 & 3))) & 255u;
+        cb += (w[b2 >> 2] >> (8 * (b2 & 3))) & 255u;
+        ccol += (unsigned)(x0 + i);
+        const int32_t right = i < 7 ? l8[i + 1] : l_next;
+        if (right != l8[i]) link(s, right);
+        if (down && d8[i] != l8[i]) link(s, d8[i]);
+      }
+    }
+    // the open runs of the warp's lanes, merged per node
+    const unsigned peers = __match_any_sync(0xffffffffu, cn ? run_s : -1);
+    const unsigned tn = __reduce_add_sync(peers, cn), tr = __reduce_add_sync(peers, cr), tg = __reduce_add_sync(peers, cg);
+    const unsigned tb = __reduce_add_sync(peers, cb), trow = __reduce_add_sync(peers, cn * (unsigned)y);
+    const unsigned tcol = __reduce_add_sync(peers, ccol);
+    if (cn && lane == __ffs(peers) - 1) add_stats(run_s, tn, tr, tg, tb, trow, tcol);
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int s = tid; s < S; s += blockDim.x) {
+    const double n = (double)stat[s];
+    float* xo = x + ((int64_t)b * S_max + s) * 3;
+    xo[0] = (float)(((double)stat[1 * S_max + s] / 255.0) / n);
+    xo[1] = (float)(((double)stat[2 * S_max + s] / 255.0) / n);
+    xo[2] = (float)(((double)stat[3 * S_max + s] / 255.0) / n);
+    float* po = pos + ((int64_t)b * S_max + s) * 2;
+    po[0] = (float)((double)stat[4 * S_max + s] / n);
+    po[1] = (float)((double)stat[5 * S_max + s] / n);
+    int cnt = 0;
+    for (int t = s + 1; t < S; ++t) cnt += A[(int64_t)s * S_max + t];
+    rowoff[s] = cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int s = 0; s < S; ++s) { const int c = rowoff[s]; rowoff[s] = acc; acc += c; }
+    rowoff[S] = acc;
+    n_edges[b] = 2 * acc;
+    if (2 * (int64_t)acc > E_max && bad) atomicExch(bad, 3);
+  }
+  __syncthreads();
+  int64_t* e0 = edges + (int64_t)b * 2 * E_max;
+  int64_t* e1 = e0 + E_max;
+  for (int s = tid; s < S; s += blockDim.x) {
+    int64_t k = 2 * (int64_t)rowoff[s];
+    for (int t = s + 1; t < S; ++t) {
+      if (A[(int64_t)s * S_max + t]) {
+        if (k + 1 < E_max) {
+          e0[k] = s; e1[k] = t;
+          e0[k + 1] = t; e1[k + 1] = s;
+        }
+        k += 2;
+      }
+    }
+  }
+}
+
 }  // namespace gnc
 
 using namespace gnc;
@@ -507,6 +659,12 @@ int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B,
   if (e != cudaSuccess) return fail(GNC_ECUDA, "superpixel memset: %s", cudaGetErrorString(e));
   const size_t smem = (size_t)wpi * sizeof(int32_t);
   const int use_smem = smem <= 40 * 1024 ? 1 : 0;
+  static const bool force_scalar = getenv("GNC_SUPERPIXEL_SCALAR") != nullptr;      // debug: the per-pixel kernel
+  if (W % 8 == 0 && !force_scalar && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(labels)) & 15u) == 0) {
+    superpixel_graph_run8_kernel<<<B, 1024, use_smem ? smem : 0, st>>>(img, labels, H, W, max_label, S_max, E_max, n_nodes,
+                                                                       x, pos, adj, n_edges, edges, work, wpi, use_smem, nullptr);
+    return check_launch("superpixel_graph_run8_kernel");
+  }
   superpixel_graph_kernel<<<B, 256, use_smem ? smem : 0, st>>>(img, labels, H, W, max_label, S_max, E_max, n_nodes, x,
                                                                pos, adj, n_edges, edges, work, wpi, use_smem, nullptr);
   return check_launch("superpixel_graph_kernel");

@@ -1,0 +1,507 @@
+// Baseline JPEG decode on the device: the other half of the reference's input staging,
+//   Image.open(path).convert('RGB')       utils/dataloader.py:34 (ImageFolder's loader),
+//                                         utils/image_to_graph/image_to_graph_optimized.py:65-68, utils/inference.py:47
+// i.e. libjpeg(-turbo) behind Pillow with its defaults: Huffman sequential DCT, the accurate integer inverse DCT
+// (JDCT_ISLOW, jidctint.c), "fancy" triangle-filter chroma upsampling (jdsample.c) and the 16-bit fixed-point
+// YCbCr -> RGB tables (jdcolor.c).  libjpeg is an un-vendored dependency of an un-vendored dependency (Pillow); its
+// decoder is a published integer algorithm, restated here stage by stage so that the pixels are bit for bit the ones
+// Pillow hands the reference (tests/test_gpu_jpeg.py compares with Pillow on generated files and on the reference's
+// shipped JPEGs).
+//
+// Scope: what `Image.save(..., 'JPEG')` and ordinary cameras write and the shipped dataset uses - 8-bit baseline /
+// extended-sequential Huffman (SOF0 / SOF1), one interleaved scan, greyscale or YCbCr with 4:4:4, 4:2:2 (h2v1) or 4:2:0
+// (h2v2) chroma, optional restart intervals, optional JFIF / EXIF / ICC segments (skipped; Pillow's convert('RGB') does
+// not apply them either).  Anything else (progressive, arithmetic coding, CMYK / Adobe transforms, 12-bit, multi-scan)
+// is reported as unsupported by the parser and decoded by Pillow on the host (utils/staging.py) - same pixels either way.
+//
+// Stages:
+//   host   gnc_jpeg_parse         : markers -> geometry, dequantisation tables (natural order), Huffman decode tables
+//                                   (9-bit lookahead + canonical maxcode / valptr for longer codes), scan position
+//   device jpeg_huffman_kernel    : entropy decode is sequential per image (no restart markers in Pillow's files), so one
+//                                   warp's lane 0 walks one image's bit stream (64-bit bit buffer, byte unstuffing,
+//                                   cached byte loads) and writes the non-zero coefficients of every block; images of a batch
+//                                   decode side by side on different warps (one scheduler slot each)
+//          jpeg_idct_kernel       : one thread per 8 x 8 block, jidctint.c's two passes in registers, range-limited
+//                                   samples into per-component planes
+//          jpeg_color_kernel      : one thread per output pixel: fancy upsampling of the chroma planes evaluated at the
+//                                   pixel (libjpeg's rounding terms and edge rules) + the fixed-point colour tables
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gnc {
+namespace jpeg {
+
+constexpr int kLook = 9;                      // lookahead bits of the Huffman tables
+
+// zigzag position -> natural (row-major) position
+__constant__ uint8_t c_natural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+static const uint8_t h_natural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ---- entropy decode -------------------------------------------------------------------------------------------------
+struct BitReader {
+  const uint8_t* p;        // next byte of the stream
+  const uint8_t* end;
+  uint64_t acc;            // bits, MSB-aligned
+  int n;                   // valid bits in acc
+  bool marker;             // a marker (FF xx, xx != 0) was met: feed zeros, as libjpeg does past the end of a segment
+};
+
+__device__ __forceinline__ void refill(BitReader& br) {
+  while (br.n <= 56) {
+    uint32_t byte = 0;
+    if (!br.marker && br.p < br.end) {
+      byte = *br.p;
+      if (byte == 0xFF) {
+        const uint32_t nxt = (br.p + 1 < br.end) ? br.p[1] : 0xD9;
+        if (nxt == 0) br.p += 2;                 // stuffed zero: a data byte FF
+        else { br.marker = true; byte = 0; }     // stay on the marker
+      } else {
+        br.p += 1;
+      }
+    }
+    br.acc |= (uint64_t)byte << (56 - br.n);
+    br.n += 8;
+  }
+}
+__device__ __forceinline__ uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (64 - k)); }
+__device__ __forceinline__ void skip(BitReader& br, int k) { br.acc <<= k; br.n -= k; }
+
+// one Huffman symbol (jdhuff.c: lookahead table, then the canonical code walk)
+__device__ __forceinline__ int decode_symbol(BitReader& br, const gnc_jpeg_huff_t* t) {
+  if (br.n < 16) refill(br);
+  const uint32_t look = t->look[peek(br, kLook)];
+  if (look) { skip(br, (int)(look >> 8)); return (int)(look & 0xff); }
+  int l = kLook + 1;
+  int32_t code = (int32_t)peek(br, l);
+  while (l <= 16 && code > t->maxcode[l]) { ++l; code = (int32_t)peek(br, l); }
+  if (l > 16) { skip(br, 16); return 0; }        // corrupt stream: libjpeg warns and returns 0
+  skip(br, l);
+  return t->vals[(code + t->valoff[l]) & 0xff];
+}
+__device__ __forceinline__ int receive_extend(BitReader& br, int s) {
+  if (br.n < s) refill(br);
+  const int r = (int)peek(br, s);
+  skip(br, s);
+  return r < (1 << (s - 1)) ? r - (1 << s) + 1 : r;      // HUFF_EXTEND
+}
+
+__global__ void __launch_bounds__(128) jpeg_huffman_kernel(const uint8_t* __restrict__ stream, const gnc_jpeg_image_t* __restrict__ infos,
+                                                          int B, int16_t* __restrict__ coef) {
+  const int img = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (img >= B || (threadIdx.x & 31) != 0) return;
+  const gnc_jpeg_image_t* im = infos + img;
+  BitReader br;
+  br.p = stream + im->scan_offset;
+  br.end = br.p + im->scan_bytes;
+  br.acc = 0; br.n = 0; br.marker = false;
+  int16_t* cimg = coef + im->coef_offset;
+  const int ncomp = im->ncomp;
+  int pred[3] = {0, 0, 0};
+  int64_t comp_base[3];
+  int hs[3], vs[3], bw[3];
+  {
+    int64_t off = 0;
+    for (int c = 0; c < 3; ++c) {
+      hs[c] = c < ncomp ? im->hsamp[c] : 0; vs[c] = c < ncomp ? im->vsamp[c] : 0;
+      bw[c] = im->mcu_x * hs[c];                 // blocks per row of the component's (MCU-padded) plane
+      comp_base[c] = off;
+      off += (int64_t)bw[c] * im->mcu_y * vs[c] * 64;
+    }
+  }
+  const int restart = im->restart_interval;
+  int to_restart = restart;
+  for (int my = 0; my < im->mcu_y; ++my) {
+    for (int mx = 0; mx < im->mcu_x; ++mx) {
+      if (restart && to_restart == 0) {
+        // byte-align, step over the RSTn marker, reset the predictions (jdhuff.c process_restart)
+        br.acc = 0; br.n = 0;
+        if (br.marker) { br.p += 2; br.marker = false; }
+        else {                                   // the marker has not been reached by the reader yet: find it
+          while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] >= 0xD0 && br.p[1] <= 0xD7)) ++br.p;
+          br.p += 2;
+        }
+        pred[0] = pred[1] = pred[2] = 0;
+        to_restart = restart;
+      }
+      for (int c = 0; c < ncomp; ++c) {
+        const gnc_jpeg_huff_t* dct = &im->huff[im->dc_tab[c]];
+        const gnc_jpeg_huff_t* act = &im->huff[4 + im->ac_tab[c]];
+        for (int by = 0; by < vs[c]; ++by) {
+          for (int bx = 0; bx < hs[c]; ++bx) {
+            int16_t* blk = cimg + comp_base[c] + ((int64_t)(my * vs[c] + by) * bw[c] + (mx * hs[c] + bx)) * 64;
+            int s = decode_symbol(br, dct);
+            if (s) pred[c] += receive_extend(br, s);
+            blk[0] = (int16_t)pred[c];
+            for (int k = 1; k < 64; ++k) {
+              s = decode_symbol(br, act);
+              const int r = s >> 4;
+              s &= 15;
+              if (s) {
+                k += r;
+                const int v = receive_extend(br, s);
+                blk[c_natural[k & 63]] = (int16_t)v;
+              } else {
+                if (r != 15) break;              // end of block
+                k += 15;                         // sixteen zeros
+              }
+            }
+          }
+        }
+      }
+      if (restart) --to_restart;
+    }
+  }
+}
+
+// ---- inverse DCT (jidctint.c, jpeg_idct_islow) -------------------------------------------------------------------------
+constexpr int CONST_BITS = 13, PASS1_BITS = 2;
+constexpr int FIX_0_298631336 = 2446, FIX_0_390180644 = 3196, FIX_0_541196100 = 4433, FIX_0_765366865 = 6270,
+              FIX_0_899976223 = 7373, FIX_1_175875602 = 9633, FIX_1_501321110 = 12299, FIX_1_847759065 = 15137,
+              FIX_1_961570560 = 16069, FIX_2_053119869 = 16819, FIX_2_562915447 = 20995, FIX_3_072711026 = 25172;
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+// IDCT_range_limit[x & RANGE_MASK]: x + 128 clamped to 0..255 for |x| < 512 (and libjpeg's wrap-around beyond)
+__device__ __forceinline__ uint8_t range_limit(int x) {
+  const int v = x & 1023;
+  return (uint8_t)(v < 128 ? v + 128 : (v < 512 ? 255 : (v < 896 ? 0 : v - 896)));
+}
+
+__device__ __forceinline__ void idct_1d(const int in[8], int out[8], bool pass1) {
+  int z2 = in[2], z3 = in[6];
+  int z1 = (z2 + z3) * FIX_0_541196100;
+  int tmp2 = z1 + z3 * (-FIX_1_847759065);
+  int tmp3 = z1 + z2 * FIX_0_765366865;
+  z2 = in[0]; z3 = in[4];
+  int tmp0 = (z2 + z3) << CONST_BITS;
+  int tmp1 = (z2 - z3) << CONST_BITS;
+  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+  z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+  int z4 = tmp1 + tmp3;
+  const int z5 = (z3 + z4) * FIX_1_175875602;
+  tmp0 *= FIX_0_298631336; tmp1 *= FIX_2_053119869; tmp2 *= FIX_3_072711026; tmp3 *= FIX_1_501321110;
+  z1 *= -FIX_0_899976223; z2 *= -FIX_2_562915447; z3 *= -FIX_1_961570560; z4 *= -FIX_0_390180644;
+  z3 += z5; z4 += z5;
+  tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+  const int sh = pass1 ? CONST_BITS - PASS1_BITS : CONST_BITS + PASS1_BITS + 3;
+  out[0] = descale(tmp10 + tmp3, sh); out[7] = descale(tmp10 - tmp3, sh);
+  out[1] = descale(tmp11 + tmp2, sh); out[6] = descale(tmp11 - tmp2, sh);
+  out[2] = descale(tmp12 + tmp1, sh); out[5] = descale(tmp12 - tmp1, sh);
+  out[3] = descale(tmp13 + tmp0, sh); out[4] = descale(tmp13 - tmp0, sh);
+}
+
+// one thread per block; blocks of all images and components are numbered through `block_offset`
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(const gnc_jpeg_image_t* __restrict__ infos, int B, const int16_t* __restrict__ coef,
+                                                        uint8_t* __restrict__ planes, int64_t total_blocks) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_blocks) return;
+  // image of this block: binary search over the per-image block offsets
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (infos[mid].block_offset <= g) lo = mid; else hi = mid - 1;
+  }
+  const gnc_jpeg_image_t* im = infos + lo;
+  int64_t rel = g - im->block_offset;
+  int c = 0;
+  int bwc = 0;
+  for (; c < im->ncomp; ++c) {
+    bwc = im->mcu_x * im->hsamp[c];
+    const int64_t nb = (int64_t)bwc * im->mcu_y * im->vsamp[c];
+    if (rel < nb) break;
+    rel -= nb;
+  }
+  const int by = (int)(rel / bwc), bx = (int)(rel - (int64_t)by * bwc);
+  const int16_t* blk = coef + im->coef_offset + (g - im->block_offset) * 64;
+  const uint16_t* q = im->quant[im->qtab[c]];
+  int ws[64];
+#pragma unroll
+  for (int col = 0; col < 8; ++col) {                     // pass 1: columns, dequantised
+    int in[8], out[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) in[r] = (int)blk[r * 8 + col] * (int)q[r * 8 + col];
+    idct_1d(in, out, true);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ws[r * 8 + col] = out[r];
+  }
+  // component plane: MCU-padded width bwc * 8
+  int64_t plane_off = im->plane_offset;
+  for (int cc = 0; cc < c; ++cc) plane_off += (int64_t)im->mcu_x * im->hsamp[cc] * 8 * im->mcu_y * im->vsamp[cc] * 8;
+  uint8_t* dst = planes + plane_off + ((int64_t)by * 8) * (bwc * 8) + bx * 8;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {                           // pass 2: rows
+    int in[8], out[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) in[k] = ws[r * 8 + k];
+    idct_1d(in, out, false);
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w0 |= (uint32_t)range_limit(out[k]) << (8 * k); w1 |= (uint32_t)range_limit(out[4 + k]) << (8 * k); }
+    *reinterpret_cast<uint2*>(dst + (int64_t)r * (bwc * 8)) = make_uint2(w0, w1);
+  }
+}
+
+// ---- chroma upsampling + colour conversion, evaluated per output pixel ---------------------------------------------------
+// jdsample.c: the upsampled value at an output position is a fixed function of at most 4 samples of the component:
+//   h2v1 fancy: out[2i] = (3 s[i] + s[i-1] + 1) >> 2, out[2i+1] = (3 s[i] + s[i+1] + 2) >> 2, edges copy s[0] / s[last]
+//   h2v2 fancy: vertically v(i) = 3 s[near][i] + s[far][i] (near = the sample row, far = the row above for the upper
+//               output row and below for the lower one; the first / last REAL rows stand in for rows beyond the image),
+//               then out[2i] = (3 v(i) + v(i-1) + 8) >> 4, out[2i+1] = (3 v(i) + v(i+1) + 7) >> 4,
+//               edges (4 v(0) + 8) >> 4 and (4 v(last) + 7) >> 4
+// with `last` = the component's true downsampled width - 1 (not the MCU padding).  Components of at most 2 samples in a
+// row are replicated instead (jinit_upsampler).
+__device__ __forceinline__ int upsampled(const uint8_t* plane, int pw, int dw, int dh, int hfac, int vfac, int x, int y) {
+  if (hfac == 1 && vfac == 1) return plane[(int64_t)y * pw + x];
+  const int i = x >> 1;
+  if (vfac == 1) {                                        // h2v1
+    const uint8_t* row = plane + (int64_t)y * pw;
+    if (dw <= 2) return row[i];
+    const int s = row[i];
+    if ((x & 1) == 0) return i == 0 ? s : (3 * s + row[i - 1] + 1) >> 2;
+    return i == dw - 1 ? s : (3 * s + row[i + 1] + 2) >> 2;
+  }
+  const int j = y >> 1;                                   // h2v2
+  if (dw <= 2) return plane[(int64_t)j * pw + i];
+  int jf = (y & 1) ? j + 1 : j - 1;
+  jf = jf < 0 ? 0 : (jf > dh - 1 ? dh - 1 : jf);
+  const uint8_t* near = plane + (int64_t)j * pw;
+  const uint8_t* far = plane + (int64_t)jf * pw;
+  const int v = 3 * near[i] + far[i];
+  if ((x & 1) == 0) {
+    if (i == 0) return (4 * v + 8) >> 4;
+    return (3 * v + (3 * near[i - 1] + far[i - 1]) + 8) >> 4;
+  }
+  if (i == dw - 1) return (4 * v + 7) >> 4;
+  return (3 * v + (3 * near[i + 1] + far[i + 1]) + 7) >> 4;
+}
+__device__ __forceinline__ uint8_t clamp255(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+__global__ void __launch_bounds__(256) jpeg_color_kernel(const gnc_jpeg_image_t* __restrict__ infos, int B, const uint8_t* __restrict__ planes,
+                                                         uint8_t* __restrict__ out, int64_t total_pixels) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_pixels) return;
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (infos[mid].pixel_offset <= g) lo = mid; else hi = mid - 1;
+  }
+  const gnc_jpeg_image_t* im = infos + lo;
+  const int64_t rel = g - im->pixel_offset;
+  const int y = (int)(rel / im->width), x = (int)(rel - (int64_t)y * im->width);
+  const uint8_t* p0 = planes + im->plane_offset;
+  const int pw0 = im->mcu_x * im->hsamp[0] * 8;
+  const int Y = p0[(int64_t)y * pw0 + x];
+  uint8_t* o = out + (im->pixel_offset + rel) * 3;
+  if (im->ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)Y; return; }
+  const int64_t n0 = (int64_t)pw0 * im->mcu_y * im->vsamp[0] * 8;
+  const int pw1 = im->mcu_x * im->hsamp[1] * 8;
+  const int64_t n1 = (int64_t)pw1 * im->mcu_y * im->vsamp[1] * 8;
+  const int hf = im->hsamp[0] / im->hsamp[1], vf = im->vsamp[0] / im->vsamp[1];
+  const int dw = (im->width * im->hsamp[1] + im->hsamp[0] - 1) / im->hsamp[0];       // true downsampled size
+  const int dh = (im->height * im->vsamp[1] + im->vsamp[0] - 1) / im->vsamp[0];
+  const int cb = upsampled(p0 + n0, pw1, dw, dh, hf, vf, x, y) - 128;
+  const int cr = upsampled(p0 + n0 + n1, pw1, dw, dh, hf, vf, x, y) - 128;
+  // jdcolor.c build_ycc_rgb_table: SCALEBITS 16, ONE_HALF 32768, FIX(v) = (int)(v * 65536 + 0.5)
+  const int r = Y + ((91881 * cr + 32768) >> 16);
+  const int gch = Y + ((-22554 * cb + 32768 + (-46802 * cr)) >> 16);
+  const int bch = Y + ((116130 * cb + 32768) >> 16);
+  o[0] = clamp255(r); o[1] = clamp255(gch); o[2] = clamp255(bch);
+}
+
+// ---- host: marker parser ----------------------------------------------------------------------------------------------
+static int build_huff(const uint8_t* bits /*[17], bits[0] unused*/, const uint8_t* vals, int nvals, gnc_jpeg_huff_t* t) {
+  memset(t, 0, sizeof(*t));
+  int huffsize[257];
+  int p = 0;
+  for (int l = 1; l <= 16; ++l) {
+    const int n = bits[l];
+    if (p + n > 256) return 1;
+    for (int i = 0; i < n; ++i) huffsize[p++] = l;
+  }
+  if (p != nvals) return 1;
+  huffsize[p] = 0;
+  int huffcode[257];
+  int code = 0, si = huffsize[0];
+  for (int i = 0; i < p;) {
+    while (i < p && huffsize[i] == si) huffcode[i++] = code++;
+    if (code > (1 << si)) return 1;
+    code <<= 1;
+    ++si;
+  }
+  int q = 0;
+  for (int l = 1; l <= 16; ++l) {
+    if (bits[l]) {
+      t->valoff[l] = q - huffcode[q];
+      q += bits[l];
+      t->maxcode[l] = huffcode[q - 1];
+    } else {
+      t->maxcode[l] = -1;
+      t->valoff[l] = 0;
+    }
+  }
+  t->maxcode[17] = 0x7fffffff;
+  for (int i = 0; i < p; ++i) t->vals[i] = vals[i];
+  q = 0;
+  for (int l = 1; l <= kLook; ++l) {
+    for (int i = 0; i < bits[l]; ++i, ++q) {
+      const int first = huffcode[q] << (kLook - l);
+      for (int k = 0; k < (1 << (kLook - l)); ++k) t->look[first + k] = (uint16_t)((l << 8) | vals[q]);
+    }
+  }
+  return 0;
+}
+
+}  // namespace jpeg
+}  // namespace gnc
+
+using namespace gnc;
+
+extern "C" {
+
+int gnc_jpeg_parse(const uint8_t* data, int64_t size, gnc_jpeg_image_t* out) {
+  if (!data || !out || size < 4) return GNC_JPEG_UNSUPPORTED;
+  memset(out, 0, sizeof(*out));
+  if (data[0] != 0xFF || data[1] != 0xD8) return GNC_JPEG_UNSUPPORTED;
+  uint8_t dht_bits[8][17];
+  uint8_t dht_vals[8][256];
+  int dht_n[8];
+  bool dht_set[8] = {false, false, false, false, false, false, false, false};
+  bool q_set[4] = {false, false, false, false};
+  int comp_id[3] = {0, 0, 0};
+  bool have_sof = false;
+  int adobe_transform = -1;
+  int64_t pos = 2;
+  while (pos + 4 <= size) {
+    if (data[pos] != 0xFF) return GNC_JPEG_UNSUPPORTED;
+    int m = data[pos + 1];
+    if (m == 0xFF) { ++pos; continue; }                   // fill byte
+    pos += 2;
+    if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+    if (m == 0xD9) return GNC_JPEG_UNSUPPORTED;           // EOI before a scan
+    const int64_t len = ((int64_t)data[pos] << 8) | data[pos + 1];
+    if (len < 2 || pos + len > size) return GNC_JPEG_UNSUPPORTED;
+    const uint8_t* seg = data + pos + 2;
+    const int64_t n = len - 2;
+    if (m == 0xC0 || m == 0xC1) {                         // baseline / extended sequential, Huffman
+      if (n < 6 || seg[0] != 8) return GNC_JPEG_UNSUPPORTED;
+      out->height = (seg[1] << 8) | seg[2];
+      out->width = (seg[3] << 8) | seg[4];
+      out->ncomp = seg[5];
+      if ((out->ncomp != 1 && out->ncomp != 3) || out->width <= 0 || out->height <= 0 || n < 6 + 3 * out->ncomp) return GNC_JPEG_UNSUPPORTED;
+      for (int c = 0; c < out->ncomp; ++c) {
+        comp_id[c] = seg[6 + 3 * c];
+        out->hsamp[c] = seg[7 + 3 * c] >> 4;
+        out->vsamp[c] = seg[7 + 3 * c] & 15;
+        out->qtab[c] = seg[8 + 3 * c];
+        if (out->qtab[c] > 3) return GNC_JPEG_UNSUPPORTED;
+      }
+      have_sof = true;
+    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      return GNC_JPEG_UNSUPPORTED;                        // progressive, lossless, arithmetic, hierarchical
+    } else if (m == 0xCC) {
+      return GNC_JPEG_UNSUPPORTED;
+    } else if (m == 0xC4) {                               // DHT
+      int64_t i = 0;
+      while (i + 17 <= n) {
+        const int tc = seg[i] >> 4, th = seg[i] & 15;
+        if (tc > 1 || th > 3) return GNC_JPEG_UNSUPPORTED;
+        const int slot = tc * 4 + th;
+        int cnt = 0;
+        dht_bits[slot][0] = 0;
+        for (int l = 1; l <= 16; ++l) { dht_bits[slot][l] = seg[i + l]; cnt += seg[i + l]; }
+        if (cnt > 256 || i + 17 + cnt > n) return GNC_JPEG_UNSUPPORTED;
+        memcpy(dht_vals[slot], seg + i + 17, (size_t)cnt);
+        dht_n[slot] = cnt;
+        dht_set[slot] = true;
+        i += 17 + cnt;
+      }
+    } else if (m == 0xDB) {                               // DQT
+      int64_t i = 0;
+      while (i < n) {
+        const int pq = seg[i] >> 4, tq = seg[i] & 15;
+        if (tq > 3 || pq > 1 || i + 1 + 64 * (pq + 1) > n) return GNC_JPEG_UNSUPPORTED;
+        for (int k = 0; k < 64; ++k) {
+          const int v = pq ? ((seg[i + 1 + 2 * k] << 8) | seg[i + 2 + 2 * k]) : seg[i + 1 + k];
+          out->quant[tq][jpeg::h_natural[k]] = (uint16_t)v;
+        }
+        q_set[tq] = true;
+        i += 1 + 64 * (pq + 1);
+      }
+    } else if (m == 0xDD) {                               // DRI
+      if (n < 2) return GNC_JPEG_UNSUPPORTED;
+      out->restart_interval = (seg[0] << 8) | seg[1];
+    } else if (m == 0xEE) {                               // Adobe: the colour transform flag
+      if (n >= 12 && memcmp(seg, "Adobe", 5) == 0) adobe_transform = seg[11];
+    } else if (m == 0xDA) {                               // SOS
+      if (!have_sof || n < 1 || seg[0] != out->ncomp || n < 1 + 2 * out->ncomp + 3) return GNC_JPEG_UNSUPPORTED;
+      for (int c = 0; c < out->ncomp; ++c) {
+        if (seg[1 + 2 * c] != comp_id[c]) return GNC_JPEG_UNSUPPORTED;      // one interleaved scan in frame order
+        out->dc_tab[c] = seg[2 + 2 * c] >> 4;
+        out->ac_tab[c] = seg[2 + 2 * c] & 15;
+        if (out->dc_tab[c] > 3 || out->ac_tab[c] > 3) return GNC_JPEG_UNSUPPORTED;
+        if (!dht_set[out->dc_tab[c]] || !dht_set[4 + out->ac_tab[c]] || !q_set[out->qtab[c]]) return GNC_JPEG_UNSUPPORTED;
+      }
+      // colour space as libjpeg guesses it: 3 components are YCbCr unless an Adobe marker says RGB (transform 0) or
+      // the component ids spell R, G, B
+      if (out->ncomp == 3) {
+        if (adobe_transform == 0) return GNC_JPEG_UNSUPPORTED;
+        if (adobe_transform < 0 && comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B') return GNC_JPEG_UNSUPPORTED;
+        // chroma: both at 1 x 1, luma 1 x 1, 2 x 1 or 2 x 2 (4:4:4, 4:2:2, 4:2:0)
+        if (out->hsamp[1] != 1 || out->vsamp[1] != 1 || out->hsamp[2] != 1 || out->vsamp[2] != 1) return GNC_JPEG_UNSUPPORTED;
+        const int h = out->hsamp[0], v = out->vsamp[0];
+        if (!((h == 1 && v == 1) || (h == 2 && v == 1) || (h == 2 && v == 2))) return GNC_JPEG_UNSUPPORTED;
+      } else {
+        out->hsamp[0] = out->vsamp[0] = 1;                // a single component is never interleaved: 1 x 1 blocks
+      }
+      for (int s = 0; s < 8; ++s)
+        if (dht_set[s] && jpeg::build_huff(dht_bits[s], dht_vals[s], dht_n[s], &out->huff[s])) return GNC_JPEG_UNSUPPORTED;
+      out->mcu_x = (out->width + 8 * out->hsamp[0] - 1) / (8 * out->hsamp[0]);
+      out->mcu_y = (out->height + 8 * out->vsamp[0] - 1) / (8 * out->vsamp[0]);
+      out->scan_offset = pos + len;
+      // the entropy-coded segment runs to the next marker that is not RSTn / stuffing; a second scan is not supported
+      int64_t e = out->scan_offset;
+      while (e + 1 < size) {
+        if (data[e] == 0xFF && data[e + 1] != 0 && !(data[e + 1] >= 0xD0 && data[e + 1] <= 0xD7) && data[e + 1] != 0xFF) break;
+        ++e;
+      }
+      if (e + 1 >= size) e = size;
+      else if (data[e + 1] != 0xD9) return GNC_JPEG_UNSUPPORTED;            // something other than EOI follows the scan
+      out->scan_bytes = e - out->scan_offset;
+      int64_t blocks = 0, plane = 0;
+      for (int c = 0; c < out->ncomp; ++c) {
+        const int64_t nb = (int64_t)out->mcu_x * out->hsamp[c] * out->mcu_y * out->vsamp[c];
+        blocks += nb;
+        plane += nb * 64;
+      }
+      out->n_blocks = blocks;
+      out->plane_bytes = plane;
+      return GNC_OK;
+    }
+    pos += len;
+  }
+  return GNC_JPEG_UNSUPPORTED;
+}
+
+int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos, int B, int64_t total_blocks,
+                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out, gnc_stream_t stream_) {
+  GNC_REQUIRE(B >= 0 && total_blocks >= 0 && total_pixels >= 0, "jpeg_decode: bad sizes");
+  if (B == 0) return GNC_OK;
+  GNC_REQUIRE(stream && infos && coef && planes && out, "jpeg_decode: null pointer");
+  cudaStream_t st = (cudaStream_t)stream_;
+  cudaError_t e = cudaMemsetAsync(coef, 0, (size_t)total_blocks * 64 * sizeof(int16_t), st);
+  if (e != cudaSuccess) return fail(GNC_ECUDA, "jpeg memset: %s", cudaGetErrorString(e));
+  jpeg::jpeg_huffman_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)B * 32, 128), 128, 0, st>>>(stream, infos, B, coef);
+  if (int rc = check_launch("jpeg_huffman_kernel")) return rc;
+  jpeg::jpeg_idct_kernel<<<(unsigned)ceil_div<int64_t>(total_blocks, 128), 128, 0, st>>>(infos, B, coef, planes, total_blocks);
+  if (int rc = check_launch("jpeg_idct_kernel")) return rc;
+  jpeg::jpeg_color_kernel<<<(unsigned)ceil_div<int64_t>(total_pixels, 256), 256, 0, st>>>(infos, B, planes, out, total_pixels);
+  return check_launch("jpeg_color_kernel");
+}
+
+}  // extern "C"

@@ -14,7 +14,8 @@
 //   3. centre k = gy nx + gx starts at the middle of its cell with the colour of the pixel under it;
 //   4. `iters` Lloyd iterations (10 in scikit-image): every pixel (at (y + 0.5, x + 0.5)) takes the nearest of the
 //      centres of the 3 x 3 grid cells around its own cell (centres move by less than one step) under
-//      d = |dLab|^2 + |dyx|^2 / S^2 - one fp32 FMA chain (slic_dist), ties to the lowest centre index; a centre moves
+//      d = |dLab|^2 + |dyx|^2 / S^2 - ranked by |c|^2 - 2 p.c, one fp32 FMA chain (slic_score), ties to the lowest
+//      centre index; a centre moves
 //      to the mean of its pixels; the sums are 2^-20 fixed-point integers, so the result does not depend on the order
 //      the atomics arrive in (deterministic); a centre without pixels stays;
 //   5. one more assignment gives the labels 0..K-1.
@@ -40,10 +41,22 @@ __device__ __forceinline__ float lab_f(float t) {
   return t > 0.008856f ? cbrtf(t) : 7.787f * t + 16.0f / 116.0f;
 }
 
-// squared distance in the scaled (Lab / compactness, yx / step) space; the FMA chain is spelled out so that every kernel
-// that evaluates it rounds the same way
-__device__ __forceinline__ float slic_dist(float dl, float da, float db, float sy, float sx) {
-  return __fmaf_rn(sx, sx, __fmaf_rn(sy, sy, __fmaf_rn(db, db, __fmaf_rn(da, da, dl * dl))));
+// Nearest centre in the scaled (Lab / compactness, yx / S) space.  |p - c|^2 = |p|^2 - 2 p.c + |c|^2 and |p|^2 is common
+// to all candidates of a pixel, so candidates are ranked by the SCORE |c|^2 - 2 p.c: five FMAs per pixel and candidate
+// against a centre prepared once per iteration (-2 c and |c|^2).  Every kernel evaluates the same FMA chain in the
+// same order, so all device forms round identically.
+struct SlicCen { float m2L, m2A, m2B, m2x, m2y, cc; };
+__device__ __forceinline__ SlicCen slic_prepare(float cL, float cA, float cB, float cy, float cx, float inv_step) {
+  const float ys = cy * inv_step, xs = cx * inv_step;
+  SlicCen c;
+  c.m2L = -2.f * cL; c.m2A = -2.f * cA; c.m2B = -2.f * cB; c.m2x = -2.f * xs; c.m2y = -2.f * ys;
+  c.cc = __fmaf_rn(xs, xs, __fmaf_rn(ys, ys, __fmaf_rn(cB, cB, __fmaf_rn(cA, cA, cL * cL))));
+  return c;
+}
+// first link of the chain (shared by the pixels of a row), then the rest; ys / xs = (pixel centre) / S
+__device__ __forceinline__ float slic_score_row(const SlicCen& c, float ys) { return __fmaf_rn(c.m2y, ys, c.cc); }
+__device__ __forceinline__ float slic_score(const SlicCen& c, float row, float L, float A, float B, float xs) {
+  return __fmaf_rn(c.m2B, B, __fmaf_rn(c.m2A, A, __fmaf_rn(c.m2L, L, __fmaf_rn(c.m2x, xs, row))));
 }
 __device__ __forceinline__ void rgb_to_lab(float r, float g, float b, float inv_c, float& L, float& A, float& Bc) {
   const float X = (0.412453f * r + 0.357580f * g + 0.180423f * b) / 0.95047f;
@@ -157,9 +170,8 @@ __global__ void __launch_bounds__(256, 2) slic_assign_kernel(const float* __rest
             if (xx < 0 || xx >= d.nx) continue;
             const int k = yy * d.nx + xx;
             const float* c = cb + (long long)k * 5;
-            const float dl = L - __ldg(c), da = A - __ldg(c + 1), db = Bc - __ldg(c + 2);
-            const float sy = ((y + 0.5f) - __ldg(c + 3)) * inv_step, sxx = ((x + 0.5f) - __ldg(c + 4)) * inv_step;
-            const float dist = slic_dist(dl, da, db, sy, sxx);
+            const SlicCen pc = slic_prepare(__ldg(c), __ldg(c + 1), __ldg(c + 2), __ldg(c + 3), __ldg(c + 4), inv_step);
+            const float dist = slic_score(pc, slic_score_row(pc, (y + 0.5f) * inv_step), L, A, Bc, (x + 0.5f) * inv_step);
             if (dist < best) { best = dist; best_k = k; }     // ties: lowest centre index (scan order)
           }
         }
@@ -252,11 +264,10 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
                                                                    float* __restrict__ lab_ws, int32_t* __restrict__ labels) {
   extern __shared__ unsigned char slic_smem[];
   long long* acc = reinterpret_cast<long long*>(slic_smem);                 // [K][6]
-  float* cen = reinterpret_cast<float*>(acc + (size_t)d.K * 6);            // [K][8]: L, a, b, x, y, - (32-byte records)
+  float* cen = reinterpret_cast<float*>(acc + (size_t)d.K * 6);            // [K][8]: prepared centres -2 (L, a, b, x / S, y / S), |c|^2 (32-byte records)
   float* lut = cen + (size_t)d.K * 8;                                      // [256]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int K = d.K, gpr = d.W >> 3, G = d.H * gpr;
-  const int Gs = ((d.H + 31) >> 5) * 32 * gpr;                             // strip form: 32-row bands
   const long long pix0 = (long long)b * d.H * d.W;
   float* lab = lab_ws + pix0 * 3;
   const float inv_step = 1.0f / d.step;
@@ -290,44 +301,84 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
     int py = (int)cy, px = (int)cx;
     py = py < d.H ? py : d.H - 1; px = px < d.W ? px : d.W - 1;
     const float* l = lab + ((long long)py * d.W + px) * 3;
-    cen[8 * k] = l[0]; cen[8 * k + 1] = l[1]; cen[8 * k + 2] = l[2]; cen[8 * k + 3] = cx; cen[8 * k + 4] = cy;
+    const SlicCen pc = slic_prepare(l[0], l[1], l[2], cy, cx, inv_step);
+    cen[8 * k] = pc.m2L; cen[8 * k + 1] = pc.m2A; cen[8 * k + 2] = pc.m2B; cen[8 * k + 3] = pc.m2x;
+    cen[8 * k + 4] = pc.m2y; cen[8 * k + 5] = pc.cc;
   }
   __syncthreads();
 
+  // 64-bit adds are two native 32-bit shared-memory atomics with the carry passed on (integer sums: any order gives the
+  // same total); position and count sums stay below 2^32 per image for every shape this kernel is launched for
+  auto add64 = [&](int k, int j, long long v) {
+    unsigned* a = reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j);
+    const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
+    if (d.dbg & 2) return;
+    const unsigned old = atomicAdd(a, lo);
+    const unsigned h2 = hi + (((old + lo) < old) ? 1u : 0u);
+    if (h2) atomicAdd(a + 1, h2);
+  };
+  auto add32 = [&](int k, int j, int v) {
+    if (d.dbg & 2) return;
+    atomicAdd(reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j), (unsigned)v);
+  };
+  // the open label runs of a warp's lanes are merged per label (match.any + redux.sync on 16-bit halves): one lane per
+  // label and warp issues the atomics
+  auto merge_and_add = [&](int key, int sL, int sA, int sB, int vy, int sx, int cnt) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int tL = __reduce_add_sync(peers, sL & 0xffff), hL = __reduce_add_sync(peers, sL >> 16);
+    const int tA = __reduce_add_sync(peers, sA & 0xffff), hA = __reduce_add_sync(peers, sA >> 16);
+    const int tB = __reduce_add_sync(peers, sB & 0xffff), hB = __reduce_add_sync(peers, sB >> 16);
+    const int ty = __reduce_add_sync(peers, vy), tx = __reduce_add_sync(peers, sx), tn = __reduce_add_sync(peers, cnt);
+    if (key >= 0 && lane == __ffs(peers) - 1) {
+      add64(key, 0, ((long long)hL << 16) + tL); add64(key, 1, ((long long)hA << 16) + tA);
+      add64(key, 2, ((long long)hB << 16) + tB);
+      add32(key, 3, ty); add32(key, 4, tx); add32(key, 5, tn);
+    }
+  };
+  // A thread owns an 8-pixel run in each of kRowsT consecutive rows and a warp an 8-pixel-wide strip of 32 * kRowsT
+  // rows: its lanes share the candidate grid columns (uniform control flow in the candidate loop), a thread's label
+  // usually survives from one row to the next (its sums stay in registers across the rows: |v| <= 108 / compactness
+  // with compactness >= 4 keeps 32 pixels below 2^31 in 2^-20 fixed point), and the warp meets only a few labels.
+  constexpr int kRowsT = 4;
+  const int Gt = ((d.H + 32 * kRowsT - 1) / (32 * kRowsT)) * 32 * gpr;     // work items: (band, strip, lane)
   for (int it = 0; it <= iters; ++it) {
     const bool last = it == iters;
-    // a warp owns an 8-pixel-wide strip of 32 rows: its lanes share the candidate grid columns (uniform control flow
-    // in the candidate loop) and meet only a few labels (few label groups in the warp-level merge of the sums)
-    for (int base = 0; base < Gs; base += kImgThreads) {                   // warp-uniform trip count
+    for (int base = 0; base < Gt; base += kImgThreads) {                   // warp-uniform trip count
       const int gi = base + tid;
       const int band = gi / (gpr * 32), rem = gi - band * gpr * 32;
-      const int y0 = band * 32 + (rem & 31), x0 = (rem >> 5) << 3;
-      const bool active = y0 < d.H;
-      const int y = active ? y0 : d.H - 1;
-      const int gy = (int)((long long)y * d.ny / d.H);
-      float px[24];
-      {
-        const float4* src = reinterpret_cast<const float4*>(lab + ((long long)y * d.W + x0) * 3);
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const float4 v = src[j];
-          px[4 * j] = v.x; px[4 * j + 1] = v.y; px[4 * j + 2] = v.z; px[4 * j + 3] = v.w;
-        }
-      }
+      const int x0 = (rem >> 5) << 3, yb = band * (32 * kRowsT) + (rem & 31) * kRowsT;
       // candidate grid columns of the run: its pixels lie in cell gx_lo or, past x_b, in gx_lo + 1 (the launcher
       // takes this kernel only for grid cells at least 8 pixels wide)
       const int gx_lo = (int)((long long)x0 * d.nx / d.W), gx_hi = (int)((long long)(x0 + 7) * d.nx / d.W);
-      int out[8];
-      {
-        const int x_b = (int)(((long long)(gx_lo + 1) * d.W + d.nx - 1) / d.nx);      // first x of cell gx_lo + 1
-        const int ib = x_b - x0;                                           // pixels i >= ib lie in cell gx_lo + 1
-        const unsigned m_hi = ib >= 8 ? 0u : (0xffu << (ib < 0 ? 0 : ib)) & 0xffu;
-        const float xf0 = x0 + 0.5f, yf = y + 0.5f;
+      const int x_b = (int)(((long long)(gx_lo + 1) * d.W + d.nx - 1) / d.nx);        // first x of cell gx_lo + 1
+      const int ib = x_b - x0;                                             // pixels i >= ib lie in cell gx_lo + 1
+      const unsigned m_hi = ib >= 8 ? 0u : (0xffu << (ib < 0 ? 0 : ib)) & 0xffu;
+      const float xf0 = x0 + 0.5f;
+      float xs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xs[i] = (xf0 + (float)i) * inv_step;     // xf0 + i is exact: the value of (x + 0.5f)
+      int run_k = -1, sL = 0, sA = 0, sB = 0, sy = 0, sx = 0, cnt = 0;     // the thread's open label run
+#pragma unroll 1
+      for (int r = 0; r < kRowsT; ++r) {
+        const bool active = yb + r < d.H;
+        const int y = active ? yb + r : d.H - 1;
+        const int gy = (int)((long long)y * d.ny / d.H);
+        float px[24];
+        {
+          const float4* src = reinterpret_cast<const float4*>(lab + ((long long)y * d.W + x0) * 3);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float4 v = src[j];
+            px[4 * j] = v.x; px[4 * j + 1] = v.y; px[4 * j + 2] = v.z; px[4 * j + 3] = v.w;
+          }
+        }
+        const float ys = (y + 0.5f) * inv_step;
+        int out[8];
         float best[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { best[i] = 3.4e38f; out[i] = gy * d.nx + gx_lo + (int)((m_hi >> i) & 1u); }
-        // candidates outermost (ascending centre index, as the per-pixel scan visits them): a centre's five values
-        // are read from shared memory once per run instead of once per pixel
+        // candidates outermost (ascending centre index, as the per-pixel scan visits them): a prepared centre is read
+        // from shared memory once per run instead of once per pixel
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
           const int yy = gy + dy;
@@ -336,90 +387,49 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
           for (int xx = gx_lo - 1; xx <= gx_hi + 1; ++xx) {
             if (xx < 0 || xx >= d.nx) continue;
             const int k = yy * d.nx + xx;
-            const float4 c4 = *reinterpret_cast<const float4*>(cen + 8 * k);      // L, a, b, x
-            const float sy = (yf - cen[8 * k + 4]) * inv_step;
+            const float4 c4 = *reinterpret_cast<const float4*>(cen + 8 * k);      // -2 (L, a, b, x / S)
+            const float2 c2 = *reinterpret_cast<const float2*>(cen + 8 * k + 4);  // -2 y / S, |c|^2
+            SlicCen pc;
+            pc.m2L = c4.x; pc.m2A = c4.y; pc.m2B = c4.z; pc.m2x = c4.w; pc.m2y = c2.x; pc.cc = c2.y;
+            const float row = slic_score_row(pc, ys);
             // pixels this centre is a candidate of: the column left of the run's first cell serves the pixels of that
             // cell only, the column right of its second cell the pixels of the second cell only
             const unsigned cand = xx == gx_lo - 1 ? (~m_hi & 0xffu) : (xx == gx_lo + 2 ? m_hi : 0xffu);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float dl = px[3 * i] - c4.x, da = px[3 * i + 1] - c4.y, db = px[3 * i + 2] - c4.z;
-              const float sxx = ((xf0 + (float)i) - c4.w) * inv_step;      // xf0 + i is exact: same value as (x + 0.5f)
-              const float dist = slic_dist(dl, da, db, sy, sxx);
+              const float dist = slic_score(pc, row, px[3 * i], px[3 * i + 1], px[3 * i + 2], xs[i]);
               if (((cand >> i) & 1u) && dist < best[i]) { best[i] = dist; out[i] = k; }
             }
           }
         }
-      }
-      if (last) {
-        if (active) {
-          int4* dst = reinterpret_cast<int4*>(labels + pix0 + (long long)y * d.W + x0);
-          dst[0] = make_int4(out[0], out[1], out[2], out[3]);
-          dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+        if (last) {
+          if (active) {
+            int4* dst = reinterpret_cast<int4*>(labels + pix0 + (long long)y * d.W + x0);
+            dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+          }
+          continue;
         }
-        continue;
-      }
-      // Sums of the run's pixels per label, in 32-bit fixed point (|v| <= 108 / compactness, compactness >= 1: eight
-      // pixels stay below 2^31).  A label run that closes inside the thread goes to the accumulators directly; the
-      // open run is first merged with the equal-label runs of the other lanes (match.any + redux.sync on 16-bit
-      // halves), so one lane per label and warp issues the atomics.  64-bit adds are two native 32-bit shared-memory
-      // atomics with the carry passed on (integer sums: any order gives the same total).
-      auto add64 = [&](int k, int j, long long v) {
-        unsigned* a = reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j);
-        const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
-        if (d.dbg & 2) return;
-        const unsigned old = atomicAdd(a, lo);
-        const unsigned h2 = hi + (((old + lo) < old) ? 1u : 0u);
-        if (h2) atomicAdd(a + 1, h2);
-      };
-      if (d.dbg & 1) continue;
-      // position and count sums stay below 2^32 per image for every shape this kernel is launched for: one 32-bit atomic
-      auto add32 = [&](int k, int j, int v) {
-        if (d.dbg & 2) return;
-        atomicAdd(reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j), (unsigned)v);
-      };
-      auto merge_and_add = [&](int key, int sL, int sA, int sB, int vy, int sx, int cnt) {
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const int tL = __reduce_add_sync(peers, sL & 0xffff), hL = __reduce_add_sync(peers, sL >> 16);
-        const int tA = __reduce_add_sync(peers, sA & 0xffff), hA = __reduce_add_sync(peers, sA >> 16);
-        const int tB = __reduce_add_sync(peers, sB & 0xffff), hB = __reduce_add_sync(peers, sB >> 16);
-        const int ty = __reduce_add_sync(peers, vy), tx = __reduce_add_sync(peers, sx), tn = __reduce_add_sync(peers, cnt);
-        if (key >= 0 && lane == __ffs(peers) - 1) {
-          add64(key, 0, ((long long)hL << 16) + tL); add64(key, 1, ((long long)hA << 16) + tA);
-          add64(key, 2, ((long long)hB << 16) + tB);
-          add32(key, 3, ty); add32(key, 4, tx); add32(key, 5, tn);
-        }
-      };
-      int fx[24];
-#pragma unroll
-      for (int j = 0; j < 24; ++j) fx[j] = __float2int_rn(px[j] * (float)kFix);
-      const bool uniform = out[0] == out[1] && out[0] == out[2] && out[0] == out[3] && out[0] == out[4] &&
-                           out[0] == out[5] && out[0] == out[6] && out[0] == out[7];
-      if (__all_sync(0xffffffffu, uniform)) {
-        // the strip holds no vertical label boundary (3 strips of 4): one label per thread, straight sums
-        int sL = 0, sA = 0, sB = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sL += fx[3 * i]; sA += fx[3 * i + 1]; sB += fx[3 * i + 2]; }
-        merge_and_add(active ? out[0] : -1, sL, sA, sB, 8 * (2 * y + 1), 16 * x0 + 64, 8);
-      } else {
-        int run_k = -1, sL = 0, sA = 0, sB = 0, sx = 0, cnt = 0;
+        if ((d.dbg & 1) || !active) continue;
+        // a label run that closes inside the thread goes to the accumulators directly (boundaries only)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (active) {
-            if (out[i] != run_k) {
-              if (cnt > 0) {
-                add64(run_k, 0, sL); add64(run_k, 1, sA); add64(run_k, 2, sB);
-                add32(run_k, 3, cnt * (2 * y + 1)); add32(run_k, 4, sx); add32(run_k, 5, cnt);
-              }
-              run_k = out[i]; sL = sA = sB = sx = cnt = 0;
+          if (out[i] != run_k) {
+            if (cnt > 0) {
+              add64(run_k, 0, sL); add64(run_k, 1, sA); add64(run_k, 2, sB);
+              add32(run_k, 3, sy); add32(run_k, 4, sx); add32(run_k, 5, cnt);
             }
-            sL += fx[3 * i]; sA += fx[3 * i + 1]; sB += fx[3 * i + 2];
-            sx += 2 * (x0 + i) + 1;
-            cnt += 1;
+            run_k = out[i]; sL = sA = sB = sy = sx = cnt = 0;
           }
+          sL += __float2int_rn(px[3 * i] * (float)kFix);
+          sA += __float2int_rn(px[3 * i + 1] * (float)kFix);
+          sB += __float2int_rn(px[3 * i + 2] * (float)kFix);
+          sy += 2 * y + 1;
+          sx += 2 * (x0 + i) + 1;
+          cnt += 1;
         }
-        merge_and_add(cnt > 0 ? run_k : -1, sL, sA, sB, cnt * (2 * y + 1), sx, cnt);
       }
+      if (!last && !(d.dbg & 1)) merge_and_add(cnt > 0 ? run_k : -1, sL, sA, sB, sy, sx, cnt);
     }
     if (last) break;
     __syncthreads();
@@ -428,11 +438,11 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
       const long long n = a[5];
       if (n > 0) {
         const double inv = 1.0 / (double)n;
-        cen[8 * k] = (float)((double)a[0] / kFix * inv);
-        cen[8 * k + 1] = (float)((double)a[1] / kFix * inv);
-        cen[8 * k + 2] = (float)((double)a[2] / kFix * inv);
-        cen[8 * k + 4] = (float)((double)a[3] * 0.5 * inv);
-        cen[8 * k + 3] = (float)((double)a[4] * 0.5 * inv);
+        const SlicCen pc = slic_prepare((float)((double)a[0] / kFix * inv), (float)((double)a[1] / kFix * inv),
+                                        (float)((double)a[2] / kFix * inv), (float)((double)a[3] * 0.5 * inv),
+                                        (float)((double)a[4] * 0.5 * inv), inv_step);
+        cen[8 * k] = pc.m2L; cen[8 * k + 1] = pc.m2A; cen[8 * k + 2] = pc.m2B; cen[8 * k + 3] = pc.m2x;
+        cen[8 * k + 4] = pc.m2y; cen[8 * k + 5] = pc.cc;
       }
 #pragma unroll
       for (int j = 0; j < 6; ++j) a[j] = 0;
@@ -490,7 +500,7 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
   const SlicDims d = slic_dims(B, H, W, n_segments, compactness);
   const long long npix = (long long)B * H * W;
   float* lab = reinterpret_cast<float*>(work);
-  if (g_slic_run == 8 && d.K <= kImgMaxK && W % 8 == 0 && d.nx * 8 <= W && (double)H * W * (2.0 * (H > W ? H : W) + 1.0) < 4.0e9 && compactness >= 1.f && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(labels) |
+  if (g_slic_run == 8 && d.K <= kImgMaxK && W % 8 == 0 && d.nx * 8 <= W && (double)H * W * (2.0 * (H > W ? H : W) + 1.0) < 4.0e9 && compactness >= 4.f && ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(labels) |
                                                          reinterpret_cast<uintptr_t>(lab)) & 15u) == 0) {
     // one CTA per image, the whole loop in one launch
     const int smem = d.K * (6 * 8 + 8 * 4) + 256 * 4;

@@ -128,6 +128,38 @@ int gnc_debug_slic_run_length(int run);
  * (one CTA per image with the forest in shared memory when H * W <= 65536).  Same result. */
 int gnc_debug_slic_connect_streaming(int on);
 
+/* Input staging, first half: the file decode behind  Image.open(path).convert('RGB')  (utils/dataloader.py:34 through
+ * ImageFolder's loader, utils/image_to_graph/image_to_graph_optimized.py:65-68, utils/inference.py:47) for baseline
+ * JPEG files, bit for bit what Pillow's libjpeg produces with its defaults (csrc/jpeg.cu).
+ * gnc_jpeg_parse (HOST): markers of one file -> geometry, dequantisation and Huffman decode tables, position of the
+ *   entropy-coded scan (relative to `data`; add the file's offset in the batch buffer before the device call).
+ *   Returns GNC_OK, or GNC_JPEG_UNSUPPORTED for anything outside baseline / extended-sequential Huffman, 8 bit, one
+ *   interleaved scan, greyscale or YCbCr 4:4:4 / 4:2:2 / 4:2:0 - decode those with Pillow on the host.
+ * gnc_jpeg_decode_rgb_u8 (DEVICE): `stream` = the files' bytes back to back, `infos` = B parsed descriptors with
+ *   scan_offset (into stream), block_offset (running sum of n_blocks), coef_offset (= 64 * block_offset), plane_offset
+ *   (running sum of plane_bytes) and pixel_offset (running sum of width * height) filled in by the caller;
+ *   coef: int16 [64 * total_blocks], planes: uint8 [sum plane_bytes], out: uint8 [3 * total_pixels] - image i's RGB
+ *   pixels, row-major, at 3 * pixel_offset. */
+#define GNC_JPEG_UNSUPPORTED 4
+typedef struct gnc_jpeg_huff {
+  uint16_t look[512];     /* 9-bit lookahead: (code length << 8) | symbol, 0 = longer code */
+  int32_t maxcode[18];    /* largest code of each length (-1: none), [17] = sentinel */
+  int32_t valoff[17];     /* index of a length's first symbol minus its first code */
+  uint8_t vals[256];
+} gnc_jpeg_huff_t;
+typedef struct gnc_jpeg_image {
+  int32_t width, height, ncomp;
+  int32_t hsamp[3], vsamp[3], qtab[3], dc_tab[3], ac_tab[3];
+  int32_t restart_interval, mcu_x, mcu_y, _pad;
+  int64_t scan_offset, scan_bytes, n_blocks, plane_bytes;
+  int64_t block_offset, coef_offset, plane_offset, pixel_offset;
+  uint16_t quant[4][64];  /* natural (row-major) order */
+  gnc_jpeg_huff_t huff[8];/* [0..3] DC tables, [4..7] AC tables */
+} gnc_jpeg_image_t;
+int gnc_jpeg_parse(const uint8_t* data, int64_t size, gnc_jpeg_image_t* out);
+int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos, int B, int64_t total_blocks,
+                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out, gnc_stream_t stream_);
+
 /* Input staging: the resize the reference applies to every image before building its graph,
  *   Image.open(path).convert('RGB').resize((r, r))     utils/image_to_graph/image_to_graph_optimized.py:65-70,
  *                                                      image_to_graph_patch.py / _superpixel.py likewise

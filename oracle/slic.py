@@ -16,7 +16,8 @@ documented conventions), step by step:
      pixels (sums in 2^-20 fixed point, so the order of summation is immaterial); a centre without pixels stays.
   5. one more assignment gives the labels (values in ``0 .. K - 1``; the connectivity post-pass is separate).
 
-The device evaluates the distance as one fp32 FMA chain; this restatement uses float64, so pixels within rounding of a
+The device ranks candidates by |c|^2 - 2 p.c (the pixel's own |p|^2 is common to them) as one fp32 FMA chain; this
+restatement evaluates the distance itself in float64, so pixels within rounding of a
 tie can differ - the test states the agreement it requires.
 """
 from __future__ import annotations

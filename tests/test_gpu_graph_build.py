@@ -159,6 +159,29 @@ def test_superpixel_batch_and_edge_cases(libgnc):
         np.testing.assert_allclose(pos[b, :S].cpu().numpy(), opos.astype(np.float32), rtol=1e-6)
 
 
+@pytest.mark.parametrize("H,W", [(40, 50), (40, 56), (33, 64), (7, 8), (64, 24)])
+def test_superpixel_both_kernels_vs_oracle(libgnc, H, W):
+    """Widths that are a multiple of 8 take the run-aggregated kernel (a thread owns 8 pixels, statistics merged per
+    label across the warp), other widths the per-pixel kernel: both against the oracle's label-map stage, with noisy
+    label maps (many short runs, labels missing from the range, one out-of-order label id)."""
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_superpixel_graphs
+    rng = np.random.default_rng(H * 100 + W)
+    B = 3
+    imgs = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    labs = np.stack([voronoi_labels(H, W, 7 + 4 * b, seed=b + W) for b in range(B)]).astype(np.int32)
+    noise = rng.random(labs.shape) < 0.1
+    labs[noise] = rng.integers(0, 40, int(noise.sum()))
+    labs[labs == 3] = 57                                   # a gap in the label range
+    n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(torch.from_numpy(imgs), torch.from_numpy(labs))
+    for b in range(B):
+        ox, opos, oei = ogb.superpixel_graph_from_labels(imgs[b], labs[b])
+        S, E = int(n_nodes[b]), int(n_edges[b])
+        assert S == len(ox) and E == oei.shape[1]
+        assert np.array_equal(edges[b, :, :E].cpu().numpy(), oei)
+        np.testing.assert_allclose(x[b, :S].cpu().numpy(), ox.astype(np.float32), rtol=1e-6)
+        np.testing.assert_allclose(pos[b, :S].cpu().numpy(), opos.astype(np.float32), rtol=1e-6)
+
+
 def test_reference_named_builders(golden, libgnc):
     from PIL import Image
     from graphnet_classifier_b200.utils.image_to_graph import (

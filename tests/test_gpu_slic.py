@@ -124,6 +124,6 @@ def test_slic_kmeans_against_cpu_restatement(libgnc):
 
         for y, x in zip(ys, xs):
             a, b = dist(int(got[y, x]), y, x), dist(int(want[y, x]), y, x)
-            assert abs(a - b) <= 2e-3 * max(a, b) + 1e-9, (y, x, a, b)
+            assert abs(a - b) <= 2e-3 * max(a, b) + 1e-4, (y, x, a, b)
         print(f"SLIC k-means {H}x{W}, {S} segments: {100 * agree:.3f} % of the labels equal the CPU restatement, "
               f"{len(ys)} near-tie pixels differ")
