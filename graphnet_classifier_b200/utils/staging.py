@@ -2,7 +2,11 @@
 ``Image.open(path).convert('RGB').resize((r, r))`` (utils/dataloader.py:34 through torchvision's ImageFolder,
 utils/image_to_graph/image_to_graph_optimized.py:65-70, utils/inference.py:47).  Here
 
-* the decode (``Image.open`` + ``convert('RGB')``: libjpeg inside Pillow) runs on a pool of host PROCESSES (Pillow's
+* baseline JPEG files are decoded ON THE DEVICE (``utils/jpeg.py``, csrc/jpeg.cu: libjpeg's integer algorithm restated,
+  bit for bit Pillow's pixels): the pool's threads only read the files and parse their markers, and only the compressed
+  bytes cross PCIe;
+* everything else (PNG, progressive / CMYK JPEG, ...; or all files with ``device_jpeg=False``): the decode
+  (``Image.open`` + ``convert('RGB')``: libjpeg inside Pillow) runs on a pool of host PROCESSES (Pillow's
   Python-level file handling holds the GIL for about half of a small file's decode time: 8 threads give 2 x one
   thread, processes scale with the cores), each image decoded straight into its slot of a shared-memory staging
   buffer that is registered with CUDA as pinned memory; PIL images that are already open (no path to hand to another
@@ -12,8 +16,6 @@ utils/image_to_graph/image_to_graph_optimized.py:65-70, utils/inference.py:47). 
 * the resize is the Pillow-exact device kernel (``ops.resize_bicubic``), so the pixels that reach the graph builder are
   bit for bit the reference's.
 
-The entropy decode stays on the host: it is sequential per image (no restart markers in Pillow-written files), and one
-GPU thread per image runs it at a few hundred MIPS - not worth a kernel while the box's cores are idle.
 """
 from __future__ import annotations
 
@@ -64,7 +66,8 @@ class DecodePool:
     ``processes=True`` (default) decodes file paths on worker processes into shared pinned memory; PIL images and
     ``processes=False`` use the thread pool."""
 
-    def __init__(self, workers: Optional[int] = None, device=None, processes: bool = True, slot_bytes: int = 1 << 20):
+    def __init__(self, workers: Optional[int] = None, device=None, processes: bool = True, slot_bytes: int = 1 << 20,
+                 device_jpeg: bool = True):
         self.workers = int(workers) if workers else max(1, (os.cpu_count() or 2) - 1)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
@@ -77,6 +80,9 @@ class DecodePool:
         self.slot_bytes = int(slot_bytes)       # one decoded image per slot (1 MiB holds 512 x 682 RGB; larger images come back through the pipe)
         self._procs = None
         self._shared = [None, None]
+        self.device_jpeg = bool(device_jpeg)    # baseline JPEG files: Huffman + IDCT + colour on the GPU
+        self._jpeg_staging = [{}, {}]
+        self.stats = {"device_jpeg": 0, "host_decoded": 0}
 
     def _process_pool(self):
         if self._procs is None:
@@ -144,8 +150,53 @@ class DecodePool:
             groups[(h, w, 3)][1].append(view)
         return [(shape, idxs, views) for shape, (idxs, views) in groups.items()]
 
+    def _read_chunk_jpeg(self, paths: Sequence, slot: int):
+        """Device-JPEG form of a chunk: the pool's threads read the files and parse their markers (the C parser
+        releases the GIL); files the device decoder does not cover are decoded by Pillow here, on the host."""
+        from . import jpeg as gjpeg
+
+        def read_parse(path):
+            with open(path, "rb") as f:
+                data = f.read()
+            return data, gjpeg.parse(data)
+
+        pairs = list(self.pool.map(read_parse, paths))
+        rest = [i for i, (_, inf) in enumerate(pairs) if inf is None]
+        host = dict(zip(rest, self.pool.map(_decode, [paths[i] for i in rest]))) if rest else {}
+        self.stats["device_jpeg"] += len(pairs) - len(rest)
+        self.stats["host_decoded"] += len(rest)
+        return {"jpeg": pairs, "host": host, "slot": slot}
+
+    def _upload_jpeg(self, chunk, resize_value: int) -> Tensor:
+        from . import jpeg as gjpeg
+        r = int(resize_value)
+        pairs, host = chunk["jpeg"], chunk["host"]
+        imgs = gjpeg.decode_batch([d for d, _ in pairs], self.device, infos=[inf for _, inf in pairs],
+                                  staging=self._jpeg_staging[chunk["slot"]])
+        for i, a in host.items():
+            imgs[i] = torch.from_numpy(np.array(a, dtype=np.uint8)).to(self.device)
+        groups = {}
+        for i, t in enumerate(imgs):
+            groups.setdefault(tuple(t.shape), []).append(i)
+        n = len(imgs)
+        out = None
+        for shape, idxs in groups.items():
+            if len(idxs) == n and all(imgs[i].data_ptr() + imgs[i].numel() == imgs[i + 1].data_ptr() for i in range(n - 1)):
+                batch = torch.as_strided(imgs[0], (n, *shape), (imgs[0].numel(), shape[1] * 3, 3, 1))     # already packed
+            else:
+                batch = torch.stack([imgs[i] for i in idxs])
+            px = batch if (shape[0] == r and shape[1] == r) else ops.resize_bicubic(batch, r, r)
+            if len(groups) == 1:
+                return px
+            if out is None:
+                out = torch.empty(n, r, r, 3, dtype=torch.uint8, device=self.device)
+            out[torch.as_tensor(idxs, device=self.device)] = px
+        return out
+
     def _decode_chunk(self, items: Sequence, slot: int):
         """Decodes ``items`` on the pool; returns ``[(shape, indices, pinned view [k, H, W, 3])]`` grouped by shape."""
+        if self.device_jpeg and items and all(isinstance(it, (str, os.PathLike)) for it in items):
+            return self._read_chunk_jpeg(items, slot)
         if self._events[slot] is not None:
             self._events[slot].synchronize()            # the previous copy out of this buffer is done
         if self.processes and items and all(isinstance(it, (str, os.PathLike)) for it in items):
@@ -174,6 +225,8 @@ class DecodePool:
     def _upload(self, groups, slot: int, resize_value: int) -> Tensor:
         """Host->device copies on the copy stream, Pillow-exact resize on the device; returns ``[n, r, r, 3]`` in item
         order.  The caller's stream waits for the copies only."""
+        if isinstance(groups, dict):
+            return self._upload_jpeg(groups, resize_value)
         r = int(resize_value)
         n = sum(len(idxs) for _, idxs, _ in groups)
         cur = torch.cuda.current_stream(self.device)

@@ -335,6 +335,29 @@ def gen_checkpoint(ref):
     print("checkpoint.npz:", len(out), "entries; large-activation case max", max(acts))
 
 
+def gen_jpeg(ref):
+    """The shipped JPEG files themselves (bytes) with the pixels the unmodified reference builder is fed from them:
+    ``image_to_graph_pixel_optimized(path, r)`` with ``r`` = the file's own size returns the decoded RGB pixels as its
+    node features (reference image_to_graph_optimized.py:65-72: open, convert('RGB'), resize to the same size is the
+    identity, reshape).  oracle/jpeg.py must reproduce them bit for bit; the device decoder is tested against both."""
+    from oracle.jpeg import decode_baseline
+    out = {}
+    for rel, r_ in (("static/chihuahua/img_4_799_32.jpg", 32), ("static/muffin/img_4_880_32.jpg", 32),
+                    ("static/chihuahua/img_4_799_64.jpg", 64), ("static/muffin/img_4_880_64.jpg", 64),
+                    ("static/muffin/img_0_187_128.jpg", 128), ("static/chihuahua/img_4_799_256.jpg", 256)):
+        path = os.path.join(rl.REFERENCE_ROOT, rel)
+        data = open(path, "rb").read()
+        x, _, _ = ref.optimized.image_to_graph_pixel_optimized(path, r_)
+        px = np.asarray(x, dtype=np.uint8).reshape(r_, r_, 3)
+        _check(np.array_equal(px, np.array(Image.open(path).convert("RGB"))), f"reference builder pixels {rel}")
+        _check(np.array_equal(decode_baseline(data), px), f"oracle JPEG decode {rel}")
+        k = os.path.basename(rel).replace(".jpg", "")
+        out[k + "_bytes"] = np.frombuffer(data, dtype=np.uint8)
+        out[k + "_rgb"] = px
+    np.savez_compressed(os.path.join(GOLDEN, "jpeg_files.npz"), **out)
+    print("jpeg_files.npz:", len(out), "entries,", sum(v.nbytes for k, v in out.items() if k.endswith("_bytes")), "file bytes")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = rl.load_reference()
@@ -348,12 +371,16 @@ def main():
     if "--only-checkpoint" in sys.argv:
         gen_checkpoint(ref)
         return
+    if "--only-jpeg" in sys.argv:
+        gen_jpeg(ref)
+        return
     gen_grids(ref)
     gen_builders(ref)
     gen_model(ref)
     gen_resize(ref)
     gen_mlp(ref)
     gen_checkpoint(ref)
+    gen_jpeg(ref)
     print("all reference-vs-oracle comparisons passed; golden vectors written to", GOLDEN)
 
 

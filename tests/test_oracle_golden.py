@@ -187,3 +187,68 @@ def test_oracle_reproduces_reference_on_shipped_checkpoint():
         for b in range(2):
             out = om(ogb.to_model_inputs(*ogb.pixel_graph(g["big_imgs"][b])))
             np.testing.assert_allclose(out.numpy(), g["big_logits"][b], rtol=2e-6, atol=1e-7)
+
+
+# ---- JPEG decode: the oracle restatement of libjpeg against Pillow and the reference's shipped files (CPU) ----
+def test_jpeg_oracle_equals_pillow_and_shipped_files():
+    import io
+    from PIL import Image
+    from oracle.jpeg import decode_baseline
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg_files.npz"))
+    for k in [k for k in g.files if k.endswith("_bytes")]:
+        data = g[k].tobytes()
+        assert np.array_equal(decode_baseline(data), g[k[:-6] + "_rgb"]), k
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")), g[k[:-6] + "_rgb"]), k
+    rng = np.random.default_rng(3)
+    for h, w, kw in ((33, 47, dict(quality=75)), (17, 23, dict(quality=95, subsampling=0)), (40, 50, dict(quality=60, subsampling=1)),
+                     (31, 65, dict(quality=90)), (50, 70, dict(quality=80, restart_marker_blocks=3)), (20, 3, dict(quality=90)),
+                     (64, 48, dict(quality=85, optimize=True))):
+        arr = np.asarray(Image.fromarray(rng.integers(0, 256, (h // 5 + 2, w // 5 + 2, 3), dtype=np.uint8)).resize((w, h)))
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format="JPEG", **kw)
+        ref = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB"))
+        assert np.array_equal(decode_baseline(buf.getvalue()), ref), (h, w, kw)
+
+
+def test_jpeg_host_parser_matches_oracle_parser(libgnc):
+    """gnc_jpeg_parse (host code of csrc/jpeg.cu, no GPU needed): geometry, tables and scan position against the
+    oracle's own marker parser; files outside the decoder's scope are reported as unsupported."""
+    import ctypes
+    import io
+    from PIL import Image
+    from graphnet_classifier_b200 import _lib
+    from oracle.jpeg import parse
+    rng = np.random.default_rng(5)
+    arr = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for kw in (dict(quality=80), dict(quality=92, subsampling=0), dict(quality=50, subsampling=1, optimize=True),
+               dict(quality=85, restart_marker_blocks=2)):
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, format="JPEG", **kw)
+        data = buf.getvalue()
+        info = _lib.GncJpegImage()
+        assert libgnc.gnc_jpeg_parse(data, len(data), ctypes.byref(info)) == 0
+        (H, W, comps), quant, huff, dri, tabs, pos = parse(data)
+        assert (info.height, info.width, info.ncomp) == (H, W, len(comps)) and info.restart_interval == dri
+        assert [info.hsamp[c] for c in range(3)] == [c[1] for c in comps] and [info.vsamp[c] for c in range(3)] == [c[2] for c in comps]
+        assert info.scan_offset == pos and data[pos + info.scan_bytes:pos + info.scan_bytes + 2] == b"\xff\xd9"
+        for c in range(3):
+            assert np.array_equal(np.array(info.quant[info.qtab[c]][:]), quant[comps[c][3]])
+            # every code of the oracle's canonical table decodes to the same symbol through the lookahead / maxcode tables
+            for (tc, th), slot in (((0, tabs[c][1]), info.dc_tab[c]), ((1, tabs[c][2]), 4 + info.ac_tab[c])):
+                t = info.huff[slot]
+                for (length, code), sym in huff[(tc, th)].items():
+                    if length <= 9:
+                        e = t.look[code << (9 - length)]
+                        assert (e >> 8, e & 255) == (length, sym)
+                    else:
+                        assert code <= t.maxcode[length] and t.vals[code + t.valoff[length]] == sym
+        assert info.n_blocks == info.mcu_x * info.mcu_y * sum(info.hsamp[c] * info.vsamp[c] for c in range(3))
+    for bad in (dict(progressive=True), None):
+        buf = io.BytesIO()
+        if bad is None:
+            Image.fromarray(arr).save(buf, format="PNG")
+        else:
+            Image.fromarray(arr).save(buf, format="JPEG", **bad)
+        info = _lib.GncJpegImage()
+        assert libgnc.gnc_jpeg_parse(buf.getvalue(), len(buf.getvalue()), ctypes.byref(info)) == _lib.GNC_JPEG_UNSUPPORTED
