@@ -734,7 +734,8 @@ def run_ours(args):
                                        "what": "gnc_jpeg_decode_rgb_u8 on the files' bytes (host -> device copy of the "
                                                "compressed bytes included), CUDA events"},
                 "host_decode_form": {"value": n_files / dt_host, "unit": UNIT, "ms_per_step": dt_host * 1e3,
-                                     "what": "the same call with device_jpeg=False: Pillow on worker processes"},
+                                     "what": "Pillow on worker processes into shared pinned memory, double-buffered copies",
+                                     "h2d_bytes_per_step": n_files * ph * pw * 3},
                 "decode_threads": workers, "host_cpu_count": os.cpu_count(),
                     "one_thread_pil_decode_images_per_s": one_core, "file_bytes_per_step": file_bytes,
                     "h2d_bytes_per_step": file_bytes, "d2h_bytes_per_step": n_files * 8,

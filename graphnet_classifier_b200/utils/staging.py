@@ -67,7 +67,7 @@ class DecodePool:
     ``processes=False`` use the thread pool."""
 
     def __init__(self, workers: Optional[int] = None, device=None, processes: bool = True, slot_bytes: int = 1 << 20,
-                 device_jpeg: bool = True):
+                 device_jpeg="auto"):
         self.workers = int(workers) if workers else max(1, (os.cpu_count() or 2) - 1)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
@@ -80,7 +80,14 @@ class DecodePool:
         self.slot_bytes = int(slot_bytes)       # one decoded image per slot (1 MiB holds 512 x 682 RGB; larger images come back through the pipe)
         self._procs = None
         self._shared = [None, None]
-        self.device_jpeg = bool(device_jpeg)    # baseline JPEG files: Huffman + IDCT + colour on the GPU
+        # baseline JPEG files: Huffman + IDCT + colour on the GPU.  "auto": where the host is short of cores for its GPUs
+        # (a box's 16 cores feeding 8 GPUs decode ~2 k files/s per GPU; the device decoder does ~28 k/s per GPU).  With
+        # many idle cores per GPU the host processes win end to end: their decode overlaps the GPU's inference, while
+        # the device decoder's entropy stage is latency-bound (~18 ms per launch whatever the number of files) and
+        # cannot share SMs with the persistent inference kernels.
+        if device_jpeg == "auto":
+            device_jpeg = (os.cpu_count() or 1) / max(1, torch.cuda.device_count()) < 6
+        self.device_jpeg = bool(device_jpeg)
         self._jpeg_staging = [{}, {}]
         self.stats = {"device_jpeg": 0, "host_decoded": 0}
 
@@ -276,11 +283,14 @@ class DecodePool:
             feeder.shutdown(wait=True)
 
 
-def infer_files(pipeline, paths: Iterable, pool: Optional[DecodePool] = None, chunk: int = 128) -> Tensor:
+def infer_files(pipeline, paths: Iterable, pool: Optional[DecodePool] = None, chunk: Optional[int] = None) -> Tensor:
     """File paths (or PIL images) -> logits ``[n, classes]`` through ``GraphClassifierPipeline.infer``: threaded decode,
     double-buffered pinned copies, device resize, graph build and GraphNet on the stream."""
     own = pool is None
     pool = pool or DecodePool(device=pipeline.device)
+    # the device decoder's entropy stage costs the same per launch for 1 or 500 files: large chunks; host decode
+    # overlaps with the GPU chunk by chunk: smaller ones
+    chunk = chunk or (512 if pool.device_jpeg else 128)
     try:
         outs = [pipeline.infer(px) for px in pool.batches(list(paths), pipeline.resize_value, chunk)]
     finally:

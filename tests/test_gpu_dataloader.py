@@ -121,15 +121,16 @@ def test_decode_pool_equals_reference_pixels(libgnc, tmp_path):
         img.save(path, quality=90) if path.suffix == ".jpg" else img.save(path)
         paths.append(str(path))
     want = np.stack([np.array(Image.open(p).convert("RGB").resize((r, r))) for p in paths])
-    with DecodePool(workers=3) as pool:
-        got = pool.stage(paths, r)
-        assert got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (len(paths), r, r, 3)
-        assert np.array_equal(got.cpu().numpy(), want)
-        chunks = list(pool.batches(paths, r, chunk=4))
-        assert [c.shape[0] for c in chunks] == [4, 4, 1]
-        assert np.array_equal(torch.cat(chunks).cpu().numpy(), want)
-        again = torch.cat(list(pool.batches(paths, r, chunk=2))).cpu().numpy()     # staging buffers reused many times
-        assert np.array_equal(again, want)
+    for device_jpeg in (True, False):
+        with DecodePool(workers=3, device_jpeg=device_jpeg) as pool:
+            got = pool.stage(paths, r)
+            assert got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (len(paths), r, r, 3)
+            assert np.array_equal(got.cpu().numpy(), want)
+            chunks = list(pool.batches(paths, r, chunk=4))
+            assert [c.shape[0] for c in chunks] == [4, 4, 1]
+            assert np.array_equal(torch.cat(chunks).cpu().numpy(), want)
+            again = torch.cat(list(pool.batches(paths, r, chunk=2))).cpu().numpy()     # staging buffers reused many times
+            assert np.array_equal(again, want)
 
 
 def test_infer_files_equals_infer(libgnc, tmp_path):

@@ -80,7 +80,7 @@ def test_unsupported_files_fall_back_to_the_host(libgnc, tmp_path):
     infos = [gjpeg.parse(open(p, "rb").read()) for p in paths]
     assert [i is not None for i in infos] == [True, False, False, True, False]
     want = np.stack([np.array(Image.open(p).convert("RGB").resize((24, 24))) for p in paths])
-    with DecodePool(workers=2) as pool:
+    with DecodePool(workers=2, device_jpeg=True) as pool:
         got = pool.stage(paths, 24)
         assert pool.stats == {"device_jpeg": 2, "host_decoded": 3}
         assert np.array_equal(got.cpu().numpy(), want)
