@@ -693,7 +693,7 @@ def run_ours(args):
                 for pth in paths[:32]:
                     np.asarray(Image.open(pth).convert("RGB"))
                 one_core = 32 / (time.perf_counter() - t0)
-                with DecodePool(device=dev) as pool:
+                with DecodePool(device=dev, device_jpeg=True) as pool:
                     infer_files(pipe, paths, pool=pool).cpu()                # warm-up: staging buffers, resize tables
                     torch.cuda.synchronize()
                     reps = 3
@@ -726,22 +726,34 @@ def run_ours(args):
                         infer_files(pipe, paths, pool=pool).cpu()
                     torch.cuda.synchronize()
                     dt_host = (time.perf_counter() - t0) / reps
+                probe = DecodePool(device=dev)
+                auto_is_device = probe.device_jpeg
+                probe.close()
+                dt_auto = dt if auto_is_device else dt_host
                 staging["e2e_from_files"] = {
-                    "value": n_files / dt, "unit": UNIT, "files_per_step": n_files, "ms_per_step": dt * 1e3,
-                    "decoder": "device (csrc/jpeg.cu: Huffman + IDCT + upsampling + colour on the GPU, bit-identical to Pillow); "
-                           "pool threads only read and parse the files", "files_by_decoder": pool_stats,
-                "device_jpeg_decode": {"images_per_s": n_files / (jms / 1e3), "ms_per_step": jms,
-                                       "what": "gnc_jpeg_decode_rgb_u8 on the files' bytes (host -> device copy of the "
-                                               "compressed bytes included), CUDA events"},
-                "host_decode_form": {"value": n_files / dt_host, "unit": UNIT, "ms_per_step": dt_host * 1e3,
-                                     "what": "Pillow on worker processes into shared pinned memory, double-buffered copies",
-                                     "h2d_bytes_per_step": n_files * ph * pw * 3},
-                "decode_threads": workers, "host_cpu_count": os.cpu_count(),
+                    "value": n_files / dt_auto, "unit": UNIT, "files_per_step": n_files, "ms_per_step": dt_auto * 1e3,
+                    "default_decoder": "device" if auto_is_device else "host processes",
+                    "default_rule": "device JPEG decode when the box has fewer than 6 host cores per visible GPU",
+                    "device_decode_form": {
+                        "value": n_files / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "files_by_decoder": pool_stats,
+                        "h2d_bytes_per_step": file_bytes,
+                        "what": "csrc/jpeg.cu: Huffman + IDCT + upsampling + colour on the GPU, bit-identical to Pillow; the "
+                                "pool's threads only read and parse the files; only the compressed bytes cross PCIe"},
+                    "host_decode_form": {
+                        "value": n_files / dt_host, "unit": UNIT, "ms_per_step": dt_host * 1e3,
+                        "h2d_bytes_per_step": n_files * ph * pw * 3,
+                        "what": "Pillow on worker processes into shared pinned memory, double-buffered copies"},
+                    "device_jpeg_decode": {
+                        "images_per_s": n_files / (jms / 1e3), "ms_per_step": jms,
+                        "what": "gnc_jpeg_decode_rgb_u8 alone on the files' bytes (host -> device copy of the compressed "
+                                "bytes included), CUDA events"},
+                    "decode_workers": workers, "host_cpu_count": os.cpu_count(),
                     "one_thread_pil_decode_images_per_s": one_core, "file_bytes_per_step": file_bytes,
-                    "h2d_bytes_per_step": file_bytes, "d2h_bytes_per_step": n_files * 8,
-                    "timing": "wall clock around the whole call (host decode is part of it), this rank only",
-                    "api": "utils.staging.infer_files(pipeline, jpeg paths): threaded PIL decode -> pinned double-buffered H2D "
-                           "-> device resize -> graph build -> GraphNet -> logits.cpu()"}
+                    "h2d_bytes_per_step": file_bytes if auto_is_device else n_files * ph * pw * 3,
+                    "d2h_bytes_per_step": n_files * 8,
+                    "timing": "wall clock around the whole call (host work is part of it), this rank only",
+                    "api": "utils.staging.infer_files(pipeline, jpeg paths) -> logits.cpu(): decode (device or host "
+                           "processes) -> Pillow-exact device resize -> graph build -> GraphNet"}
                 # nvJPEG (library: torchvision.io.decode_jpeg on the device) on the same files, measured as the
                 # alternative to the host decode.  NOT on the default path: its IDCT / chroma upsampling differ from
                 # libjpeg's, so the pixels are not the reference's - the difference against PIL is stated here.
@@ -758,7 +770,7 @@ def run_ours(args):
                     nv_dt = (time.perf_counter() - t0) / 3
                     worst, mean, same = 0, 0.0, 0
                     for pth, dimg in list(zip(paths, dec))[:64]:
-                        ref_px = torch.from_numpy(np.asarray(Image.open(pth).convert("RGB"))).to(dev)
+                        ref_px = torch.from_numpy(np.array(Image.open(pth).convert("RGB"))).to(dev)
                         diff = (dimg.permute(1, 2, 0).int() - ref_px.int()).abs()
                         worst = max(worst, int(diff.max()))
                         mean += float(diff.float().mean()) / 64

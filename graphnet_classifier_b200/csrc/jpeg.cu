@@ -44,6 +44,10 @@ static const uint8_t h_natural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32
                                       30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 // ---- entropy decode -------------------------------------------------------------------------------------------------
+// A single thread runs at a few hundred MIPS on this machine (every instruction waits ~5 cycles for the one before it),
+// so the loop is written for a short dependent chain per symbol: ONE refill check per symbol (>= 32 valid bits cover the
+// longest code + the longest value), the code and its value bits taken from the same 32-bit window, the tables of the
+// warp's image in shared memory, four stream bytes appended at a time unless one of them is 0xFF.
 struct BitReader {
   const uint8_t* p;        // next byte of the stream
   const uint8_t* end;
@@ -52,7 +56,7 @@ struct BitReader {
   bool marker;             // a marker (FF xx, xx != 0) was met: feed zeros, as libjpeg does past the end of a segment
 };
 
-__device__ __forceinline__ void refill(BitReader& br) {
+__device__ __forceinline__ void refill_bytes(BitReader& br) {
   while (br.n <= 56) {
     uint32_t byte = 0;
     if (!br.marker && br.p < br.end) {
@@ -69,55 +73,103 @@ __device__ __forceinline__ void refill(BitReader& br) {
     br.n += 8;
   }
 }
-__device__ __forceinline__ uint32_t peek(const BitReader& br, int k) { return (uint32_t)(br.acc >> (64 - k)); }
-__device__ __forceinline__ void skip(BitReader& br, int k) { br.acc <<= k; br.n -= k; }
-
-// one Huffman symbol (jdhuff.c: lookahead table, then the canonical code walk)
-__device__ __forceinline__ int decode_symbol(BitReader& br, const gnc_jpeg_huff_t* t) {
-  if (br.n < 16) refill(br);
-  const uint32_t look = t->look[peek(br, kLook)];
-  if (look) { skip(br, (int)(look >> 8)); return (int)(look & 0xff); }
-  int l = kLook + 1;
-  int32_t code = (int32_t)peek(br, l);
-  while (l <= 16 && code > t->maxcode[l]) { ++l; code = (int32_t)peek(br, l); }
-  if (l > 16) { skip(br, 16); return 0; }        // corrupt stream: libjpeg warns and returns 0
-  skip(br, l);
-  return t->vals[(code + t->valoff[l]) & 0xff];
+// at least 32 valid bits
+__device__ __forceinline__ void ensure32(BitReader& br) {
+  if (br.n >= 32) return;
+  if (!br.marker && br.p + 4 <= br.end) {
+    const uint32_t b0 = br.p[0], b1 = br.p[1], b2 = br.p[2], b3 = br.p[3];      // independent loads
+    if (b0 != 0xFF && b1 != 0xFF && b2 != 0xFF && b3 != 0xFF) {
+      const uint32_t w = (b0 << 24) | (b1 << 16) | (b2 << 8) | b3;
+      br.acc |= (uint64_t)w << (32 - br.n);
+      br.n += 32;
+      br.p += 4;
+      return;
+    }
+  }
+  refill_bytes(br);
 }
-__device__ __forceinline__ int receive_extend(BitReader& br, int s) {
-  if (br.n < s) refill(br);
-  const int r = (int)peek(br, s);
-  skip(br, s);
-  return r < (1 << (s - 1)) ? r - (1 << s) + 1 : r;      // HUFF_EXTEND
+// one Huffman symbol and the `size` value bits behind it (jdhuff.c: lookahead table, canonical code walk, HUFF_EXTEND);
+// for AC symbols size = low nibble, for DC symbols size = the symbol.  Returns the symbol, the extended value in `val`.
+template <bool kDC>
+__device__ __forceinline__ int decode_pair(BitReader& br, const gnc_jpeg_huff_t* t, int& val) {
+  ensure32(br);
+  const uint32_t w = (uint32_t)(br.acc >> 32);
+  const uint32_t look = t->look[w >> (32 - kLook)];
+  int len, sym;
+  if (look) {
+    len = (int)(look >> 8); sym = (int)(look & 0xff);
+  } else {
+    len = kLook + 1;
+    int32_t code = (int32_t)(w >> (32 - len));
+    while (len <= 16 && code > t->maxcode[len]) { ++len; code = (int32_t)(w >> (32 - len)); }
+    if (len > 16) { len = 16; sym = 0; }         // corrupt stream: libjpeg warns and uses 0
+    else sym = t->vals[(code + t->valoff[len]) & 0xff];
+  }
+  const int s = kDC ? (sym & 15) : (sym & 15);
+  const uint32_t bits = s ? ((w << len) >> (32 - s)) : 0u;                      // len + s <= 27
+  val = s ? ((int)bits < (1 << (s - 1)) ? (int)bits - (1 << s) + 1 : (int)bits) : 0;
+  br.acc <<= (len + s);
+  br.n -= (len + s);
+  return sym;
 }
 
-__global__ void __launch_bounds__(128) jpeg_huffman_kernel(const uint8_t* __restrict__ stream, const gnc_jpeg_image_t* __restrict__ infos,
-                                                          int B, int16_t* __restrict__ coef) {
-  const int img = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (img >= B || (threadIdx.x & 31) != 0) return;
+constexpr int kHuffWarps = 4;
+
+__global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const uint8_t* __restrict__ stream,
+                                                                       const gnc_jpeg_image_t* __restrict__ infos, int B,
+                                                                       int16_t* __restrict__ coef) {
+  extern __shared__ __align__(16) uint8_t s_tables[];                   // [kHuffWarps][8] gnc_jpeg_huff_t
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * kHuffWarps + warp;
+  if (img >= B) return;
   const gnc_jpeg_image_t* im = infos + img;
+  gnc_jpeg_huff_t* tabs = reinterpret_cast<gnc_jpeg_huff_t*>(s_tables) + warp * 8;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(im->huff);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tabs);
+    for (int i = lane; i < (int)(8 * sizeof(gnc_jpeg_huff_t) / 4); i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncwarp();
+  if (lane != 0) return;
   BitReader br;
   br.p = stream + im->scan_offset;
   br.end = br.p + im->scan_bytes;
   br.acc = 0; br.n = 0; br.marker = false;
   int16_t* cimg = coef + im->coef_offset;
-  const int ncomp = im->ncomp;
-  int pred[3] = {0, 0, 0};
-  int64_t comp_base[3];
-  int hs[3], vs[3], bw[3];
-  {
-    int64_t off = 0;
-    for (int c = 0; c < 3; ++c) {
-      hs[c] = c < ncomp ? im->hsamp[c] : 0; vs[c] = c < ncomp ? im->vsamp[c] : 0;
-      bw[c] = im->mcu_x * hs[c];                 // blocks per row of the component's (MCU-padded) plane
-      comp_base[c] = off;
-      off += (int64_t)bw[c] * im->mcu_y * vs[c] * 64;
+  const int ncomp = im->ncomp, mcu_x = im->mcu_x, mcu_y = im->mcu_y;
+  const int h0 = im->hsamp[0], v0 = im->vsamp[0];
+  const int64_t base1 = (int64_t)mcu_x * h0 * mcu_y * v0 * 64;          // chroma planes: one block per MCU each
+  const int64_t base2 = base1 + (int64_t)mcu_x * mcu_y * 64;
+  const gnc_jpeg_huff_t* dc0 = tabs + im->dc_tab[0];
+  const gnc_jpeg_huff_t* ac0 = tabs + 4 + im->ac_tab[0];
+  const gnc_jpeg_huff_t* dc1 = tabs + im->dc_tab[ncomp > 1 ? 1 : 0];
+  const gnc_jpeg_huff_t* ac1 = tabs + 4 + im->ac_tab[ncomp > 1 ? 1 : 0];
+  const gnc_jpeg_huff_t* dc2 = tabs + im->dc_tab[ncomp > 2 ? 2 : 0];
+  const gnc_jpeg_huff_t* ac2 = tabs + 4 + im->ac_tab[ncomp > 2 ? 2 : 0];
+  int pred0 = 0, pred1 = 0, pred2 = 0;
+  auto block = [&](int16_t* blk, const gnc_jpeg_huff_t* dct, const gnc_jpeg_huff_t* act, int& pred) {
+    int v;
+    decode_pair<true>(br, dct, v);
+    pred += v;
+    blk[0] = (int16_t)pred;
+    int k = 1;
+    while (k < 64) {
+      const int sym = decode_pair<false>(br, act, v);
+      const int r = sym >> 4;
+      if (sym & 15) {
+        k += r;
+        blk[c_natural[k & 63]] = (int16_t)v;
+        ++k;
+      } else {
+        if (r != 15) break;                      // end of block
+        k += 16;                                 // sixteen zeros
+      }
     }
-  }
+  };
   const int restart = im->restart_interval;
   int to_restart = restart;
-  for (int my = 0; my < im->mcu_y; ++my) {
-    for (int mx = 0; mx < im->mcu_x; ++mx) {
+  for (int my = 0; my < mcu_y; ++my) {
+    for (int mx = 0; mx < mcu_x; ++mx) {
       if (restart && to_restart == 0) {
         // byte-align, step over the RSTn marker, reset the predictions (jdhuff.c process_restart)
         br.acc = 0; br.n = 0;
@@ -126,33 +178,15 @@ __global__ void __launch_bounds__(128) jpeg_huffman_kernel(const uint8_t* __rest
           while (br.p + 1 < br.end && !(br.p[0] == 0xFF && br.p[1] >= 0xD0 && br.p[1] <= 0xD7)) ++br.p;
           br.p += 2;
         }
-        pred[0] = pred[1] = pred[2] = 0;
+        pred0 = pred1 = pred2 = 0;
         to_restart = restart;
       }
-      for (int c = 0; c < ncomp; ++c) {
-        const gnc_jpeg_huff_t* dct = &im->huff[im->dc_tab[c]];
-        const gnc_jpeg_huff_t* act = &im->huff[4 + im->ac_tab[c]];
-        for (int by = 0; by < vs[c]; ++by) {
-          for (int bx = 0; bx < hs[c]; ++bx) {
-            int16_t* blk = cimg + comp_base[c] + ((int64_t)(my * vs[c] + by) * bw[c] + (mx * hs[c] + bx)) * 64;
-            int s = decode_symbol(br, dct);
-            if (s) pred[c] += receive_extend(br, s);
-            blk[0] = (int16_t)pred[c];
-            for (int k = 1; k < 64; ++k) {
-              s = decode_symbol(br, act);
-              const int r = s >> 4;
-              s &= 15;
-              if (s) {
-                k += r;
-                const int v = receive_extend(br, s);
-                blk[c_natural[k & 63]] = (int16_t)v;
-              } else {
-                if (r != 15) break;              // end of block
-                k += 15;                         // sixteen zeros
-              }
-            }
-          }
-        }
+      for (int by = 0; by < v0; ++by)
+        for (int bx = 0; bx < h0; ++bx)
+          block(cimg + ((int64_t)(my * v0 + by) * (mcu_x * h0) + (mx * h0 + bx)) * 64, dc0, ac0, pred0);
+      if (ncomp == 3) {
+        block(cimg + base1 + ((int64_t)my * mcu_x + mx) * 64, dc1, ac1, pred1);
+        block(cimg + base2 + ((int64_t)my * mcu_x + mx) * 64, dc2, ac2, pred2);
       }
       if (restart) --to_restart;
     }
@@ -496,7 +530,8 @@ int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos,
   cudaStream_t st = (cudaStream_t)stream_;
   cudaError_t e = cudaMemsetAsync(coef, 0, (size_t)total_blocks * 64 * sizeof(int16_t), st);
   if (e != cudaSuccess) return fail(GNC_ECUDA, "jpeg memset: %s", cudaGetErrorString(e));
-  jpeg::jpeg_huffman_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)B * 32, 128), 128, 0, st>>>(stream, infos, B, coef);
+  jpeg::jpeg_huffman_kernel<<<(unsigned)ceil_div<int>(B, jpeg::kHuffWarps), 32 * jpeg::kHuffWarps,
+                              jpeg::kHuffWarps * 8 * sizeof(gnc_jpeg_huff_t), st>>>(stream, infos, B, coef);
   if (int rc = check_launch("jpeg_huffman_kernel")) return rc;
   jpeg::jpeg_idct_kernel<<<(unsigned)ceil_div<int64_t>(total_blocks, 128), 128, 0, st>>>(infos, B, coef, planes, total_blocks);
   if (int rc = check_launch("jpeg_idct_kernel")) return rc;
