@@ -598,6 +598,56 @@ __global__ void __launch_bounds__(1024) superpixel_graph_run8_kernel(
   }
 }
 
+
+// Block-diagonal batch of per-image superpixel graphs (different node / edge counts): offsets by one single-CTA scan,
+// then one CTA per image copies its valid rows to their place and shifts the edge endpoints by the image's node offset.
+__global__ void __launch_bounds__(1024) superpixel_offsets_kernel(const int32_t* __restrict__ n_nodes, const int32_t* __restrict__ n_edges,
+                                                                  int B, int S_max, int64_t E_max, int32_t* __restrict__ node_ptr,
+                                                                  int64_t* __restrict__ edge_ptr) {
+  __shared__ long long s_n[1024], s_e[1024];
+  const int t = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  long long an = 0, ae = 0;
+  for (int i = t * per; i < min(B, (t + 1) * per); ++i) {
+    an += min(n_nodes[i], S_max);
+    ae += min((long long)n_edges[i], (long long)E_max);
+  }
+  s_n[t] = an; s_e[t] = ae;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const long long vn = t >= off ? s_n[t - off] : 0, ve = t >= off ? s_e[t - off] : 0;
+    __syncthreads();
+    s_n[t] += vn; s_e[t] += ve;
+    __syncthreads();
+  }
+  long long rn = s_n[t] - an, re = s_e[t] - ae;
+  for (int i = t * per; i < min(B, (t + 1) * per); ++i) {
+    node_ptr[i] = (int32_t)rn; edge_ptr[i] = re;
+    rn += min(n_nodes[i], S_max);
+    re += min((long long)n_edges[i], (long long)E_max);
+  }
+  if (t == 1023) { node_ptr[B] = (int32_t)s_n[1023]; edge_ptr[B] = s_e[1023]; }
+}
+
+__global__ void __launch_bounds__(256) superpixel_compact_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                                 const int64_t* __restrict__ edges, int S_max, int64_t E_max,
+                                                                 const int32_t* __restrict__ node_ptr, const int64_t* __restrict__ edge_ptr,
+                                                                 float* __restrict__ xb, float* __restrict__ pb,
+                                                                 int64_t* __restrict__ eb, int64_t e_total) {
+  const int b = blockIdx.x;
+  const int n0 = node_ptr[b], nn = node_ptr[b + 1] - n0;
+  const int64_t e0 = edge_ptr[b], ne = edge_ptr[b + 1] - e0;
+  const float* xs = x + (int64_t)b * S_max * 3;
+  const float* ps = pos + (int64_t)b * S_max * 2;
+  for (int i = threadIdx.x; i < nn * 3; i += blockDim.x) xb[(int64_t)n0 * 3 + i] = xs[i];
+  for (int i = threadIdx.x; i < nn * 2; i += blockDim.x) pb[(int64_t)n0 * 2 + i] = ps[i];
+  const int64_t* es = edges + (int64_t)b * 2 * E_max;
+  for (int64_t i = threadIdx.x; i < ne; i += blockDim.x) {
+    eb[e0 + i] = es[i] + n0;
+    eb[e_total + e0 + i] = es[E_max + i] + n0;
+  }
+}
+
 }  // namespace gnc
 
 using namespace gnc;
@@ -668,6 +718,22 @@ int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B,
   superpixel_graph_kernel<<<B, 256, use_smem ? smem : 0, st>>>(img, labels, H, W, max_label, S_max, E_max, n_nodes, x,
                                                                pos, adj, n_edges, edges, work, wpi, use_smem, nullptr);
   return check_launch("superpixel_graph_kernel");
+}
+
+int gnc_superpixel_batch_offsets(const int32_t* n_nodes, const int32_t* n_edges, int B, int S_max, int64_t E_max,
+                                 int32_t* node_ptr, int64_t* edge_ptr, gnc_stream_t stream) {
+  GNC_REQUIRE(n_nodes && n_edges && node_ptr && edge_ptr && B > 0 && S_max > 0 && E_max >= 0, "superpixel_batch_offsets: bad arguments");
+  superpixel_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_nodes, n_edges, B, S_max, E_max, node_ptr, edge_ptr);
+  return check_launch("superpixel_offsets_kernel");
+}
+
+int gnc_superpixel_batch_compact(const float* x, const float* pos, const int64_t* edges, int B, int S_max, int64_t E_max,
+                                 const int32_t* node_ptr, const int64_t* edge_ptr, float* xb, float* pb, int64_t* eb,
+                                 int64_t e_total, gnc_stream_t stream) {
+  GNC_REQUIRE(x && pos && edges && node_ptr && edge_ptr && xb && pb && (eb || e_total == 0) && B > 0 && S_max > 0 && E_max >= 0 &&
+              e_total >= 0, "superpixel_batch_compact: bad arguments");
+  superpixel_compact_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, pos, edges, S_max, E_max, node_ptr, edge_ptr, xb, pb, eb, e_total);
+  return check_launch("superpixel_compact_kernel");
 }
 
 int64_t gnc_csr_workspace(int64_t N) { return N + (N + 1) / 1024 + 64; }

@@ -200,14 +200,19 @@ def build_superpixel_batch(images, labels=None, n_segments: int = 100, compactne
     if labels is None:
         labels = slic_labels(img, n_segments=n_segments, compactness=compactness)
     n_nodes, x, pos, n_edges, edges = build_superpixel_graphs(img, labels, max_nodes=max_nodes, device=dev)
-    B, S_max = x.shape[0], x.shape[1]
-    node_ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-    torch.cumsum(n_nodes, 0, out=node_ptr[1:])
-    nmask = torch.arange(S_max, device=dev)[None, :] < n_nodes[:, None]
-    xb, pb = x[nmask], pos[nmask]
-    E_max = edges.shape[2]
-    emask = torch.arange(E_max, device=dev)[None, :] < n_edges[:, None]
-    eb = (edges + node_ptr[:-1, None, None].long()).permute(1, 0, 2)[:, emask].contiguous()
+    B, S_max, E_max = x.shape[0], x.shape[1], edges.shape[2]
+    lib = _lib.load()
+    node_ptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    edge_ptr = torch.empty(B + 1, dtype=torch.int64, device=dev)
+    check(lib.gnc_superpixel_batch_offsets(n_nodes.data_ptr(), n_edges.data_ptr(), B, S_max, E_max, node_ptr.data_ptr(),
+                                           edge_ptr.data_ptr(), _stream()), "superpixel_batch_offsets")
+    n_total, e_total = int(node_ptr[B].item()), int(edge_ptr[B].item())          # the one host sync: output sizes
+    xb = torch.empty(n_total, 3, dtype=torch.float32, device=dev)
+    pb = torch.empty(n_total, 2, dtype=torch.float32, device=dev)
+    eb = torch.empty(2, e_total, dtype=torch.int64, device=dev)
+    check(lib.gnc_superpixel_batch_compact(x.data_ptr(), pos.data_ptr(), edges.data_ptr(), B, S_max, E_max, node_ptr.data_ptr(),
+                                           edge_ptr.data_ptr(), xb.data_ptr(), pb.data_ptr(), eb.data_ptr(), e_total, _stream()),
+          "superpixel_batch_compact")
     graph = GraphIndex.from_edge_index(eb, xb.shape[0])
     graph.node_ptr = node_ptr
     attach_graph(eb, graph)

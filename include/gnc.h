@@ -110,6 +110,15 @@ int gnc_build_superpixel_graph(const uint8_t* img, const int32_t* labels, int B,
                                int32_t* n_nodes, float* x, float* pos, uint8_t* adj,
                                int32_t* n_edges, int64_t* edges, int32_t* work,
                                gnc_stream_t stream);
+/* Block-diagonal batch of the per-image graphs above (graphs of DIFFERENT sizes, as superpixel graphs are):
+ * offsets:  node_ptr int32 [B + 1], edge_ptr int64 [B + 1] = running sums of min(n_nodes, S_max) / min(n_edges, E_max);
+ * compact:  xb float [node_ptr[B], 3], pb float [node_ptr[B], 2], eb int64 [2, e_total] (e_total = edge_ptr[B]) with
+ *           the endpoints shifted by the image's node offset; graph b owns nodes node_ptr[b] .. node_ptr[b + 1]. */
+int gnc_superpixel_batch_offsets(const int32_t* n_nodes, const int32_t* n_edges, int B, int S_max, int64_t E_max,
+                                 int32_t* node_ptr, int64_t* edge_ptr, gnc_stream_t stream);
+int gnc_superpixel_batch_compact(const float* x, const float* pos, const int64_t* edges, int B, int S_max, int64_t E_max,
+                                 const int32_t* node_ptr, const int64_t* edge_ptr, float* xb, float* pb, int64_t* eb,
+                                 int64_t e_total, gnc_stream_t stream);
 
 /* SLIC superpixel labels for B images (the stage the reference delegates to scikit-image,
  * image_to_graph_superpixel.py:31; parity unpinned - see csrc/slic.cu): RGB -> Lab, regular-grid
