@@ -256,7 +256,7 @@ __global__ void slic_update_kernel(SlicDims d, long long* __restrict__ acc, floa
 //   * labels are written once, after the last iteration.
 // Same integer sums, same update arithmetic, same tie rule: the labels are those of the streaming form bit for bit
 // (tests/test_gpu_graph_build.py compares them).
-constexpr int kImgThreads = 512;
+constexpr int kImgThreads = 256;
 constexpr int kImgMaxK = 1024;
 
 template <int kMinBlocks>
@@ -395,10 +395,18 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
             // pixels this centre is a candidate of: the column left of the run's first cell serves the pixels of that
             // cell only, the column right of its second cell the pixels of the second cell only
             const unsigned cand = xx == gx_lo - 1 ? (~m_hi & 0xffu) : (xx == gx_lo + 2 ? m_hi : 0xffu);
+            if (cand == 0xffu) {                 // the usual case (uniform over the warp: its lanes share x0): no mask
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float dist = slic_score(pc, row, px[3 * i], px[3 * i + 1], px[3 * i + 2], xs[i]);
-              if (((cand >> i) & 1u) && dist < best[i]) { best[i] = dist; out[i] = k; }
+              for (int i = 0; i < 8; ++i) {
+                const float dist = slic_score(pc, row, px[3 * i], px[3 * i + 1], px[3 * i + 2], xs[i]);
+                if (dist < best[i]) { best[i] = dist; out[i] = k; }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float dist = slic_score(pc, row, px[3 * i], px[3 * i + 1], px[3 * i + 2], xs[i]);
+                if (((cand >> i) & 1u) && dist < best[i]) { best[i] = dist; out[i] = k; }
+              }
             }
           }
         }
@@ -504,14 +512,17 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
                                                          reinterpret_cast<uintptr_t>(lab)) & 15u) == 0) {
     // one CTA per image, the whole loop in one launch
     const int smem = d.K * (6 * 8 + 8 * 4) + 256 * 4;
-    static SmemAttrOnce smem_attr1, smem_attr2;
-    static const int min_blocks = getenv("GNC_SLIC_MINB") ? atoi(getenv("GNC_SLIC_MINB")) : 2;
-    if (min_blocks == 1) {
-      if (int rc_attr = smem_attr1.ensure(slic_image_kernel<1>, 227 * 1024, "slic_image")) return rc_attr;
-      slic_image_kernel<1><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
-    } else {
+    static SmemAttrOnce smem_attr2, smem_attr3, smem_attr4;
+    static const int min_blocks = getenv("GNC_SLIC_MINB") ? atoi(getenv("GNC_SLIC_MINB")) : 4;   // 256 threads x 4 CTAs per SM (64 registers, 32 warps); 2 and 3 were slower
+    if (min_blocks == 2) {
       if (int rc_attr = smem_attr2.ensure(slic_image_kernel<2>, 227 * 1024, "slic_image")) return rc_attr;
       slic_image_kernel<2><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
+    } else if (min_blocks == 4) {
+      if (int rc_attr = smem_attr4.ensure(slic_image_kernel<4>, 227 * 1024, "slic_image")) return rc_attr;
+      slic_image_kernel<4><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
+    } else {
+      if (int rc_attr = smem_attr3.ensure(slic_image_kernel<3>, 227 * 1024, "slic_image")) return rc_attr;
+      slic_image_kernel<3><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
     }
     return check_launch("slic_image_kernel");
   }
