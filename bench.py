@@ -784,13 +784,18 @@ def run_ours(args):
                     del dec, datas
                 except Exception as exc:            # torchvision built without nvJPEG, or absent
                     staging["nvjpeg_alternative"] = {"unavailable": str(exc)[:200]}
+            except Exception as exc:                # a secondary block must never cost the headline line
+                staging["e2e_from_files"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             finally:
                 shutil.rmtree(tmpd, ignore_errors=True)
 
     configs = None
     if rank == 0 and world == 1 and not args.no_configs:
         torch.cuda.empty_cache()
-        configs = run_config_blocks(args, dev, pk, flush)
+        try:
+            configs = run_config_blocks(args, dev, pk, flush)
+        except Exception as exc:                    # a secondary block must never cost the headline line
+            configs = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank == 0:
         line = {
