@@ -706,15 +706,14 @@ def run_ours(args):
                 # the device JPEG decoder alone (csrc/jpeg.cu): file bytes already in host memory -> RGB pixels in HBM
                 from graphnet_classifier_b200.utils import jpeg as gjpeg
                 datas = [open(pth, "rb").read() for pth in paths]
-                jinfos = [gjpeg.parse(dd) for dd in datas]
-                jst = {}
+                                jst = {}
                 for _ in range(2):
-                    gjpeg.decode_batch(datas, dev, infos=jinfos, staging=jst)
+                    gjpeg.decode_batch(datas, dev, staging=jst)
                 torch.cuda.synchronize()
                 jms = []
                 for _ in range(5):
                     s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s_.record(); gjpeg.decode_batch(datas, dev, infos=jinfos, staging=jst); e_.record()
+                    s_.record(); gjpeg.decode_batch(datas, dev, staging=jst); e_.record()
                     torch.cuda.synchronize()
                     jms.append(s_.elapsed_time(e_))
                 jms = sorted(jms)[2]

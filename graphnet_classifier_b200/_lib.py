@@ -149,7 +149,10 @@ SIGNATURES = {
     "gnc_superpixel_batch_offsets": (c_int, [_P, _P, c_int, c_int, c_int64, _P, _P, _P]),
     "gnc_superpixel_batch_compact": (c_int, [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, c_int64, _P]),
     "gnc_jpeg_parse": (c_int, [_P, c_int64, POINTER(GncJpegImage)]),
-    "gnc_jpeg_decode_rgb_u8": (c_int, [_P, _P, c_int, c_int64, c_int64, _P, _P, _P, _P]),
+    "gnc_jpeg_pack": (c_int, [_P, _P, c_int, c_int, _P, c_int64, _P, _P, _P]),
+    "gnc_jpeg_scratch_bytes": (c_int64, [c_int64, c_int]),
+    "gnc_jpeg_decode_rgb_u8": (c_int, [_P, _P, c_int, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "gnc_debug_jpeg_sequential": (c_int, [c_int]),
     "gnc_tc_bwd_layer_parts": (c_int32, [c_int64]),
     "gnc_tc_bwd_reduce_batch_f32": (c_int, [POINTER(GncBwdReduceItem), c_int32, _P]),
 }

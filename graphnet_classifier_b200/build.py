@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-Xcompiler", "-pthread",
     "-Xcompiler", "-ffp-contract=off",      # host: the resize coefficient tables follow Pillow's double arithmetic
 ]
 

@@ -28,6 +28,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gnc {
@@ -115,22 +118,10 @@ __device__ __forceinline__ int decode_pair(BitReader& br, const gnc_jpeg_huff_t*
 
 constexpr int kHuffWarps = 4;
 
-__global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const uint8_t* __restrict__ stream,
-                                                                       const gnc_jpeg_image_t* __restrict__ infos, int B,
-                                                                       int16_t* __restrict__ coef) {
-  extern __shared__ __align__(16) uint8_t s_tables[];                   // [kHuffWarps][8] gnc_jpeg_huff_t
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * kHuffWarps + warp;
-  if (img >= B) return;
-  const gnc_jpeg_image_t* im = infos + img;
-  gnc_jpeg_huff_t* tabs = reinterpret_cast<gnc_jpeg_huff_t*>(s_tables) + warp * 8;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(im->huff);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(tabs);
-    for (int i = lane; i < (int)(8 * sizeof(gnc_jpeg_huff_t) / 4); i += 32) dst[i] = __ldg(src + i);
-  }
-  __syncwarp();
-  if (lane != 0) return;
+// sequential form: one thread walks the whole scan (images with restart intervals, very short scans, and the reference
+// the parallel form below is tested against)
+__device__ __noinline__ void decode_sequential(const uint8_t* __restrict__ stream, const gnc_jpeg_image_t* im,
+                                               const gnc_jpeg_huff_t* tabs, int16_t* __restrict__ coef) {
   BitReader br;
   br.p = stream + im->scan_offset;
   br.end = br.p + im->scan_bytes;
@@ -190,6 +181,242 @@ __global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const uin
       }
       if (restart) --to_restart;
     }
+  }
+}
+
+// ---- parallel form: the 32 lanes of the image's warp decode 32 segments of its scan ---------------------------------------
+// Huffman streams are self-synchronising: a decoder started at an arbitrary bit soon falls into step with the true one.
+// (Weissenberger & Schmidt, "Massively Parallel Huffman Decoding on GPUs", ICPP 2018; for JPEG the state that has to agree
+// is the bit position, the block's position in the MCU - it selects the tables - and the coefficient index.)
+//   0. the warp removes the stuffed zeros (FF 00 -> FF) into a scratch copy of the scan: a position is then a plain bit
+//      index and a 32-bit window two aligned loads and a funnel shift - no refill state to hand from lane to lane;
+//   1. lane i decodes segment i from a guessed state (start of an MCU) up to the segment's end and records the state it
+//      leaves in and the number of blocks it completed;
+//   2. lane i > 0 compares its entry state with the exit state of lane i - 1 and decodes again from there if they differ;
+//      repeated until no entry changes.  Lane 0 starts from the true state, so at the fixed point every entry is true
+//      (at worst after 31 rounds, in practice after one or two);
+//   3. prefix sum of the block counts -> the first block of every segment; 4. the lanes decode once more and write the
+//      coefficients (DC still as differences); 5. per component a warp scan turns the DC differences into DC values.
+struct SegState { uint32_t T; int z, k; };
+__device__ __forceinline__ bool same(const SegState& a, const SegState& b) { return a.T == b.T && a.z == b.z && a.k == b.k; }
+__device__ __forceinline__ uint32_t window32(const uint8_t* us, uint32_t T) {
+  const uint32_t idx = T >> 3;
+  const uint32_t* wp = reinterpret_cast<const uint32_t*>(us + (idx & ~3u));
+  const uint32_t hi = __byte_perm(wp[0], 0, 0x0123), lo = __byte_perm(wp[1], 0, 0x0123);
+  return __funnelshift_l(lo, hi, (idx & 3u) * 8u + (T & 7u));
+}
+// one symbol + its value bits at bit T of the unstuffed stream (same tables and rules as decode_pair)
+__device__ __forceinline__ int symbol_at(const uint8_t* us, uint32_t& T, const gnc_jpeg_huff_t* t, int& val) {
+  const uint32_t w = window32(us, T);
+  const uint32_t look = t->look[w >> (32 - kLook)];
+  int len, sym;
+  if (look) {
+    len = (int)(look >> 8); sym = (int)(look & 0xff);
+  } else {
+    len = kLook + 1;
+    int32_t code = (int32_t)(w >> (32 - len));
+    while (len <= 16 && code > t->maxcode[len]) { ++len; code = (int32_t)(w >> (32 - len)); }
+    if (len > 16) { len = 16; sym = 0; }
+    else sym = t->vals[(code + t->valoff[len]) & 0xff];
+  }
+  const int s = sym & 15;
+  const uint32_t bits = s ? ((w << len) >> (32 - s)) : 0u;
+  val = s ? ((int)bits < (1 << (s - 1)) ? (int)bits - (1 << s) + 1 : (int)bits) : 0;
+  T += (uint32_t)(len + s);
+  return sym;
+}
+
+struct ImgGeom {
+  int16_t* cimg;
+  int mcu_x, h0, nY, bpm;                         // luma blocks per MCU, blocks per MCU
+  int64_t base1, base2, n_blocks;
+  const gnc_jpeg_huff_t *dcY, *acY, *dc1, *ac1, *dc2, *ac2;
+};
+__device__ __forceinline__ int16_t* block_ptr(const ImgGeom& g, int64_t blk) {
+  const int64_t mcu = blk / g.bpm;
+  const int z = (int)(blk - mcu * g.bpm);
+  const int my = (int)(mcu / g.mcu_x), mx = (int)(mcu - (int64_t)my * g.mcu_x);
+  if (z < g.nY) {
+    const int by = z / g.h0, bx = z - by * g.h0;
+    const int v0 = g.nY / g.h0;
+    return g.cimg + ((int64_t)(my * v0 + by) * (g.mcu_x * g.h0) + (mx * g.h0 + bx)) * 64;
+  }
+  return g.cimg + (z == g.nY ? g.base1 : g.base2) + mcu * 64;
+}
+// decode from `st` until the position reaches t_end; kWrite: coefficients go to the blocks starting at `blk`.
+// The 32 lanes of a warp run this loop on 32 different segments, so the symbol step is written without branches on the
+// kind of symbol (DC / coefficient / zero run / end of block take the same instructions, selected by predicates) and the
+// block bookkeeping at the end of a block - some lane ends a block in almost every iteration - has no divisions: the
+// block's place is carried as (MCU row, MCU column, index in the MCU).
+template <bool kWrite>
+__device__ __forceinline__ void run_segment(const uint8_t* us, const ImgGeom& g, SegState& st, uint32_t t_end, int& nblocks, int64_t blk) {
+  nblocks = 0;
+  uint32_t T = st.T;
+  int z = st.z, k = st.k;
+  int mx = 0, my = 0;
+  int16_t* bp = nullptr;
+  const int hsh = g.h0 - 1;                         // h0 is 1 or 2: z -> (z >> hsh, z & hsh) inside the MCU
+  const int v0 = g.nY / g.h0;
+  auto place = [&]() -> int16_t* {
+    if (z < g.nY) return g.cimg + ((int64_t)(my * v0 + (z >> hsh)) * (g.mcu_x * g.h0) + (mx * g.h0 + (z & hsh))) * 64;
+    return g.cimg + (z == g.nY ? g.base1 : g.base2) + ((int64_t)my * g.mcu_x + mx) * 64;
+  };
+  int64_t left = 0;                                 // blocks that may still be written
+  if (kWrite) {
+    const int64_t mcu = blk / g.bpm;
+    my = (int)(mcu / g.mcu_x); mx = (int)(mcu - (int64_t)my * g.mcu_x);
+    left = g.n_blocks - blk;
+    bp = left > 0 ? place() : nullptr;
+  }
+  const gnc_jpeg_huff_t* dct = z < g.nY ? g.dcY : (z == g.nY ? g.dc1 : g.dc2);
+  const gnc_jpeg_huff_t* act = z < g.nY ? g.acY : (z == g.nY ? g.ac1 : g.ac2);
+  while (T < t_end) {
+    const bool isdc = k == 0;
+    int v;
+    const int sym = symbol_at(us, T, isdc ? dct : act, v);
+    const int s = sym & 15, r = isdc ? 0 : sym >> 4;
+    const bool coef = isdc || s != 0;
+    const int kp = isdc ? 0 : k + r;
+    if (kWrite && coef && bp && kp < 64) bp[c_natural[kp]] = (int16_t)v;       // DC: the DIFFERENCE; step 5 integrates
+    k = coef ? kp + 1 : (r == 15 ? k + 16 : 64);
+    if (k >= 64) {                                  // end of block
+      k = 0;
+      ++nblocks;
+      ++z;
+      if (z == g.bpm) { z = 0; if (kWrite) { ++mx; if (mx == g.mcu_x) { mx = 0; ++my; } } }
+      dct = z < g.nY ? g.dcY : (z == g.nY ? g.dc1 : g.dc2);
+      act = z < g.nY ? g.acY : (z == g.nY ? g.ac1 : g.ac2);
+      if (kWrite) { --left; bp = left > 0 ? place() : nullptr; }
+    }
+  }
+  st.T = T; st.z = z; st.k = k;
+}
+
+constexpr int kMinParallelBytes = 4096;           // shorter scans: one thread is as fast
+
+__global__ void __launch_bounds__(32 * kHuffWarps) jpeg_huffman_kernel(const uint8_t* __restrict__ stream,
+                                                                       const gnc_jpeg_image_t* __restrict__ infos, int B,
+                                                                       int16_t* __restrict__ coef, uint8_t* __restrict__ scratch,
+                                                                       int force_sequential) {
+  extern __shared__ __align__(16) uint8_t s_tables[];                   // [kHuffWarps][8] gnc_jpeg_huff_t
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * kHuffWarps + warp;
+  if (img >= B) return;
+  const gnc_jpeg_image_t* im = infos + img;
+  gnc_jpeg_huff_t* tabs = reinterpret_cast<gnc_jpeg_huff_t*>(s_tables) + warp * 8;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(im->huff);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tabs);
+    for (int i = lane; i < (int)(8 * sizeof(gnc_jpeg_huff_t) / 4); i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncwarp();
+  if (!scratch || (force_sequential & 1) || im->restart_interval || im->scan_bytes < kMinParallelBytes) {
+    if (lane == 0) decode_sequential(stream, im, tabs, coef);
+    return;
+  }
+  const unsigned kFull = 0xffffffffu;
+  // 0. unstuffed copy of the scan
+  const uint8_t* raw = stream + im->scan_offset;
+  const uint32_t nraw = (uint32_t)im->scan_bytes;
+  uint8_t* us = scratch + (((uint64_t)im->scan_offset + 3u) & ~(uint64_t)3u) + 16ull * (uint64_t)img;
+  uint32_t outpos = 0, carry = 0;
+  for (uint32_t base = 0; base < nraw; base += 128) {                   // 4 bytes per lane: a byte is dropped iff it is
+    const uint32_t i0 = base + 4u * lane;                               // the 00 behind an FF
+    uint32_t by[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) by[j] = i0 + j < nraw ? raw[i0 + j] : 0x100u;
+    uint32_t prev = __shfl_up_sync(kFull, by[3], 1);
+    if (lane == 0) prev = carry;
+    bool keep[4];
+    int nk = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      keep[j] = by[j] < 0x100u && !(by[j] == 0u && prev == 0xFFu);
+      nk += keep[j] ? 1 : 0;
+      prev = by[j];
+    }
+    int incl = nk;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    uint8_t* dst = us + outpos + (incl - nk);
+    int at = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (keep[j]) dst[at] = (uint8_t)by[j];
+      at += keep[j] ? 1 : 0;
+    }
+    outpos += __shfl_sync(kFull, incl, 31);
+    carry = __shfl_sync(kFull, by[3], 31);
+  }
+  if (lane < 12) us[outpos + lane] = 0;           // zeros behind the data: a window may read past the last byte
+  __syncwarp();
+  const uint32_t total_bits = outpos * 8u;
+  ImgGeom g;
+  g.cimg = coef + im->coef_offset;
+  g.mcu_x = im->mcu_x; g.h0 = im->hsamp[0]; g.nY = im->hsamp[0] * im->vsamp[0];
+  g.bpm = g.nY + (im->ncomp == 3 ? 2 : 0);
+  g.base1 = (int64_t)im->mcu_x * im->mcu_y * g.nY * 64;
+  g.base2 = g.base1 + (int64_t)im->mcu_x * im->mcu_y * 64;
+  g.n_blocks = im->n_blocks;
+  g.dcY = tabs + im->dc_tab[0]; g.acY = tabs + 4 + im->ac_tab[0];
+  g.dc1 = tabs + im->dc_tab[im->ncomp > 1 ? 1 : 0]; g.ac1 = tabs + 4 + im->ac_tab[im->ncomp > 1 ? 1 : 0];
+  g.dc2 = tabs + im->dc_tab[im->ncomp > 2 ? 2 : 0]; g.ac2 = tabs + 4 + im->ac_tab[im->ncomp > 2 ? 2 : 0];
+  // 1. speculative pass
+  const uint32_t seg = ((total_bits + 31u) / 32u + 7u) & ~7u;            // bits per segment
+  const uint32_t t_end = min(total_bits, (uint32_t)(lane + 1) * seg);
+  SegState entry;
+  entry.T = min(total_bits, (uint32_t)lane * seg); entry.z = 0; entry.k = 0;
+  SegState ex = entry;
+  int nblk;
+  run_segment<false>(us, g, ex, t_end, nblk, 0);
+  // 2. until every lane starts where its predecessor stopped
+  int rounds = 0, reruns = 0;
+  for (int round = 0; round < 32; ++round) {
+    SegState pe;
+    pe.T = __shfl_up_sync(kFull, ex.T, 1); pe.z = __shfl_up_sync(kFull, ex.z, 1); pe.k = __shfl_up_sync(kFull, ex.k, 1);
+    const bool need = lane > 0 && !same(pe, entry);
+    if (!__any_sync(kFull, need)) break;
+    ++rounds;
+    if (need) {
+      ++reruns;
+      entry = pe;
+      ex = pe;
+      run_segment<false>(us, g, ex, t_end, nblk, 0);
+    }
+  }
+  if ((force_sequential & 2) && img < 3) {
+    const unsigned long long t1 = clock64();
+    printf("img %d lane %2d: rounds %d reruns %d entry (T %u z %d k %d) blocks %d seg %u bits\n", img, lane, rounds, reruns, entry.T,
+           entry.z, entry.k, nblk, seg);
+    (void)t1;
+  }
+  // 3. first block of every segment
+  int incl = nblk;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+  // 4. write pass
+  {
+    SegState st = entry;
+    int n2;
+    run_segment<true>(us, g, st, t_end, n2, (int64_t)(incl - nblk));
+  }
+  __syncwarp();
+  // 5. DC differences -> DC values, per component in decode order
+  const int64_t nmcu = (int64_t)im->mcu_x * im->mcu_y;
+  for (int c = 0; c < im->ncomp; ++c) {
+    const int64_t len = c == 0 ? nmcu * g.nY : nmcu;
+    const int64_t per = (len + 31) / 32, lo = min(len, per * lane), hi = min(len, lo + per);
+    auto ptr = [&](int64_t j) -> int16_t* {
+      if (c == 0) { const int64_t mcu = j / g.nY; return block_ptr(g, mcu * g.bpm + (j - mcu * g.nY)); }
+      return g.cimg + (c == 1 ? g.base1 : g.base2) + j * 64;
+    };
+    int sum = 0;
+    for (int64_t j = lo; j < hi; ++j) sum += ptr(j)[0];
+    int run = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, run, o); if (lane >= o) run += v; }
+    int acc = run - sum;
+    for (int64_t j = lo; j < hi; ++j) { int16_t* q = ptr(j); acc += q[0]; q[0] = (int16_t)acc; }
   }
 }
 
@@ -522,8 +749,63 @@ int gnc_jpeg_parse(const uint8_t* data, int64_t size, gnc_jpeg_image_t* out) {
   return GNC_JPEG_UNSUPPORTED;
 }
 
+// HOST: descriptors + byte stream of a whole batch in one call (parse and copies spread over `threads` host threads).
+// Files the device decoder does not cover are left out; index_out lists the files that are in, in order.
+int gnc_jpeg_pack(const uint8_t* const* datas, const int64_t* sizes, int n, int threads, uint8_t* stream_out,
+                  int64_t stream_capacity, gnc_jpeg_image_t* infos_out, int32_t* index_out, int64_t* totals) {
+  GNC_REQUIRE(n >= 0 && (n == 0 || (datas && sizes && stream_out && infos_out && index_out)) && totals, "jpeg_pack: bad arguments");
+  std::vector<int> ok((size_t)n, 0);
+  const int nt = threads < 1 ? 1 : (threads > 32 ? 32 : threads);
+  auto parallel = [&](auto&& fn) {
+    if (nt == 1 || n < 8) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back([&, t]() { for (int i = t; i < n; i += nt) fn(i); });
+    for (auto& th : pool) th.join();
+  };
+  parallel([&](int i) { ok[i] = gnc_jpeg_parse(datas[i], sizes[i], infos_out + i) == GNC_OK; });
+  int m = 0;
+  int64_t off = 0, blocks = 0, plane = 0, pixels = 0;
+  std::vector<int64_t> dst((size_t)n, 0);
+  for (int i = 0; i < n; ++i) {
+    if (!ok[i]) continue;
+    if (m != i) memcpy(infos_out + m, infos_out + i, sizeof(gnc_jpeg_image_t));
+    gnc_jpeg_image_t& d = infos_out[m];
+    dst[m] = off;
+    d.scan_offset += off;
+    d.block_offset = blocks; d.coef_offset = 64 * blocks; d.plane_offset = plane; d.pixel_offset = pixels;
+    index_out[m] = i;
+    off += sizes[i]; blocks += d.n_blocks; plane += d.plane_bytes; pixels += (int64_t)d.width * d.height;
+    ++m;
+  }
+  GNC_REQUIRE(off <= stream_capacity, "jpeg_pack: stream buffer too small");
+  const int mm = m;
+  {
+    const int n_keep = mm;
+    auto copy = [&](int j) { memcpy(stream_out + dst[j], datas[index_out[j]], (size_t)sizes[index_out[j]]); };
+    if (nt == 1 || n_keep < 8) { for (int j = 0; j < n_keep; ++j) copy(j); }
+    else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t) pool.emplace_back([&, t]() { for (int j = t; j < n_keep; j += nt) copy(j); });
+      for (auto& th : pool) th.join();
+    }
+  }
+  totals[0] = mm; totals[1] = off; totals[2] = blocks; totals[3] = plane; totals[4] = pixels;
+  return GNC_OK;
+}
+
+static int g_jpeg_sequential = 0;
+
+// Debug: 1 = the entropy stage always runs its sequential form (one thread per image).  Same coefficients.
+int gnc_debug_jpeg_sequential(int on) {
+  g_jpeg_sequential = on;                         // bit 0: sequential form; bit 1: print the synchronisation rounds of images 0-2
+  return GNC_OK;
+}
+
+int64_t gnc_jpeg_scratch_bytes(int64_t stream_bytes, int B) { return stream_bytes + 16 * (int64_t)(B > 0 ? B : 0) + 64; }
+
 int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos, int B, int64_t total_blocks,
-                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out, gnc_stream_t stream_) {
+                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out, uint8_t* scratch,
+                           gnc_stream_t stream_) {
   GNC_REQUIRE(B >= 0 && total_blocks >= 0 && total_pixels >= 0, "jpeg_decode: bad sizes");
   if (B == 0) return GNC_OK;
   GNC_REQUIRE(stream && infos && coef && planes && out, "jpeg_decode: null pointer");
@@ -531,7 +813,8 @@ int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos,
   cudaError_t e = cudaMemsetAsync(coef, 0, (size_t)total_blocks * 64 * sizeof(int16_t), st);
   if (e != cudaSuccess) return fail(GNC_ECUDA, "jpeg memset: %s", cudaGetErrorString(e));
   jpeg::jpeg_huffman_kernel<<<(unsigned)ceil_div<int>(B, jpeg::kHuffWarps), 32 * jpeg::kHuffWarps,
-                              jpeg::kHuffWarps * 8 * sizeof(gnc_jpeg_huff_t), st>>>(stream, infos, B, coef);
+                              jpeg::kHuffWarps * 8 * sizeof(gnc_jpeg_huff_t), st>>>(stream, infos, B, coef, scratch,
+                                                                                    g_jpeg_sequential);
   if (int rc = check_launch("jpeg_huffman_kernel")) return rc;
   jpeg::jpeg_idct_kernel<<<(unsigned)ceil_div<int64_t>(total_blocks, 128), 128, 0, st>>>(infos, B, coef, planes, total_blocks);
   if (int rc = check_launch("jpeg_idct_kernel")) return rc;

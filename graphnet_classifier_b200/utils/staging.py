@@ -162,24 +162,30 @@ class DecodePool:
         releases the GIL); files the device decoder does not cover are decoded by Pillow here, on the host."""
         from . import jpeg as gjpeg
 
-        def read_parse(path):
+        def read(path):
             with open(path, "rb") as f:
-                data = f.read()
-            return data, gjpeg.parse(data)
+                return f.read()
 
-        pairs = list(self.pool.map(read_parse, paths))
-        rest = [i for i, (_, inf) in enumerate(pairs) if inf is None]
+        datas = list(self.pool.map(read, paths))
+        # which files the device decoder covers is known only after the pack step (on upload); files it rejects are
+        # decoded here by Pillow when their magic is not JPEG's, and after the device call otherwise
+        rest = [i for i, d in enumerate(datas) if d[:2] != b"\xff\xd8"]
         host = dict(zip(rest, self.pool.map(_decode, [paths[i] for i in rest]))) if rest else {}
-        self.stats["device_jpeg"] += len(pairs) - len(rest)
-        self.stats["host_decoded"] += len(rest)
-        return {"jpeg": pairs, "host": host, "slot": slot}
+        pairs = [(d, None) for d in datas]
+        return {"jpeg": pairs, "host": host, "slot": slot, "paths": list(paths)}
 
     def _upload_jpeg(self, chunk, resize_value: int) -> Tensor:
         from . import jpeg as gjpeg
         r = int(resize_value)
         pairs, host = chunk["jpeg"], chunk["host"]
-        imgs = gjpeg.decode_batch([d for d, _ in pairs], self.device, infos=[inf for _, inf in pairs],
-                                  staging=self._jpeg_staging[chunk["slot"]])
+        datas = [d if i not in host else b"" for i, (d, _) in enumerate(pairs)]
+        imgs = gjpeg.decode_batch(datas, self.device, staging=self._jpeg_staging[chunk["slot"]])
+        late = [i for i, t in enumerate(imgs) if t is None and i not in host]     # JPEGs outside the device decoder's scope
+        if late:
+            host = dict(host)
+            host.update(zip(late, self.pool.map(_decode, [chunk["paths"][i] for i in late])))
+        self.stats["device_jpeg"] += len(imgs) - len(host)
+        self.stats["host_decoded"] += len(host)
         for i, a in host.items():
             imgs[i] = torch.from_numpy(np.array(a, dtype=np.uint8)).to(self.device)
         groups = {}

@@ -148,7 +148,10 @@ int gnc_debug_slic_connect_streaming(int on);
  *   scan_offset (into stream), block_offset (running sum of n_blocks), coef_offset (= 64 * block_offset), plane_offset
  *   (running sum of plane_bytes) and pixel_offset (running sum of width * height) filled in by the caller;
  *   coef: int16 [64 * total_blocks], planes: uint8 [sum plane_bytes], out: uint8 [3 * total_pixels] - image i's RGB
- *   pixels, row-major, at 3 * pixel_offset. */
+ *   pixels, row-major, at 3 * pixel_offset; `stream` itself must be 4-byte aligned.  Entropy decode: the 32 lanes of a
+ *   warp decode 32 segments of an image's scan from guessed states and iterate until every segment starts where its
+ *   predecessor stopped (Huffman streams are self-synchronising); scans with restart intervals or shorter than 4 KB,
+ *   and all scans when `scratch` is NULL, are decoded by one thread. */
 #define GNC_JPEG_UNSUPPORTED 4
 typedef struct gnc_jpeg_huff {
   uint16_t look[512];     /* 9-bit lookahead: (code length << 8) | symbol, 0 = longer code */
@@ -166,8 +169,19 @@ typedef struct gnc_jpeg_image {
   gnc_jpeg_huff_t huff[8];/* [0..3] DC tables, [4..7] AC tables */
 } gnc_jpeg_image_t;
 int gnc_jpeg_parse(const uint8_t* data, int64_t size, gnc_jpeg_image_t* out);
+/* HOST: a whole batch in one call - parses every file (on `threads` host threads), leaves out the unsupported ones
+ * (index_out[j] = index of the j-th file that is in), copies the bytes of the others back to back into stream_out
+ * (pinned memory, capacity >= sum of sizes) and fills infos_out[0 .. totals[0]) with all offsets set.
+ * totals[5] = { files in, stream bytes, total blocks, plane bytes, pixels }. */
+int gnc_jpeg_pack(const uint8_t* const* datas, const int64_t* sizes, int n, int threads, uint8_t* stream_out,
+                  int64_t stream_capacity, gnc_jpeg_image_t* infos_out, int32_t* index_out, int64_t* totals);
+int64_t gnc_jpeg_scratch_bytes(int64_t stream_bytes, int B);
 int gnc_jpeg_decode_rgb_u8(const uint8_t* stream, const gnc_jpeg_image_t* infos, int B, int64_t total_blocks,
-                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out, gnc_stream_t stream_);
+                           int64_t total_pixels, int16_t* coef, uint8_t* planes, uint8_t* out,
+                           uint8_t* scratch /* gnc_jpeg_scratch_bytes(stream bytes, B), 4-byte aligned; NULL: sequential entropy decode */,
+                           gnc_stream_t stream_);
+/* Debug aid: 1 = the entropy stage always runs its sequential form (one thread per image); same coefficients. */
+int gnc_debug_jpeg_sequential(int on);
 
 /* Input staging: the resize the reference applies to every image before building its graph,
  *   Image.open(path).convert('RGB').resize((r, r))     utils/image_to_graph/image_to_graph_optimized.py:65-70,

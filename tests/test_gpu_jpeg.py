@@ -36,7 +36,11 @@ CASES = [(32, 32, dict(quality=90)), (33, 47, dict(quality=75)), (17, 23, dict(q
          (57, 91, dict(quality=80, restart_marker_rows=1, subsampling=1)), (20, 3, dict(quality=90)), (5, 4, dict(quality=90)),
          (100, 150, dict(quality=30)), (16, 16, dict(quality=100, subsampling=2)), (8, 8, dict(quality=50, subsampling=0)),
          (1, 1, dict(quality=90)), (375, 500, dict(quality=90)), (256, 256, dict(quality=97, noise=60)),
-         (129, 255, dict(quality=88, subsampling=1, optimize=True))]
+         (129, 255, dict(quality=88, subsampling=1, optimize=True)),
+         # scans of more than 4 KB take the parallel entropy decoder (32 segments per image, self-synchronisation)
+         (300, 420, dict(quality=85, subsampling=0)), (333, 517, dict(quality=70, subsampling=1)),
+         (400, 300, dict(quality=92, gray=True)), (512, 512, dict(quality=99, noise=90)), (240, 320, dict(quality=95, optimize=True, noise=40)),
+         (600, 800, dict(quality=25)), (97, 1201, dict(quality=90, subsampling=2))]
 
 
 def test_shipped_jpegs_equal_reference_pixels(libgnc):
@@ -50,11 +54,19 @@ def test_shipped_jpegs_equal_reference_pixels(libgnc):
         assert np.array_equal(t.cpu().numpy(), g[n + "_rgb"]), n
 
 
-def test_generated_files_equal_pillow(libgnc):
+@pytest.mark.parametrize("sequential", [0, 1])
+def test_generated_files_equal_pillow(libgnc, sequential):
+    """Both forms of the entropy stage: the parallel one (default for scans of at least 4 KB without restart intervals)
+    and the sequential one (debug switch; always used for short scans and restart intervals)."""
     from graphnet_classifier_b200.utils.jpeg import decode_batch
     rng = np.random.default_rng(7)
     datas = [_jpeg(rng, h, w, **dict(kw)) for h, w, kw in CASES]
-    out = decode_batch(datas)                          # one batch: images of different sizes and layouts side by side
+    libgnc.gnc_debug_jpeg_sequential(sequential)
+    try:
+        out = decode_batch(datas)                      # one batch: images of different sizes and layouts side by side
+        torch.cuda.synchronize()
+    finally:
+        libgnc.gnc_debug_jpeg_sequential(0)
     for (h, w, kw), data, t in zip(CASES, datas, out):
         ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
         assert t is not None, (h, w, kw)

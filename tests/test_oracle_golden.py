@@ -252,3 +252,36 @@ def test_jpeg_host_parser_matches_oracle_parser(libgnc):
             Image.fromarray(arr).save(buf, format="JPEG", **bad)
         info = _lib.GncJpegImage()
         assert libgnc.gnc_jpeg_parse(buf.getvalue(), len(buf.getvalue()), ctypes.byref(info)) == _lib.GNC_JPEG_UNSUPPORTED
+
+
+def test_jpeg_batch_pack_host(libgnc):
+    """gnc_jpeg_pack (host): one call parses a batch on several threads, drops the files the device decoder does not cover
+    and lays descriptors and bytes out with all offsets set - checked against per-file gnc_jpeg_parse."""
+    import ctypes
+    import io
+    from PIL import Image
+    from graphnet_classifier_b200 import _lib
+    rng = np.random.default_rng(8)
+    datas = []
+    for h, w, fmt in [(33, 47, "JPEG"), (20, 20, "PNG"), (64, 48, "JPEG"), (100, 90, "JPEG")] * 4:
+        buf = io.BytesIO()
+        Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(buf, format=fmt)
+        datas.append(buf.getvalue())
+    datas.append(b"")
+    n = len(datas)
+    stream = np.zeros(sum(map(len, datas)), np.uint8)
+    infos, index, totals = (_lib.GncJpegImage * n)(), (ctypes.c_int32 * n)(), (ctypes.c_int64 * 5)()
+    ptrs, sizes = (ctypes.c_char_p * n)(*datas), (ctypes.c_int64 * n)(*[len(d) for d in datas])
+    cast = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    assert libgnc.gnc_jpeg_pack(cast(ptrs), cast(sizes), n, 4, stream.ctypes.data, stream.size, cast(infos), cast(index), cast(totals)) == 0
+    m = int(totals[0])
+    assert [index[j] for j in range(m)] == [i for i in range(n - 1) if i % 4 != 1]
+    off = blocks = plane = pixels = 0
+    for j in range(m):
+        d = datas[index[j]]
+        ref = _lib.GncJpegImage()
+        assert libgnc.gnc_jpeg_parse(d, len(d), ctypes.byref(ref)) == 0
+        assert bytes(stream[off:off + len(d)]) == d and infos[j].scan_offset == ref.scan_offset + off
+        assert (infos[j].block_offset, infos[j].coef_offset, infos[j].plane_offset, infos[j].pixel_offset) == (blocks, 64 * blocks, plane, pixels)
+        off, blocks, plane, pixels = off + len(d), blocks + ref.n_blocks, plane + ref.plane_bytes, pixels + ref.width * ref.height
+    assert list(totals) == [m, off, blocks, plane, pixels]
