@@ -706,7 +706,7 @@ def run_ours(args):
                 # the device JPEG decoder alone (csrc/jpeg.cu): file bytes already in host memory -> RGB pixels in HBM
                 from graphnet_classifier_b200.utils import jpeg as gjpeg
                 datas = [open(pth, "rb").read() for pth in paths]
-                                jst = {}
+                jst = {}
                 for _ in range(2):
                     gjpeg.decode_batch(datas, dev, staging=jst)
                 torch.cuda.synchronize()

@@ -59,3 +59,12 @@ def test_state_dict_names_match_reference_contract(golden):
     om = ognn.build_reference_config_model(8, seed=0)
     for k, v in om.state_dict().items():
         assert torch.equal(v, sd[k]), k
+
+
+def test_entry_points_and_scripts_compile():
+    """bench.py, __graft_entry__.py and every script under scripts/ are valid Python (they only run on the GPU box)."""
+    import glob
+    import py_compile
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "scripts", "*.py")))
+    for f in files:
+        py_compile.compile(f, doraise=True)
