@@ -732,7 +732,7 @@ def run_ours(args):
                 staging["e2e_from_files"] = {
                     "value": n_files / dt_auto, "unit": UNIT, "files_per_step": n_files, "ms_per_step": dt_auto * 1e3,
                     "default_decoder": "device" if auto_is_device else "host processes",
-                    "default_rule": "device JPEG decode when the box has fewer than 6 host cores per visible GPU",
+                    "default_rule": "baseline JPEG files are decoded on the device, everything else by Pillow on worker processes",
                     "device_decode_form": {
                         "value": n_files / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "files_by_decoder": pool_stats,
                         "h2d_bytes_per_step": file_bytes,
