@@ -17,10 +17,11 @@
 // Stages:
 //   host   gnc_jpeg_parse         : markers -> geometry, dequantisation tables (natural order), Huffman decode tables
 //                                   (9-bit lookahead + canonical maxcode / valptr for longer codes), scan position
-//   device jpeg_huffman_kernel    : entropy decode is sequential per image (no restart markers in Pillow's files), so one
-//                                   warp's lane 0 walks one image's bit stream (64-bit bit buffer, byte unstuffing,
-//                                   cached byte loads) and writes the non-zero coefficients of every block; images of a batch
-//                                   decode side by side on different warps (one scheduler slot each)
+//   device jpeg_huffman_kernel    : one warp per image.  Entropy decode is sequential by nature (no restart markers in
+//                                   Pillow's files), but Huffman streams are self-synchronising: the warp's 32 lanes decode
+//                                   32 segments of the scan from guessed states and iterate until every segment starts where
+//                                   its predecessor stopped (see "parallel form" below); short scans and scans with restart
+//                                   intervals are walked by one thread (64-bit bit buffer, byte unstuffing)
 //          jpeg_idct_kernel       : one thread per 8 x 8 block, jidctint.c's two passes in registers, range-limited
 //                                   samples into per-component planes
 //          jpeg_color_kernel      : one thread per output pixel: fancy upsampling of the chroma planes evaluated at the
