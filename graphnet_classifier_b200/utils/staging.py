@@ -268,21 +268,40 @@ class DecodePool:
     def stage(self, items: Sequence, resize_value: int) -> Tensor:
         return self._upload(self._decode_chunk(list(items), 0), 0, resize_value)
 
+    def _stage_async(self, items: Sequence, slot: int, resize_value: int):
+        """Feeder-thread half of ``batches``: read / decode one chunk.  The device-JPEG form also packs, copies and decodes
+        here, on the copy stream, so that none of a chunk's host work sits between two chunks of the consumer's GPU work."""
+        torch.cuda.set_device(self.device)
+        chunk = self._decode_chunk(items, slot)
+        if not isinstance(chunk, dict):
+            return chunk, None, None
+        with torch.cuda.stream(self.copy_stream):
+            px = self._upload_jpeg(chunk, resize_value)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return None, px, ev
+
     def batches(self, items: Sequence, resize_value: int, chunk: int = 128) -> Iterator[Tensor]:
-        """Chunks of ``chunk`` items as device tensors; chunk ``i + 1`` is decoded (pool threads) while the caller
-        consumes chunk ``i``."""
+        """Chunks of ``chunk`` items as device tensors; chunk ``i + 1`` is read, decoded and (device-JPEG form) resized on
+        the feeder thread / copy stream while the caller consumes chunk ``i``."""
         items = list(items)
         chunks = [items[lo:lo + chunk] for lo in range(0, len(items), chunk)]
         if not chunks:
             return
         feeder = ThreadPoolExecutor(max_workers=1, thread_name_prefix="gnc-stage")
         try:
-            pending = feeder.submit(self._decode_chunk, chunks[0], 0)
+            pending = feeder.submit(self._stage_async, chunks[0], 0, resize_value)
             for i in range(len(chunks)):
-                groups = pending.result()
+                groups, px, ev = pending.result()
                 if i + 1 < len(chunks):
-                    pending = feeder.submit(self._decode_chunk, chunks[i + 1], (i + 1) & 1)
-                yield self._upload(groups, i & 1, resize_value)
+                    pending = feeder.submit(self._stage_async, chunks[i + 1], (i + 1) & 1, resize_value)
+                if px is None:
+                    yield self._upload(groups, i & 1, resize_value)
+                else:
+                    cur = torch.cuda.current_stream(self.device)
+                    cur.wait_event(ev)
+                    px.record_stream(cur)
+                    yield px
         finally:
             feeder.shutdown(wait=True)
 
@@ -292,9 +311,8 @@ def infer_files(pipeline, paths: Iterable, pool: Optional[DecodePool] = None, ch
     double-buffered pinned copies, device resize, graph build and GraphNet on the stream."""
     own = pool is None
     pool = pool or DecodePool(device=pipeline.device)
-    # the device decoder's entropy stage costs the same per launch for 1 or 500 files: large chunks; host decode
-    # overlaps with the GPU chunk by chunk: smaller ones
-    chunk = chunk or (512 if pool.device_jpeg else 128)
+    # chunk i + 1 is staged (host work + decode kernels on the copy stream) while the model runs on chunk i
+    chunk = chunk or 256
     try:
         outs = [pipeline.infer(px) for px in pool.batches(list(paths), pipeline.resize_value, chunk)]
     finally:
