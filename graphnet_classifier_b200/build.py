@@ -19,7 +19,7 @@ SOURCES = ["graph_build.cu", "aggregate.cu", "dense.cu", "tc_linear.cu", "tc_cha
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo",
+    "-lineinfo", "--threads", "0",
     "-Xcompiler", "-fPIC", "-shared", "-Xcompiler", "-pthread",
     "-Xcompiler", "-ffp-contract=off",      # host: the resize coefficient tables follow Pillow's double arithmetic
 ]

@@ -432,11 +432,9 @@ extern "C" int gnc_resize_bicubic_u8(const uint8_t* src, int64_t B, int H, int W
     if (rc < 0) {                         // rows too wide for the staged forms: generic kernel, one row per CTA
       const size_t smem = (size_t)3 * W + 32;
       GNC_REQUIRE(smem <= 200 * 1024, "resize_bicubic: source rows wider than 68 000 pixels are not supported");
-      static size_t configured = 48 * 1024;
-      if (smem > configured) {
+      if (smem > 48 * 1024) {             // the attribute is per device: set it on every such launch (cheap, rare path)
         cudaError_t e = cudaFuncSetAttribute(rsz::resize_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return fail(GNC_ECUDA, "resize_bicubic: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = 200 * 1024;
       }
       rsz::resize_h_kernel<<<(unsigned)(B * H), rsz::kThreads, smem, st>>>(src, H, W, src_pitch, src_image_stride, OW, bounds_x,
                                                                           kk_x, ksize_x, hdst);
