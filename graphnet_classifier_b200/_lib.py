@@ -7,7 +7,8 @@ import os
 from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint64,
                     c_void_p)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnc.so")
+# GNC_LIB: kernel-development hook (scripts/chain_ab.py loads alternative builds of the same library side by side)
+_LIB_PATH = os.environ.get("GNC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgnc.so")
 
 GNC_OK, GNC_EINVAL, GNC_ECUDA, GNC_EWORKSPACE, GNC_JPEG_UNSUPPORTED = 0, 1, 2, 3, 4
 
@@ -43,7 +44,9 @@ class GncTcChain(Structure):
                 ("dot_w", c_void_p), ("dot_b", c_void_p),
                 ("gather2", c_void_p), ("gather2_idx", c_void_p), ("ld_gather2", c_int64), ("pre_bias", c_void_p),
                 ("operand2", c_void_p), ("ld_operand2", c_int64), ("W_operand2", c_void_p), ("ldw_operand2", c_int64),
-                ("narrow_W", c_void_p), ("ld_narrow_W", c_int64), ("narrow_b", c_void_p), ("narrow_k", c_int32), ("_pad2", c_int32)]
+                ("narrow_W", c_void_p), ("ld_narrow_W", c_int64), ("narrow_b", c_void_p), ("narrow_k", c_int32), ("_pad2", c_int32),
+                ("stash_a1", c_void_p), ("stash_a2", c_void_p), ("stash_z", c_void_p), ("ld_stash", c_int64),
+                ("stash_mean", c_void_p), ("stash_rstd", c_void_p)]
 
 
 class GncBwdReduceItem(Structure):

@@ -88,6 +88,8 @@ struct Params {
   const float* A2; long long lda2; const float* W_A2; long long ldw_A2;
   // narrow first layer folded into the loader: the operand is relu(A[:, :syn_k] syn_W^T + syn_b), syn_k <= 8
   const float* syn_W; long long ld_syn_W; const float* syn_b; int syn_k;
+  // training forward (two-tile kernel, Spec<1> / Spec<2>): a1, a2 (hidden ReLU outputs), z (LayerNorm input), row statistics
+  float* st_a1; float* st_a2; float* st_z; long long ld_st; float* st_mean; float* st_rstd;
   long long num_tiles;
   unsigned long long* trace; int trace_cap;   // debug timeline of CTA 0 (gnc_debug_chain_trace), normally NULL
 };
@@ -214,6 +216,11 @@ __device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, u
 __device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
+}
+// 256-bit store (sm_100: STG.256): a lane that owns 32 contiguous bytes of a row writes a whole sector per instruction
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
@@ -857,8 +864,10 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
   }
 }
 
-template <int SPEC>
+template <int SPEC, bool STASH = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain2_kernel(const Params p) {
+  // STASH (training forward): the hidden ReLU outputs, the LayerNorm input and the row statistics are written out as well
+  static_assert(!STASH || !Spec<SPEC>::pre, "the stash belongs to the three-layer forms");
   // kPre (Spec<7>): the first operand is built by the epilogue warps from three gathers (no loader, two MMA layers,
   // residual through a small table read directly); otherwise three MMA layers, residual rows = the tile's rows.
   constexpr bool kPre = Spec<SPEC>::pre;
@@ -1109,9 +1118,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       cp_async_commit();
       ++issued;
     };
-    auto emit_chunk = [&](const float* vc, const float* s_bias, int S, int c, const float* ext, bool has_ext) {
+    // `strow` (STASH): where this thread's row of the activation being emitted is kept for the backward pass (NULL past M)
+    auto emit_chunk = [&](const float* vc, const float* s_bias, int S, int c, const float* ext, bool has_ext, float* strow) {
       const int col0 = 32 * c + 16 * hf;
       uint32_t p1[8], p2[8];
+      float st[STASH ? 16 : 1];
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4) {
         const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j4);
@@ -1121,9 +1132,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
           y0 = fmaf(ext[4 * j4], kScaleA, y0); y1 = fmaf(ext[4 * j4 + 1], kScaleA, y1);
           y2 = fmaf(ext[4 * j4 + 2], kScaleA, y2); y3 = fmaf(ext[4 * j4 + 3], kScaleA, y3);
         }
-        split2(relu_nan(y0), relu_nan(y1), p1[2 * j4], p2[2 * j4]);
-        split2(relu_nan(y2), relu_nan(y3), p1[2 * j4 + 1], p2[2 * j4 + 1]);
+        y0 = relu_nan(y0); y1 = relu_nan(y1); y2 = relu_nan(y2); y3 = relu_nan(y3);
+        if (STASH) {                                // exact: kScaleA is a power of two
+          st[4 * j4] = y0 * (1.f / kScaleA); st[4 * j4 + 1] = y1 * (1.f / kScaleA);
+          st[4 * j4 + 2] = y2 * (1.f / kScaleA); st[4 * j4 + 3] = y3 * (1.f / kScaleA);
+        }
+        split2(y0, y1, p1[2 * j4], p2[2 * j4]);
+        split2(y2, y3, p1[2 * j4 + 1], p2[2 * j4 + 1]);
       }
+      if (STASH && strow) { stg256(strow + col0, st); stg256(strow + col0 + 8, st + 8); }
       const uint32_t ta = lane_addr + (uint32_t)S * 256 + 128 + (uint32_t)(16 * c + 8 * hf);
       tmem_st8(ta, p1);
       tmem_st8(ta + 64, p2);
@@ -1159,6 +1176,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         if (S == 1 && !hasY) break;
         float v[64];
         const float* trow = nullptr;
+        float* st1 = nullptr;
+        if (STASH) {
+          const long long gr = tile_row0(2 * g + S) + lane;
+          if (gr < p.M) st1 = p.st_a1 + gr * p.ld_st;
+        }
         if (kPre) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = 0.f;
@@ -1206,7 +1228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
             mbar_wait(a_empty(S, c), (uint32_t)((g & 1) ^ 1));      // the slot's previous tile has read chunk c
             tc_fence_after();
           }
-          emit_chunk(v + 16 * c, s_const + (kPre ? 2 * kD : 0), S, c, ext, true);
+          emit_chunk(v + 16 * c, s_const + (kPre ? 2 * kD : 0), S, c, ext, true, st1);
         }
       }
       // all addend steps of this group are issued: gather rows of the next group's tiles (X' straight into the
@@ -1218,9 +1240,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
       for (int S = 0; S < 2; ++S) {
         if (S == 1 && !hasY) break;
         float v[64];
+        float* st2 = nullptr;
+        if (STASH) {
+          const long long gr = tile_row0(2 * g + S) + lane;
+          if (gr < p.M) st2 = p.st_a2 + gr * p.ld_st;
+        }
         wait_acc(S, v);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) emit_chunk(v + 16 * c, s_const + (kPre ? 0 : kD), S, c, v, false);
+        for (int c = 0; c < 4; ++c) emit_chunk(v + 16 * c, s_const + (kPre ? 0 : kD), S, c, v, false, st2);
       }
       // ---- last layer: LayerNorm + residual + store
 #pragma unroll 1
@@ -1249,6 +1276,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
             xx[0] = fmaf(xx[0], kUnscaleD, b4.x); xx[1] = fmaf(xx[1], kUnscaleD, b4.y);
             xx[2] = fmaf(xx[2], kUnscaleD, b4.z); xx[3] = fmaf(xx[3], kUnscaleD, b4.w);
           }
+        const bool st_row = STASH && row0 + lane < p.M;
+        if (STASH && st_row) {                                      // the LayerNorm input, as the backward reads it
+          float* zr = p.st_z + (row0 + lane) * p.ld_st + 16 * hf;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { stg256(zr + 32 * c, x + 16 * c); stg256(zr + 32 * c + 8, x + 16 * c + 8); }
+        }
         float* xa = xchg + (ew * 32 + lane);
         float* xb = xchg + (kEpiWarps * 32) + (ew * 32 + lane);
         const int partner = (ew ^ 4) * 32 + lane;
@@ -1271,6 +1304,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         named_bar_sync(1 + q, 64);
         const float var = (s2 + xchg[kEpiWarps * 32 + partner]) * (1.0f / kD);
         const float rstd = 1.0f / sqrtf(var + p.eps);
+        if (STASH && st_row && hf == 0) { p.st_mean[row0 + lane] = mu; p.st_rstd[row0 + lane] = rstd; }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -1817,12 +1851,12 @@ static int launch_spec2n(const Params& p, cudaStream_t st) {
   return check_launch("tc_chain2n_kernel");
 }
 
-template <int SPEC>
+template <int SPEC, bool STASH = false>
 static int launch_spec2(const Params& p, cudaStream_t st) {
   static SmemAttrOnce smem_attr;
-  if (int rc_attr = smem_attr.ensure(tc_chain2_kernel<SPEC>, kSmemBytes, "tc_chain2")) return rc_attr;
+  if (int rc_attr = smem_attr.ensure(tc_chain2_kernel<SPEC, STASH>, kSmemBytes, "tc_chain2")) return rc_attr;
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  tc_chain2_kernel<SPEC><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
+  tc_chain2_kernel<SPEC, STASH><<<(unsigned)(2 * pairs), kThreads, kSmemBytes, st>>>(p);
   return check_launch("tc_chain2_kernel");
 }
 
@@ -1837,6 +1871,9 @@ static int launch_spec(const Params& p, cudaStream_t st) {
 
 // picks the specialised instantiation when the launch has exactly its shape (Spec<> above)
 static int launch(const Params& p, cudaStream_t st) {
+  if (p.st_a1) {                                  // training forward (form validated by the caller)
+    return (p.g1 && p.i0) ? launch_spec2<1, true>(p, st) : launch_spec2<2, true>(p, st);
+  }
   if (p.multi) return launch_spec<6>(p, st);
   if (!p.A) {
     static const bool two = []() { const char* e = getenv("GNC_CHAIN_TWO_TILES"); return !e || e[0] != '0'; }();
@@ -1926,6 +1963,20 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
   p.Y = Y; p.ldy = ldy;
   p.num_tiles = (M + chain::kTileM - 1) / chain::kTileM;
   p.trace = chain::g_trace; p.trace_cap = chain::g_trace_cap;
+  if (ch->stash_a1) {
+    const bool edge_form = ch->gather0 && ch->gather0_idx && ch->gather1 && ch->gather1_idx;
+    const bool node_form = ch->gather0 && !ch->gather0_idx && !ch->gather1;
+    GNC_REQUIRE(A && ch->nlayers == 3 && (edge_form || node_form) && ch->gamma && ch->residual && !ch->residual_idx && !ch->dot_w &&
+                !ch->operand2 && !ch->narrow_W,
+                "tc_mlp_chain: the stash goes with 3 layers + addends (two indexed gathers, or one plain addend) + LayerNorm + "
+                "residual by row");
+    GNC_REQUIRE(ch->stash_a2 && ch->stash_z && ch->stash_mean && ch->stash_rstd && ch->ld_stash >= chain::kD && ch->ld_stash % 4 == 0 &&
+                ch->ld_stash % 8 == 0 && ((uintptr_t)ch->stash_a1 | (uintptr_t)ch->stash_a2 | (uintptr_t)ch->stash_z) % 32 == 0,
+                "tc_mlp_chain: stash_a1 / a2 / z must be 32-byte aligned [M, 128] row sets (pitch a multiple of 8), with mean and rstd [M]");
+    p.st_a1 = ch->stash_a1; p.st_a2 = ch->stash_a2; p.st_z = ch->stash_z; p.ld_st = ch->ld_stash;
+    p.st_mean = ch->stash_mean; p.st_rstd = ch->stash_rstd;
+    p.trace = nullptr;
+  }
   return chain::launch(p, (cudaStream_t)stream);
 }
 

@@ -735,7 +735,7 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain")
 def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
                  dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None, operand2=None,
-                 narrow=None) -> Tensor:
+                 narrow=None, stash=None) -> Tensor:
     """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
     all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
     ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
@@ -745,6 +745,9 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
     encoders' first layer folded into the launch).  ``operand2=(A2, W_A2)`` adds ``A2 @ W_A2.T`` to the first layer (two-operand contraction, no addend tensor).
     ``A=None`` with ``pre=(table, idx int32 [M], bias)`` is the pre-stage form: the first operand is
     ``relu(table[idx] + gather0 + gather1 + bias)`` and ``layers`` are the two layers after it.
+    ``stash=(a1, a2, z, mean, rstd)`` (training forward of a block's edge / node MLP: 3 layers, addends, LayerNorm, residual
+    by row): the launch also writes the hidden ReLU outputs ``a1``, ``a2``, the LayerNorm input ``z`` (``[M, 128]`` each) and
+    the row statistics ``mean``, ``rstd`` (``[M]``) - what the backward pass of the MLP reads.
     See include/gnc.h ``gnc_tc_chain_t``."""
     ch = GncTcChain()
     keep = []
@@ -826,6 +829,17 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
     if out is None:
         out = torch.empty(M, n_out, dtype=torch.float32, device=dev)
     nbytes += 4.0 * M * n_out
+    if stash is not None:
+        a1s, a2s, zs, means, rstds = stash
+        for t in (a1s, a2s, zs):
+            if t.dtype != torch.float32 or t.device != dev or tuple(t.shape) != (M, 128) or t.stride(1) != 1 or t.stride(0) != a1s.stride(0):
+                raise ValueError("tc_mlp_chain: stash a1 / a2 / z must be float32 [M, 128] row sets of one pitch on the operands' device")
+        for t in (means, rstds):
+            if t.dtype != torch.float32 or t.device != dev or t.numel() != M or not t.is_contiguous():
+                raise ValueError("tc_mlp_chain: stash mean / rstd must be contiguous float32 [M]")
+        ch.stash_a1, ch.stash_a2, ch.stash_z, ch.ld_stash = a1s.data_ptr(), a2s.data_ptr(), zs.data_ptr(), a1s.stride(0)
+        ch.stash_mean, ch.stash_rstd = means.data_ptr(), rstds.data_ptr()
+        nbytes += 4.0 * M * (3 * 128 + 2)
     check(_call("tc_mlp_chain", 2.0 * M * 128 * 128 * (len(layers) + (operand2 is not None)), nbytes,
                 _lib.load().gnc_tc_mlp_chain_f32,
                 a_ptr, a_ld, M, ctypes.byref(ch), out.data_ptr(), _ld(out), _stream()), "tc_mlp_chain")

@@ -37,6 +37,10 @@ _f32 = torch.float32
 # (csrc/tc_bwd.cu); "pair" = the round-1 schedule (tc_linear data gradient + tc_wgrad), kept as the implementation
 # the fused kernel is tested against.
 BWD = os.environ.get("GNC_BWD", "fused")
+# Forward of a block's edge / node MLP: "chain" = ONE launch of the chained kernel that also writes what the backward
+# reads (a1, a2, the LayerNorm input and its row statistics; fp16 two-piece operands like the inference path), "layer" =
+# three per-layer launches (3xTF32) that write and re-read the hidden activations - the form "chain" is tested against.
+FWD = os.environ.get("GNC_TRAIN_FWD", "chain")
 # Test hook (tests/test_gpu_tc_engine.py): when set to a dict, the forward records the sign pattern ``activation > 0``
 # of every ReLU of the core under the reference's module path, e.g. ``("graph_processor.blocks.0.edge_model.
 # edge_processor", 1)`` for ``model[1]`` - what a mask-conditioned gradient comparison against the oracle needs.
@@ -121,6 +125,18 @@ def _tail_fwd(a1: Tensor, tail_params, eps_l: float, residual: Optional[Tensor])
     mean = torch.empty(M, dtype=_f32, device=a2.device)
     rstd = torch.empty(M, dtype=_f32, device=a2.device)
     y = ops.tc_linear(a2, W4, bias=b4, gamma=g, beta=bt, eps=eps_l, residual=residual, ln_save=(z3, mean, rstd))
+    return y, (a1, a2, z3, mean, rstd)
+
+
+def _mlp_fwd_chain(x: Tensor, W0c: Tensor, b0: Tensor, tail_params, eps_l: float, residual: Tensor, gather0, gather1=None):
+    """``LayerNorm(W4 relu(W2 relu(x W0c^T + b0 + gathers) + b2) + b4) + residual`` in one launch; returns the output and
+    the ``_tail_bwd`` tuple ``(a1, a2, z3, mean, rstd)``."""
+    W2, b2, W4, b4, g, bt = tail_params
+    M, dev = x.shape[0], x.device
+    a1, a2, z3 = (torch.empty(M, 128, dtype=_f32, device=dev) for _ in range(3))
+    mean, rstd = torch.empty(M, dtype=_f32, device=dev), torch.empty(M, dtype=_f32, device=dev)
+    y = ops.tc_mlp_chain(x, [(W0c, b0), (W2, b2), (W4, b4)], gather0=gather0, gather1=gather1, gamma=g, beta=bt, eps=eps_l,
+                         residual=residual, stash=(a1, a2, z3, mean, rstd))
     return y, (a1, a2, z3, mean, rstd)
 
 
@@ -220,15 +236,30 @@ class GraphNetCoreFn(torch.autograd.Function):
             # the two node-side products of the edge processor and the node processor's h-side product read the
             # same rows: one launch of the chained kernel in multi mode (h read once, kept in tensor memory)
             P, Q, T = ops.tc_linear_multi(h, [W0[:, 0:128], W0[:, 128:256], V0[:, 0:128]])
-            a1 = tcl(e, W0[:, 256:384], bias=b0, relu=True, gather0=(P, graph.src), gather1=(Q, graph.dst))
-            del P, Q
-            e_in = e
-            e = tail(a1, pe + 2, e_in, eps[2 + 2 * k], f"graph_processor.blocks.{k}.edge_model.edge_processor")
-            agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
-            n1 = tcl(agg, V0[:, 128:256], bias=c0, relu=True, addend=T)
-            del T
-            h_in = h
-            h = tail(n1, pn + 2, h_in, eps[3 + 2 * k], f"graph_processor.blocks.{k}.node_model.node_processor")
+            e_in, h_in = e, h
+            path_e = f"graph_processor.blocks.{k}.edge_model.edge_processor"
+            path_n = f"graph_processor.blocks.{k}.node_model.node_processor"
+            if FWD == "chain":
+                e, sv = _mlp_fwd_chain(e_in, W0[:, 256:384], b0, params[pe + 2:pe + 8], eps[2 + 2 * k], e_in,
+                                       (P, graph.src), (Q, graph.dst))
+                del P, Q
+                saved.append(sv)
+                _capture(path_e, 1, sv[0])
+                _capture(path_e, 3, sv[1])
+                agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
+                h, sv = _mlp_fwd_chain(agg, V0[:, 128:256], c0, params[pn + 2:pn + 8], eps[3 + 2 * k], h_in, (T, None))
+                del T
+                saved.append(sv)
+                _capture(path_n, 1, sv[0])
+                _capture(path_n, 3, sv[1])
+            else:
+                a1 = tcl(e, W0[:, 256:384], bias=b0, relu=True, gather0=(P, graph.src), gather1=(Q, graph.dst))
+                del P, Q
+                e = tail(a1, pe + 2, e_in, eps[2 + 2 * k], path_e)
+                agg = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, e, graph.num_nodes)
+                n1 = tcl(agg, V0[:, 128:256], bias=c0, relu=True, addend=T)
+                del T
+                h = tail(n1, pn + 2, h_in, eps[3 + 2 * k], path_n)
             blocks.append((h_in, e_in, agg))
         Wd0, bd0, Wd2, bd2, Wd4, bd4 = params[12 + 16 * n_blocks:12 + 16 * n_blocks + 6]
         d1 = tcl(h, Wd0, bias=bd0, relu=True)

@@ -381,6 +381,12 @@ typedef struct gnc_tc_chain {
    * edge geometry): A has narrow_k <= 8 columns and the chain's first operand is relu(A narrow_W^T + narrow_b),
    * followed by nlayers = 2 layers and LayerNorm.  narrow_W is [128, narrow_k] with row stride ld_narrow_W. */
   const float* narrow_W; int64_t ld_narrow_W; const float* narrow_b; int32_t narrow_k; int32_t _pad2;
+  /* training forward (stash_a1 != NULL; 3 layers, gather0 [+ gather1], LayerNorm, residual by row - the edge / node
+   * processor of a block, models/GNN.py:57-64, 95-104): the same launch also writes what the backward pass of the MLP
+   * reads - the two hidden ReLU outputs a1, a2 and the LayerNorm input z (each [M, 128], row pitch ld_stash) and the
+   * row statistics mean[M], rstd[M] = 1 / sqrt(var + eps) - instead of three per-layer launches that write and
+   * re-read them. */
+  float* stash_a1; float* stash_a2; float* stash_z; int64_t ld_stash; float* stash_mean; float* stash_rstd;
 } gnc_tc_chain_t;
 
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A/B timing of one training step (graph build + forward + CE + backward + Adam, BASELINE configs[2] per-GPU shape)
 under the backward schedules of tc_train.py; prints ms per step, launches per step and the per-kernel shares.
-    python scripts/train_step_bench.py [graphs] [modes...]      modes: fused pair"""
+    python scripts/train_step_bench.py [graphs] [modes...]      modes: fused (chained forward with stash), fused-layer (per-layer
+    forward), pair (round-1 kernel pair, per-layer forward)"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,7 +13,7 @@ from graphnet_classifier_b200.pipeline import GraphClassifierPipeline
 build.build()
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-modes = sys.argv[2:] or ["fused", "pair"]
+modes = sys.argv[2:] or ["fused", "fused-layer", "pair"]
 r = 128
 torch.manual_seed(0)
 model = CombinedModel(GraphNet(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3), num_nodes=r * r, classes=2).cuda()
@@ -23,7 +24,8 @@ img = torch.from_numpy(rng.integers(0, 256, (B, r, r, 3), dtype=np.uint8)).cuda(
 lab = torch.from_numpy(rng.integers(0, 2, B)).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for mode in modes:
-    tc_train.BWD = mode
+    tc_train.BWD = mode.split("-")[0]
+    tc_train.FWD = "layer" if (mode.endswith("-layer") or mode == "pair") else "chain"
     for _ in range(2):
         pipe.train_step(img, lab, opt)
     torch.cuda.synchronize()

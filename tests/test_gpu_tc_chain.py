@@ -166,6 +166,55 @@ def test_two_tile_kernel_many_tiles(libgnc, tiles_per_pair, form):
     assert torch.isfinite(got).all()
 
 
+@pytest.mark.parametrize("tiles_per_pair", [1, 2, 5])
+@pytest.mark.parametrize("form", ["edge", "node"])
+def test_two_tile_kernel_training_stash(libgnc, tiles_per_pair, form):
+    """Training forward of a block MLP: the chained launch also writes a1, a2, the LayerNorm input and the row statistics
+    (what the backward reads) - against float64 and against the per-layer engine's saved tensors; the output must be
+    the bits of the same launch without the stash.  Row pitch of the stash wider than 128; ragged last tile."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(tiles_per_pair * 5 + len(form))
+    M = 256 * 74 * (tiles_per_pair - 1) + 256 * 33 + 101
+    R = 2500
+    A = torch.randn(M, 128, generator=gen).cuda()
+    layers = [(W.cuda(), b.cuda()) for W, b in _layers(gen, 3)]
+    gamma, beta = (torch.rand(128, generator=gen) + 0.5).cuda(), (torch.randn(128, generator=gen) * 0.2).cuda()
+    if form == "edge":
+        P, Q = torch.randn(R, 128, generator=gen).cuda(), torch.randn(R, 128, generator=gen).cuda()
+        i0 = torch.randint(0, R, (M,), generator=gen).int().cuda()
+        i1 = torch.randint(0, R, (M,), generator=gen).int().cuda()
+        kw = dict(gather0=(P, i0), gather1=(Q, i1))
+        pre = P[i0.long()].double() + Q[i1.long()].double()
+    else:
+        T = torch.randn(M, 128, generator=gen).cuda()
+        kw = dict(gather0=(T, None))
+        pre = T.double()
+    back = torch.full((3, M, 160), float("nan"), device="cuda")          # pitch 160: the stash honours ld_stash
+    a1, a2, z = back[0, :, :128], back[1, :, :128], back[2, :, :128]
+    mean, rstd = torch.full((M,), float("nan"), device="cuda"), torch.full((M,), float("nan"), device="cuda")
+    got = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A, stash=(a1, a2, z, mean, rstd), **kw)
+    plain = ops.tc_mlp_chain(A, layers, gamma=gamma, beta=beta, eps=1e-5, residual=A, **kw)
+    assert torch.equal(got, plain)
+    assert torch.isnan(back[:, :, 128:]).all()                           # nothing written beside the rows
+    z0 = A.double() @ layers[0][0].double().t() + layers[0][1].double() + pre
+    r1 = torch.relu(z0)
+    r2 = torch.relu(r1 @ layers[1][0].double().t() + layers[1][1].double())
+    z3 = r2 @ layers[2][0].double().t() + layers[2][1].double()
+    assert _maxrel(a1, r1) < RTOL and _maxrel(a2, r2) < RTOL and _maxrel(z, z3) < RTOL
+    mu = z3.mean(1)
+    rs = 1.0 / torch.sqrt(z3.var(1, unbiased=False) + 1e-5)
+    assert _maxrel(mean, mu) < RTOL and _maxrel(rstd, rs) < RTOL
+    # the ReLU masks the backward derives from a1 / a2 are those of the per-layer engine wherever the float64
+    # pre-activation is not within rounding of zero
+    safe = (z0.abs() > 1e-4).cuda()
+    assert bool((((a1 > 0) == (z0 > 0).cuda()) | ~safe).all())
+    # and the LayerNorm output follows from the stashed tensors
+    y = (z.double() - mean.double()[:, None]) * rstd.double()[:, None] * gamma.double() + beta.double() + A.double()
+    assert _maxrel(got, y) < RTOL
+    with pytest.raises(Exception):                                       # the stash belongs to the 3-layer block forms
+        ops.tc_mlp_chain(A, layers[:2], gamma=gamma, beta=beta, residual=A, stash=(a1, a2, z, mean, rstd))
+
+
 def test_chain_out_of_domain_is_loud(libgnc):
     """fp16 two-piece operands cover |activation| < 4094 (include/gnc.h): beyond it the result must be
     non-finite, never a finite wrong number."""

@@ -147,6 +147,7 @@ def _gradient_parity(monkeypatch, engine, r, diag, B, fixture_seed=11):
     from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
     monkeypatch.setattr(ops, "TRAIN_PATH", "opwise" if engine == "tc-opwise" else "core")
     monkeypatch.setattr(tc_train, "BWD", "pair" if engine == "tc-pair" else "fused")
+    monkeypatch.setattr(tc_train, "FWD", "layer" if engine in ("tc-pair", "tc-layerfwd") else "chain")
     engine = engine.split("-")[0]
     monkeypatch.setattr(ops, "ENGINE", engine)
     cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
@@ -191,12 +192,14 @@ def _gradient_parity(monkeypatch, engine, r, diag, B, fixture_seed=11):
     return worst, relaxed, worst_noise
 
 
-@pytest.mark.parametrize("engine", ["tc", "tc-pair", "tc-opwise", "fp32"])
+@pytest.mark.parametrize("engine", ["tc", "tc-layerfwd", "tc-pair", "tc-opwise", "fp32"])
 @pytest.mark.parametrize("r,diag,B", [(8, True, 2), (16, False, 3)])
 def test_training_gradients_both_engines(libgnc, monkeypatch, engine, r, diag, B):
     """Loss and every parameter gradient of a batched step vs the oracle, on each dense engine ("tc": the
     hand-scheduled core backward of tc_train.py on the fused backward-layer kernel, "tc-pair": the same schedule on the
-    round-1 kernel pair, "tc-opwise": one autograd.Function per layer)."""
+    round-1 kernel pair and the per-layer forward, "tc-layerfwd": the fused backward behind the per-layer forward - "tc"
+    itself runs the block MLPs' forward as one chained launch that stashes the activations -, "tc-opwise": one
+    autograd.Function per layer)."""
     _gradient_parity(monkeypatch, engine, r, diag, B)
 
 
@@ -231,6 +234,7 @@ def test_training_gradients_at_baseline_shapes(libgnc, monkeypatch, r, B):
     monkeypatch.setattr(ops, "ENGINE", "tc")
     monkeypatch.setattr(ops, "TRAIN_PATH", "core")
     monkeypatch.setattr(tc_train, "BWD", "fused")
+    monkeypatch.setattr(tc_train, "FWD", "chain")
     cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
     N, E = r * r, 2 * r * (r - 1)
     om = ognn.OracleCombinedModel(ognn.OracleGraphNet(**cfg), num_nodes=N, classes=2)
