@@ -129,17 +129,27 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = float(r[1])
+                clk, mx = float(r[0]), float(r[1])
             except (ValueError, IndexError):
                 continue
+            try:
+                watts = float(r[2])
+            except (ValueError, IndexError):
+                watts = None
+            sm.append((clk, watts))
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        sm.sort()
-        # the median over samples taken while the GPU was busy (the top half of the samples)
-        busy = sm[len(sm) // 2:] if sm else []
-        med = busy[len(busy) // 2] if busy else None
-        return dict(sm_mhz=med, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        # "under load" = samples whose board power is within 40 % of the highest seen (the tensor-core kernels of this path
+        # run AT the board's power cap, where the SM clock sits below its maximum: selecting by clock would pick the idle
+        # samples); without power readings, all samples
+        pw = [w for _, w in sm if w is not None]
+        busy = [(c, w) for c, w in sm if w is not None and w >= 0.6 * max(pw)] if pw else sm
+        clks = sorted(c for c, _ in busy)
+        med = clks[len(clks) // 2] if clks else None
+        watts = sorted(w for _, w in busy if w is not None)
+        return dict(sm_mhz=med, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), samples_under_load=len(busy),
+                    power_w=watts[len(watts) // 2] if watts else None)
 
 
 # ------------------------------------------------------------------------------

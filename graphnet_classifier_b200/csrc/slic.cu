@@ -251,8 +251,7 @@ __global__ void slic_update_kernel(SlicDims d, long long* __restrict__ acc, floa
 //   * sRGB -> linear through a 256-entry table built with the streaming form's expression (same Lab bits);
 //   * a thread owns runs of 8 pixels: the 3 candidate grid rows (and their scaled y distances) are found once per run,
 //     the 3 candidate columns once per pixel, centres come from shared memory, the distance is the same FMA chain;
-//   * sums leave the registers once per label run, are merged across the warp by the same segmented reduction and land
-//     in shared-memory atomics; the centre update is a __syncthreads() away instead of a launch away;
+//   * sums leave the registers once per label run and land in shared-memory atomics (no warp merge: measured slower); the centre update is a __syncthreads() away instead of a launch away;
 //   * labels are written once, after the last iteration.
 // Same integer sums, same update arithmetic, same tie rule: the labels are those of the streaming form bit for bit
 // (tests/test_gpu_graph_build.py compares them).
@@ -321,20 +320,6 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
     if (d.dbg & 2) return;
     atomicAdd(reinterpret_cast<unsigned*>(acc + (size_t)k * 6 + j), (unsigned)v);
   };
-  // the open label runs of a warp's lanes are merged per label (match.any + redux.sync on 16-bit halves): one lane per
-  // label and warp issues the atomics
-  auto merge_and_add = [&](int key, int sL, int sA, int sB, int vy, int sx, int cnt) {
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int tL = __reduce_add_sync(peers, sL & 0xffff), hL = __reduce_add_sync(peers, sL >> 16);
-    const int tA = __reduce_add_sync(peers, sA & 0xffff), hA = __reduce_add_sync(peers, sA >> 16);
-    const int tB = __reduce_add_sync(peers, sB & 0xffff), hB = __reduce_add_sync(peers, sB >> 16);
-    const int ty = __reduce_add_sync(peers, vy), tx = __reduce_add_sync(peers, sx), tn = __reduce_add_sync(peers, cnt);
-    if (key >= 0 && lane == __ffs(peers) - 1) {
-      add64(key, 0, ((long long)hL << 16) + tL); add64(key, 1, ((long long)hA << 16) + tA);
-      add64(key, 2, ((long long)hB << 16) + tB);
-      add32(key, 3, ty); add32(key, 4, tx); add32(key, 5, tn);
-    }
-  };
   // A thread owns an 8-pixel run in each of kRowsT consecutive rows and a warp an 8-pixel-wide strip of 32 * kRowsT
   // rows: its lanes share the candidate grid columns (uniform control flow in the candidate loop), a thread's label
   // usually survives from one row to the next (its sums stay in registers across the rows: |v| <= 108 / compactness
@@ -349,20 +334,23 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
       const int x0 = (rem >> 5) << 3, yb = band * (32 * kRowsT) + (rem & 31) * kRowsT;
       // candidate grid columns of the run: its pixels lie in cell gx_lo or, past x_b, in gx_lo + 1 (the launcher
       // takes this kernel only for grid cells at least 8 pixels wide)
-      const int gx_lo = (int)((long long)x0 * d.nx / d.W), gx_hi = (int)((long long)(x0 + 7) * d.nx / d.W);
-      const int x_b = (int)(((long long)(gx_lo + 1) * d.W + d.nx - 1) / d.nx);        // first x of cell gx_lo + 1
+      // (32-bit: the launcher takes this kernel for K <= 1024 and H, W < 2^15 only, so the products stay below 2^31)
+      const int gx_lo = (int)((unsigned)(x0 * d.nx) / (unsigned)d.W), gx_hi = (int)((unsigned)((x0 + 7) * d.nx) / (unsigned)d.W);
+      const int x_b = (int)((unsigned)((gx_lo + 1) * d.W + d.nx - 1) / (unsigned)d.nx);   // first x of cell gx_lo + 1
       const int ib = x_b - x0;                                             // pixels i >= ib lie in cell gx_lo + 1
       const unsigned m_hi = ib >= 8 ? 0u : (0xffu << (ib < 0 ? 0 : ib)) & 0xffu;
       const float xf0 = x0 + 0.5f;
       float xs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) xs[i] = (xf0 + (float)i) * inv_step;     // xf0 + i is exact: the value of (x + 0.5f)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("" : "+f"(xs[i]));         // keep them in registers (the compiler re-derived them at every use)
       int run_k = -1, sL = 0, sA = 0, sB = 0, sy = 0, sx = 0, cnt = 0;     // the thread's open label run
 #pragma unroll 1
       for (int r = 0; r < kRowsT; ++r) {
         const bool active = yb + r < d.H;
         const int y = active ? yb + r : d.H - 1;
-        const int gy = (int)((long long)y * d.ny / d.H);
+        const int gy = (int)((unsigned)(y * d.ny) / (unsigned)d.H);
         float px[24];
         {
           const float4* src = reinterpret_cast<const float4*>(lab + ((long long)y * d.W + x0) * 3);
@@ -437,7 +425,13 @@ __global__ void __launch_bounds__(kImgThreads, kMinBlocks) slic_image_kernel(con
           cnt += 1;
         }
       }
-      if (!last && !(d.dbg & 1)) merge_and_add(cnt > 0 ? run_k : -1, sL, sA, sB, sy, sx, cnt);
+      // the run still open goes to the accumulators like the others.  (Merging the lanes' open runs per label first -
+      // match.any + nine redux.sync, one lane per label issuing the atomics - was measured: 7.32 against 6.72 ms per
+      // 1024 images; so was a second register accumulator for the label on the other side of a boundary: 7.5 - 8.3 ms.)
+      if (!last && !(d.dbg & 1) && cnt > 0) {
+        add64(run_k, 0, sL); add64(run_k, 1, sA); add64(run_k, 2, sB);
+        add32(run_k, 3, sy); add32(run_k, 4, sx); add32(run_k, 5, cnt);
+      }
     }
     if (last) break;
     __syncthreads();
@@ -513,7 +507,7 @@ int gnc_slic_labels_u8(const uint8_t* img, int B, int H, int W, int n_segments, 
     // one CTA per image, the whole loop in one launch
     const int smem = d.K * (6 * 8 + 8 * 4) + 256 * 4;
     static SmemAttrOnce smem_attr2, smem_attr3, smem_attr4;
-    static const int min_blocks = getenv("GNC_SLIC_MINB") ? atoi(getenv("GNC_SLIC_MINB")) : 4;   // 256 threads x 4 CTAs per SM (64 registers, 32 warps); 2 and 3 were slower
+    static const int min_blocks = getenv("GNC_SLIC_MINB") ? atoi(getenv("GNC_SLIC_MINB")) : 3;   // 256 threads x 3 CTAs per SM (80 registers, 24 warps): 6.60 ms per 1024 images; 4 CTAs (64 registers, spills) 6.99, 2 CTAs 6.98
     if (min_blocks == 2) {
       if (int rc_attr = smem_attr2.ensure(slic_image_kernel<2>, 227 * 1024, "slic_image")) return rc_attr;
       slic_image_kernel<2><<<(unsigned)B, kImgThreads, smem, st>>>(img, d, iters, lab, labels);
