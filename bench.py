@@ -582,12 +582,15 @@ def run_ours(args):
     agg_gbs = agg_bytes / (agg_ms / 1e3) / 1e9
     roofline_agg = {"kernel": "agg_csr_sum_vec_kernel<32,1>", "bound": "hbm", "achieved": agg_gbs, "peak": pk["hbm"],
                     "unit": "GB/s", "frac": agg_gbs / pk["hbm"], "traffic": None, "edges": En, "nodes": Nn, "D": 128,
-                    "algorithmic_bytes_per_launch": agg_bytes, "ms_per_launch": agg_ms, "peak_source": pk["source"]}
+                    "algorithmic_bytes_per_launch": agg_bytes, "ms_per_launch": agg_ms, "peak_source": pk["source"],
+                    "note": "the kernel timed alone at the step's shape: training and graphs with in-degree > 2 launch it; the "
+                            "inference step on grid graphs folds this sum into the node processor's launch "
+                            "(tc_mlp_chain agg=..., GNC_FUSE_AGG=0 restores the launch)"}
     del e_lat, gb
 
     # ---- training: fwd + bwd + gradient all-reduce + Adam (BASELINE configs[2] per-GPU shape) ---
     train = None
-    if not args.no_train:
+    if not args.no_train and args.train_steps > 0:
         from graphnet_classifier_b200.utils.distributed import FlatAdam
         Bt = args.train_batch
         timg = imgs_dev[:Bt] if Bt <= B else torch.from_numpy(rng.integers(0, 256, (Bt, r, r, 3), dtype=np.uint8)).to(dev)

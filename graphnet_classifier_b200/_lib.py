@@ -46,7 +46,8 @@ class GncTcChain(Structure):
                 ("operand2", c_void_p), ("ld_operand2", c_int64), ("W_operand2", c_void_p), ("ldw_operand2", c_int64),
                 ("narrow_W", c_void_p), ("ld_narrow_W", c_int64), ("narrow_b", c_void_p), ("narrow_k", c_int32), ("_pad2", c_int32),
                 ("stash_a1", c_void_p), ("stash_a2", c_void_p), ("stash_z", c_void_p), ("ld_stash", c_int64),
-                ("stash_mean", c_void_p), ("stash_rstd", c_void_p)]
+                ("stash_mean", c_void_p), ("stash_rstd", c_void_p),
+                ("agg_rowptr", c_void_p), ("agg_eid", c_void_p)]
 
 
 class GncBwdReduceItem(Structure):

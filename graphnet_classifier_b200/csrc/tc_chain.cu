@@ -88,6 +88,9 @@ struct Params {
   const float* A2; long long lda2; const float* W_A2; long long ldw_A2;
   // narrow first layer folded into the loader: the operand is relu(A[:, :syn_k] syn_W^T + syn_b), syn_k <= 8
   const float* syn_W; long long ld_syn_W; const float* syn_b; int syn_k;
+  // aggregated first operand (two-operand node form): A is the EDGE-row table and row m of the first operand is the ordered
+  // sum of A[agg_eid[k]], k in [agg_rowptr[m], agg_rowptr[m + 1]) - at most two entries per row (caller-checked)
+  const int32_t* agg_rowptr; const int32_t* agg_eid;
   // training forward (two-tile kernel, Spec<1> / Spec<2>): a1, a2 (hidden ReLU outputs), z (LayerNorm input), row statistics
   float* st_a1; float* st_a2; float* st_z; long long ld_st; float* st_mean; float* st_rstd;
   long long num_tiles;
@@ -216,6 +219,11 @@ __device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, u
 __device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
                : "memory");
+}
+// 256-bit streaming load (sm_100: LDG.256): a lane reads 32 contiguous bytes of its own row
+__device__ __forceinline__ void ldg256_stream(const float* p, float* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
 // 256-bit store (sm_100: STG.256): a lane that owns 32 contiguous bytes of a row writes a whole sector per instruction
 __device__ __forceinline__ void stg256(float* p, const float* v) {
@@ -1372,9 +1380,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 // the second operand into the same TMEM chunks once the first operand's MMAs have read them); RES: residual = the
 // tile's own rows of p.residual; TAIL 0: LayerNorm (if gamma) + residual -> Y, TAIL 1: relu . dot_w + dot_b.
 // Shared memory: (NL + K2) weight images, loader ring, two 2 KB slots per epilogue warp (residual ring / transpose).
-template <int NL, bool K2, bool RES, int TAIL, bool SYN = false>
+template <int NL, bool K2, bool RES, int TAIL, bool SYN = false, bool AGG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chain2n_kernel(const Params p) {
   static_assert(!(SYN && K2), "the synthesised operand is a single-operand form");
+  // AGG: the first operand is not read but FORMED by the loader - row m = e[eid0] + e[eid1], the destination-ordered sum of
+  // the (at most two) edge rows arriving at node m (scatter_sum, models/GNN.py:99, for in-degree <= 2: (0 + a) + b is the
+  // reference's order bit for bit).  The aggregation launch, its [N, 128] result and the re-read of it disappear: every
+  // edge row is read once, here.  Source 0 rides the cp.async ring (row addresses through the index), source 1 comes as
+  // four 256-bit loads per chunk in the thread = row layout the ring is read back in.
+  static_assert(!AGG || (K2 && NL == 3 && RES && TAIL == 0 && !SYN), "AGG belongs to the two-operand node form");
+  constexpr int kRegsLd = AGG ? 88 : kRegsLoader, kRegsEp = AGG ? 192 : kRegsEpi;
+  static_assert(32 * (4 * kRegsLd + 4 * kRegsMma + kEpiWarps * kRegsEp) <= kThreads * 128, "setmaxnreg budget");
   constexpr int kImgs = NL + (K2 ? 1 : 0);
   static_assert(kImgs <= 4 && NL >= 2, "at most four weight images");
   constexpr int kOffLd2 = kImgs * kLayerBytes;
@@ -1469,7 +1485,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
 
   if (warp < kLoaderWarps) {
     // ======================= loaders =======================
-    reg_dec<kRegsLoader>();
+    reg_dec<kRegsLd>();
     const int q = warp;
     const uint32_t buf0 = base + kOffLd2 + (uint32_t)(warp * kLoadBufs) * kChunkBytes;
     const int rl = lane >> 3, cj = lane & 7;
@@ -1492,6 +1508,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     };
     const uint32_t a0_remote = map_to_leader(a0_full(0, 0));
     const uint64_t pol_keep = l2_policy_evict_last();
+    // AGG: the two edge ids of this lane's row (thread = row; -1: none) for the tiles j with (j & 3) = 0 .. 3 - the two
+    // tiles of the group being read back and the two of the next group, whose copies are issued up to three items ahead
+    int ea0 = -1, ea1 = -1, ea2 = -1, ea3 = -1, eb0 = -1, eb1 = -1, eb2 = -1, eb3 = -1;
+    // Both index levels are loaded a group before they are used and straight into the registers that will hold them, so
+    // the loader never waits for them: at the end of group g the row pointers read at the end of group g - 1 address the
+    // edge ids of group g + 2, and the row pointers of group g + 3 are requested.
+    int rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0;           // row pointers (begin, end) of this lane's row in the two tiles of a group
+    auto tile_row = [&](long long j) { return (pair + j * npairs) * kTileM + rank * 128 + q * 32 + lane; };
+    auto load_rowptrs = [&](long long jx) {           // tiles jx, jx + 1
+      rx0 = rx1 = ry0 = ry1 = 0;
+      if (!AGG) return;
+      if (jx < n_my) { const long long row = tile_row(jx); if (row < p.M) { rx0 = __ldg(p.agg_rowptr + row); rx1 = __ldg(p.agg_rowptr + row + 1); } }
+      if (jx + 1 < n_my) { const long long row = tile_row(jx + 1); if (row < p.M) { ry0 = __ldg(p.agg_rowptr + row); ry1 = __ldg(p.agg_rowptr + row + 1); } }
+    };
+    auto load_eids = [&](long long jx) {              // tiles jx (even), jx + 1 from rx / ry
+      if (!AGG) return;
+      if (jx & 2) {
+        ea2 = eb2 = ea3 = eb3 = -1;
+        if (rx1 > rx0) ea2 = __ldg(p.agg_eid + rx0);
+        if (rx1 > rx0 + 1) eb2 = __ldg(p.agg_eid + rx0 + 1);
+        if (ry1 > ry0) ea3 = __ldg(p.agg_eid + ry0);
+        if (ry1 > ry0 + 1) eb3 = __ldg(p.agg_eid + ry0 + 1);
+      } else {
+        ea0 = eb0 = ea1 = eb1 = -1;
+        if (rx1 > rx0) ea0 = __ldg(p.agg_eid + rx0);
+        if (rx1 > rx0 + 1) eb0 = __ldg(p.agg_eid + rx0 + 1);
+        if (ry1 > ry0) ea1 = __ldg(p.agg_eid + ry0);
+        if (ry1 > ry0 + 1) eb1 = __ldg(p.agg_eid + ry0 + 1);
+      }
+    };
+    auto ids_a = [&](long long j) { const int k = (int)(j & 3); return k == 0 ? ea0 : k == 1 ? ea1 : k == 2 ? ea2 : ea3; };
+    auto ids_b = [&](long long j) { const int k = (int)(j & 3); return k == 0 ? eb0 : k == 1 ? eb1 : k == 2 ? eb2 : eb3; };
+    if (AGG) { load_rowptrs(0); load_eids(0); load_rowptrs(2); load_eids(2); load_rowptrs(4); }
+    float x2[AGG ? 32 : 1];                           // AGG: the row's second edge row, columns 32 c .. 32 c + 31 of the item
+    auto load_x2 = [&](long long it) {                // requested an item ahead: the wait for the slot hides the latency
+      if (!AGG || it >= total) return;
+      long long j; int op, c;
+      decode(it, j, op, c);
+      if (op != 0) return;
+      const int e = ids_b(j);
+      if (e >= 0) {
+        const float* s2 = p.A + (long long)e * p.lda + c * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ldg256_stream(s2 + 8 * t, x2 + 8 * t);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) x2[t] = 0.f;
+      }
+    };
     auto issue = [&](long long it, int b) {
       if (it < total) {
         long long j; int op, c;
@@ -1501,12 +1566,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         const float* src = op ? p.A2 : p.A;
         const long long ld = op ? p.lda2 : p.lda;
         const uint32_t dst0 = buf0 + (uint32_t)b * kChunkBytes;
+        if (AGG && op == 0) {
+          const int mine = ids_a(j);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rl;
-          const long long row = row0 + r;
-          const long long rc = row < p.M ? row : p.M - 1;
-          cp_async16_hint(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), src + rc * ld + c * 32 + cj * 4, row < p.M ? 16u : 0u, pol_keep);
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rl;
+            const int e = __shfl_sync(0xffffffffu, mine, r);
+            cp_async16(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), src + (long long)(e < 0 ? 0 : e) * ld + c * 32 + cj * 4, e < 0 ? 0u : 16u);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rl;
+            const long long row = row0 + r;
+            const long long rc = row < p.M ? row : p.M - 1;
+            cp_async16_hint(dst0 + (uint32_t)(r * 128 + ((cj ^ (r & 7)) << 4)), src + rc * ld + c * 32 + cj * 4, row < p.M ? 16u : 0u, pol_keep);
+          }
         }
       }
       cp_async_commit();
@@ -1517,11 +1592,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     }
     int b = 0;
     float xin[8];                                     // SYN: this lane's input row (thread = row)
+    load_x2(0);
     for (long long it = 0; it < total; ++it) {
-      if (!SYN) asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
-      __syncwarp();
       long long j; int op, c;
       decode(it, j, op, c);
+      if (!SYN) asm volatile("cp.async.wait_group %0;" ::"n"(kLoadBufs - 1) : "memory");
+      __syncwarp();
       const int S = (int)(j & 1);
       if (SYN && c == 0) {
         const long long row = (pair + j * npairs) * kTileM + rank * 128 + q * 32 + lane;
@@ -1555,7 +1631,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         } else {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
+            float4 x = *reinterpret_cast<const float4*>(buf + (((half * 4 + jj) ^ (lane & 7)) << 4));
+            if (AGG && op == 0) {                     // (0 + a) + b: the ordered sum of the row's edges
+              const float* y = x2 + 16 * half + 4 * jj;
+              x.x += y[0]; x.y += y[1]; x.z += y[2]; x.w += y[3];
+            }
             split2(x.x * kScaleA, x.y * kScaleA, p1[2 * jj], p2[2 * jj]);
             split2(x.z * kScaleA, x.w * kScaleA, p1[2 * jj + 1], p2[2 * jj + 1]);
           }
@@ -1563,6 +1643,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
         tmem_st8(ta + half * 8, p1);
         tmem_st8(ta + 64 + half * 8, p2);
       }
+      // AGG: the last item of a group has been read back - its tiles' ids are dead, those of the group after the next
+      // take their place (the copies of the next group's first items are already in flight with ids loaded a group ago)
+      if (AGG && op == kOps - 1 && c == 3 && (((j & 1) == 1) || j + 1 >= n_my)) {
+        const long long jx = (j | 1) + 3;             // first tile of group g + 2 (g = this group)
+        load_eids(jx);
+        load_rowptrs(jx + 2);
+      }
+      load_x2(it + 1);                                // x2 of this item is consumed: the next item's second source
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_remote(a0_remote + 144u * (uint32_t)S + 8u * (uint32_t)c);
@@ -1633,7 +1721,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
     __syncwarp();
   } else {
     // ======================= epilogue =======================
-    reg_inc<kRegsEpi>();
+    reg_inc<kRegsEp>();
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3, hf = ew >> 2;
     uint8_t* slots = sm + kOffEp2 + ew * 2 * kSlotBytes;
@@ -1839,15 +1927,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) tc_chai
   }
 }
 
-template <int NL, bool K2, bool RES, int TAIL, bool SYN = false>
+template <int NL, bool K2, bool RES, int TAIL, bool SYN = false, bool AGG = false>
 static int launch_spec2n(const Params& p, cudaStream_t st) {
   // (the kernel's own layout: weight images, loader ring, 2 slots per epilogue warp, constants, barriers, slack)
   constexpr int kSmem2n = (NL + (K2 ? 1 : 0)) * kLayerBytes + kLoaderWarps * kLoadBufs * kChunkBytes + kEpiWarps * 2 * kSlotBytes +
                           5 * kD * 4 + 2 * kEpiWarps * 32 * 4 + 320 + 1024;
   static SmemAttrOnce smem_attr;
-  if (int rc_attr = smem_attr.ensure(tc_chain2n_kernel<NL, K2, RES, TAIL, SYN>, kSmem2n, "tc_chain2n")) return rc_attr;
+  if (int rc_attr = smem_attr.ensure(tc_chain2n_kernel<NL, K2, RES, TAIL, SYN, AGG>, kSmem2n, "tc_chain2n")) return rc_attr;
   long long pairs = p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2;
-  tc_chain2n_kernel<NL, K2, RES, TAIL, SYN><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
+  tc_chain2n_kernel<NL, K2, RES, TAIL, SYN, AGG><<<(unsigned)(2 * pairs), kThreads, kSmem2n, st>>>(p);
   return check_launch("tc_chain2n_kernel");
 }
 
@@ -1879,6 +1967,7 @@ static int launch(const Params& p, cudaStream_t st) {
     static const bool two = []() { const char* e = getenv("GNC_CHAIN_TWO_TILES"); return !e || e[0] != '0'; }();
     return two ? launch_spec2<7>(p, st) : launch_spec<7>(p, st);
   }
+  if (p.A2 && p.agg_rowptr) return launch_spec2n<3, true, true, 0, false, true>(p, st);
   if (p.A2) return launch_spec2n<3, true, true, 0>(p, st);
   if (p.syn_W) return launch_spec2n<2, false, false, 0, true>(p, st);     // (shape validated by the caller)
   if (p.trace && p.nlayers == 3 && p.g0 && p.i0 && p.g1 && p.i1 && p.residual && !p.res_idx && p.gamma && !p.dot_w)
@@ -1946,6 +2035,13 @@ extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, cons
     GNC_REQUIRE(ok4(ch->operand2, ch->ld_operand2) && ch->W_operand2 && aligned16(ch->W_operand2) && ch->ldw_operand2 >= chain::kD &&
                 ch->ldw_operand2 % 4 == 0, "tc_mlp_chain: operand2 / W_operand2 must be 16-byte aligned, 128 wide");
     p.A2 = ch->operand2; p.lda2 = ch->ld_operand2; p.W_A2 = ch->W_operand2; p.ldw_A2 = ch->ldw_operand2;
+    if (ch->agg_rowptr) {
+      GNC_REQUIRE(ch->agg_eid && lda % 8 == 0 && ((uintptr_t)A) % 32 == 0,
+                  "tc_mlp_chain: the aggregated operand needs agg_eid and 32-byte aligned edge rows (pitch a multiple of 8)");
+      p.agg_rowptr = ch->agg_rowptr; p.agg_eid = ch->agg_eid;
+    }
+  } else {
+    GNC_REQUIRE(!ch->agg_rowptr, "tc_mlp_chain: agg_rowptr belongs to the two-operand form");
   }
   GNC_REQUIRE(ok4(ch->gather0, ch->ld_gather0) && ok4(ch->gather1, ch->ld_gather1) && ok4(ch->residual, ch->ld_residual),
               "tc_mlp_chain: addend / residual rows must be 16-byte aligned, 128 wide");

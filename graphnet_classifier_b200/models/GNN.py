@@ -245,10 +245,15 @@ class GraphNet(nn.Module):
             else:               # the whole edge MLP in one launch: e Wc^T + P[row] + Q[col] + b0 -> ... -> LN + e
                 e = chain(e, (W0[:, 256:384], b0), em, gather0=(P, graph.src), gather1=(Q, graph.dst), residual=e)
             del P, Q
-            agg = ops.aggregate(e, graph)
             # the whole node MLP in one launch: cat([h, agg]) V0^T + c0 as a two-operand contraction -> ... -> LN + h
-            h = chain(agg, (V0[:, 128:256], c0), nm, operand2=(h, V0[:, 0:128]), residual=h)
-            del agg
+            if ops.FUSE_AGG and graph.num_edges > 0 and graph.max_in_degree() <= 2:
+                # ... and scatter_sum(e, col) inside it: the loader forms agg[m] = e[eid0] + e[eid1] (same bits)
+                h = chain(e, (V0[:, 128:256], c0), nm, operand2=(h, V0[:, 0:128]), residual=h,
+                          agg=(graph.dst_rowptr, graph.dst_eid))
+            else:
+                agg = ops.aggregate(e, graph)
+                h = chain(agg, (V0[:, 128:256], c0), nm, operand2=(h, V0[:, 0:128]), residual=h)
+                del agg
         dec = self.node_decoder.model
         return ops.tc_mlp_chain(h, [(dec[0].weight, dec[0].bias), (dec[2].weight, dec[2].bias)],
                                 dot_w=dec[4].weight, dot_b=dec[4].bias)

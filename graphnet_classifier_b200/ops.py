@@ -55,6 +55,9 @@ def grad_sink(p):
 
 
 CHAIN_GUARD = os.environ.get("GNC_CHAIN_GUARD", "1") != "0"
+# scatter_sum folded into the node processor's launch when no node has more than two in-edges (grid graphs without
+# diagonals); "0" keeps the aggregation as a launch of its own (the form the fused one is tested against)
+FUSE_AGG = os.environ.get("GNC_FUSE_AGG", "1") != "0"
 CHAIN_GUARD_EVENTS = 0          # how many forwards took the fallback (tests, diagnostics)
 
 
@@ -151,7 +154,7 @@ class GraphIndex:
     reference's summation order) and by source."""
 
     __slots__ = ("num_nodes", "num_edges", "src", "dst", "dst_rowptr", "dst_eid", "src_rowptr", "src_eid",
-                 "edge_class", "class_geom", "pos_ref", "pos_version", "class_sum_plan", "node_ptr")
+                 "edge_class", "class_geom", "pos_ref", "pos_version", "class_sum_plan", "node_ptr", "_max_in_degree")
 
     def __init__(self, num_nodes, num_edges, src, dst, dst_rowptr, dst_eid, src_rowptr, src_eid):
         self.num_nodes, self.num_edges = int(num_nodes), int(num_edges)
@@ -170,6 +173,15 @@ class GraphIndex:
         # int32 [B + 1] node offsets of a batch whose graphs have DIFFERENT node counts (superpixel graphs); None for
         # fixed-size batches, where graph b owns rows b * num_nodes .. (b + 1) * num_nodes - 1
         self.node_ptr = None
+        self._max_in_degree = None      # largest in-degree (lazy; builders that know it set it)
+
+    def max_in_degree(self) -> int:
+        """Largest number of edges arriving at one node: with at most two, the node processor's launch forms the
+        aggregated operand itself (``tc_mlp_chain(agg=...)``).  One device reduction per topology, cached."""
+        if self._max_in_degree is None:
+            rp = self.dst_rowptr
+            self._max_in_degree = int((rp[1:] - rp[:-1]).max().item()) if rp.numel() > 1 else 0
+        return self._max_in_degree
 
     def bind_positions(self, pos: Tensor) -> None:
         """Remember the ``pos`` tensor (and its in-place version) the edge classes were derived from."""
@@ -735,7 +747,7 @@ def tc_linear_multi(A: Tensor, weights: Sequence[Tensor], engine: str = "chain")
 def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1=None, gamma: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, eps: float = 1e-5, residual=None, dot_w: Optional[Tensor] = None,
                  dot_b: Optional[Tensor] = None, out: Optional[Tensor] = None, pre=None, operand2=None,
-                 narrow=None, stash=None) -> Tensor:
+                 narrow=None, stash=None, agg=None) -> Tensor:
     """Two or three chained ``Linear(128, 128)`` layers in one launch (csrc/tc_chain.cu), ReLU after
     all but the last, hidden activations kept on chip.  ``layers`` is ``[(W, bias), ...]``;
     ``gather0`` / ``gather1`` are ``(rows, idx int32 [M] | None)`` pre-activation addends of the first
@@ -745,6 +757,9 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
     encoders' first layer folded into the launch).  ``operand2=(A2, W_A2)`` adds ``A2 @ W_A2.T`` to the first layer (two-operand contraction, no addend tensor).
     ``A=None`` with ``pre=(table, idx int32 [M], bias)`` is the pre-stage form: the first operand is
     ``relu(table[idx] + gather0 + gather1 + bias)`` and ``layers`` are the two layers after it.
+    ``agg=(rowptr int32 [M + 1], eid int32)`` with ``operand2``: ``A`` is the ``[E, 128]`` edge table and the first operand's
+    row ``m`` is the ordered sum of ``A[eid[k]]``, ``k`` in ``[rowptr[m], rowptr[m + 1])`` - at most two entries per row
+    (``scatter_sum`` folded into the launch; the caller has checked the in-degrees).
     ``stash=(a1, a2, z, mean, rstd)`` (training forward of a block's edge / node MLP: 3 layers, addends, LayerNorm, residual
     by row): the launch also writes the hidden ReLU outputs ``a1``, ``a2``, the LayerNorm input ``z`` (``[M, 128]`` each) and
     the row statistics ``mean``, ``rstd`` (``[M]``) - what the backward pass of the MLP reads.
@@ -763,6 +778,15 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
         _require_cuda(A)
         A = _rows(A)
         M = A.shape[0]
+        if agg is not None:
+            if operand2 is None:
+                raise ValueError("tc_mlp_chain: agg goes with operand2 (the node processor's two-operand form)")
+            rp, ei = agg
+            if rp.dtype != torch.int32 or ei.dtype != torch.int32 or rp.device != A.device or ei.device != A.device:
+                raise ValueError("tc_mlp_chain: agg = (rowptr, eid) int32 tensors on the operands' device")
+            M = rp.numel() - 1
+            keep += [rp, ei]
+            ch.agg_rowptr, ch.agg_eid = rp.data_ptr(), ei.data_ptr()
         a_ptr, a_ld, dev = A.data_ptr(), _ld(A), A.device
         if narrow is not None:
             Wn, bn = narrow
@@ -782,7 +806,8 @@ def tc_mlp_chain(A: Optional[Tensor], layers: Sequence, *, gather0=None, gather1
         keep.append(W)
         ch.W[l], ch.ldw[l] = W.data_ptr(), W.stride(0)
         ch.bias[l] = None if b is None else b.data_ptr()
-    nbytes = 4.0 * ((M * (A.shape[1] if narrow is not None else 128) if A is not None else 0) + len(layers) * 128 * 128)
+    nbytes = 4.0 * (((A.shape[0] if agg is not None else M) * (A.shape[1] if narrow is not None else 128) if A is not None else 0)
+                    + len(layers) * 128 * 128 + (2 * M + 1 if agg is not None else 0))
     if operand2 is not None:
         A2, W2 = operand2
         A2 = _rows(A2)

@@ -111,6 +111,9 @@ def _build_grid(images, patch: int, diagonals: bool, device, use_cache: bool) ->
         if BE == 0:
             ei, src, dst, deid, seid = ei[:, :0], src[:0], dst[:0], deid[:0], seid[:0]
         graph = GraphIndex(B * N, BE, src, dst, drp, deid, srp, seid)
+        # grid edges point right / down (and along both diagonals): a node has at most one in-edge per family, which is
+        # what lets the node processor's launch form the aggregated operand itself (GraphIndex.max_in_degree; an upper bound)
+        graph._max_in_degree = int(gw > 1) + int(gh > 1) + (2 if (diagonals and not patch and gh > 1 and gw > 1) else 0)
         if BE > 0:
             # edge classes: every edge of a grid family has the same geometry row, so the edge
             # encoder only has to see one row per family (GraphNet._forward_tc)

@@ -387,6 +387,12 @@ typedef struct gnc_tc_chain {
    * row statistics mean[M], rstd[M] = 1 / sqrt(var + eps) - instead of three per-layer launches that write and
    * re-read them. */
   float* stash_a1; float* stash_a2; float* stash_z; int64_t ld_stash; float* stash_mean; float* stash_rstd;
+  /* aggregated first operand (agg_rowptr != NULL; the two-operand form above): A is the [E, 128] EDGE table and row m of the
+   * first operand is sum_{k in [agg_rowptr[m], agg_rowptr[m + 1])} A[agg_eid[k]] in ascending k - scatter_sum(edge_attr, col)
+   * of NodeProcessor.forward (models/GNN.py:99) formed by the kernel's loader instead of a launch of its own.  M is the number
+   * of NODE rows; agg_rowptr is int32 [M + 1]; every row must have AT MOST TWO entries (the caller checks the topology once:
+   * grid graphs without diagonals) - with those the sum is the reference's bit for bit. */
+  const int32_t* agg_rowptr; const int32_t* agg_eid;
 } gnc_tc_chain_t;
 
 int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* chain /*HOST*/,

@@ -249,6 +249,43 @@ def test_chain_two_operand_node_form(libgnc, M):
     assert _maxrel(got, ref) < RTOL
 
 
+@pytest.mark.parametrize("M", [1, 200, 256 * 74 + 77, 256 * 74 * 4 + 256 * 11 + 3, 256 * 74 * 5 + 31])
+def test_chain_node_form_with_aggregating_loader(libgnc, M):
+    """NodeProcessor form with scatter_sum folded into the launch: the loader forms agg[m] = e[eid0] + e[eid1] from the
+    edge table (in-degree 0, 1 or 2 per node, edge ids in any order) - the bits of the aggregation kernel followed by the
+    two-operand launch, odd / even tile counts per CTA pair, ragged last tile."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(M + 5)
+    deg = torch.randint(0, 3, (M,), generator=gen)
+    if M > 2:
+        deg[0], deg[M - 1] = 2, 1
+    E = int(deg.sum())
+    rowptr = torch.zeros(M + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).int()
+    eid = torch.randperm(max(E, 1), generator=gen)[:E].int()        # a permutation: every edge row has one destination
+    e = (torch.randn(max(E, 1), 128, generator=gen) * 2).cuda()
+    h = torch.randn(M, 128, generator=gen).cuda()
+    V0 = (torch.randn(128, 256, generator=gen) / 16).cuda()
+    c0 = (torch.randn(128, generator=gen) * 0.2).cuda()
+    rest = [(W.cuda(), b.cuda()) for W, b in _layers(gen, 2)]
+    gamma, beta = (torch.rand(128, generator=gen) + 0.5).cuda(), (torch.randn(128, generator=gen) * 0.2).cuda()
+    rp, ei = rowptr.cuda(), eid.cuda()
+    agg = ops._agg_raw(rp, ei, e, M)
+    layers = [(V0[:, 128:256], c0)] + rest
+    ref = ops.tc_mlp_chain(agg, layers, operand2=(h, V0[:, 0:128]), gamma=gamma, beta=beta, residual=h)
+    got = ops.tc_mlp_chain(e, layers, operand2=(h, V0[:, 0:128]), gamma=gamma, beta=beta, residual=h, agg=(rp, ei))
+    assert got.shape == (M, 128) and torch.isfinite(got).all()
+    assert torch.equal(got, ref)
+    # and against float64 from the edge table itself
+    a64 = torch.zeros(M, 128, dtype=torch.float64)
+    dst = torch.repeat_interleave(torch.arange(M), deg)
+    a64.index_add_(0, dst, e.cpu().double()[eid.long()])
+    z = torch.relu(torch.cat([h.cpu().double(), a64], 1) @ V0.cpu().double().t() + c0.cpu().double())
+    z = torch.relu(z @ rest[0][0].cpu().double().t() + rest[0][1].cpu().double()) @ rest[1][0].cpu().double().t() + rest[1][1].cpu().double()
+    want = torch.nn.functional.layer_norm(z, (128,), gamma.cpu().double(), beta.cpu().double(), 1e-5) + h.cpu().double()
+    assert _maxrel(got, want) < RTOL
+
+
 @pytest.mark.parametrize("M,k", [(500, 3), (256 * 74 * 3 + 100, 3), (1000, 8), (700, 1)])
 def test_chain_narrow_first_layer(libgnc, M, k):
     """Encoder form: relu(x Wn^T + bn) built by the loader from k <= 8 input columns, two layers, LayerNorm."""
