@@ -15,14 +15,13 @@
 namespace gnc {
 
 template <int LPR, int VPL, bool ACC>
-__global__ void __launch_bounds__(256) agg_csr_sum_vec_kernel(
+__device__ __forceinline__ void agg_rows(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid, const float* __restrict__ src,
-    int64_t ld_src, int64_t N, int D4 /* D/4 */, float* __restrict__ out, int64_t ld_out) {
+    int64_t ld_src, int64_t N, int D4 /* D/4 */, float* __restrict__ out, int64_t ld_out, int64_t warp_global,
+    int64_t warps_total) {
   constexpr int ROWS_PER_WARP = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t v0 = warp_global * ROWS_PER_WARP; v0 < N; v0 += warps_total * ROWS_PER_WARP) {
     const int64_t v = v0 + sub;
     if (v >= N) continue;
@@ -88,6 +87,28 @@ __global__ void __launch_bounds__(256) agg_csr_sum_vec_kernel(
       }
     }
   }
+}
+
+template <int LPR, int VPL, bool ACC>
+__global__ void __launch_bounds__(256) agg_csr_sum_vec_kernel(
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid, const float* __restrict__ src,
+    int64_t ld_src, int64_t N, int D4 /* D/4 */, float* __restrict__ out, int64_t ld_out) {
+  agg_rows<LPR, VPL, ACC>(rowptr, eid, src, ld_src, N, D4, out, ld_out, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                          ((int64_t)gridDim.x * blockDim.x) >> 5);
+}
+
+// Two segmented sums over the SAME rows in one launch (the backward of the x[row] / x[col] gathers: the edge gradient summed
+// by source and by destination, models/GNN.py:57-58): even warps take CSR A, odd warps CSR B, both walk the node rows in
+// step, so on locality-preserving topologies (grids) a source row fetched for one sum is still in L2 for the other - one
+// pass over the [E, D] tensor from DRAM instead of two.  Same per-row arithmetic as the single form (same bits).
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) agg_csr_sum_pair_kernel(
+    const int32_t* __restrict__ rowptrA, const int32_t* __restrict__ eidA, float* __restrict__ outA,
+    const int32_t* __restrict__ rowptrB, const int32_t* __restrict__ eidB, float* __restrict__ outB,
+    const float* __restrict__ src, int64_t ld_src, int64_t N, int D4, int64_t ld_out) {
+  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, wt = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  if (wg & 1) agg_rows<LPR, VPL, false>(rowptrB, eidB, src, ld_src, N, D4, outB, ld_out, wg >> 1, wt >> 1);
+  else agg_rows<LPR, VPL, false>(rowptrA, eidA, src, ld_src, N, D4, outA, ld_out, wg >> 1, wt >> 1);
 }
 
 // Any D / alignment: one thread per (row, feature).
@@ -316,6 +337,30 @@ int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   return accumulate ? launch_agg<true>(rowptr, eid, src, ld_src, N, D, out, ld_out, st)
                     : launch_agg<false>(rowptr, eid, src, ld_src, N, D, out, ld_out, st);
+}
+
+int gnc_agg_csr_sum_pair_f32(const int32_t* rowptr_a, const int32_t* eid_a, float* out_a, const int32_t* rowptr_b,
+                             const int32_t* eid_b, float* out_b, const float* src, int64_t ld_src, int64_t N, int D,
+                             int64_t ld_out, gnc_stream_t stream) {
+  GNC_REQUIRE(N >= 0 && D > 0 && ld_src >= D && ld_out >= D, "agg_csr_sum_pair: bad sizes");
+  if (N == 0) return GNC_OK;
+  GNC_REQUIRE(rowptr_a && rowptr_b && out_a && out_b, "agg_csr_sum_pair: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (D % 4 == 0) && D <= 128 && (ld_src % 4 == 0) && (ld_out % 4 == 0) && aligned16(src) && aligned16(out_a) && aligned16(out_b);
+  if (!vec) {                                         // shapes outside the paired kernel: the two sums one after the other
+    if (int rc = launch_agg<false>(rowptr_a, eid_a, src, ld_src, N, D, out_a, ld_out, st)) return rc;
+    return launch_agg<false>(rowptr_b, eid_b, src, ld_src, N, D, out_b, ld_out, st);
+  }
+  const int D4 = D / 4;
+#define GNC_AGGP(LPR)                                                                                                  \
+  agg_csr_sum_pair_kernel<LPR, 1><<<row_grid(2 * N, 8 * (32 / LPR)), 256, 0, st>>>(rowptr_a, eid_a, out_a, rowptr_b, eid_b, out_b, \
+                                                                                    src, ld_src, N, D4, ld_out)
+  if (D4 <= 4) GNC_AGGP(4);
+  else if (D4 <= 8) GNC_AGGP(8);
+  else if (D4 <= 16) GNC_AGGP(16);
+  else GNC_AGGP(32);
+#undef GNC_AGGP
+  return check_launch("agg_csr_sum_pair_kernel");
 }
 
 int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D, float* out,

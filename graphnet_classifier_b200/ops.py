@@ -257,6 +257,19 @@ def _agg_raw(rowptr: Tensor, eid: Tensor, src: Tensor, n_rows: int, out: Optiona
     return out
 
 
+def _agg_pair_raw(rowptr_a: Tensor, eid_a: Tensor, rowptr_b: Tensor, eid_b: Tensor, src: Tensor, n_rows: int):
+    """``(_agg_raw(rowptr_a, eid_a, src), _agg_raw(rowptr_b, eid_b, src))`` in one launch: ``src`` comes from DRAM once."""
+    src = _rows(src)
+    D = src.shape[1]
+    out = torch.empty(2, n_rows, D, dtype=torch.float32, device=src.device)
+    E = int(eid_a.shape[0])
+    nbytes = 4.0 * (E * D + 2 * E + 2 * (n_rows + 1) + 2 * n_rows * D)
+    check(_call("agg_csr_sum_pair", 0.0, nbytes, _lib.load().gnc_agg_csr_sum_pair_f32, rowptr_a.data_ptr(), _p(eid_a),
+                out[0].data_ptr(), rowptr_b.data_ptr(), _p(eid_b), out[1].data_ptr(), src.data_ptr(), _ld(src), n_rows, D,
+                _ld(out[0]), _stream()), "agg_csr_sum_pair")
+    return out[0], out[1]
+
+
 def _gather_raw(src: Tensor, idx: Tensor, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
     src = _rows(src)
     M, D = int(idx.shape[0]), src.shape[1]

@@ -41,6 +41,8 @@ BWD = os.environ.get("GNC_BWD", "fused")
 # reads (a1, a2, the LayerNorm input and its row statistics; fp16 two-piece operands like the inference path), "layer" =
 # three per-layer launches (3xTF32) that write and re-read the hidden activations - the form "chain" is tested against.
 FWD = os.environ.get("GNC_TRAIN_FWD", "chain")
+# Backward of the x[row] / x[col] gathers: the edge gradient summed by source and by destination in one launch ("1") or two
+AGG_PAIR = os.environ.get("GNC_AGG_PAIR", "1") != "0"
 # Test hook (tests/test_gpu_tc_engine.py): when set to a dict, the forward records the sign pattern ``activation > 0``
 # of every ReLU of the core under the reference's module path, e.g. ``("graph_processor.blocks.0.edge_model.
 # edge_processor", 1)`` for ``model[1]`` - what a mask-conditioned gradient comparison against the oracle needs.
@@ -363,8 +365,11 @@ class GraphNetCoreFn(torch.autograd.Function):
             # edge processor: e' = LN(MLP(cat[h[row], h[col], e])) + e
             da1, _ = tail_bwd(de, 2 + 2 * k, pe + 2, True)
             dW0 = sinks[pe] if acc else torch.empty(128, 384, dtype=_f32, device=dev)
-            dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
-            dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
+            if AGG_PAIR:    # both sums from one pass over da1
+                dP, dQ = ops._agg_pair_raw(graph.src_rowptr, graph.src_eid, graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
+            else:
+                dP = ops._agg_raw(graph.src_rowptr, graph.src_eid, da1, graph.num_nodes)
+                dQ = ops._agg_raw(graph.dst_rowptr, graph.dst_eid, da1, graph.num_nodes)
             if in_kernel:
                 de, _, db0 = _bwd_layer(da1, e_in, W0[:, 256:384], addend=de, dW_out=dW0[:, 256:384], want_db=True)   # + residual
             else:

@@ -226,6 +226,14 @@ int gnc_agg_csr_sum_f32(const int32_t* rowptr, const int32_t* eid,
                         const float* src, int64_t ld_src, int64_t N, int D,
                         float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);
 
+/* Two such sums over the same [E, D] tensor in ONE launch: out_a by CSR a, out_b by CSR b (N rows each, row pitch ld_out) -
+ * the backward of the x[row] and x[col] gathers of EdgeProcessor.forward (models/GNN.py:57-58), i.e. the edge gradient
+ * summed by source and by destination.  The two sums walk the node rows in step, so a row of `src` fetched for one is
+ * still in L2 for the other on locality-preserving topologies.  Same bits as two gnc_agg_csr_sum_f32 calls. */
+int gnc_agg_csr_sum_pair_f32(const int32_t* rowptr_a, const int32_t* eid_a, float* out_a,
+                             const int32_t* rowptr_b, const int32_t* eid_b, float* out_b,
+                             const float* src, int64_t ld_src, int64_t N, int D, int64_t ld_out, gnc_stream_t stream);
+
 /* out[m, :] (+)= src[idx[m], :]   (x[row], x[col]; backward of the aggregation) */
 int gnc_gather_rows_f32(const float* src, int64_t ld_src, const int32_t* idx, int64_t M, int D,
                         float* out, int64_t ld_out, int accumulate, gnc_stream_t stream);

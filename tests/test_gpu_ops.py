@@ -62,6 +62,23 @@ def test_aggregate_random_multigraph_bit_exact_and_scatter_sum_api(libgnc, golde
     assert scatter_sum(torch.zeros(0, 4).cuda(), torch.zeros(0, dtype=torch.long).cuda()).shape == (0, 4)
 
 
+@pytest.mark.parametrize("D", [128, 32, 20, 3])
+def test_aggregate_pair_equals_two_sums(libgnc, D):
+    """The edge gradient summed by source and by destination in ONE launch (backward of x[row] / x[col]): the bits of two
+    separate ordered sums, on a random multigraph with empty rows and on sizes that leave warps without rows."""
+    from graphnet_classifier_b200 import ops
+    gen = torch.Generator().manual_seed(D)
+    for N, E in ((1, 5), (37, 400), (5000, 23001)):
+        ei = torch.stack([torch.randint(0, N, (E,), generator=gen), torch.randint(0, max(N - 3, 1), (E,), generator=gen)]).cuda()
+        g = ops.GraphIndex.from_edge_index(ei, N)
+        src = torch.randn(E, D, generator=gen).cuda()
+        a, b = ops._agg_pair_raw(g.src_rowptr, g.src_eid, g.dst_rowptr, g.dst_eid, src, N)
+        assert torch.equal(a, ops._agg_raw(g.src_rowptr, g.src_eid, src, N))
+        assert torch.equal(b, ops._agg_raw(g.dst_rowptr, g.dst_eid, src, N))
+        ref = torch.zeros(N, D).index_add_(0, ei[1].cpu(), src.cpu())
+        assert torch.equal(b.cpu(), ref)
+
+
 def test_aggregate_backward_is_gather_and_gather_backward_is_ordered_sum(libgnc):
     from graphnet_classifier_b200 import ops
     gb = _graph(6, 9, True, B=2)
