@@ -179,6 +179,8 @@ class GraphIndex:
         """Largest number of edges arriving at one node: with at most two, the node processor's launch forms the
         aggregated operand itself (``tc_mlp_chain(agg=...)``).  One device reduction per topology, cached."""
         if self._max_in_degree is None:
+            if torch.cuda.is_current_stream_capturing():
+                return 1 << 30          # unknown and no synchronisation allowed here: callers take the general path
             rp = self.dst_rowptr
             self._max_in_degree = int((rp[1:] - rp[:-1]).max().item()) if rp.numel() > 1 else 0
         return self._max_in_degree

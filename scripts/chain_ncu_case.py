@@ -20,3 +20,13 @@ for _ in range(3):
     ops.tc_mlp_chain(e, layers, gather0=(P, src), gather1=(Q, dst), gamma=gamma, beta=beta, residual=e, out=out)
 torch.cuda.synchronize()
 print("ok", float(out[0, 0]))
+# second case (argv[2] == "node"): the node processor with the aggregation folded into its loader (tc_chain2n_kernel, AGG)
+if len(sys.argv) > 2 and sys.argv[2] == "node":
+    from graphnet_classifier_b200.ops import GraphIndex
+    g_idx = GraphIndex.from_edge_index(torch.stack([src.long(), dst.long()]), N)
+    h = mk(N, 128); V0 = mk(128, 256) / 16; c0 = mk(128) * 0.1; outn = torch.empty(N, 128, device=dev)
+    for _ in range(3):
+        ops.tc_mlp_chain(e, [(V0[:, 128:256], c0), layers[1], layers[2]], operand2=(h, V0[:, 0:128]), gamma=gamma, beta=beta,
+                         residual=h, out=outn, agg=(g_idx.dst_rowptr, g_idx.dst_eid))
+    torch.cuda.synchronize()
+    print("ok node", float(outn[0, 0]))
