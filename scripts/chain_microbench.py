@@ -59,6 +59,7 @@ def per_layer_node():
     return ops.tc_linear(a2, layers[2][0], bias=layers[2][1], gamma=gamma, beta=beta, residual=h, out=outn)
 
 
+g_idx = ops.GraphIndex.from_edge_index(torch.stack([src.long(), dst.long()]), N)
 cases = {
     "edge MLP per-layer (3 launches)": (per_layer_edge, E, 3, 4.0 * 128 * (2 * E + 2 * N)),
     "edge MLP chained": (chain_edge, E, 3, 4.0 * 128 * (2 * E + 2 * N)),
@@ -68,6 +69,7 @@ cases = {
     "node MLP per-layer (3 launches)": (per_layer_node, N, 3, 4.0 * 128 * 4 * N),
     "node MLP chained": (lambda: ops.tc_mlp_chain(agg, layers, gather0=(T, None), gamma=gamma, beta=beta, residual=h, out=outn), N, 3, 4.0 * 128 * 4 * N),
     "node MLP chained, two-operand L0": (lambda: ops.tc_mlp_chain(agg, layers, operand2=(h, layers[0][0]), gamma=gamma, beta=beta, residual=h, out=outn), N, 4, 4.0 * 128 * 3 * N),
+    "node MLP, two-operand L0 + aggregating loader": (lambda: ops.tc_mlp_chain(e, layers, operand2=(h, layers[0][0]), gamma=gamma, beta=beta, residual=h, out=outn, agg=(g_idx.dst_rowptr, g_idx.dst_eid)), N, 4, 4.0 * 128 * (E + 2 * N)),
     "P,Q,T products (multi, 3 sets)": (lambda: ops.tc_linear_multi(h, [layers[0][0], layers[1][0], layers[2][0]]), N, 3, 4.0 * 128 * 4 * N),
     "P,Q products (multi, 2 sets)": (lambda: ops.tc_linear_multi(h, [layers[0][0], layers[1][0]]), N, 2, 4.0 * 128 * 3 * N),
     "encoder tail (2 layers, LN)": (lambda: ops.tc_mlp_chain(h, layers[:2], gamma=gamma, beta=beta, out=outn), N, 2, 4.0 * 128 * 2 * N),
