@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-staging", action="store_true")
+    ap.add_argument("--no-power", action="store_true", help="skip the board-power block")
+    ap.add_argument("--power-seconds", type=float, default=3.0)
     ap.add_argument("--cpu-graphs", type=int, default=256, help="graphs in the bounded CPU sample")
     ap.add_argument("--ref-graphs-per-step", type=int, default=32)
     return ap.parse_args()
@@ -100,13 +102,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
+    def __init__(self, index: int, period_ms: int = 200):
+        self.index, self.rows, self.proc, self.thread, self.period_ms = index, [], None, None, int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -464,6 +466,38 @@ def run_ours(args):
     ms_total, wall = timed(infer_step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     value = n_gpus * B * args.steps / (ms_total / 1e3)
+
+    # ---- board power under this step (outside every timed region) ---------------------------------------------------
+    # The tensor-core launches of the path run AT the board's power cap: the same step back to back
+    # for a few seconds, power and SM clock sampled every 50 ms, next to the enforced limit.
+    power = None
+    if rank == 0 and not args.no_power:
+        try:
+            ps = ClockSampler(local_rank, period_ms=50)
+            ps.start()
+            t0 = time.perf_counter()
+            n_pw = 0
+            while time.perf_counter() - t0 < args.power_seconds:
+                infer_step()
+                n_pw += 1
+                if n_pw % 4 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            pw = ps.stop()
+            lim = subprocess.run(["nvidia-smi", "--query-gpu=power.limit", "--format=csv,noheader,nounits", "-i", str(local_rank)],
+                                 capture_output=True, text=True).stdout.strip()
+            try:
+                lim = float(lim)
+            except ValueError:
+                lim = None
+            power = {"board_w_under_load": pw.get("power_w"), "limit_w": lim, "sm_mhz_under_load": pw.get("sm_mhz"),
+                     "sm_max_mhz": pw.get("sm_max_mhz"), "reasons": pw.get("reasons"), "samples_under_load": pw.get("samples_under_load"),
+                     "at_power_cap": (pw.get("power_w") is not None and lim is not None and pw["power_w"] >= 0.95 * lim),
+                     "steps": n_pw, "seconds": dt, "graphs_per_s_sustained": B * n_pw / dt,
+                     "what": "the inference step back to back (no L2 flush, no per-step events), nvidia-smi every 50 ms"}
+        except Exception as ex:           # a secondary block never fails the line
+            power = {"error": repr(ex)}
 
     # ---- end to end: pinned host images in, logits back on the host -----------------
     def e2e_step():
@@ -828,6 +862,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
+            "power": power,
             "roofline": roofline,
             "roofline_aggregation": roofline_agg,
             "kernel_shares": kernel_shares,
