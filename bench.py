@@ -294,6 +294,12 @@ def run_config_blocks(args, dev, pk, flush):
           "inference": {"value": B1 / inf_ms * 1e3, "unit": UNIT, "ms_per_step": inf_ms},
           "e2e": {"value": B1 / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms,
                   "h2d_bytes_per_step": int(im1.numel()), "d2h_bytes_per_step": B1 * 8}}
+    try:        # the same batch through the captured CUDA graph (GraphClassifierPipeline.infer_graphed): this size is launch-bound
+        g_ms = med_ms(lambda: p1.infer_graphed(im1d))
+        same = bool(torch.equal(p1.infer_graphed(im1d), p1.infer(im1d)))
+        c1["inference_graphed"] = {"value": B1 / g_ms * 1e3, "unit": UNIT, "ms_per_step": g_ms, "equal_to_infer": same}
+    except Exception as ex:
+        c1["inference_graphed"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         sd = {k: v.detach().cpu() for k, v in m1.state_dict().items()}
         v, dt, cores, ref_logits, ref_imgs = cpu_reference_run(r1, B1, 1, state_dict=sd, seed=99)
