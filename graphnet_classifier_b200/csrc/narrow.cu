@@ -118,10 +118,11 @@ extern "C" {
 
 int gnc_linear_narrowk_fwd_f32(const float* X, int64_t ldx, int64_t M, int K, const float* W, int64_t ldw,
                                const float* bias, int N, int relu, float* Y, int64_t ldy, gnc_stream_t stream) {
-  GNC_REQUIRE(K >= 1 && K <= kMaxK && N > 0 && N % 4 == 0 && M >= 0 && X && W && Y && ldx >= K && ldw >= K && ldy >= N,
+  GNC_REQUIRE(K >= 1 && K <= kMaxK && N > 0 && N % 4 == 0 && M >= 0 && ldx >= K && ldw >= K && ldy >= N,
               "linear_narrowk_fwd: need 1 <= K <= 8, N % 4 == 0");
+  if (M == 0) return GNC_OK;                          // an edge-less graph (1 x 1 image): empty tensors have no pointers
+  GNC_REQUIRE(X && W && Y, "linear_narrowk_fwd: null pointer");
   GNC_REQUIRE(ldy % 4 == 0 && aligned16(Y), "linear_narrowk_fwd: Y rows must be 16-byte aligned");
-  if (M == 0) return GNC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   long long blocks = ceil_div<long long>(M, 8);
   if (blocks > (long long)kNumSMs * 8) blocks = (long long)kNumSMs * 8;
@@ -137,9 +138,9 @@ int64_t gnc_linear_narrowk_wgrad_workspace(int64_t M, int N, int K) { return nar
 int gnc_linear_narrowk_wgrad_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
                                  int64_t M, int N, int K, float* dW, int64_t lddw, float* db, int accumulate,
                                  float* work, int64_t work_elems, gnc_stream_t stream) {
-  GNC_REQUIRE(K >= 1 && K <= kMaxK && N > 0 && N % 4 == 0 && N <= 128 && M >= 0 && dY && X && lddy >= N && ldx >= K,
+  GNC_REQUIRE(K >= 1 && K <= kMaxK && N > 0 && N % 4 == 0 && N <= 128 && M >= 0 && (M == 0 || (dY && X)) && lddy >= N && ldx >= K,
               "linear_narrowk_wgrad: need 1 <= K <= 8, N % 4 == 0, N <= 128");
-  GNC_REQUIRE(lddy % 4 == 0 && aligned16(dY) && (!Y || (ldy % 4 == 0 && aligned16(Y))) && (!dW || lddw >= K),
+  GNC_REQUIRE(lddy % 4 == 0 && (M == 0 || aligned16(dY)) && (!Y || (ldy % 4 == 0 && aligned16(Y))) && (!dW || lddw >= K),
               "linear_narrowk_wgrad: dY / Y rows must be 16-byte aligned");
   const long long blocks = M > 0 ? narrow_blocks(M) : 0;
   if (!work || !aligned16(work) || work_elems < blocks * (long long)(K + 1) * N)

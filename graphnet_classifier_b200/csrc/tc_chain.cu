@@ -1997,9 +1997,10 @@ using namespace gnc;
 
 extern "C" int gnc_tc_mlp_chain_f32(const float* A, int64_t lda, int64_t M, const gnc_tc_chain_t* ch, float* Y, int64_t ldy,
                                     gnc_stream_t stream) {
-  GNC_REQUIRE(ch && Y && M >= 0, "tc_mlp_chain: bad arguments");
+  GNC_REQUIRE(ch && M >= 0, "tc_mlp_chain: bad arguments");
   GNC_REQUIRE(ch->nlayers >= 2 && ch->nlayers <= chain::kMaxLayers, "tc_mlp_chain: 2 or 3 layers");
-  if (M == 0) return GNC_OK;
+  if (M == 0) return GNC_OK;                          // (empty tensors have no pointers: an edge-less graph)
+  GNC_REQUIRE(Y, "tc_mlp_chain: null output");
   chain::Params p = {};
   p.A = A; p.lda = lda; p.M = M; p.nlayers = ch->nlayers;
   auto ok4 = [](const float* q, int64_t ld) { return !q || (aligned16(q) && ld % 4 == 0 && ld >= chain::kD); };

@@ -616,8 +616,9 @@ extern "C" int gnc_tc_linear_f32(const float* A, int64_t lda, int64_t M, int K, 
                                  int transpose_w, const gnc_tc_epilogue_t* epi, float* Y, int64_t ldy,
                                  gnc_stream_t stream) {
   GNC_REQUIRE(K == tc::kD && N == tc::kD, "tc_linear: this engine is specialised for 128 x 128 weight tiles");
-  GNC_REQUIRE(A && W && Y && epi && M >= 0 && lda >= K && ldw >= tc::kD, "tc_linear: bad arguments");
-  if (M == 0) return GNC_OK;
+  GNC_REQUIRE(W && epi && M >= 0 && lda >= K && ldw >= tc::kD, "tc_linear: bad arguments");
+  if (M == 0) return GNC_OK;                          // (empty tensors have no pointers: an edge-less graph)
+  GNC_REQUIRE(A && Y, "tc_linear: null pointer");
   GNC_REQUIRE(lda % 4 == 0 && aligned16(A) && aligned16(W) && ldw % 4 == 0, "tc_linear: A / W rows must be 16-byte aligned");
   tc::Params p;
   p.A = A; p.lda = lda; p.M = M; p.W = W; p.ldw = ldw; p.transpose_w = transpose_w;

@@ -366,6 +366,36 @@ def test_grid_edge_class_shortcut_equals_generic_path(libgnc, diag):
     assert _maxrel(y_tab, y_gen) < 5e-6 and _maxrel(y_tab, y_or) < RTOL and _maxrel(y_gen, y_or) < RTOL
 
 
+@pytest.mark.parametrize("r,B,diag,generic", [(16, 3, False, False), (16, 3, False, True), (16, 2, True, False), (64, 4, False, False),
+                                              (128, 8, False, False), (1, 2, False, False)])
+def test_aggregation_folded_into_node_launch_equals_separate_launch(libgnc, monkeypatch, r, B, diag, generic):
+    """Inference with scatter_sum formed by the node processor's loader (grid graphs: in-degree <= 2) gives the BITS of the
+    aggregation kernel + node launch, at the tests' small shapes and at BASELINE configs[0] / [1] shapes; graphs with diagonals
+    (in-degree 4) and single-pixel graphs (no edges; the reference's MLP.forward raises on their empty edge tensors,
+    models/MLP.py:46 - here they run) keep the separate launch either way."""
+    from graphnet_classifier_b200 import ops, _lib
+    from graphnet_classifier_b200.models.GNN import CombinedModel, GraphNet
+    from graphnet_classifier_b200.utils.image_to_graph.batched import build_pixel_graphs
+    cfg = dict(num_local_features=3, space_dim=2, out_channels=1, n_blocks=3)
+    torch.manual_seed(r + B)
+    gm = CombinedModel(GraphNet(**cfg), num_nodes=r * r, classes=2).cuda().eval()
+    imgs = synthetic_images(B, r, seed=5 * r + 1)
+    gb = build_pixel_graphs(torch.from_numpy(imgs), diagonals=diag, use_cache=False)
+    pos = gb.pos.clone() if generic else gb.pos
+    assert gb.graph.max_in_degree() == (0 if r == 1 else (4 if diag else 2))
+    outs, launches = [], []
+    for fuse in (True, False):
+        monkeypatch.setattr(ops, "FUSE_AGG", fuse)
+        _lib.reset_launch_count()
+        with torch.no_grad():
+            outs.append(gm.graph_net(gb.x, pos, gb.edge_index))
+        torch.cuda.synchronize()
+        launches.append(_lib.launch_count())
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+    folded = (not diag) and r > 1
+    assert launches[1] - launches[0] == (3 if folded else 0)        # one aggregation launch per block disappears
+
+
 @pytest.mark.parametrize("engine", ["chain", "tf32"])
 @pytest.mark.parametrize("M", [77, 128 * 49 + 3, 128 * 500])
 def test_tc_linear_multi(libgnc, M, engine):
