@@ -30,3 +30,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "node":
                          residual=h, out=outn, agg=(g_idx.dst_rowptr, g_idx.dst_eid))
     torch.cuda.synchronize()
     print("ok node", float(outn[0, 0]))
+# third case (argv[2] == "stash"): the training forward of the edge MLP (chained launch that also writes a1, a2, z, mean, rstd)
+if len(sys.argv) > 2 and sys.argv[2] == "stash":
+    st = [torch.empty(E, 128, device=dev) for _ in range(3)] + [torch.empty(E, device=dev), torch.empty(E, device=dev)]
+    for _ in range(3):
+        ops.tc_mlp_chain(e, layers, gather0=(P, src), gather1=(Q, dst), gamma=gamma, beta=beta, residual=e, out=out, stash=tuple(st))
+    torch.cuda.synchronize()
+    print("ok stash", float(st[0][0, 0]))
